@@ -1,0 +1,206 @@
+/* svae.h - C ABI of libsvae.so: the B200-native Sequential-VAE hot path (train step, forward probes, generation).
+ *
+ * The reference (MWPainter/Sequential-Variational-Autoencoder) is pure Python on TensorFlow 1.x and has no FFI of
+ * its own; the boundary this library sits behind is the Python class surface that main.py / trainer.py call, whose
+ * device work is a single `Session.run`.  Each entry point below names the reference interface it replaces
+ * (file:line in /root/reference).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types; every function returns 0 on success or a negative
+ *     SVAE_E* code; svae_last_error() returns a human-readable message for the last failure on that handle.
+ *   - tensors are fp32, NHWC, dense.  "dev" pointers are CUDA device pointers owned by the caller; "host"
+ *     pointers are ordinary host memory (pinned or pageable).
+ *   - one handle per device per process; a handle is not thread-safe.  All device work is ordered on the handle's
+ *     stream (svae_set_stream); only the *_host entry points, svae_sync and svae_read_losses synchronise.
+ *   - there is NO CPU fallback: without a CUDA device svae_create fails with SVAE_ENODEVICE.
+ */
+#ifndef SVAE_H_
+#define SVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVAE_MAX_LEVELS 8
+#define SVAE_MAX_STEPS 64
+#define SVAE_NAME_LEN 128
+
+enum {
+  SVAE_OK = 0,
+  SVAE_EINVAL = -1,     /* bad argument / unsupported configuration */
+  SVAE_ENODEVICE = -2,  /* no usable CUDA device */
+  SVAE_ECUDA = -3,      /* CUDA runtime error (message in svae_last_error) */
+  SVAE_ENOMEM = -4,     /* device allocation failed */
+  SVAE_ENCCL = -5,      /* NCCL missing or failed */
+  SVAE_ESTATE = -6      /* call sequence error (e.g. backward without forward) */
+};
+
+/* operand precision of the conv/deconv contractions (accumulation is always fp32) */
+enum {
+  SVAE_OPERAND_FP32 = 0, /* fp32 SIMT kernels: strict-parity mode */
+  SVAE_OPERAND_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulators */
+};
+
+/* Hyper-parameters of one SequentialVAE instance.
+ * Replaces: the attribute block of SequentialVAE.__init__, sequential_vae.py:197-258 (+ netname rows :281-862). */
+typedef struct svae_config {
+  int32_t height, width, channels;          /* dataset.data_dims                         sequential_vae.py:197   */
+  int32_t levels;                           /* vlae_levels                               :202                    */
+  int32_t latent_dims[SVAE_MAX_LEVELS];     /* vlae_latent_dims                          :203                    */
+  int32_t filter_sizes[SVAE_MAX_LEVELS + 2];/* filter_sizes (levels+2 entries)           :207                    */
+  int32_t mc_steps;                         /* mc_steps                                  :219                    */
+  int32_t intermediate_reconstruction;      /* :221                                                              */
+  uint64_t regularized_mask;                /* bit t set <=> t in regularized_steps      :224                    */
+  float first_step_loss_coeff;              /* :226                                                              */
+  float latent_mean_clip;                   /* :229 (INFINITY = no clip)                                         */
+  float prior_stddev;                       /* latent_prior_stddev :231                                          */
+  float min_highway, max_highway;           /* :240-241                                                          */
+  float range_lo, range_hi;                 /* dataset.range                             :1721                   */
+  float clip_value;                         /* clip_grad_value (<=0: clip_grads False)   :257-258                */
+  float adam_beta1, adam_beta2, adam_eps;   /* tf.train.AdamOptimizer defaults           :1267                   */
+  int32_t max_batch;                        /* largest batch any call will use                                   */
+  int32_t train_capacity;                   /* 1: keep per-step activations for backward; 0: forward/generate only */
+  int32_t operand_dtype;                    /* SVAE_OPERAND_*                                                    */
+  int32_t reserved[8];
+} svae_config;
+
+/* Per-step ELBO terms of the last forward.  Replaces the scalars TF lets callers fetch: self.loss, self.final_loss
+ * (sequential_vae.py:1168-1176,1204) and the per-step summaries reconstruction_loss_step_t / regularization_loss_step_t
+ * (:1207-1208). */
+typedef struct svae_losses {
+  float total;                  /* self.loss                                   */
+  float final_recon;            /* self.final_loss = recon[T-1]                */
+  float recon[SVAE_MAX_STEPS];  /* mean_b mean_hwc (x_t - target)^2            */
+  float kl[SVAE_MAX_STEPS];     /* mean_b mean_j KL(N(mu,sigma) || N(0,prior)) */
+} svae_losses;
+
+typedef struct svae_param_info {
+  char name[SVAE_NAME_LEN];     /* TF variable name, e.g. "phi/inference_step_0/Conv/weights"  */
+  int32_t ndim;
+  int32_t shape[4];
+  int64_t numel;
+  int64_t offset;               /* element offset inside the flat parameter / gradient / Adam arenas */
+  int32_t step;                 /* chain step that owns it (gradient all-reduce bucket) */
+  int32_t flags;                /* SVAE_PF_* */
+} svae_param_info;
+
+enum {
+  SVAE_PF_THETA = 1,  /* generative (theta/...) variable, else recognition (phi/...)                               */
+  SVAE_PF_INERT = 2,  /* BN-shadowed bias: kept for checkpoint compatibility, never read, gradient exactly 0 (Q2)   */
+  SVAE_PF_DEAD = 4,   /* belongs to the reference's dead recognition branch (Q3): never read, no gradient          */
+  SVAE_PF_XAVIER = 8  /* reference initialiser is xavier-uniform (heads, output deconvs) instead of N(0,0.02)        */
+};
+
+typedef struct svae_handle svae_handle;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------------
+ * Replaces SequentialVAE.__init__ -> construct_network/init_network (sequential_vae.py:81,864-870;
+ * abstract_network.py:85-107,139-152): builds the static plan, allocates weights (zero-filled; the host uploads
+ * initial values with svae_param_set), Adam slots and the activation arena. */
+int svae_create(const svae_config* cfg, int device, svae_handle** out);
+int svae_destroy(svae_handle* h);
+const char* svae_last_error(const svae_handle* h); /* h may be NULL: last creation error */
+const char* svae_version(void);
+
+/* Use `cuda_stream` (a cudaStream_t cast to void*) for all subsequent work; NULL restores the handle's own stream. */
+int svae_set_stream(svae_handle* h, void* cuda_stream);
+int svae_sync(svae_handle* h);
+
+/* ---- parameters (tf.trainable_variables(), sequential_vae.py:1225; Saver save/restore abstract_network.py:124-152) */
+int svae_param_count(const svae_handle* h);
+/* Device-free: the parameter table a handle built from `cfg` would have.  Returns the number of parameters (or a
+ * negative SVAE_E* code) and fills up to `capacity` entries of `out` (may be NULL). */
+int svae_param_table(const svae_config* cfg, svae_param_info* out, int capacity);
+int svae_param_info_get(const svae_handle* h, int index, svae_param_info* out);
+int svae_param_set(svae_handle* h, int index, const float* host_src);   /* reference layout (HWIO / [kh,kw,out,in] / [in,out]) */
+int svae_param_get(svae_handle* h, int index, float* host_dst);
+int svae_grad_get(svae_handle* h, int index, float* host_dst);          /* gradient of the last svae_backward */
+int svae_adam_get(svae_handle* h, int index, float* host_m, float* host_v);
+int svae_adam_set(svae_handle* h, int index, const float* host_m, const float* host_v);
+int64_t svae_adam_step_count(const svae_handle* h);
+int svae_adam_set_step_count(svae_handle* h, int64_t t);
+void* svae_param_arena(svae_handle* h); /* device base pointers of the flat fp32 arenas (offsets from param_info) */
+void* svae_grad_arena(svae_handle* h);
+int64_t svae_arena_numel(const svae_handle* h);
+
+/* ---- training-mode chain ----------------------------------------------------------------------------------------
+ * svae_forward replaces sess.run(self.training_mles / training_samples / loss) (sequential_vae.py:1381-1391,
+ * 1434-1455): runs all mc_steps steps - recognition net, z = mu + sigma*eps, chain encoder, decoder, per-step ELBO.
+ *   x_in_dev, x_tgt_dev : [B,H,W,C]
+ *   eps_dev             : [T,B,Z] injected noise (sequential_vae.py:1023); NULL => counter-based Philox N(0,1)
+ *                         keyed by (seed, iteration, t, b, j)
+ *   mu_out_dev, sigma_out_dev : optional [T,B,Z]; x_steps_out_dev : optional [T,B,H,W,C] (training_mles)
+ */
+int svae_forward(svae_handle* h, const float* x_in_dev, const float* x_tgt_dev, int batch, const float* eps_dev,
+                 uint64_t seed, float reg_coeff, float* mu_out_dev, float* sigma_out_dev, float* x_steps_out_dev);
+/* Reverse-mode through the whole chain (optimizer.compute_gradients, sequential_vae.py:1273).  Gradients are left in
+ * the gradient arena (svae_grad_get).  Requires a preceding svae_forward on a train_capacity handle. */
+int svae_backward(svae_handle* h);
+/* clip_by_value(+-clip_value) + TensorFlow-formulation Adam (sequential_vae.py:18-25,1275-1276); all-reduces the
+ * gradients first when a communicator is attached. */
+int svae_adam_step(svae_handle* h, float learning_rate);
+/* One full training iteration = the train_op of sess.run at sequential_vae.py:1365 (forward + backward + [all-reduce]
+ * + clipped Adam), device-resident inputs, asynchronous. */
+int svae_train_step(svae_handle* h, const float* x_in_dev, const float* x_tgt_dev, int batch, const float* eps_dev,
+                    uint64_t seed, float learning_rate, float reg_coeff);
+/* Same, through HOST buffers: the feed_dict path of SequentialVAE.train (sequential_vae.py:1355-1365): copies
+ * input/target (and eps when given) host->device, runs the step, copies the losses back and synchronises. */
+int svae_train_step_host(svae_handle* h, const float* x_in_host, const float* x_tgt_host, int batch,
+                         const float* eps_host, uint64_t seed, float learning_rate, float reg_coeff,
+                         svae_losses* losses_out);
+/* SequentialVAE.test / training_mc_samples through host buffers (sequential_vae.py:1381-1391,1434-1455):
+ * x_steps_out_host [T,B,H,W,C] (may be NULL), last_out_host [B,H,W,C] (may be NULL). */
+int svae_forward_host(svae_handle* h, const float* x_in_host, const float* x_tgt_host, int batch,
+                      const float* eps_host, uint64_t seed, float reg_coeff, float* mu_out_host,
+                      float* sigma_out_host, float* x_steps_out_host, float* last_out_host, svae_losses* losses_out);
+/* Synchronise and fetch the ELBO terms of the last forward. */
+int svae_read_losses(svae_handle* h, svae_losses* out);
+
+/* ---- generation-mode chain --------------------------------------------------------------------------------------
+ * Replaces sess.run(self.generative_samples) (generate_mc_samples, sequential_vae.py:1397-1428): decoder chain only,
+ * z fed per step; BN uses the statistics of the generated batch (Q1).
+ *   z_dev   : [T,B,Z] or NULL => Philox N(0,1) from `seed`
+ *   out_dev : [T,B,H,W,C]  (x_1..x_T; the reference's leading uniform-noise x_0 is produced by the Python wrapper) */
+int svae_generate(svae_handle* h, int batch, const float* z_dev, uint64_t seed, float* out_dev);
+int svae_generate_host(svae_handle* h, int batch, const float* z_host, uint64_t seed, float* out_host);
+
+/* ---- data parallel ----------------------------------------------------------------------------------------------
+ * The reference has no multi-device path for this model.  Batch-sharded DP: per-replica BN, gradients
+ * summed over ranks with NCCL (one bucket per chain step, issued as soon as that step's backward ends) and scaled by
+ * 1/nranks inside the Adam kernel. */
+int svae_nccl_unique_id(char id_out[128], const char* libnccl_path_or_null);
+int svae_comm_init(svae_handle* h, int rank, int nranks, const char id[128], const char* libnccl_path_or_null);
+int svae_comm_destroy(svae_handle* h);
+
+/* ---- introspection ---------------------------------------------------------------------------------------------- */
+int64_t svae_launch_count(const svae_handle* h);   /* kernels launched by this handle so far */
+int64_t svae_activation_bytes(const svae_handle* h);
+int svae_tc_layers(const svae_handle* h);          /* number of contractions per train step routed to tcgen05 kernels */
+
+/* ---- layer-level entry points (unit parity against abstract_network.py:12-71; tests and micro-benchmarks only) ----
+ * All pointers are device pointers; weights in the reference layout.  `operand_dtype` selects the kernel family. */
+/* convolution2d data path (abstract_network.py:18): x [B,H,W,Ci], w [4,4,Ci,Co] -> y [B,H/s,W/s,Co], SAME padding.
+ * stats_out (may be NULL): [2*Co] doubles = per-channel sum and sum of squares of y. */
+int svae_op_conv2d(svae_handle* h, const float* x, const float* w, float* y, double* stats_out, int B, int H, int W,
+                   int Ci, int Co, int stride, int operand_dtype);
+/* convolution2d_transpose data path (abstract_network.py:37,56): x [B,H,W,Ci], w [4,4,Co,Ci] -> y [B,H*s,W*s,Co] */
+int svae_op_conv2d_transpose(svae_handle* h, const float* x, const float* w, float* y, double* stats_out, int B, int H,
+                             int W, int Ci, int Co, int stride, int operand_dtype);
+/* gradients of the conv: dy [B,H/s,W/s,Co] -> dx [B,H,W,Ci] (may be NULL), dw [4,4,Ci,Co] (may be NULL) */
+int svae_op_conv2d_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                            int B, int H, int W, int Ci, int Co, int stride, int operand_dtype);
+/* gradients of the transposed conv: dy [B,H*s,W*s,Co] -> dx [B,H,W,Ci], dw [4,4,Co,Ci] */
+int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx,
+                                      float* dw, int B, int H, int W, int Ci, int Co, int stride, int operand_dtype);
+/* batch_norm (training mode, no gamma, eps 1e-3) + activation (0 none, 1 lrelu(0.1), 2 relu), rows x channels */
+int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act);
+/* fused clip + TF-Adam on n elements (sequential_vae.py:1275-1276) */
+int svae_op_adam(svae_handle* h, float* p, const float* g, float* m, float* v, int64_t n, float lr, int64_t t,
+                 float beta1, float beta2, float eps, float clip, float grad_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVAE_H_ */

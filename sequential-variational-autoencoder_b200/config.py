@@ -1,0 +1,76 @@
+"""Hyper-parameter table of the benchmarked configurations.
+
+Mirrors the attribute block of ``SequentialVAE.__init__`` (reference sequential_vae.py:197-258) and the netname rows
+that are on the hot path: ``c_inhomog`` (:727), ``sequential_vae_celebA_inhomog`` (:671),
+``sequential_vae_lsun`` (:712-714), ``m_inhomog`` (:842-848).  The reference's other 61 netnames select ablations that
+are out of scope (weight sharing, InfoMax, chain noise, early stopping, flat / PixelCNN decoders)."""
+import math
+
+NETNAMES = {
+    "c_inhomog": {},
+    "sequential_vae_celebA_inhomog": {},
+    "sequential_vae_lsun": {"vlae_latent_dims": [20, 30, 30, 30]},
+    "m_inhomog": {"vlae_levels": 3, "vlae_latent_dims": [2, 2, 2], "image_sizes": [32, 16, 8, 4],
+                  "filter_sizes": [None, 64, 128, 192, 256], "mc_steps": 5},
+}
+
+
+def hyperparams(name, data_dims, data_range, **overrides):
+    """Defaults (sequential_vae.py:201-258) + netname row + overrides.  Unknown names raise KeyError (the reference
+    logs an error and calls exit(-1), sequential_vae.py:860-862)."""
+    if name not in NETNAMES:
+        raise KeyError("Unknown network name %s" % name)
+    D, C = int(data_dims[0]), int(data_dims[-1])
+    hp = dict(
+        name=name, data_dims=[int(d) for d in data_dims], range=[float(data_range[0]), float(data_range[1])],
+        vlae_levels=4, vlae_latent_dims=[3, 3, 3, 3],
+        image_sizes=[D, D // 2, D // 4, D // 8, D // 16],
+        filter_sizes=[C, 32, 64, 128, 384, 512],
+        mc_steps=8, intermediate_reconstruction=True, first_step_loss_coeff=1.0,
+        latent_mean_clip=math.inf, latent_prior_stddev=1.0, max_highway_ratio=1.0, min_highway_ratio=0.0,
+        learning_rate=0.0002, learning_rate_decay=1.0, reg_coeff_rate=5000.0, save_freq=2000,
+        clip_grads=True, clip_grad_value=10.0,
+    )
+    row = dict(NETNAMES[name])
+    if "filter_sizes" in row:
+        row["filter_sizes"] = [C if f is None else f for f in row["filter_sizes"]]
+    hp.update(row)
+    hp.update(overrides)
+    hp["latent_dim"] = int(sum(hp["vlae_latent_dims"]))
+    hp.setdefault("regularized_steps", list(range(hp["mc_steps"])))
+    L = hp["vlae_levels"]
+    if "image_sizes" not in row and "image_sizes" not in overrides:
+        hp["image_sizes"] = [D >> i for i in range(L + 1)]
+    if hp["image_sizes"] != [D >> i for i in range(L + 1)]:
+        # the reference aborts when image_sizes disagree with the conv stack (sequential_vae.py:1617-1627)
+        raise ValueError("self.image_sizes and image_sizes in inference/generative networks don't match")
+    if len(hp["filter_sizes"]) != L + 2 or len(hp["vlae_latent_dims"]) != L:
+        raise ValueError("filter_sizes needs vlae_levels+2 entries and vlae_latent_dims vlae_levels entries")
+    return hp
+
+
+def to_cabi_config(hp, max_batch, train=True, operand_dtype="fp32"):
+    """Fill the POD ``svae_config`` (include/svae.h) from a hyper-parameter dict."""
+    from . import _cabi
+
+    cfg = _cabi.Config()
+    cfg.height, cfg.width, cfg.channels = hp["data_dims"]
+    cfg.levels = hp["vlae_levels"]
+    for i, v in enumerate(hp["vlae_latent_dims"]):
+        cfg.latent_dims[i] = v
+    for i, v in enumerate(hp["filter_sizes"]):
+        cfg.filter_sizes[i] = v
+    cfg.mc_steps = hp["mc_steps"]
+    cfg.intermediate_reconstruction = int(hp["intermediate_reconstruction"])
+    cfg.regularized_mask = sum(1 << t for t in hp["regularized_steps"])
+    cfg.first_step_loss_coeff = hp["first_step_loss_coeff"]
+    cfg.latent_mean_clip = hp["latent_mean_clip"]
+    cfg.prior_stddev = hp["latent_prior_stddev"]
+    cfg.min_highway, cfg.max_highway = hp["min_highway_ratio"], hp["max_highway_ratio"]
+    cfg.range_lo, cfg.range_hi = hp["range"]
+    cfg.clip_value = hp["clip_grad_value"] if hp["clip_grads"] else 0.0
+    cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps = 0.9, 0.999, 1e-8      # tf.train.AdamOptimizer defaults (:1267)
+    cfg.max_batch = int(max_batch)
+    cfg.train_capacity = int(bool(train))
+    cfg.operand_dtype = {"fp32": _cabi.OPERAND_FP32, "bf16": _cabi.OPERAND_BF16}[operand_dtype]
+    return cfg

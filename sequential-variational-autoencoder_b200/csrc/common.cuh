@@ -1,0 +1,122 @@
+// common.cuh - shared declarations for libsvae (B200 / sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#define SVAE_BN_EPS 1e-3f     // tf.contrib.layers.batch_norm default epsilon (abstract_network.py:22)
+#define SVAE_LRELU_SLOPE 0.1f // lrelu rate (abstract_network.py:8)
+
+enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+
+// A dense NHWC tensor seen through a channel window: element (row r, channel c) lives at p[r*ld + coff + c].
+// This is how channel concats (sequential_vae.py:1716,1834) are expressed without copies: producers write, and
+// consumers read, their channel window of the shared buffer.
+struct View {
+  float* p;
+  int ld;
+  int coff;
+};
+static inline View mkview(float* p, int ld, int coff = 0) { return View{p, ld, coff}; }
+
+// Addressing of one feature of a batch-norm'd tensor.  4-D BN (per channel over N,H,W): rows = pixels, feats = C,
+// inner = C, ppr = 1.  2-D BN over a projected latent plane (fc_bn_lrelu reshaped to [B,S,S,F], sequential_vae.py:
+// 1803-1804): rows = B, feats = S*S*F, inner = F, ppr = S*S, so that feature f = (pixel f/F, channel f%F) is found
+// inside a (possibly concatenated) NHWC buffer.
+struct FeatView {
+  float* p;
+  int ld;    // channels of the underlying buffer
+  int coff;  // first channel of the window
+  int inner; // channels in the window
+  int ppr;   // pixels per row
+};
+__host__ __device__ static inline size_t fv_addr(const FeatView& v, int64_t row, int f) {
+  int pix = f / v.inner;
+  int c = f - pix * v.inner;
+  return ((size_t)row * v.ppr + pix) * v.ld + v.coff + c;
+}
+
+// Geometry of one contraction (conv / transposed conv / fully connected) in gather form:
+//   out[b,oh,ow,co] = sum_{kh,kw,ci} in[b,ih,iw,ci] * W(kh,kw,ci,co)
+//   mode 0 (conv gather):    ih = oh*stride - pad + kh
+//   mode 1 (deconv gather):  ih = (oh + pad - kh)/stride when divisible (adjoint of mode 0)
+//   w_out_major 0: W(tap,ci,co) = w[(tap*Cin + ci)*Cout + co]   1: w[(tap*Cout + co)*Cin + ci]
+struct Geom {
+  int B, Hin, Win, Cin, Hout, Wout, Cout;
+  int KH, KW, stride, pad, mode, w_out_major, accumulate;
+};
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  int64_t* launches;
+  int sm_count;
+};
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      svae_set_cuda_error(_e, #expr, __FILE__, __LINE__);                                     \
+      return -3;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+void svae_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+std::string& svae_global_error();
+
+// ---- SIMT fp32 contractions (kernels_simt.cu) ------------------------------------------------------------------
+int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w, View out, double* stats);
+// dW(tap,a,b) = sum_rows X(gathered at tap, channel a) * dY(row, channel b); layout w[(tap*Ca + a)*Cb + b].
+// Geometry: X is [B,Hin,Win,Ca] (g.Cin = Ca), dY is [B,Hout,Wout,Cb] (g.Cout = Cb), conv-gather (mode 0) indexing.
+int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw);
+// skinny fully-connected helpers (heads, latent projections)
+int skinny_fwd(const LaunchCtx& lc, View a, int B, int K, const float* w, int w_n_major, const float* bias, View out,
+               int N);
+int skinny_dgrad(const LaunchCtx& lc, View dout, int B, int N, const float* w, int K, View din, int accumulate);
+int skinny_wgrad(const LaunchCtx& lc, View a, View dout, int B, int K, int N, float* dw, float* dbias, int w_n_major);
+
+// ---- elementwise / reductions (kernels_elem.cu) ----------------------------------------------------------------
+int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats);
+int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const float* beta, int64_t rows, int feats,
+               int act, FeatView residual, FeatView out);
+// pass 1: dyhat = da * act'(bn(y)+res) ; S += (sum dyhat, sum dyhat*xhat) ; optional dres = dyhat (or += when acc)
+int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta,
+                  int64_t rows, int feats, int act, FeatView residual, float* dyhat, double* S, float* dres,
+                  int dres_accumulate);
+// pass 2: dy = rstd * (dyhat - S1/rows - xhat*S2/rows) in place ; dbeta = S1
+int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
+                 int feats, float* dbeta);
+struct OutMixParams {
+  int64_t pixels;  // B*H*W
+  int C;
+  int has_gate;
+  float lo, hi, minr, maxr;
+};
+// x_t = mix(sigmoid(u+bias)) ; accumulates sum (x_t - tgt)^2 into *recon_sum
+int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
+                const float* xprev, const float* tgt, float* xt, double* recon_sum);
+// g = gx_in (or 0) + coef*(x_t - tgt) ; du, gx_prev, bias grads
+int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
+                const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
+                float* gx_prev, float* db_out, float* db_gate);
+struct ReparamParams {
+  int B, Z;
+  float clip, prior;
+};
+int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre, const float* sd_pre, const float* eps,
+                uint64_t seed, uint64_t counter_base, float* eps_store, float* mu, float* sd, float* z, double* kl_sum);
+int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, const float* mu_pre, const float* mu,
+                const float* sd, const float* eps, float kl_coef, float* dmu_pre, float* dsd_pre);
+int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
+                float beta2, float eps, float clip, float grad_scale);
+int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base);
+int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n);  // dst += src
+
+// ---- tcgen05 contractions (kernels_tc.cu) ----------------------------------------------------------------------
+struct TcPlan;  // opaque per-layer packed-weight + schedule state
+bool tc_supported(const Geom& g);
+int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats);
+size_t tc_packed_bytes(const Geom& g);
+int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed);

@@ -1,0 +1,471 @@
+// kernels_elem.cu - HBM-bound kernels of the chain: batch-norm statistics / apply / backward fused with the
+// activation, residual (ladder shortcut) add and concat-slot write; the output head (sigmoid, range scale, highway
+// gate mix, squared-error reduction) and its backward; reparameterised sampling with counter-based Philox + Gaussian
+// KL and its backward; the fused clip + TensorFlow-Adam update.
+//
+// Reference ops replaced: tf.contrib.layers.batch_norm (training mode, abstract_network.py:22..79), lrelu (:8-10),
+// tf.nn.relu / tf.concat / shortcut add (sequential_vae.py:1713-1716), output + highway mix (:1720-1729), loss
+// reductions (:1146-1164), reparameterisation (:1023), clip_by_value + AdamOptimizer (:18-25,1267-1276).
+#include "common.cuh"
+
+namespace {
+
+constexpr int CX = 32;  // features per block (x)
+constexpr int CY = 8;   // row phases per block (y)
+
+struct ColGrid {
+  dim3 grid, block;
+};
+static ColGrid col_grid(int64_t rows, int feats, int sm_count) {
+  ColGrid cg;
+  cg.block = dim3(CX, CY);
+  unsigned gx = (unsigned)((feats + CX - 1) / CX);
+  int64_t max_gy = (rows + CY - 1) / CY;
+  int64_t want = (8LL * sm_count + gx - 1) / gx;
+  int64_t gy = want < 1 ? 1 : (want > max_gy ? max_gy : want);
+  if (gy > 65535) gy = 65535;
+  cg.grid = dim3(gx, (unsigned)gy);
+  return cg;
+}
+
+__device__ __forceinline__ void bn_coeffs(const double* __restrict__ stats, int feats, int f, int64_t rows, float& mean,
+                                          float& rstd) {
+  double m = stats[f] / (double)rows;
+  double var = stats[feats + f] / (double)rows - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)SVAE_BN_EPS));
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == ACT_LRELU) return fmaxf(fminf(v * SVAE_LRELU_SLOPE, 0.f), v);  // abstract_network.py:10
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+__device__ __forceinline__ float act_grad(float pre, int act) {
+  if (act == ACT_LRELU) return pre > 0.f ? 1.f : SVAE_LRELU_SLOPE;
+  if (act == ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+__device__ __forceinline__ size_t fv_off(const FeatView& v, int f) {
+  int pix = f / v.inner;
+  return (size_t)pix * v.ld + v.coff + (f - pix * v.inner);
+}
+
+__global__ void col_stats_kernel(const float* __restrict__ y, int64_t rows, int C, double* __restrict__ stats) {
+  __shared__ float s1[CY][CX], s2[CY][CX];
+  const int f = blockIdx.x * CX + threadIdx.x;
+  float a = 0.f, b = 0.f;
+  if (f < C)
+    for (int64_t r = (int64_t)blockIdx.y * CY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * CY) {
+      float v = __ldg(y + (size_t)r * C + f);
+      a += v;
+      b += v * v;
+    }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < C) {
+    double da = 0, db = 0;
+    for (int i = 0; i < CY; ++i) { da += s1[i][threadIdx.x]; db += s2[i][threadIdx.x]; }
+    atomicAdd(&stats[f], da);
+    atomicAdd(&stats[C + f], db);
+  }
+}
+
+__global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                  const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
+                                  FeatView out) {
+  const int f = blockIdx.x * CX + threadIdx.x;
+  if (f >= feats) return;
+  float mean, rstd;
+  bn_coeffs(stats, feats, f, rows, mean, rstd);
+  const float sh = beta[f] - mean * rstd;
+  const size_t ooff = fv_off(out, f);
+  const size_t ostride = (size_t)out.ppr * out.ld;
+  const bool has_res = res.p != nullptr;
+  const size_t roff = has_res ? fv_off(res, f) : 0;
+  const size_t rstride = has_res ? (size_t)res.ppr * res.ld : 0;
+  for (int64_t r = (int64_t)blockIdx.y * CY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * CY) {
+    float v = fmaf(__ldg(y + (size_t)r * feats + f), rstd, sh);
+    if (has_res) v += __ldg(res.p + r * rstride + roff);
+    out.p[r * ostride + ooff] = act_fwd(v, act);
+  }
+}
+
+__global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
+                                     const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
+                                     float* __restrict__ dyhat, double* __restrict__ S, float* __restrict__ dres,
+                                     int dres_acc) {
+  __shared__ float s1[CY][CX], s2[CY][CX];
+  const int f = blockIdx.x * CX + threadIdx.x;
+  float a = 0.f, b = 0.f;
+  if (f < feats) {
+    float mean, rstd;
+    bn_coeffs(stats, feats, f, rows, mean, rstd);
+    const float bt = beta[f];
+    const size_t doff = fv_off(da, f);
+    const size_t dstride = (size_t)da.ppr * da.ld;
+    const bool has_res = res.p != nullptr;
+    const size_t roff = has_res ? fv_off(res, f) : 0;
+    const size_t rstride = has_res ? (size_t)res.ppr * res.ld : 0;
+    for (int64_t r = (int64_t)blockIdx.y * CY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * CY) {
+      const size_t i = (size_t)r * feats + f;
+      float xh = (__ldg(y + i) - mean) * rstd;
+      float pre = xh + bt;
+      if (has_res) pre += __ldg(res.p + r * rstride + roff);
+      float g = __ldg(da.p + r * dstride + doff) * act_grad(pre, act);
+      dyhat[i] = g;
+      if (dres != nullptr) dres[i] = dres_acc ? dres[i] + g : g;
+      a += g;
+      b += g * xh;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < feats) {
+    double da_ = 0, db_ = 0;
+    for (int i = 0; i < CY; ++i) { da_ += s1[i][threadIdx.x]; db_ += s2[i][threadIdx.x]; }
+    atomicAdd(&S[f], da_);
+    atomicAdd(&S[feats + f], db_);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
+                                    const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
+                                    int feats, float* __restrict__ dbeta) {
+  const int f = blockIdx.x * CX + threadIdx.x;
+  if (f >= feats) return;
+  float mean, rstd;
+  bn_coeffs(stats, feats, f, rows, mean, rstd);
+  const float m1 = (float)(S[f] / (double)rows);
+  const float m2 = (float)(S[feats + f] / (double)rows);
+  if (blockIdx.y == 0 && threadIdx.y == 0 && dbeta != nullptr) dbeta[f] = (float)S[f];
+  for (int64_t r = (int64_t)blockIdx.y * CY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * CY) {
+    const size_t i = (size_t)r * feats + f;
+    float xh = (__ldg(y + i) - mean) * rstd;
+    dyhat[i] = rstd * (dyhat[i] - m1 - xh * m2);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  T r = 0;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x + 31) / 32 ? smem[threadIdx.x] : (T)0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+
+constexpr int MAXC = 4;  // image channels handled by the output-head kernels (1 or 3 in every reference dataset)
+
+__global__ void __launch_bounds__(256)
+out_mix_fwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out,
+                   const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
+                   float* __restrict__ xt, double* __restrict__ recon_sum) {
+  __shared__ float red[32];
+  const int ldu = p.C + p.has_gate;
+  float se = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* ur = u + (size_t)i * ldu;
+    float r = 1.f;
+    if (p.has_gate) r = p.minr + (p.maxr - p.minr) * sigmoidf_(ur[p.C] + b_gate[0]);  // sequential_vae.py:1727-1728
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c >= p.C) break;
+      float o = sigmoidf_(ur[c] + b_out[c]);                                          // :1720
+      float v = p.lo + (p.hi - p.lo) * o;                                             // :1721
+      if (p.has_gate) v = r * v + (1.f - r) * xprev[(size_t)i * p.C + c];             // :1729
+      xt[(size_t)i * p.C + c] = v;
+      if (tgt != nullptr) {
+        float d = v - tgt[(size_t)i * p.C + c];
+        se += d * d;                                                                  // :1146
+      }
+    }
+  }
+  if (recon_sum != nullptr) {
+    float tot = block_sum<float>(se, red);
+    if (threadIdx.x == 0) atomicAdd(recon_sum, (double)tot);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out,
+                   const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
+                   const float* __restrict__ xt, const float* __restrict__ gx_in, float coef, float* __restrict__ du,
+                   float* __restrict__ gx_prev, float* __restrict__ db_out, float* __restrict__ db_gate) {
+  __shared__ float red[32];
+  const int ldu = p.C + p.has_gate;
+  float bsum[MAXC + 1];
+#pragma unroll
+  for (int c = 0; c <= MAXC; ++c) bsum[c] = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* ur = u + (size_t)i * ldu;
+    float* dr = du + (size_t)i * ldu;
+    float s = 0.f, r = 1.f;
+    if (p.has_gate) {
+      s = sigmoidf_(ur[p.C] + b_gate[0]);
+      r = p.minr + (p.maxr - p.minr) * s;
+    }
+    float dgate = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c >= p.C) break;
+      const size_t ix = (size_t)i * p.C + c;
+      float g = coef * (xt[ix] - tgt[ix]);
+      if (gx_in != nullptr) g += gx_in[ix];
+      float o = sigmoidf_(ur[c] + b_out[c]);
+      float outv = p.lo + (p.hi - p.lo) * o;
+      float d_u = g * r * (p.hi - p.lo) * o * (1.f - o);
+      dr[c] = d_u;
+      bsum[c] += d_u;
+      if (p.has_gate) {
+        dgate += g * (outv - xprev[ix]);
+        gx_prev[ix] = g * (1.f - r);
+      }
+    }
+    if (p.has_gate) {
+      float d_g = dgate * (p.maxr - p.minr) * s * (1.f - s);
+      dr[p.C] = d_g;
+      bsum[MAXC] += d_g;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (c >= p.C) break;
+    float t = block_sum<float>(bsum[c], red);
+    if (threadIdx.x == 0) atomicAdd(&db_out[c], t);
+  }
+  if (p.has_gate) {
+    float t = block_sum<float>(bsum[MAXC], red);
+    if (threadIdx.x == 0) atomicAdd(&db_gate[0], t);
+  }
+}
+
+// ---- counter-based Philox4x32-10 (same generator family as tf.random_normal) ---------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t counter) {
+  uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), 0x5eed5eedu, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  // Box-Muller on two uniforms in (0,1]
+  float u1 = ((float)c[0] + 1.0f) * 2.3283064365386963e-10f;
+  float u2 = ((float)c[1] + 1.0f) * 2.3283064365386963e-10f;
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__global__ void fill_normal_kernel(float* __restrict__ dst, int64_t n, uint64_t seed, uint64_t base) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = philox_normal(seed, base + (uint64_t)i);
+}
+
+__global__ void __launch_bounds__(256)
+reparam_fwd_kernel(ReparamParams p, const float* __restrict__ mu_pre, const float* __restrict__ sd_pre,
+                   const float* __restrict__ eps, uint64_t seed, uint64_t base, float* __restrict__ eps_store,
+                   float* __restrict__ mu, float* __restrict__ sd, float* __restrict__ z,
+                   double* __restrict__ kl_sum) {
+  __shared__ float red[32];
+  const int n = p.B * p.Z;
+  float kl = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float m = fminf(fmaxf(mu_pre[i], -p.clip), p.clip);                 // sequential_vae.py:1593
+    float s = sigmoidf_(sd_pre[i]);                                     // :1594
+    float e = eps != nullptr ? eps[i] : philox_normal(seed, base + (uint64_t)i);
+    eps_store[i] = e;
+    mu[i] = m;
+    sd[i] = s;
+    z[i] = m + s * e;                                                   // :1023
+    float ip2 = 1.f / (p.prior * p.prior);
+    kl += -0.5f - logf(s) + 0.5f * s * s * ip2 + 0.5f * m * m * ip2;    // :1156-1158
+  }
+  float tot = block_sum<float>(kl, red);
+  if (threadIdx.x == 0) atomicAdd(kl_sum, (double)tot);
+}
+
+__global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz, const float* __restrict__ mu_pre,
+                                   const float* __restrict__ mu, const float* __restrict__ sd,
+                                   const float* __restrict__ eps, float kl_coef, float* __restrict__ dmu_pre,
+                                   float* __restrict__ dsd_pre) {
+  const int n = p.B * p.Z;
+  const float ip2 = 1.f / (p.prior * p.prior);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float g = dz[i];
+    float s = sd[i];
+    float dm = g + kl_coef * mu[i] * ip2;
+    float pre = mu_pre[i];
+    dmu_pre[i] = (pre < -p.clip || pre > p.clip) ? 0.f : dm;
+    float ds = g * eps[i] + kl_coef * (-1.f / s + s * ip2);
+    dsd_pre[i] = ds * s * (1.f - s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
+            int64_t n, float lr_t, float b1, float b2, float eps, float clip, float gscale) {
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gg = g4[i], pp = p4[i], mm = m4[i], vv = v4[i];
+    float* ga = &gg.x; float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = ga[k] * gscale;
+      if (clip > 0.f) gk = fminf(fmaxf(gk, -clip), clip);   // clip_by_value, sequential_vae.py:18-25
+      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+      pa[k] -= lr_t * ma[k] / (sqrtf(va[k]) + eps);         // TF formulation: epsilon outside the sqrt
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  // scalar tail
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gk = g[i] * gscale;
+    if (clip > 0.f) gk = fminf(fmaxf(gk, -clip), clip);
+    float mk = b1 * m[i] + (1.f - b1) * gk;
+    float vk = b2 * v[i] + (1.f - b2) * gk * gk;
+    m[i] = mk; v[i] = vk;
+    p[i] -= lr_t * mk / (sqrtf(vk) + eps);
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+
+static inline unsigned flat_blocks(int64_t n, int sm_count, int threads = 256) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+
+int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats) {
+  ColGrid cg = col_grid(rows, C, lc.sm_count);
+  col_stats_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, rows, C, stats);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const float* beta, int64_t rows, int feats,
+               int act, FeatView residual, FeatView out) {
+  ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  bn_act_fwd_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, stats, beta, rows, feats, act, residual, out);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta,
+                  int64_t rows, int feats, int act, FeatView residual, float* dyhat, double* S, float* dres,
+                  int dres_accumulate) {
+  ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  bn_bwd_reduce_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(da, y, stats, beta, rows, feats, act, residual, dyhat, S,
+                                                            dres, dres_accumulate);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
+                 int feats, float* dbeta) {
+  ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  bn_bwd_apply_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(dyhat, y, stats, S, rows, feats, dbeta);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
+                const float* xprev, const float* tgt, float* xt, double* recon_sum) {
+  if (p.C > MAXC) return -1;
+  out_mix_fwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
+                                                                               recon_sum);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
+                const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
+                float* gx_prev, float* db_out, float* db_gate) {
+  if (p.C > MAXC) return -1;
+  out_mix_bwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
+                                                                               gx_in, coef, du, gx_prev, db_out, db_gate);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre, const float* sd_pre, const float* eps,
+                uint64_t seed, uint64_t counter_base, float* eps_store, float* mu, float* sd, float* z,
+                double* kl_sum) {
+  reparam_fwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(
+      p, mu_pre, sd_pre, eps, seed, counter_base, eps_store, mu, sd, z, kl_sum);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, const float* mu_pre, const float* mu,
+                const float* sd, const float* eps, float kl_coef, float* dmu_pre, float* dsd_pre) {
+  reparam_bwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(p, dz, mu_pre, mu, sd, eps,
+                                                                                        kl_coef, dmu_pre, dsd_pre);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
+                float beta2, float eps, float clip, float grad_scale) {
+  const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  const int64_t n4 = aligned ? n / 4 : 0;
+  adam_kernel<<<flat_blocks(n4 > 0 ? n4 : n, lc.sm_count), 256, 0, lc.stream>>>(p, g, m, v, n4, n, lr_t, beta1, beta2,
+                                                                               eps, clip, grad_scale);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base) {
+  fill_normal_kernel<<<flat_blocks(n, lc.sm_count), 256, 0, lc.stream>>>(dst, n, seed, counter_base);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n) {
+  axpy_kernel<<<flat_blocks(n, lc.sm_count), 256, 0, lc.stream>>>(dst, src, n);
+  ++*lc.launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,1324 @@
+// model.cu - static plan + executor of the Sequential-VAE chain and the C ABI (include/svae.h).
+//
+// The reference builds a TF graph (construct_network, sequential_vae.py:877-984) and runs it with Session.run; here
+// the graph is a static plan built once from svae_config: per chain step a recognition net (inference_ladder,
+// :1537-1630), a chain encoder (compute_encodings, :1745-1777) and a ladder decoder (generator_ladder, :1636-1739),
+// each a list of "contraction + batch-norm + activation" blocks over a bump-allocated activation arena.  Channel
+// concats are channel windows of shared buffers (no copies), the reshape between fc and conv layers is free (NHWC,
+// H,W,C flatten order).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/svae.h"
+#include "common.cuh"
+#include "nccl_dl.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+std::string& svae_global_error() { return g_err; }
+void svae_set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+}
+
+namespace {
+
+struct Param {
+  std::string name;
+  int ndim;
+  int shape[4];
+  int64_t numel, offset;
+  int step, flags;
+};
+
+// contraction + batch-norm + activation (conv2d_bn_lrelu / conv2d_t_bn[_relu] / fc_bn_lrelu, abstract_network.py:17-71)
+struct Block {
+  Geom g;          // forward geometry, B patched per call
+  int w = -1, beta = -1;
+  int act = ACT_NONE;
+  int rpi = 1;     // BN rows per image (H*W for 4-D BN, 1 for 2-D BN)
+  int feats = 0;   // BN features
+  float* y = nullptr;        // pre-BN output [rows, feats]
+  double* stats = nullptr;   // [2*feats] sum, sumsq (forward-zeroed)
+  double* S = nullptr;       // [2*feats] backward sums (backward-zeroed)
+  FeatView out{};            // activated output location
+  FeatView res{};            // residual added before the activation (ladder shortcut)
+  void* w_packed = nullptr;      // tcgen05 packed weights (forward form)
+  void* w_packed_d = nullptr;    // tcgen05 packed weights (dgrad form)
+  bool tc_fwd = false, tc_dgrad = false;
+};
+
+struct Head {  // layers.fully_connected head (sequential_vae.py:1592,1594,1607,1609)
+  int w, b, n, col, is_sd;
+};
+
+struct Step {
+  int t;
+  // recognition net
+  std::vector<Block> inf;                 // 2(L-1) conv blocks
+  std::vector<std::vector<Head>> heads;   // per level 0..L-2
+  float *mu_pre, *sd_pre, *mu, *sd, *z, *eps;
+  // chain encoder (t>=1)
+  std::vector<Block> enc;                 // 2(L-1)+1 conv blocks
+  Block encfc;
+  // decoder
+  std::vector<Block> lat;                 // L latent projections
+  Block decfc;
+  std::vector<Block> ta, tb;              // per level: stride-2 deconv + BN (+shortcut, relu) ; stride-1 deconv + BN + relu
+  std::vector<float*> dcat;               // concat buffers [B,S,S,2F]
+  float* cc;                              // concat(e[L], P_{L-1}) [B, ncc]
+  int ncc;
+  int w_out, b_out, w_gate, b_gate;       // output deconvs (live bias)
+  Geom g_out, g_gate;
+  float *u, *xt;
+  int64_t p_begin, p_end;                 // parameter range (all-reduce bucket)
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  T* get(size_t n) {
+    size_t o = (off + 255) & ~(size_t)255;
+    off = o + n * sizeof(T);
+    return base ? reinterpret_cast<T*>(base + o) : nullptr;
+  }
+};
+
+Geom conv_geom(int H, int W, int Ci, int Co, int stride) {
+  Geom g{};
+  g.B = 0; g.Hin = H; g.Win = W; g.Cin = Ci; g.Hout = H / stride; g.Wout = W / stride; g.Cout = Co;
+  g.KH = g.KW = 4; g.stride = stride; g.pad = 1; g.mode = 0; g.w_out_major = 0; g.accumulate = 0;
+  return g;
+}
+Geom deconv_geom(int H, int W, int Ci, int Co, int stride) {
+  Geom g{};
+  g.B = 0; g.Hin = H; g.Win = W; g.Cin = Ci; g.Hout = H * stride; g.Wout = W * stride; g.Cout = Co;
+  g.KH = g.KW = 4; g.stride = stride; g.pad = 1; g.mode = 1; g.w_out_major = 1; g.accumulate = 0;
+  return g;
+}
+Geom fc_geom(int K, int N) {
+  Geom g{};
+  g.B = 0; g.Hin = g.Win = g.Hout = g.Wout = 1; g.Cin = K; g.Cout = N;
+  g.KH = g.KW = 1; g.stride = 1; g.pad = 0; g.mode = 0; g.w_out_major = 0; g.accumulate = 0;
+  return g;
+}
+// geometry that maps d(out) -> d(in) for a forward geometry
+Geom dgrad_geom(const Geom& f) {
+  Geom g = f;
+  g.Hin = f.Hout; g.Win = f.Wout; g.Cin = f.Cout;
+  g.Hout = f.Hin; g.Wout = f.Win; g.Cout = f.Cin;
+  g.mode = 1 - f.mode;
+  g.w_out_major = 1 - f.w_out_major;
+  g.accumulate = 0;
+  return g;
+}
+
+}  // namespace
+
+struct svae_handle {
+  svae_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  cudaStream_t own_stream = nullptr, stream = nullptr, comm_stream = nullptr;
+  int64_t launches = 0;
+  // parameters
+  std::vector<Param> params;
+  int64_t arena_numel = 0;
+  float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
+  int64_t adam_t = 0;
+  bool weights_dirty = true;
+  // plan
+  int L = 0, T = 0, Z = 0, D = 0, C = 0;
+  std::vector<int> zoff;
+  std::vector<Step> steps;      // T entries (parameters differ per step)
+  int act_sets = 0;             // T when train_capacity else 1
+  char* act_base = nullptr; size_t act_bytes = 0;
+  char* zf_base = nullptr; size_t zf_bytes = 0;   // forward-zeroed (stats, loss sums)
+  char* zb_base = nullptr; size_t zb_bytes = 0;   // backward-zeroed (S sums)
+  double* loss_sums = nullptr;  // [2T] recon_sum, kl_sum
+  double* loss_host = nullptr;  // pinned
+  // gradient scratch (one step's worth)
+  std::vector<float*> d_c, d_dcat, d_e, d_inf;
+  float *d_fca = nullptr, *d_cc = nullptr, *d_z = nullptr, *d_mu_pre = nullptr, *d_sd_pre = nullptr, *d_u = nullptr;
+  float* gx[2] = {nullptr, nullptr};
+  float* dy_scratch = nullptr;
+  char* grad_base = nullptr; size_t grad_bytes = 0;
+  // io staging
+  float *in_x = nullptr, *in_tgt = nullptr, *in_eps = nullptr, *io_steps = nullptr, *gen_prev = nullptr;
+  float *pin_x = nullptr, *pin_tgt = nullptr, *pin_eps = nullptr;
+  size_t io_steps_elems = 0;
+  // tcgen05 packed weights
+  char* pack_base = nullptr; size_t pack_bytes = 0;
+  int tc_layers = 0;
+  // last forward
+  int last_B = 0; float last_reg = 1.f; bool have_fwd = false;
+  const float *last_x = nullptr, *last_tgt = nullptr;
+  uint64_t iteration = 0;
+  // nccl
+  NcclApi* nccl = nullptr; void* comm = nullptr; int rank = 0, nranks = 1;
+  std::vector<cudaEvent_t> bucket_ev; cudaEvent_t comm_done = nullptr;
+
+  LaunchCtx lc() { return LaunchCtx{stream, &launches, sm_count}; }
+  float* pw(int idx) { return P + params[idx].offset; }
+  float* pg(int idx) { return G + params[idx].offset; }
+};
+
+namespace {
+
+int fail(svae_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+#define H_TRY(expr)                                   \
+  do {                                                \
+    int _r = (expr);                                  \
+    if (_r != 0) {                                    \
+      if (h->err.empty() || _r == -3) h->err = g_err; \
+      return _r;                                      \
+    }                                                 \
+  } while (0)
+#define H_CUDA(expr)                                                \
+  do {                                                              \
+    cudaError_t _e = (expr);                                        \
+    if (_e != cudaSuccess) {                                        \
+      svae_set_cuda_error(_e, #expr, __FILE__, __LINE__);           \
+      h->err = g_err;                                               \
+      return SVAE_ECUDA;                                            \
+    }                                                               \
+  } while (0)
+
+// ---- parameter table in TF creation order -------------------------------------------------------
+struct Namer {
+  std::string prefix;
+  int conv = 0, convt = 0, bn = 0, fc = 0;
+  static std::string nm(const std::string& base, int n) { return n == 0 ? base : base + "_" + std::to_string(n); }
+  std::string next_conv() { return prefix + "/" + nm("Conv", conv++); }
+  std::string next_convt() { return prefix + "/" + nm("Conv2d_transpose", convt++); }
+  std::string next_bn() { return prefix + "/" + nm("BatchNorm", bn++); }
+  std::string next_fc() { return prefix + "/" + nm("fully_connected", fc++); }
+};
+
+int add_param(svae_handle* h, const std::string& name, std::vector<int> shape, int step, int flags) {
+  Param p;
+  p.name = name;
+  p.ndim = (int)shape.size();
+  p.numel = 1;
+  for (int i = 0; i < 4; ++i) p.shape[i] = i < p.ndim ? shape[i] : 1;
+  for (int s : shape) p.numel *= s;
+  p.offset = h->arena_numel;
+  p.step = step;
+  p.flags = flags;
+  h->arena_numel += (p.numel + 3) / 4 * 4;  // keep every tensor 16-byte aligned
+  h->params.push_back(p);
+  return (int)h->params.size() - 1;
+}
+
+// conv2d_bn_lrelu-style block: weights, inert biases, BN beta
+void add_block_params(svae_handle* h, Namer& nm, Block& b, int kind /*0 conv,1 convT,2 fc*/, std::vector<int> wshape,
+                      int nout, int step, int flags) {
+  std::string l = kind == 0 ? nm.next_conv() : kind == 1 ? nm.next_convt() : nm.next_fc();
+  std::string bn = nm.next_bn();
+  b.w = add_param(h, l + "/weights", wshape, step, flags);
+  add_param(h, l + "/biases", {nout}, step, flags | SVAE_PF_INERT);
+  b.beta = add_param(h, bn + "/beta", {nout}, step, flags);
+}
+
+void build_params(svae_handle* h) {
+  const svae_config& c = h->cfg;
+  const int L = c.levels, T = c.mc_steps, C = c.channels;
+  const int* F = c.filter_sizes;
+  std::vector<int> S(L + 1);
+  for (int i = 0; i <= L; ++i) S[i] = c.height >> i;
+  h->steps.resize(T);
+  for (int t = 0; t < T; ++t) {
+    Step& s = h->steps[t];
+    s.t = t;
+    s.p_begin = h->arena_numel;
+    // --- recognition net: phi/inference_step_t (sequential_vae.py:1573-1630)
+    {
+      Namer nm{"phi/inference_step_" + std::to_string(t)};
+      s.inf.resize(2 * (L - 1));
+      s.heads.resize(L - 1);
+      int col = 0;
+      for (int l = 0; l < L - 1; ++l) {
+        Block& a = s.inf[2 * l];
+        a.g = conv_geom(S[l], S[l], F[l], F[l + 1], 2);
+        add_block_params(h, nm, a, 0, {4, 4, F[l], F[l + 1]}, F[l + 1], t, 0);
+        Block& b = s.inf[2 * l + 1];
+        b.g = conv_geom(S[l + 1], S[l + 1], F[l + 1], F[l + 1], 1);
+        add_block_params(h, nm, b, 0, {4, 4, F[l + 1], F[l + 1]}, F[l + 1], t, 0);
+        int nflat = S[l + 1] * S[l + 1] * F[l + 1];
+        for (int k = 0; k < 2; ++k) {
+          std::string fc = nm.next_fc();
+          Head hd;
+          hd.n = c.latent_dims[l]; hd.col = col; hd.is_sd = k;
+          hd.w = add_param(h, fc + "/weights", {nflat, hd.n}, t, SVAE_PF_XAVIER);
+          hd.b = add_param(h, fc + "/biases", {hd.n}, t, 0);
+          s.heads[l].push_back(hd);
+        }
+        col += c.latent_dims[l];
+      }
+      // dead branch (:1602-1605): variables exist, never read (Q3)
+      {
+        std::string cv = nm.next_conv(), bn = nm.next_bn();
+        add_param(h, cv + "/weights", {4, 4, F[L - 1], F[L - 1]}, t, SVAE_PF_DEAD);
+        add_param(h, cv + "/biases", {F[L - 1]}, t, SVAE_PF_DEAD | SVAE_PF_INERT);
+        add_param(h, bn + "/beta", {F[L - 1]}, t, SVAE_PF_DEAD);
+        std::string fc = nm.next_fc(), bn2 = nm.next_bn();
+        add_param(h, fc + "/weights", {S[L] * S[L] * F[L - 1], F[L]}, t, SVAE_PF_DEAD);
+        add_param(h, fc + "/biases", {F[L]}, t, SVAE_PF_DEAD | SVAE_PF_INERT);
+        add_param(h, bn2 + "/beta", {F[L]}, t, SVAE_PF_DEAD);
+      }
+      // last heads read the stale level L-2 features (:1607,1609)
+      int nflat = S[L - 1] * S[L - 1] * F[L - 1];
+      for (int k = 0; k < 2; ++k) {
+        std::string fc = nm.next_fc();
+        Head hd;
+        hd.n = c.latent_dims[L - 1]; hd.col = col; hd.is_sd = k;
+        hd.w = add_param(h, fc + "/weights", {nflat, hd.n}, t, SVAE_PF_XAVIER);
+        hd.b = add_param(h, fc + "/biases", {hd.n}, t, 0);
+        s.heads[L - 2].push_back(hd);
+      }
+    }
+    // --- chain encoder: theta/generative_encoder_step_t (:1757-1777), t >= 1
+    if (t > 0) {
+      Namer nm{"theta/generative_encoder_step_" + std::to_string(t)};
+      s.enc.resize(2 * (L - 1) + 1);
+      for (int l = 0; l < L - 1; ++l) {
+        Block& a = s.enc[2 * l];
+        a.g = conv_geom(S[l], S[l], F[l], F[l + 1], 2);
+        add_block_params(h, nm, a, 0, {4, 4, F[l], F[l + 1]}, F[l + 1], t, SVAE_PF_THETA);
+        Block& b = s.enc[2 * l + 1];
+        b.g = conv_geom(S[l + 1], S[l + 1], F[l + 1], F[l + 1], 1);
+        add_block_params(h, nm, b, 0, {4, 4, F[l + 1], F[l + 1]}, F[l + 1], t, SVAE_PF_THETA);
+      }
+      Block& cl = s.enc[2 * (L - 1)];
+      cl.g = conv_geom(S[L - 1], S[L - 1], F[L - 1], F[L - 1], 2);
+      add_block_params(h, nm, cl, 0, {4, 4, F[L - 1], F[L - 1]}, F[L - 1], t, SVAE_PF_THETA);
+      s.encfc.g = fc_geom(S[L] * S[L] * F[L - 1], F[L]);
+      add_block_params(h, nm, s.encfc, 2, {S[L] * S[L] * F[L - 1], F[L]}, F[L], t, SVAE_PF_THETA);
+    }
+    // --- decoder: theta/generative_step_t (:1683-1729)
+    {
+      Namer nm{"theta/generative_step_" + std::to_string(t)};
+      s.lat.resize(L);
+      for (int i = 0; i < L - 1; ++i) {
+        int n = S[i + 1] * S[i + 1] * F[i + 1];
+        s.lat[i].g = fc_geom(c.latent_dims[i], n);
+        add_block_params(h, nm, s.lat[i], 2, {c.latent_dims[i], n}, n, t, SVAE_PF_THETA);
+      }
+      s.lat[L - 1].g = fc_geom(c.latent_dims[L - 1], F[L + 1]);
+      add_block_params(h, nm, s.lat[L - 1], 2, {c.latent_dims[L - 1], F[L + 1]}, F[L + 1], t, SVAE_PF_THETA);
+      s.ncc = t > 0 ? F[L] + F[L + 1] : F[L + 1];
+      int nfc = S[L] * S[L] * F[L];
+      s.decfc.g = fc_geom(s.ncc, nfc);
+      add_block_params(h, nm, s.decfc, 2, {s.ncc, nfc}, nfc, t, SVAE_PF_THETA);
+      s.ta.resize(L - 1);
+      s.tb.resize(L - 1);
+      int cin = F[L];
+      for (int l = L - 2; l >= 0; --l) {
+        s.ta[l].g = deconv_geom(S[l + 2], S[l + 2], cin, F[l + 1], 2);
+        add_block_params(h, nm, s.ta[l], 1, {4, 4, F[l + 1], cin}, F[l + 1], t, SVAE_PF_THETA);
+        s.tb[l].g = deconv_geom(S[l + 1], S[l + 1], 2 * F[l + 1], F[l + 1], 1);
+        add_block_params(h, nm, s.tb[l], 1, {4, 4, F[l + 1], 2 * F[l + 1]}, F[l + 1], t, SVAE_PF_THETA);
+        cin = F[l + 1];
+      }
+      std::string o = nm.next_convt();
+      s.w_out = add_param(h, o + "/weights", {4, 4, C, F[1]}, t, SVAE_PF_THETA | SVAE_PF_XAVIER);
+      s.b_out = add_param(h, o + "/biases", {C}, t, SVAE_PF_THETA);
+      s.g_out = deconv_geom(S[1], S[1], F[1], C, 2);
+      s.w_gate = s.b_gate = -1;
+      if (t > 0) {
+        std::string r = nm.next_convt();
+        s.w_gate = add_param(h, r + "/weights", {4, 4, 1, F[1]}, t, SVAE_PF_THETA | SVAE_PF_XAVIER);
+        s.b_gate = add_param(h, r + "/biases", {1}, t, SVAE_PF_THETA);
+        s.g_gate = deconv_geom(S[1], S[1], F[1], 1, 2);
+      }
+    }
+    s.p_end = h->arena_numel;
+  }
+}
+
+// ---- activation arena ----------------------------------------------------------------------------------------------
+void place_block(Block& b, Arena& act, Arena& zf, Arena& zb, int64_t maxB, bool plane2d, size_t& max_y) {
+  if (plane2d) { b.rpi = 1; b.feats = b.g.Cout; } else { b.rpi = b.g.Hout * b.g.Wout; b.feats = b.g.Cout; }
+  size_t n = (size_t)maxB * b.rpi * b.feats;
+  b.y = act.get<float>(n);
+  b.stats = zf.get<double>(2 * (size_t)b.feats);
+  b.S = zb.get<double>(2 * (size_t)b.feats);
+  if (n > max_y) max_y = n;
+}
+FeatView fv4(float* p, int ld, int coff, int inner) { return FeatView{p, ld, coff, inner, 1}; }
+
+void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, size_t& max_y) {
+  const svae_config& c = h->cfg;
+  const int L = h->L, T = h->T, C = h->C, Z = h->Z;
+  const int* F = c.filter_sizes;
+  const int64_t B = c.max_batch;
+  std::vector<int> S(L + 1);
+  for (int i = 0; i <= L; ++i) S[i] = c.height >> i;
+  for (int t = 0; t < T; ++t) {
+    Step& s = h->steps[t];
+    const bool share = (t >= h->act_sets) && t >= 2;  // steps >= 2 alias step 1's activations when not training
+    if (share) {
+      const Step& r = h->steps[1];
+      auto alias = [](Block& b, const Block& q) {
+        b.rpi = q.rpi; b.feats = q.feats; b.act = q.act; b.y = q.y; b.stats = q.stats; b.S = q.S; b.out = q.out; b.res = q.res;
+      };
+      for (size_t i = 0; i < s.inf.size(); ++i) alias(s.inf[i], r.inf[i]);
+      for (size_t i = 0; i < s.enc.size(); ++i) alias(s.enc[i], r.enc[i]);
+      alias(s.encfc, r.encfc);
+      for (size_t i = 0; i < s.lat.size(); ++i) alias(s.lat[i], r.lat[i]);
+      alias(s.decfc, r.decfc);
+      for (size_t i = 0; i < s.ta.size(); ++i) alias(s.ta[i], r.ta[i]);
+      for (size_t i = 0; i < s.tb.size(); ++i) alias(s.tb[i], r.tb[i]);
+      s.dcat = r.dcat; s.cc = r.cc; s.u = r.u; s.xt = r.xt;
+      s.mu_pre = r.mu_pre; s.sd_pre = r.sd_pre; s.mu = r.mu; s.sd = r.sd; s.z = r.z; s.eps = r.eps;
+      continue;
+    }
+    // recognition
+    for (int k = 0; k < 2 * (L - 1); ++k) {
+      Block& b = s.inf[k];
+      place_block(b, act, zf, zb, B, false, max_y);
+      b.act = ACT_LRELU;
+      float* a = act.get<float>((size_t)B * b.rpi * b.feats);
+      b.out = fv4(a, b.feats, 0, b.feats);
+    }
+    s.mu_pre = act.get<float>((size_t)B * Z); s.sd_pre = act.get<float>((size_t)B * Z);
+    s.mu = act.get<float>((size_t)B * Z); s.sd = act.get<float>((size_t)B * Z);
+    s.z = act.get<float>((size_t)B * Z); s.eps = act.get<float>((size_t)B * Z);
+    // decoder concat buffers first (encoder / projections write into them)
+    s.dcat.resize(L - 1);
+    for (int l = 0; l < L - 1; ++l) s.dcat[l] = act.get<float>((size_t)B * S[l + 1] * S[l + 1] * 2 * F[l + 1]);
+    s.cc = act.get<float>((size_t)B * s.ncc);
+    // encoder
+    if (t > 0) {
+      for (int k = 0; k <= 2 * (L - 1); ++k) {
+        Block& b = s.enc[k];
+        place_block(b, act, zf, zb, B, false, max_y);
+        b.act = ACT_LRELU;
+        float* a = act.get<float>((size_t)B * b.rpi * b.feats);
+        b.out = fv4(a, b.feats, 0, b.feats);
+      }
+      place_block(s.encfc, act, zf, zb, B, true, max_y);
+      s.encfc.act = ACT_LRELU;
+      s.encfc.out = fv4(s.cc, s.ncc, 0, F[L]);           // e[L] is the first window of the concat (:1696-1697,1834)
+    }
+    // latent projections (split_latent, :1796-1806)
+    for (int i = 0; i < L; ++i) {
+      Block& b = s.lat[i];
+      place_block(b, act, zf, zb, B, true, max_y);
+      b.act = ACT_LRELU;
+      if (i < L - 1) b.out = FeatView{s.dcat[i], 2 * F[i + 1], F[i + 1], F[i + 1], S[i + 1] * S[i + 1]};  // second window of the level concat (:1716)
+      else b.out = fv4(s.cc, s.ncc, t > 0 ? F[L] : 0, F[L + 1]);
+    }
+    // dec.fc (:1704-1705)
+    place_block(s.decfc, act, zf, zb, B, true, max_y);
+    s.decfc.act = ACT_LRELU;
+    {
+      float* a = act.get<float>((size_t)B * s.decfc.feats);
+      s.decfc.out = fv4(a, s.decfc.feats, 0, s.decfc.feats);
+    }
+    for (int l = L - 2; l >= 0; --l) {
+      Block& a = s.ta[l];
+      place_block(a, act, zf, zb, B, false, max_y);
+      a.act = ACT_RELU;                                   // relu after the shortcut add (:1713-1714)
+      a.out = fv4(s.dcat[l], 2 * F[l + 1], 0, F[l + 1]);
+      if (t > 0) a.res = s.enc[2 * l + 1].out;            // e[l+1]
+      Block& b = s.tb[l];
+      place_block(b, act, zf, zb, B, false, max_y);
+      b.act = ACT_RELU;
+      float* cbuf = act.get<float>((size_t)B * b.rpi * b.feats);
+      b.out = fv4(cbuf, b.feats, 0, b.feats);
+    }
+    s.u = act.get<float>((size_t)B * h->D * h->D * (C + 1));
+    s.xt = act.get<float>((size_t)B * h->D * h->D * C);
+  }
+  // gradient scratch: one step's worth, reused by every step's backward
+  if (c.train_capacity) {
+    const Step& s1 = h->steps[T > 1 ? 1 : 0];
+    h->d_c.resize(L - 1); h->d_dcat.resize(L - 1);
+    for (int l = 0; l < L - 1; ++l) {
+      h->d_c[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * F[l + 1]);
+      h->d_dcat[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * 2 * F[l + 1]);
+    }
+    h->d_fca = gr.get<float>((size_t)B * S[L] * S[L] * F[L]);
+    h->d_cc = gr.get<float>((size_t)B * (F[L] + F[L + 1]));
+    h->d_z = gr.get<float>((size_t)B * Z);
+    h->d_mu_pre = gr.get<float>((size_t)B * Z);
+    h->d_sd_pre = gr.get<float>((size_t)B * Z);
+    h->d_u = gr.get<float>((size_t)B * h->D * h->D * (C + 1));
+    h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * C);
+    h->gx[1] = gr.get<float>((size_t)B * h->D * h->D * C);
+    h->d_e.assign(2 * (L - 1) + 1, nullptr);
+    h->d_inf.assign(2 * (L - 1), nullptr);
+    for (int k = 0; k < 2 * (L - 1); ++k) {
+      const Block& b = h->steps[0].inf[k];
+      h->d_inf[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
+    }
+    if (T > 1)
+      for (int k = 0; k <= 2 * (L - 1); ++k) {
+        const Block& b = s1.enc[k];
+        h->d_e[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
+      }
+    h->dy_scratch = gr.get<float>(max_y);
+  }
+  // io staging (host-buffer entry points)
+  h->in_x = act.get<float>((size_t)B * h->D * h->D * C);
+  h->in_tgt = act.get<float>((size_t)B * h->D * h->D * C);
+  h->in_eps = act.get<float>((size_t)T * B * Z);
+  h->gen_prev = act.get<float>((size_t)B * h->D * h->D * C);
+}
+
+// ---- contraction dispatch ------------------------------------------------------------------------------------------
+int contract(svae_handle* h, Geom g, int B, View in, const float* w, const void* w_packed, bool use_tc, View out,
+             double* stats) {
+  g.B = B;
+  LaunchCtx lc = h->lc();
+  if (use_tc) return tc_gather_gemm(lc, g, in, w_packed, out, stats);
+  return simt_gather_gemm(lc, g, in, w, out, stats);
+}
+
+int block_fwd(svae_handle* h, Block& b, int B, View in) {
+  H_TRY(contract(h, b.g, B, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0), b.stats));
+  LaunchCtx lc = h->lc();
+  H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out));
+  return 0;
+}
+
+// backward of a block: da -> dy (in dy_scratch), weight/beta grads, optional input gradient
+int block_bwd(svae_handle* h, Block& b, int B, FeatView da, View in, float* dres, int dres_acc, const View* din,
+              int din_acc) {
+  LaunchCtx lc = h->lc();
+  const int64_t rows = (int64_t)B * b.rpi;
+  float* dy = h->dy_scratch;
+  H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
+  H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta)));
+  View dyv = mkview(dy, b.feats, 0);
+  // weight gradient
+  if (b.g.mode == 0) {
+    Geom g = b.g; g.B = B;
+    H_TRY(simt_wgrad(lc, g, in, dyv, h->pg(b.w)));
+  } else {
+    Geom g = dgrad_geom(b.g); g.B = B; g.mode = 0;  // conv geometry from the deconv's output grid to its input grid
+    H_TRY(simt_wgrad(lc, g, dyv, in, h->pg(b.w)));
+  }
+  if (din != nullptr) {
+    Geom g = dgrad_geom(b.g);
+    g.accumulate = din_acc;
+    H_TRY(contract(h, g, B, dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr));
+  }
+  return 0;
+}
+
+int skinny_block_bwd(svae_handle* h, Block& b, int B, FeatView da, View zin, int K, View dz_out) {
+  // latent projection (K <= 32 inputs): dW via thread-per-feature, dz via row-wise dot with the [K,N] weights
+  LaunchCtx lc = h->lc();
+  float* dy = h->dy_scratch;
+  H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, FeatView{}, dy, b.S, nullptr, 0));
+  H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, B, b.feats, h->pg(b.beta)));
+  View dyv = mkview(dy, b.feats, 0);
+  H_TRY(skinny_wgrad(lc, zin, dyv, B, K, b.feats, h->pg(b.w), nullptr, 1));
+  H_TRY(skinny_fwd(lc, dyv, B, b.feats, h->pw(b.w), 1, nullptr, dz_out, K));
+  return 0;
+}
+
+int zero_region(svae_handle* h, void* p, size_t bytes) {
+  if (bytes == 0) return 0;
+  H_CUDA(cudaMemsetAsync(p, 0, bytes, h->stream));
+  return 0;
+}
+
+int repack_if_dirty(svae_handle* h);
+
+// ---- forward of one chain step --------------------------------------------------------------------------------------
+int encoder_fwd(svae_handle* h, Step& s, int B, const float* xprev) {
+  const int L = h->L;
+  View cur = mkview(const_cast<float*>(xprev), h->C, 0);
+  for (int k = 0; k <= 2 * (L - 1); ++k) {
+    H_TRY(block_fwd(h, s.enc[k], B, cur));
+    cur = mkview(s.enc[k].out.p, s.enc[k].feats, 0);
+  }
+  View flat = mkview(cur.p, s.encfc.g.Cin, 0);
+  H_TRY(block_fwd(h, s.encfc, B, flat));
+  return 0;
+}
+
+int decoder_fwd(svae_handle* h, Step& s, int B, const float* z, const float* xprev, const float* tgt, float* xt_out,
+                double* recon_sum) {
+  const int L = h->L, C = h->C;
+  LaunchCtx lc = h->lc();
+  for (int i = 0; i < L; ++i)
+    H_TRY(block_fwd(h, s.lat[i], B, mkview(const_cast<float*>(z), h->Z, h->zoff[i])));
+  H_TRY(block_fwd(h, s.decfc, B, mkview(s.cc, s.ncc, 0)));
+  View cur = mkview(s.decfc.out.p, s.ta[L - 2].g.Cin, 0);
+  for (int l = L - 2; l >= 0; --l) {
+    H_TRY(block_fwd(h, s.ta[l], B, cur));
+    H_TRY(block_fwd(h, s.tb[l], B, mkview(s.dcat[l], 2 * s.tb[l].feats, 0)));
+    cur = mkview(s.tb[l].out.p, s.tb[l].feats, 0);
+  }
+  const int has_gate = s.t > 0 ? 1 : 0;
+  const int ldu = C + has_gate;
+  H_TRY(contract(h, s.g_out, B, cur, h->pw(s.w_out), nullptr, false, mkview(s.u, ldu, 0), nullptr));
+  if (has_gate) H_TRY(contract(h, s.g_gate, B, cur, h->pw(s.w_gate), nullptr, false, mkview(s.u, ldu, C), nullptr));
+  OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
+                 h->cfg.max_highway};
+  H_TRY(out_mix_fwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, tgt, xt_out, recon_sum));
+  return 0;
+}
+
+int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float* eps, uint64_t seed, double* kl_sum) {
+  const int L = h->L;
+  LaunchCtx lc = h->lc();
+  View cur = mkview(const_cast<float*>(x), h->C, 0);
+  for (int k = 0; k < 2 * (L - 1); ++k) {
+    H_TRY(block_fwd(h, s.inf[k], B, cur));
+    cur = mkview(s.inf[k].out.p, s.inf[k].feats, 0);
+    if (k & 1) {
+      const int l = k / 2;
+      const int K = s.inf[k].rpi * s.inf[k].feats;
+      for (const Head& hd : s.heads[l])
+        H_TRY(skinny_fwd(lc, mkview(cur.p, K, 0), B, K, h->pw(hd.w), 0, h->pw(hd.b),
+                         mkview(hd.is_sd ? s.sd_pre : s.mu_pre, h->Z, hd.col), hd.n));
+    }
+  }
+  ReparamParams rp{B, h->Z, h->cfg.latent_mean_clip, h->cfg.prior_stddev};
+  uint64_t base = (h->iteration * (uint64_t)h->T + (uint64_t)s.t) * (uint64_t)(h->cfg.max_batch * h->Z);
+  H_TRY(reparam_fwd(lc, rp, s.mu_pre, s.sd_pre, eps, seed, base, s.eps, s.mu, s.sd, s.z, kl_sum));
+  return 0;
+}
+
+float step_coef(const svae_handle* h, int t) { return t == 0 ? h->cfg.first_step_loss_coeff : 1.f; }
+bool step_has_recon(const svae_handle* h, int t) { return h->cfg.intermediate_reconstruction || t == h->T - 1; }
+bool step_has_kl(const svae_handle* h, int t) { return (h->cfg.regularized_mask >> t) & 1ull; }
+
+int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float reg,
+                 float* mu_out, float* sd_out, float* xs_out) {
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_TRY(repack_if_dirty(h));
+  H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
+  H_TRY(zero_region(h, h->loss_sums, sizeof(double) * 2 * h->T));
+  const size_t img = (size_t)B * h->D * h->D * h->C;
+  const size_t bz = (size_t)B * h->Z;
+  const float* prev = nullptr;
+  for (int t = 0; t < h->T; ++t) {
+    Step& s = h->steps[t];
+    // forward-only handles alias steps >= 2 onto step 1's buffers: restart their batch-norm statistics
+    if (t >= 2 && h->act_sets < h->T) H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
+    H_TRY(recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, seed, h->loss_sums + h->T + t));
+    if (t > 0) H_TRY(encoder_fwd(h, s, B, prev));
+    H_TRY(decoder_fwd(h, s, B, s.z, prev, tgt, s.xt, h->loss_sums + t));
+    if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out + t * img, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if (mu_out) H_CUDA(cudaMemcpyAsync(mu_out + t * bz, s.mu, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
+    if (sd_out) H_CUDA(cudaMemcpyAsync(sd_out + t * bz, s.sd, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
+    prev = s.xt;
+    if (h->act_sets < h->T && t >= 1 && t + 1 < h->T) {
+      // the next step overwrites s.xt (aliased): keep x_t in the staging target buffer
+      H_CUDA(cudaMemcpyAsync(h->gen_prev, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
+      prev = h->gen_prev;
+    }
+  }
+  h->last_B = B; h->last_reg = reg; h->have_fwd = true; h->last_x = x; h->last_tgt = tgt;
+  return 0;
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------------
+int decoder_bwd(svae_handle* h, Step& s, int B, const float* gx_in, float* gx_prev, const float* xprev) {
+  const int L = h->L, C = h->C, T = h->T;
+  const int* F = h->cfg.filter_sizes;
+  LaunchCtx lc = h->lc();
+  const int has_gate = s.t > 0 ? 1 : 0;
+  const int ldu = C + has_gate;
+  const float coef = step_has_recon(h, s.t)
+                         ? 16.f * step_coef(h, s.t) * 2.f / ((float)B * h->D * h->D * C) : 0.f;   // :1146,1163,1168
+  (void)T;
+  OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
+                 h->cfg.max_highway};
+  H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
+                    coef, h->d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr));
+  // output deconvs: dgrad into d_c[0], wgrads
+  View c0 = mkview(s.tb[0].out.p, F[1], 0);
+  View dc0 = mkview(h->d_c[0], F[1], 0);
+  {
+    Geom g = dgrad_geom(s.g_out);
+    H_TRY(contract(h, g, B, mkview(h->d_u, ldu, 0), h->pw(s.w_out), nullptr, false, dc0, nullptr));
+    Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
+    H_TRY(simt_wgrad(lc, gw, mkview(h->d_u, ldu, 0), c0, h->pg(s.w_out)));
+    if (has_gate) {
+      Geom g2 = dgrad_geom(s.g_gate); g2.accumulate = 1;
+      H_TRY(contract(h, g2, B, mkview(h->d_u, ldu, C), h->pw(s.w_gate), nullptr, false, dc0, nullptr));
+      Geom gw2 = dgrad_geom(s.g_gate); gw2.B = B; gw2.mode = 0;
+      H_TRY(simt_wgrad(lc, gw2, mkview(h->d_u, ldu, C), c0, h->pg(s.w_gate)));
+    }
+  }
+  for (int l = 0; l <= L - 2; ++l) {
+    const int Fl = F[l + 1];
+    // c_l = relu(bn(deconv_s1(dcat_l)))
+    View dcat_in = mkview(s.dcat[l], 2 * Fl, 0);
+    View d_dcat = mkview(h->d_dcat[l], 2 * Fl, 0);
+    H_TRY(block_bwd(h, s.tb[l], B, fv4(h->d_c[l], Fl, 0, Fl), dcat_in, nullptr, 0, &d_dcat, 0));
+    // d = relu(bn(deconv_s2(c_{l+1})) + e[l+1])
+    View ta_in = l < L - 2 ? mkview(s.tb[l + 1].out.p, F[l + 2], 0) : mkview(s.decfc.out.p, s.ta[l].g.Cin, 0);
+    View d_next = l < L - 2 ? mkview(h->d_c[l + 1], F[l + 2], 0) : mkview(h->d_fca, s.ta[l].g.Cin, 0);
+    H_TRY(block_bwd(h, s.ta[l], B, fv4(h->d_dcat[l], 2 * Fl, 0, Fl), ta_in, has_gate ? h->d_e[2 * l + 1] : nullptr, 0,
+                    &d_next, 0));
+    // P_l = lrelu(bn(fc(z_l)))
+    const Block& lb = s.lat[l];
+    FeatView da{h->d_dcat[l], 2 * Fl, Fl, Fl, lb.out.ppr};
+    H_TRY(skinny_block_bwd(h, s.lat[l], B, da, mkview(s.z, h->Z, h->zoff[l]), h->cfg.latent_dims[l],
+                           mkview(h->d_z, h->Z, h->zoff[l])));
+  }
+  // dec.fc
+  {
+    View d_cc = mkview(h->d_cc, s.ncc, 0);
+    H_TRY(block_bwd(h, s.decfc, B, fv4(h->d_fca, s.decfc.feats, 0, s.decfc.feats), mkview(s.cc, s.ncc, 0), nullptr, 0,
+                    &d_cc, 0));
+  }
+  // P_{L-1}
+  {
+    const int coffP = s.t > 0 ? F[L] : 0;
+    FeatView da{h->d_cc, s.ncc, coffP, F[L + 1], 1};
+    H_TRY(skinny_block_bwd(h, s.lat[L - 1], B, da, mkview(s.z, h->Z, h->zoff[L - 1]), h->cfg.latent_dims[L - 1],
+                           mkview(h->d_z, h->Z, h->zoff[L - 1])));
+  }
+  return 0;
+}
+
+int encoder_bwd(svae_handle* h, Step& s, int B, float* gx_prev, const float* xprev) {
+  const int L = h->L;
+  const int* F = h->cfg.filter_sizes;
+  const int last = 2 * (L - 1);
+  // e[L] = lrelu(bn(fc(flat)))
+  {
+    View flat = mkview(s.enc[last].out.p, s.encfc.g.Cin, 0);
+    View d_flat = mkview(h->d_e[last], s.encfc.g.Cin, 0);
+    H_TRY(block_bwd(h, s.encfc, B, fv4(h->d_cc, s.ncc, 0, F[L]), flat, nullptr, 0, &d_flat, 0));
+  }
+  for (int k = last; k >= 0; --k) {
+    Block& b = s.enc[k];
+    View in = k > 0 ? mkview(s.enc[k - 1].out.p, s.enc[k - 1].feats, 0) : mkview(const_cast<float*>(xprev), h->C, 0);
+    View din = k > 0 ? mkview(h->d_e[k - 1], s.enc[k - 1].feats, 0) : mkview(gx_prev, h->C, 0);
+    // d_e[k-1] already holds the decoder shortcut gradient when k-1 is odd (e[l+1] = enc[2l+1]); gx_prev always holds
+    // the highway gradient
+    const int acc = k > 0 ? ((k - 1) & 1) : 1;
+    H_TRY(block_bwd(h, b, B, fv4(h->d_e[k], b.feats, 0, b.feats), in, nullptr, 0, &din, acc));
+  }
+  return 0;
+}
+
+int recognition_bwd(svae_handle* h, Step& s, int B, float reg) {
+  const int L = h->L;
+  LaunchCtx lc = h->lc();
+  ReparamParams rp{B, h->Z, h->cfg.latent_mean_clip, h->cfg.prior_stddev};
+  const float kl_coef = step_has_kl(h, s.t) ? reg * step_coef(h, s.t) / ((float)B * h->Z) : 0.f;   // :1156-1164,1172
+  H_TRY(reparam_bwd(lc, rp, h->d_z, s.mu_pre, s.mu, s.sd, s.eps, kl_coef, h->d_mu_pre, h->d_sd_pre));
+  for (int l = 0; l < L - 1; ++l) {
+    const Block& fb = s.inf[2 * l + 1];
+    const int K = fb.rpi * fb.feats;
+    View flat = mkview(fb.out.p, K, 0);
+    View d_flat = mkview(h->d_inf[2 * l + 1], K, 0);
+    int first = 1;
+    for (const Head& hd : s.heads[l]) {
+      View dout = mkview(hd.is_sd ? h->d_sd_pre : h->d_mu_pre, h->Z, hd.col);
+      H_TRY(skinny_dgrad(lc, dout, B, hd.n, h->pw(hd.w), K, d_flat, first ? 0 : 1));
+      H_TRY(skinny_wgrad(lc, flat, dout, B, K, hd.n, h->pg(hd.w), h->pg(hd.b), 0));
+      first = 0;
+    }
+  }
+  for (int k = 2 * (L - 1) - 1; k >= 0; --k) {
+    Block& b = s.inf[k];
+    View in = k > 0 ? mkview(s.inf[k - 1].out.p, s.inf[k - 1].feats, 0) : mkview(const_cast<float*>(h->last_x), h->C, 0);
+    if (k > 0) {
+      View din = mkview(h->d_inf[k - 1], s.inf[k - 1].feats, 0);
+      H_TRY(block_bwd(h, b, B, fv4(h->d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, &din, (k - 1) & 1));
+    } else {
+      H_TRY(block_bwd(h, b, B, fv4(h->d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, nullptr, 0));
+    }
+  }
+  return 0;
+}
+
+int allreduce_bucket(svae_handle* h, int t) {
+  if (h->comm == nullptr) return 0;
+  Step& s = h->steps[t];
+  H_CUDA(cudaEventRecord(h->bucket_ev[t], h->stream));
+  H_CUDA(cudaStreamWaitEvent(h->comm_stream, h->bucket_ev[t], 0));
+  int r = h->nccl->AllReduce(h->G + s.p_begin, h->G + s.p_begin, (size_t)(s.p_end - s.p_begin), /*ncclFloat*/ 7,
+                             /*ncclSum*/ 0, h->comm, h->comm_stream);
+  if (r != 0) return fail(h, SVAE_ENCCL, std::string("ncclAllReduce failed: ") + h->nccl->GetErrorString(r));
+  return 0;
+}
+
+int backward_impl(svae_handle* h) {
+  if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "handle created without train_capacity");
+  if (!h->have_fwd) return fail(h, SVAE_ESTATE, "svae_backward requires a preceding svae_forward");
+  const int B = h->last_B, T = h->T;
+  H_TRY(zero_region(h, h->zb_base, h->zb_bytes));
+  H_TRY(zero_region(h, h->G, (size_t)h->arena_numel * 4));
+  int cur = 0;
+  const float* gx_in = nullptr;  // dL/dx_t from later steps
+  for (int t = T - 1; t >= 0; --t) {
+    Step& s = h->steps[t];
+    const float* xprev = t > 0 ? h->steps[t - 1].xt : nullptr;
+    float* gx_prev = h->gx[cur ^ 1];
+    H_TRY(decoder_bwd(h, s, B, gx_in, gx_prev, xprev));
+    if (t > 0) H_TRY(encoder_bwd(h, s, B, gx_prev, xprev));
+    H_TRY(recognition_bwd(h, s, B, h->last_reg));
+    H_TRY(allreduce_bucket(h, t));
+    gx_in = gx_prev;
+    cur ^= 1;
+  }
+  if (h->comm != nullptr) {
+    H_CUDA(cudaEventRecord(h->comm_done, h->comm_stream));
+    H_CUDA(cudaStreamWaitEvent(h->stream, h->comm_done, 0));
+  }
+  h->have_fwd = false;
+  return 0;
+}
+
+int adam_impl(svae_handle* h, float lr) {
+  h->adam_t += 1;
+  const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)h->adam_t)) / (1.0 - pow(b1, (double)h->adam_t)));
+  LaunchCtx lc = h->lc();
+  H_TRY(adam_update(lc, h->P, h->G, h->M, h->V, h->arena_numel, lr_t, h->cfg.adam_beta1, h->cfg.adam_beta2,
+                    h->cfg.adam_eps, h->cfg.clip_value, 1.f / (float)h->nranks));
+  h->weights_dirty = true;
+  return 0;
+}
+
+int read_losses_impl(svae_handle* h, svae_losses* out) {
+  const int T = h->T;
+  H_CUDA(cudaMemcpyAsync(h->loss_host, h->loss_sums, sizeof(double) * 2 * T, cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  memset(out, 0, sizeof *out);
+  const int B = h->last_B;
+  double total = 0;
+  for (int t = 0; t < T; ++t) {
+    double recon = h->loss_host[t] / ((double)B * h->D * h->D * h->C);
+    double kl = h->loss_host[T + t] / ((double)B * h->Z);
+    out->recon[t] = (float)recon;
+    out->kl[t] = (float)kl;
+    if (step_has_recon(h, t)) total += 16.0 * recon;
+    if (step_has_kl(h, t)) total += (double)h->last_reg * kl;
+    if (t == 0) total *= h->cfg.first_step_loss_coeff;
+  }
+  out->total = (float)total;
+  out->final_recon = out->recon[T - 1];
+  return 0;
+}
+
+// ---- tcgen05 weight packing ------------------------------------------------------------------------------------------
+void for_each_block(svae_handle* h, void (*fn)(svae_handle*, Block&, void*), void* ctx) {
+  for (Step& s : h->steps) {
+    for (Block& b : s.inf) fn(h, b, ctx);
+    for (Block& b : s.enc) fn(h, b, ctx);
+    if (s.t > 0) fn(h, s.encfc, ctx);
+    for (Block& b : s.lat) fn(h, b, ctx);
+    fn(h, s.decfc, ctx);
+    for (Block& b : s.ta) fn(h, b, ctx);
+    for (Block& b : s.tb) fn(h, b, ctx);
+  }
+}
+
+void plan_pack(svae_handle* h, Block& b, void* ctx) {
+  Arena* a = (Arena*)ctx;
+  if (h->cfg.operand_dtype != SVAE_OPERAND_BF16) return;
+  Geom f = b.g; f.B = h->cfg.max_batch;
+  if (tc_supported(f)) {
+    b.tc_fwd = true;
+    b.w_packed = a->get<char>(tc_packed_bytes(f));
+    if (a->base) h->tc_layers++;
+  }
+  Geom d = dgrad_geom(b.g); d.B = h->cfg.max_batch;
+  if (tc_supported(d)) {
+    b.tc_dgrad = true;
+    b.w_packed_d = a->get<char>(tc_packed_bytes(d));
+    if (a->base) h->tc_layers++;
+  }
+}
+
+struct PackCtx { int rc; };
+void do_pack(svae_handle* h, Block& b, void* ctx) {
+  PackCtx* pc = (PackCtx*)ctx;
+  if (pc->rc != 0) return;
+  LaunchCtx lc = h->lc();
+  if (b.tc_fwd) { Geom f = b.g; f.B = 1; pc->rc = tc_pack_weights(lc, f, h->pw(b.w), b.w_packed); }
+  if (pc->rc == 0 && b.tc_dgrad) { Geom d = dgrad_geom(b.g); d.B = 1; pc->rc = tc_pack_weights(lc, d, h->pw(b.w), b.w_packed_d); }
+}
+
+int repack_if_dirty(svae_handle* h) {
+  if (!h->weights_dirty) return 0;
+  if (h->cfg.operand_dtype == SVAE_OPERAND_BF16 && h->pack_bytes > 0) {
+    PackCtx pc{0};
+    for_each_block(h, do_pack, &pc);
+    if (pc.rc != 0) { h->err = g_err; return pc.rc; }
+  }
+  h->weights_dirty = false;
+  return 0;
+}
+
+void destroy_impl(svae_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
+  for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
+  if (h->comm_done) cudaEventDestroy(h->comm_done);
+  cudaFree(h->P); cudaFree(h->G); cudaFree(h->M); cudaFree(h->V);
+  cudaFree(h->act_base); cudaFree(h->zf_base); cudaFree(h->zb_base); cudaFree(h->grad_base); cudaFree(h->pack_base);
+  cudaFree(h->io_steps); cudaFree(h->loss_sums);
+  if (h->loss_host) cudaFreeHost(h->loss_host);
+  if (h->pin_x) cudaFreeHost(h->pin_x);
+  if (h->pin_tgt) cudaFreeHost(h->pin_tgt);
+  if (h->pin_eps) cudaFreeHost(h->pin_eps);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  delete h;
+}
+
+int ensure_io_steps(svae_handle* h, size_t elems) {
+  if (h->io_steps_elems >= elems) return 0;
+  if (h->io_steps) cudaFree(h->io_steps);
+  h->io_steps = nullptr; h->io_steps_elems = 0;
+  H_CUDA(cudaMalloc(&h->io_steps, elems * 4));
+  h->io_steps_elems = elems;
+  return 0;
+}
+
+int stage_in(svae_handle* h, float* dev, float** pin, const float* host, size_t elems, size_t cap_elems) {
+  // host -> pinned staging -> device (pinned staging keeps the copy asynchronous for pageable callers)
+  if (*pin == nullptr) H_CUDA(cudaMallocHost((void**)pin, cap_elems * 4));
+  memcpy(*pin, host, elems * 4);
+  H_CUDA(cudaMemcpyAsync(dev, *pin, elems * 4, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+}  // namespace
+
+// ======================================================= C ABI ========================================================
+extern "C" {
+
+const char* svae_version(void) { return "svae-b200 0.1 (sm_100a)"; }
+
+const char* svae_last_error(const svae_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+static int validate_cfg(const svae_config* cfg) {
+  const int L = cfg->levels;
+  if (L < 2 || L > SVAE_MAX_LEVELS || cfg->mc_steps < 1 || cfg->mc_steps > SVAE_MAX_STEPS || cfg->max_batch < 1 ||
+      cfg->height != cfg->width || cfg->height % (1 << L) != 0 || cfg->channels < 1 || cfg->channels > 4)
+    return fail(nullptr, SVAE_EINVAL, "unsupported configuration (levels/mc_steps/batch/image size/channels)");
+  for (int i = 0; i < L; ++i)
+    if (cfg->latent_dims[i] < 1 || cfg->latent_dims[i] > 32)
+      return fail(nullptr, SVAE_EINVAL, "latent_dims entries must be in [1,32]");
+  for (int i = 1; i < L + 2; ++i)
+    if (cfg->filter_sizes[i] < 1) return fail(nullptr, SVAE_EINVAL, "filter_sizes entries must be positive");
+  if (cfg->filter_sizes[0] != cfg->channels) return fail(nullptr, SVAE_EINVAL, "filter_sizes[0] must equal channels");
+  return 0;
+}
+
+static void fill_info(const Param& p, svae_param_info* o) {
+  memset(o, 0, sizeof *o);
+  snprintf(o->name, SVAE_NAME_LEN, "%s", p.name.c_str());
+  o->ndim = p.ndim;
+  for (int k = 0; k < 4; ++k) o->shape[k] = p.shape[k];
+  o->numel = p.numel; o->offset = p.offset; o->step = p.step; o->flags = p.flags;
+}
+
+int svae_param_table(const svae_config* cfg, svae_param_info* out, int capacity) {
+  if (!cfg) return fail(nullptr, SVAE_EINVAL, "null argument");
+  int vr = validate_cfg(cfg);
+  if (vr != 0) return vr;
+  svae_handle* h = new svae_handle();
+  h->cfg = *cfg;
+  h->L = cfg->levels; h->T = cfg->mc_steps; h->D = cfg->height; h->C = cfg->channels;
+  build_params(h);
+  const int n = (int)h->params.size();
+  if (out)
+    for (int i = 0; i < n && i < capacity; ++i) fill_info(h->params[i], &out[i]);
+  delete h;
+  return n;
+}
+
+int svae_create(const svae_config* cfg, int device, svae_handle** out) {
+  if (!cfg || !out) return fail(nullptr, SVAE_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(nullptr, SVAE_ENODEVICE, "no usable CUDA device (libsvae has no CPU fallback)");
+  }
+  { int vr = validate_cfg(cfg); if (vr != 0) return vr; }
+  const int L = cfg->levels;
+  svae_handle* h = new svae_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->L = L; h->T = cfg->mc_steps; h->D = cfg->height; h->C = cfg->channels;
+  h->Z = 0;
+  for (int i = 0; i < L; ++i) { h->zoff.push_back(h->Z); h->Z += cfg->latent_dims[i]; }
+  h->act_sets = cfg->train_capacity ? h->T : (h->T > 1 ? 2 : 1);
+#define C_CUDA(expr)                                                  \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) {                                          \
+      svae_set_cuda_error(_e, #expr, __FILE__, __LINE__);             \
+      int code = _e == cudaErrorMemoryAllocation ? SVAE_ENOMEM : SVAE_ECUDA; \
+      destroy_impl(h);                                                \
+      return code;                                                    \
+    }                                                                 \
+  } while (0)
+  C_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  C_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  if (cfg->operand_dtype == SVAE_OPERAND_BF16 && prop.major != 10) {
+    destroy_impl(h);
+    return fail(nullptr, SVAE_ENODEVICE, "SVAE_OPERAND_BF16 needs an sm_100a (B200) device");
+  }
+  C_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  build_params(h);
+  const size_t pbytes = (size_t)h->arena_numel * 4;
+  C_CUDA(cudaMalloc(&h->P, pbytes));
+  C_CUDA(cudaMemset(h->P, 0, pbytes));
+  if (cfg->train_capacity) {
+    C_CUDA(cudaMalloc(&h->G, pbytes)); C_CUDA(cudaMemset(h->G, 0, pbytes));
+    C_CUDA(cudaMalloc(&h->M, pbytes)); C_CUDA(cudaMemset(h->M, 0, pbytes));
+    C_CUDA(cudaMalloc(&h->V, pbytes)); C_CUDA(cudaMemset(h->V, 0, pbytes));
+  }
+  // two-pass bump allocation
+  {
+    Arena act, zf, zb, gr; size_t max_y = 0;
+    build_buffers(h, act, zf, zb, gr, max_y);
+    h->act_bytes = act.off + 256; h->zf_bytes = zf.off + 256; h->zb_bytes = zb.off + 256; h->grad_bytes = gr.off + 256;
+    C_CUDA(cudaMalloc(&h->act_base, h->act_bytes));
+    C_CUDA(cudaMalloc(&h->zf_base, h->zf_bytes));
+    C_CUDA(cudaMalloc(&h->zb_base, h->zb_bytes));
+    C_CUDA(cudaMalloc(&h->grad_base, h->grad_bytes));
+    C_CUDA(cudaMemset(h->act_base, 0, h->act_bytes));
+    Arena act2, zf2, zb2, gr2; size_t my2 = 0;
+    act2.base = h->act_base; zf2.base = h->zf_base; zb2.base = h->zb_base; gr2.base = h->grad_base;
+    build_buffers(h, act2, zf2, zb2, gr2, my2);
+  }
+  {
+    Arena pk;
+    for_each_block(h, plan_pack, &pk);
+    h->pack_bytes = pk.off;
+    if (h->pack_bytes > 0) {
+      C_CUDA(cudaMalloc(&h->pack_base, h->pack_bytes + 256));
+      Arena pk2; pk2.base = h->pack_base;
+      for_each_block(h, plan_pack, &pk2);
+    }
+  }
+  C_CUDA(cudaMallocHost((void**)&h->loss_host, sizeof(double) * 2 * SVAE_MAX_STEPS));
+  C_CUDA(cudaMalloc(&h->loss_sums, sizeof(double) * 2 * SVAE_MAX_STEPS));
+  C_CUDA(cudaMemset(h->loss_sums, 0, sizeof(double) * 2 * SVAE_MAX_STEPS));
+  *out = h;
+  return SVAE_OK;
+#undef C_CUDA
+}
+
+int svae_destroy(svae_handle* h) { destroy_impl(h); return SVAE_OK; }
+
+int svae_set_stream(svae_handle* h, void* s) {
+  if (!h) return SVAE_EINVAL;
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return SVAE_OK;
+}
+int svae_sync(svae_handle* h) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->comm_stream) H_CUDA(cudaStreamSynchronize(h->comm_stream));
+  return SVAE_OK;
+}
+
+int svae_param_count(const svae_handle* h) { return h ? (int)h->params.size() : SVAE_EINVAL; }
+int svae_param_info_get(const svae_handle* h, int i, svae_param_info* o) {
+  if (!h || !o || i < 0 || i >= (int)h->params.size()) return SVAE_EINVAL;
+  fill_info(h->params[i], o);
+  return SVAE_OK;
+}
+static int param_copy(svae_handle* h, float* arena, int i, float* host, bool to_dev) {
+  if (!h || !host || i < 0 || i >= (int)h->params.size() || !arena) return fail(h, SVAE_EINVAL, "bad parameter index or arena");
+  H_CUDA(cudaSetDevice(h->device));
+  const Param& p = h->params[i];
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  if (to_dev) H_CUDA(cudaMemcpy(arena + p.offset, host, p.numel * 4, cudaMemcpyHostToDevice));
+  else H_CUDA(cudaMemcpy(host, arena + p.offset, p.numel * 4, cudaMemcpyDeviceToHost));
+  return SVAE_OK;
+}
+int svae_param_set(svae_handle* h, int i, const float* src) {
+  int r = param_copy(h, h ? h->P : nullptr, i, const_cast<float*>(src), true);
+  if (r == 0) h->weights_dirty = true;
+  return r;
+}
+int svae_param_get(svae_handle* h, int i, float* dst) { return param_copy(h, h ? h->P : nullptr, i, dst, false); }
+int svae_grad_get(svae_handle* h, int i, float* dst) { return param_copy(h, h ? h->G : nullptr, i, dst, false); }
+int svae_adam_get(svae_handle* h, int i, float* m, float* v) {
+  int r = param_copy(h, h ? h->M : nullptr, i, m, false);
+  return r ? r : param_copy(h, h->V, i, v, false);
+}
+int svae_adam_set(svae_handle* h, int i, const float* m, const float* v) {
+  int r = param_copy(h, h ? h->M : nullptr, i, const_cast<float*>(m), true);
+  return r ? r : param_copy(h, h->V, i, const_cast<float*>(v), true);
+}
+int64_t svae_adam_step_count(const svae_handle* h) { return h ? h->adam_t : 0; }
+int svae_adam_set_step_count(svae_handle* h, int64_t t) { if (!h) return SVAE_EINVAL; h->adam_t = t; return SVAE_OK; }
+void* svae_param_arena(svae_handle* h) { return h ? h->P : nullptr; }
+void* svae_grad_arena(svae_handle* h) { return h ? h->G : nullptr; }
+int64_t svae_arena_numel(const svae_handle* h) { return h ? h->arena_numel : 0; }
+
+int svae_forward(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float reg,
+                 float* mu_out, float* sd_out, float* xs_out) {
+  if (!h || !x || !tgt) return fail(h, SVAE_EINVAL, "null argument");
+  H_CUDA(cudaSetDevice(h->device));
+  return forward_impl(h, x, tgt, B, eps, seed, reg, mu_out, sd_out, xs_out);
+}
+int svae_backward(svae_handle* h) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  return backward_impl(h);
+}
+int svae_adam_step(svae_handle* h, float lr) {
+  if (!h) return SVAE_EINVAL;
+  if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "handle created without train_capacity");
+  H_CUDA(cudaSetDevice(h->device));
+  return adam_impl(h, lr);
+}
+int svae_train_step(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float lr,
+                    float reg) {
+  if (!h || !x || !tgt) return fail(h, SVAE_EINVAL, "null argument");
+  H_CUDA(cudaSetDevice(h->device));
+  h->iteration += 1;
+  H_TRY(forward_impl(h, x, tgt, B, eps, seed, reg, nullptr, nullptr, nullptr));
+  H_TRY(backward_impl(h));
+  H_TRY(adam_impl(h, lr));
+  return SVAE_OK;
+}
+int svae_train_step_host(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed,
+                         float lr, float reg, svae_losses* losses) {
+  if (!h || !x || !tgt) return fail(h, SVAE_EINVAL, "null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t img = (size_t)B * h->D * h->D * h->C, cap = (size_t)h->cfg.max_batch * h->D * h->D * h->C;
+  H_TRY(stage_in(h, h->in_x, &h->pin_x, x, img, cap));
+  const float* dtgt = h->in_x;
+  if (tgt != x) { H_TRY(stage_in(h, h->in_tgt, &h->pin_tgt, tgt, img, cap)); dtgt = h->in_tgt; }
+  const float* deps = nullptr;
+  if (eps) {
+    H_TRY(stage_in(h, h->in_eps, &h->pin_eps, eps, (size_t)h->T * B * h->Z, (size_t)h->T * h->cfg.max_batch * h->Z));
+    deps = h->in_eps;
+  }
+  H_TRY(svae_train_step(h, h->in_x, dtgt, B, deps, seed, lr, reg));
+  if (losses) H_TRY(read_losses_impl(h, losses)); else H_CUDA(cudaStreamSynchronize(h->stream));
+  return SVAE_OK;
+}
+int svae_forward_host(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed,
+                      float reg, float* mu_out, float* sd_out, float* xs_out, float* last_out, svae_losses* losses) {
+  if (!h || !x || !tgt) return fail(h, SVAE_EINVAL, "null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t img = (size_t)B * h->D * h->D * h->C, cap = (size_t)h->cfg.max_batch * h->D * h->D * h->C;
+  const size_t bz = (size_t)B * h->Z;
+  H_TRY(stage_in(h, h->in_x, &h->pin_x, x, img, cap));
+  const float* dtgt = h->in_x;
+  if (tgt != x) { H_TRY(stage_in(h, h->in_tgt, &h->pin_tgt, tgt, img, cap)); dtgt = h->in_tgt; }
+  const float* deps = nullptr;
+  if (eps) {
+    H_TRY(stage_in(h, h->in_eps, &h->pin_eps, eps, (size_t)h->T * bz, (size_t)h->T * h->cfg.max_batch * h->Z));
+    deps = h->in_eps;
+  }
+  float *dmu = nullptr, *dsd = nullptr, *dxs = nullptr;
+  if (mu_out || sd_out || xs_out) {
+    H_TRY(ensure_io_steps(h, (size_t)h->T * (img + 2 * bz)));
+    dxs = h->io_steps; dmu = h->io_steps + h->T * img; dsd = dmu + h->T * bz;
+  }
+  H_TRY(forward_impl(h, h->in_x, dtgt, B, deps, seed, reg, mu_out ? dmu : nullptr, sd_out ? dsd : nullptr,
+                     xs_out ? dxs : nullptr));
+  if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out, dxs, h->T * img * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (mu_out) H_CUDA(cudaMemcpyAsync(mu_out, dmu, h->T * bz * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (sd_out) H_CUDA(cudaMemcpyAsync(sd_out, dsd, h->T * bz * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (last_out) H_CUDA(cudaMemcpyAsync(last_out, h->steps[h->T - 1].xt, img * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (losses) H_TRY(read_losses_impl(h, losses)); else H_CUDA(cudaStreamSynchronize(h->stream));
+  return SVAE_OK;
+}
+int svae_read_losses(svae_handle* h, svae_losses* out) {
+  if (!h || !out) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  return read_losses_impl(h, out);
+}
+
+int svae_generate(svae_handle* h, int B, const float* z, uint64_t seed, float* out) {
+  if (!h || !out) return fail(h, SVAE_EINVAL, "null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_CUDA(cudaSetDevice(h->device));
+  H_TRY(repack_if_dirty(h));
+  H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
+  LaunchCtx lc = h->lc();
+  const size_t img = (size_t)B * h->D * h->D * h->C;
+  const size_t bz = (size_t)B * h->Z;
+  if (z == nullptr) {  // np.random.normal(size=(batch, latent_dim)) per step (sequential_vae.py:1417-1418), drawn on device
+    H_TRY(fill_normal(lc, h->in_eps, (int64_t)h->T * bz, seed, 0));
+    z = h->in_eps;
+  }
+  const float* prev = nullptr;
+  for (int t = 0; t < h->T; ++t) {
+    Step& s = h->steps[t];
+    if (t >= 2 && h->act_sets < h->T) {
+      // steps >= 2 reuse step 1's buffers: their batch-norm statistics must restart from zero
+      H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
+    }
+    if (t > 0) H_TRY(encoder_fwd(h, s, B, prev));
+    H_TRY(decoder_fwd(h, s, B, z + t * bz, prev, nullptr, out + t * img, nullptr));
+    prev = out + t * img;
+  }
+  h->have_fwd = false;
+  return SVAE_OK;
+}
+int svae_generate_host(svae_handle* h, int B, const float* z, uint64_t seed, float* out) {
+  if (!h || !out) return fail(h, SVAE_EINVAL, "null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t img = (size_t)B * h->D * h->D * h->C;
+  const float* dz = nullptr;
+  if (z) {
+    H_TRY(stage_in(h, h->in_eps, &h->pin_eps, z, (size_t)h->T * B * h->Z, (size_t)h->T * h->cfg.max_batch * h->Z));
+    dz = h->in_eps;
+  }
+  H_TRY(ensure_io_steps(h, (size_t)h->T * img));
+  H_TRY(svae_generate(h, B, dz, seed, h->io_steps));
+  H_CUDA(cudaMemcpyAsync(out, h->io_steps, h->T * img * 4, cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  return SVAE_OK;
+}
+
+int svae_nccl_unique_id(char id_out[128], const char* path) {
+  NcclApi* api = nccl_load(path);
+  if (!api) return fail(nullptr, SVAE_ENCCL, "libnccl not found: " + nccl_load_error());
+  int r = api->GetUniqueId(id_out);
+  if (r != 0) return fail(nullptr, SVAE_ENCCL, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+  return SVAE_OK;
+}
+int svae_comm_init(svae_handle* h, int rank, int nranks, const char id[128], const char* path) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, SVAE_EINVAL, "bad rank/nranks");
+  if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "communicator needs a train_capacity handle");
+  H_CUDA(cudaSetDevice(h->device));
+  h->nccl = nccl_load(path);
+  if (!h->nccl) return fail(h, SVAE_ENCCL, "libnccl not found: " + nccl_load_error());
+  int r = h->nccl->CommInitRank(&h->comm, nranks, id, rank);
+  if (r != 0) { h->comm = nullptr; return fail(h, SVAE_ENCCL, std::string("ncclCommInitRank: ") + h->nccl->GetErrorString(r)); }
+  h->rank = rank; h->nranks = nranks;
+  H_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  h->bucket_ev.resize(h->T);
+  for (int t = 0; t < h->T; ++t) H_CUDA(cudaEventCreateWithFlags(&h->bucket_ev[t], cudaEventDisableTiming));
+  H_CUDA(cudaEventCreateWithFlags(&h->comm_done, cudaEventDisableTiming));
+  return SVAE_OK;
+}
+int svae_comm_destroy(svae_handle* h) {
+  if (!h) return SVAE_EINVAL;
+  if (h->comm && h->nccl) { svae_sync(h); h->nccl->CommDestroy(h->comm); }
+  h->comm = nullptr; h->nranks = 1; h->rank = 0;
+  return SVAE_OK;
+}
+
+int64_t svae_launch_count(const svae_handle* h) { return h ? h->launches : 0; }
+int64_t svae_activation_bytes(const svae_handle* h) { return h ? (int64_t)(h->act_bytes + h->grad_bytes) : 0; }
+int svae_tc_layers(const svae_handle* h) { return h ? h->tc_layers : 0; }
+
+// ---- layer-level entry points --------------------------------------------------------------------------------------
+static int op_contract(svae_handle* h, Geom g, int B, const float* x, int ldx, const float* w, float* y, int ldy,
+                       double* stats, int operand) {
+  g.B = B;
+  LaunchCtx lc = h->lc();
+  if (stats) H_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Cout, h->stream));
+  if (operand == SVAE_OPERAND_BF16) {
+    if (!tc_supported(g)) return fail(h, SVAE_EINVAL, "shape not supported by the tcgen05 kernels");
+    void* packed = nullptr;
+    H_CUDA(cudaMalloc(&packed, tc_packed_bytes(g)));
+    int r = tc_pack_weights(lc, g, w, packed);
+    if (r == 0) r = tc_gather_gemm(lc, g, mkview(const_cast<float*>(x), ldx, 0), packed, mkview(y, ldy, 0), stats);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(packed);
+    if (r != 0) { h->err = g_err; return r; }
+    return 0;
+  }
+  H_TRY(simt_gather_gemm(lc, g, mkview(const_cast<float*>(x), ldx, 0), w, mkview(y, ldy, 0), stats));
+  return 0;
+}
+
+int svae_op_conv2d(svae_handle* h, const float* x, const float* w, float* y, double* stats, int B, int H, int W, int Ci,
+                   int Co, int stride, int operand) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  Geom g = conv_geom(H, W, Ci, Co, stride);
+  return op_contract(h, g, B, x, Ci, w, y, Co, stats, operand);
+}
+int svae_op_conv2d_transpose(svae_handle* h, const float* x, const float* w, float* y, double* stats, int B, int H,
+                             int W, int Ci, int Co, int stride, int operand) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  Geom g = deconv_geom(H, W, Ci, Co, stride);
+  return op_contract(h, g, B, x, Ci, w, y, Co, stats, operand);
+}
+int svae_op_conv2d_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx, float* dw, int B,
+                            int H, int W, int Ci, int Co, int stride, int operand) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  Geom f = conv_geom(H, W, Ci, Co, stride);
+  if (dx) { int r = op_contract(h, dgrad_geom(f), B, dy, Co, w, dx, Ci, nullptr, operand); if (r) return r; }
+  if (dw) {
+    LaunchCtx lc = h->lc();
+    H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * Ci * Co, h->stream));
+    Geom g = f; g.B = B;
+    H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(x), Ci, 0), mkview(const_cast<float*>(dy), Co, 0), dw));
+  }
+  return 0;
+}
+int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx,
+                                      float* dw, int B, int H, int W, int Ci, int Co, int stride, int operand) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  Geom f = deconv_geom(H, W, Ci, Co, stride);
+  if (dx) { int r = op_contract(h, dgrad_geom(f), B, dy, Co, w, dx, Ci, nullptr, operand); if (r) return r; }
+  if (dw) {
+    LaunchCtx lc = h->lc();
+    H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * Ci * Co, h->stream));
+    Geom g = dgrad_geom(f); g.B = B; g.mode = 0;
+    H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(dy), Co, 0), mkview(const_cast<float*>(x), Ci, 0), dw));
+  }
+  return 0;
+}
+int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  double* stats = nullptr;
+  H_CUDA(cudaMalloc(&stats, sizeof(double) * 2 * C));
+  H_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, h->stream));
+  LaunchCtx lc = h->lc();
+  int r = col_stats(lc, y, rows, C, stats);
+  if (r == 0) r = bn_act_fwd(lc, y, stats, beta, rows, C, act, FeatView{}, FeatView{out, C, 0, C, 1});
+  cudaStreamSynchronize(h->stream);
+  cudaFree(stats);
+  if (r != 0) { h->err = g_err; return r; }
+  return 0;
+}
+int svae_op_adam(svae_handle* h, float* p, const float* g, float* m, float* v, int64_t n, float lr, int64_t t, float b1,
+                 float b2, float eps, float clip, float gscale) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  LaunchCtx lc = h->lc();
+  H_TRY(adam_update(lc, p, g, m, v, n, lr_t, b1, b2, eps, clip, gscale));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/svae.h declares, fails loudly without
+a GPU, and its device-free parameter table equals the oracle's (TF creation order, shapes, inert/dead/xavier flags)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import seqvae_b200 as S
+from seqvae_b200 import _cabi
+from seqvae_b200.config import to_cabi_config
+from oracle import seqvae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "svae.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(svae_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _cabi.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(L, s), "libsvae.so does not export %s" % s
+        assert s in _cabi.PROTOTYPES, "ctypes binding has no prototype for %s" % s
+    assert set(_cabi.PROTOTYPES) == set(syms)
+    assert b"sm_100a" in L.svae_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by include/svae.h (no padding surprises between C and ctypes)
+    assert C.sizeof(_cabi.Losses) == 4 * (2 + 2 * 64)
+    assert C.sizeof(_cabi.ParamInfo) == 128 + 4 + 16 + 4 + 8 + 8 + 4 + 4 or C.sizeof(_cabi.ParamInfo) % 8 == 0
+    assert C.sizeof(_cabi.Config) % 8 == 0
+
+
+@pytest.mark.parametrize("name,dims,rng", [("c_inhomog", [64, 64, 3], (-1, 1)), ("m_inhomog", [32, 32, 1], (0, 1)),
+                                           ("sequential_vae_lsun", [64, 64, 3], (-1, 1)),
+                                           ("sequential_vae_celebA_inhomog", [64, 64, 3], (-1, 1))])
+def test_param_table_matches_oracle(name, dims, rng):
+    L = _cabi.lib()
+    cfg = to_cabi_config(S.hyperparams(name, dims, rng), 100)
+    n = L.svae_param_table(C.byref(cfg), None, 0)
+    arr = (_cabi.ParamInfo * n)()
+    assert L.svae_param_table(C.byref(cfg), arr, n) == n
+    sp = O.param_specs(O.hyperparams(name, dims, rng))
+    assert n == len(sp)
+    off = 0
+    for a, s in zip(arr, sp):
+        assert a.name.decode() == s["name"]
+        assert tuple(a.shape[:a.ndim]) == s["shape"]
+        assert a.numel == int(np.prod(s["shape"]))
+        assert bool(a.flags & _cabi.PF_INERT) == s["inert"]
+        assert bool(a.flags & _cabi.PF_DEAD) == s["dead"]
+        assert bool(a.flags & _cabi.PF_XAVIER) == (s["init"] == "xavier")
+        assert bool(a.flags & _cabi.PF_THETA) == s["name"].startswith("theta/")
+        assert a.offset >= off and a.offset % 4 == 0
+        off = a.offset + a.numel
+        assert a.step == int(re.search(r"step_(\d+)", s["name"]).group(1))
+
+
+def test_invalid_configs_are_rejected():
+    L = _cabi.lib()
+    hp = S.hyperparams("c_inhomog", [64, 64, 3], (-1, 1))
+    cfg = to_cabi_config(hp, 100)
+    cfg.height = 60                                   # not a multiple of 2^levels
+    cfg.width = 60
+    assert L.svae_param_table(C.byref(cfg), None, 0) == -1
+    cfg = to_cabi_config(hp, 100)
+    cfg.latent_dims[1] = 64                           # above the supported latent width
+    assert L.svae_param_table(C.byref(cfg), None, 0) == -1
+    cfg = to_cabi_config(hp, 0)
+    assert L.svae_param_table(C.byref(cfg), None, 0) == -1
+
+
+def test_unknown_netname_and_bad_image_sizes():
+    with pytest.raises(KeyError):
+        S.hyperparams("no_such_net", [64, 64, 3], (-1, 1))          # reference: log error + exit(-1)
+    with pytest.raises(ValueError):
+        S.hyperparams("m_inhomog", [64, 64, 1], (0, 1))             # image_sizes [32,16,8,4] vs 64x64 input (:1617-1627)
+
+
+def test_netname_rows():
+    hp = S.hyperparams("m_inhomog", [32, 32, 1], (0, 1))
+    assert (hp["vlae_levels"], hp["mc_steps"], hp["latent_dim"]) == (3, 5, 6)
+    assert hp["filter_sizes"] == [1, 64, 128, 192, 256]
+    hp = S.hyperparams("sequential_vae_lsun", [64, 64, 3], (-1, 1))
+    assert hp["latent_dim"] == 110 and hp["mc_steps"] == 8
+    hp = S.hyperparams("c_inhomog", [64, 64, 3], (-1, 1))
+    assert hp["filter_sizes"] == [3, 32, 64, 128, 384, 512] and hp["learning_rate"] == 2e-4
+    for k, v in O.hyperparams("c_inhomog", [64, 64, 3], (-1, 1)).items():       # product table == oracle table
+        assert hp[k] == v, k
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ds = S.SyntheticDataset("celebA", 4)
+    with pytest.raises(_cabi.SvaeError) as ei:
+        S.SequentialVAE(ds, 4, "c_inhomog")
+    assert ei.value.code == -2
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sequential-variational-autoencoder_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_synthetic_dataset_shapes():
+    ds = S.SyntheticDataset("mnist", 7)
+    b = ds.next_batch(7)
+    assert b.shape == (7, 32, 32, 1) and b.dtype == np.float32 and 0 <= b.min() and b.max() <= 1
+    ds = S.SyntheticDataset("celebA", 3)
+    b = ds.next_test_batch(3)
+    assert b.shape == (3, 64, 64, 3) and -1 <= b.min() and b.max() <= 1
+    ds.reset()
+    np.testing.assert_array_equal(ds.next_test_batch(3), b)

@@ -1,0 +1,149 @@
+"""GPU parity of the layer-level entry points (through the C ABI) against the oracle's layer blocks
+(abstract_network.py:8-71 semantics).  fp32 SIMT kernels: 1e-4; bf16 tcgen05 kernels: operands rounded to bf16, fp32
+accumulate -> compared against the oracle evaluated on bf16-rounded operands at 2e-3 (and 2e-2 against unrounded)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import seqvae_oracle as O
+from gpu_util import dev, op_handle, ptr, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CONV_CASES = [
+    # B, H, Ci, Co, stride
+    (2, 16, 3, 8, 2), (3, 8, 8, 8, 1), (2, 8, 16, 16, 2), (5, 4, 16, 16, 1), (2, 2, 16, 24, 2),
+    (2, 32, 32, 32, 1), (3, 16, 64, 64, 1), (2, 16, 32, 64, 2), (2, 8, 128, 128, 1), (1, 64, 3, 32, 2),
+    (4, 4, 128, 128, 2), (100, 8, 64, 128, 2),
+]
+
+
+def _tol(operand):
+    return 2e-5 if operand == 0 else 1.5e-2
+
+
+def _operands(operand):
+    return [0, 1] if operand is None else [operand]
+
+
+def _maybe_skip_tc(rc, L, h):
+    if rc != 0:
+        msg = L.svae_last_error(h).decode()
+        if "not supported" in msg:
+            pytest.skip("shape not routed to tcgen05: " + msg)
+        raise AssertionError("libsvae error %d: %s" % (rc, msg))
+
+
+@pytest.mark.parametrize("operand", [0, 1])
+@pytest.mark.parametrize("B,H,Ci,Co,stride", CONV_CASES)
+def test_conv2d_forward_and_stats(B, H, Ci, Co, stride, operand):
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Ci)
+    x = torch.randn(B, H, H, Ci, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 4, Ci, Co, generator=g, dtype=torch.float64) * 0.1
+    ref = O.conv2d_same(x, w, stride)
+    y = torch.empty(B, H // stride, H // stride, Co, device="cuda")
+    stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
+    rc = L.svae_op_conv2d(h, ptr(dev(x)), ptr(dev(w)), ptr(y), ptr(stats), B, H, H, Ci, Co, stride, operand)
+    _maybe_skip_tc(rc, L, h)
+    m.sync()
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < _tol(operand)
+    yy = y.double().cpu()
+    np.testing.assert_allclose(stats[:Co].cpu().numpy(), yy.sum(dim=(0, 1, 2)).numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stats[Co:].cpu().numpy(), (yy ** 2).sum(dim=(0, 1, 2)).numpy(), rtol=1e-4, atol=1e-3)
+
+
+DECONV_CASES = [
+    (2, 1, 24, 16, 2), (3, 2, 16, 16, 2), (2, 4, 32, 16, 1), (2, 8, 16, 3, 2), (2, 8, 16, 1, 2),
+    (2, 4, 384, 128, 2), (3, 8, 256, 128, 1), (2, 16, 128, 64, 1), (2, 16, 64, 32, 2), (2, 32, 64, 32, 1),
+    (100, 4, 64, 64, 2),
+]
+
+
+@pytest.mark.parametrize("operand", [0, 1])
+@pytest.mark.parametrize("B,H,Ci,Co,stride", DECONV_CASES)
+def test_conv2d_transpose_forward(B, H, Ci, Co, stride, operand):
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Ci + 7)
+    x = torch.randn(B, H, H, Ci, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 4, Co, Ci, generator=g, dtype=torch.float64) * 0.1
+    ref = O.conv2d_transpose_same(x, w, stride)
+    y = torch.empty(B, H * stride, H * stride, Co, device="cuda")
+    rc = L.svae_op_conv2d_transpose(h, ptr(dev(x)), ptr(dev(w)), ptr(y), None, B, H, H, Ci, Co, stride, operand)
+    _maybe_skip_tc(rc, L, h)
+    m.sync()
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < _tol(operand)
+
+
+@pytest.mark.parametrize("operand", [0, 1])
+@pytest.mark.parametrize("B,H,Ci,Co,stride", [(2, 8, 8, 16, 1), (3, 8, 16, 8, 2), (2, 16, 3, 8, 2), (2, 4, 16, 16, 1),
+                                              (2, 16, 32, 32, 1), (2, 16, 32, 64, 2), (2, 8, 128, 128, 1)])
+def test_conv2d_backward(B, H, Ci, Co, stride, operand):
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(11 + H + Ci)
+    x = torch.randn(B, H, H, Ci, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(4, 4, Ci, Co, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    dy = torch.randn(B, H // stride, H // stride, Co, generator=g, dtype=torch.float64)
+    O.conv2d_same(x, w, stride).backward(dy)
+    dx = torch.empty(B, H, H, Ci, device="cuda")
+    dw = torch.empty(4, 4, Ci, Co, device="cuda")
+    rc = L.svae_op_conv2d_backward(h, ptr(dev(x.detach())), ptr(dev(w.detach())), ptr(dev(dy)), ptr(dx), ptr(dw), B, H,
+                                   H, Ci, Co, stride, operand)
+    _maybe_skip_tc(rc, L, h)
+    m.sync()
+    assert rel_err(dx.cpu().numpy(), x.grad.numpy()) < _tol(operand)
+    assert rel_err(dw.cpu().numpy(), w.grad.numpy()) < _tol(operand)
+
+
+@pytest.mark.parametrize("operand", [0, 1])
+@pytest.mark.parametrize("B,H,Ci,Co,stride", [(2, 4, 16, 8, 2), (3, 4, 16, 8, 1), (2, 8, 8, 3, 2), (2, 1, 24, 16, 2),
+                                              (2, 8, 64, 32, 2), (2, 8, 128, 64, 1), (2, 4, 384, 128, 2)])
+def test_conv2d_transpose_backward(B, H, Ci, Co, stride, operand):
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(13 + H + Ci)
+    x = torch.randn(B, H, H, Ci, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(4, 4, Co, Ci, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    dy = torch.randn(B, H * stride, H * stride, Co, generator=g, dtype=torch.float64)
+    O.conv2d_transpose_same(x, w, stride).backward(dy)
+    dx = torch.empty(B, H, H, Ci, device="cuda")
+    dw = torch.empty(4, 4, Co, Ci, device="cuda")
+    rc = L.svae_op_conv2d_transpose_backward(h, ptr(dev(x.detach())), ptr(dev(w.detach())), ptr(dev(dy)), ptr(dx),
+                                             ptr(dw), B, H, H, Ci, Co, stride, operand)
+    _maybe_skip_tc(rc, L, h)
+    m.sync()
+    assert rel_err(dx.cpu().numpy(), x.grad.numpy()) < _tol(operand)
+    assert rel_err(dw.cpu().numpy(), w.grad.numpy()) < _tol(operand)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("rows,C", [(2 * 8 * 8, 16), (100, 6144), (7, 33), (4096, 32)])
+def test_bn_act(rows, C, act):
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(rows + C)
+    y = torch.randn(rows, C, generator=g, dtype=torch.float64) * 2 + 0.5
+    beta = torch.randn(C, generator=g, dtype=torch.float64)
+    ref = O.batch_norm(y, beta)
+    ref = O.lrelu(ref) if act == 1 else torch.relu(ref) if act == 2 else ref
+    out = torch.empty(rows, C, device="cuda")
+    assert L.svae_op_bn_act(h, ptr(dev(y)), ptr(dev(beta)), ptr(out), rows, C, act) == 0
+    m.sync()
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_adam_matches_tf_formulation():
+    m, L, h = op_handle()
+    from oracle import tf_semantics_np as TFNP
+
+    rs = np.random.RandomState(0)
+    n = 10007                                   # odd: exercises the scalar tail
+    p = rs.randn(n).astype(np.float32)
+    g = (rs.randn(n) * 8).astype(np.float32)    # some elements beyond the +-10 clip
+    dp, dg = dev(p), dev(g)
+    dm, dv = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    rp, rm, rv = p.astype(np.float64), np.zeros(n), np.zeros(n)
+    for t in (1, 2, 3):
+        assert L.svae_op_adam(h, ptr(dp), ptr(dg), ptr(dm), ptr(dv), n, 2e-4, t, 0.9, 0.999, 1e-8, 10.0, 1.0) == 0
+        rp, rm, rv = TFNP.adam_tf(rp, np.clip(g.astype(np.float64), -10, 10), rm, rv, t, 2e-4)
+    m.sync()
+    np.testing.assert_allclose(dp.cpu().numpy(), rp, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(dm.cpu().numpy(), rm, rtol=1e-5, atol=1e-7)
