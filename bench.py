@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the Sequential-VAE hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      (CPU arm: the oracle port of the reference graph)
+
+Metric (BASELINE.json): training images/s (forward + per-step ELBO + full backward + clipped Adam) of the CelebA-64
+default SequentialVAE, batch 100 per GPU (weak scaling, per-replica batch-norm), synthetic data, random-init weights.
+A "step" is one pass of the hot path over one batch.  ``value`` is measured with the batch resident in HBM;
+``e2e`` goes through the reference-shaped public API (``SequentialVAE.train(numpy, numpy)``) with host buffers, i.e.
+host->device copies of the inputs and the device->host read of the losses inside the timed region.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (netname, dataset shape name, batch per GPU, hyper-parameter overrides)
+    "celeba64_b100": ("c_inhomog", "celebA", 100, {}),
+    "mnist32_b100": ("m_inhomog", "mnist", 100, {}),
+    "cifar32_b100": ("c_inhomog", "cifar", 100, {}),
+    "lsun64_b256_t16": ("sequential_vae_lsun", "lsun", 256, {"mc_steps": 16}),
+}
+# Algorithmic work per image (DESIGN.md "Roofline arithmetic")
+ALGO = {
+    "celeba64_b100": dict(train_flops=13.0065e9, train_bytes=62.88e6, gen_flops=3.2303e9, gen_bytes=9.54e6),
+    "mnist32_b100": dict(train_flops=4.9002e9, train_bytes=16.46e6),
+    "cifar32_b100": dict(train_flops=3.2517e9, train_bytes=22.56e6),
+    "lsun64_b256_t16": dict(train_flops=26.8676e9, train_bytes=101.42e6),
+}
+METRIC = "train img/s (fwd+bwd+ELBO) CelebA-64 SeqVAE @1/2/4/8 B200; sample img/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=max(power))
+
+
+def cpu_oracle_arm(workload, steps, warmup, threads=None):
+    """The reference's CPU path: fp32 PyTorch-CPU restatement of the reference graph (TF 1.x is not installable,
+    SURVEY Q14), one full train step = forward over all T steps + autograd backward + clip + TF-Adam."""
+    import numpy as np
+    import torch
+
+    from oracle import seqvae_oracle as O
+    from seqvae_b200.dataset import _SHAPES
+
+    netname, shape, B, over = WORKLOADS[workload]
+    dims, rng = _SHAPES[shape]
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = O.hyperparams(netname, dims, rng, **over)
+    om = O.OracleModel(hp, seed=0, dtype=torch.float32)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand([B] + dims, generator=g) * (rng[1] - rng[0]) + rng[0]
+    times = []
+    for i in range(warmup + steps):
+        eps = torch.randn(hp["mc_steps"], B, hp["latent_dim"], generator=g)
+        t0 = time.perf_counter()
+        om.train(x, x, eps)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=B / med, ms_per_step=med * 1e3, cores=cores, B=B,
+                sample="%d full train steps (B=%d, T=%d, fp32) after %d warm-up" % (steps, B, hp["mc_steps"], warmup))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, on this box's host cores.  The reference
+    itself needs TensorFlow 1.x (tf.contrib) which cannot be installed for Python 3.12, so this is the oracle PORT."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    r = cpu_oracle_arm(args.workload, steps, warm)
+    netname, shape, B, over = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "netname": netname, "batch_per_gpu": B, "mc_steps": over.get("mc_steps"),
+                   "note": "CPU oracle port of the reference graph (TensorFlow 1.x not installable); rank 0 only"},
+        "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="celeba64_b100", choices=sorted(WORKLOADS))
+    ap.add_argument("--operand", default=os.environ.get("SVAE_OPERAND", "auto"), choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-generation", action="store_true")
+    ap.add_argument("--gen-batch", type=int, default=4096)
+    ap.add_argument("--profile-json", default=None, help="also write the per-kernel-class table to this file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import seqvae_b200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    netname, shape, B, over = WORKLOADS[args.workload]
+    operand = args.operand
+    if operand == "auto":
+        operand = "bf16"
+    ds = S.SyntheticDataset(shape, B, seed=1234 + rank)
+    model = S.SequentialVAE(ds, B, netname, device=local_rank, operand_dtype=operand, restore=False, seed=0, **over)
+    if model.tc_layers == 0:
+        operand_used = "fp32"      # no contraction was routed to the tensor-core kernels
+    else:
+        operand_used = operand
+    stream = torch.cuda.Stream(device=local_rank)
+    model.use_torch_stream(stream)
+    if world > 1:
+        from seqvae_b200.dist import attach_communicator
+
+        attach_communicator(model, dist, rank, world)
+
+    H, W, C = model.data_dims
+    T, Z = model.mc_steps, model.latent_dim
+    x_host = ds.next_batch(B)
+    tgt_host = x_host.copy()
+    with torch.cuda.stream(stream):
+        x_dev = torch.from_numpy(x_host).cuda(local_rank, non_blocking=False)
+        tgt_dev = x_dev.clone()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        model.train_async(x_dev, tgt_dev)          # eps: in-kernel Philox (benchmark mode)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    model.profile(True)
+    l0 = model.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        model.train_async(x_dev, tgt_dev)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = model.launch_count - l0
+    prof = model.profile_read()
+    model.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers ("e2e") ---------------------------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        model.train(x_host, tgt_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.train(x_host, tgt_host)             # numpy in, float out: H2D of x and target, D2H of the losses, sync
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "img/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(2 * x_host.nbytes), "d2h_bytes_per_step": int(4 * (2 + 2 * 64))}
+
+    # ---- roofline of the dominant kernel class (live CUDA-event durations from the timed region) -------------------------
+    peaks = measured_peaks()
+    roof = None
+    table = []
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        table.append(dict(kernel=name, launches_per_step=v["launches"] / args.steps, ms_per_step=v["ms"] / args.steps,
+                          share=v["ms"] / tot_ms, tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else 0.0,
+                          gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0))
+    if table:
+        top = table[0]
+        contraction = top["kernel"].startswith(("gather_gemm", "wgrad"))
+        if contraction:
+            roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"], "peak": peaks["tf_sustained"],
+                    "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_sustained"], "traffic": None,
+                    "share_of_step": top["share"], "peak_source": peaks["source"] + " bf16 sustained"}
+        else:
+            roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": top["gbs"] / peaks["hbm"], "traffic": None, "share_of_step": top["share"],
+                    "peak_source": peaks["source"]}
+    algo = ALGO.get(args.workload, {})
+    path_roof = None
+    if algo:
+        per_gpu = value / world
+        path_roof = {"tensor_frac": per_gpu * algo["train_flops"] / (peaks["tf_sustained"] * 1e12),
+                     "hbm_frac": per_gpu * algo["train_bytes"] / (peaks["hbm"] * 1e9),
+                     "flops_per_img": algo["train_flops"], "bytes_per_img": algo["train_bytes"]}
+
+    # ---- generation-mode chain (config 5: replicas only) -----------------------------------------------------------------
+    generation = None
+    if not args.no_generation and args.workload == "celeba64_b100":
+        model.close()
+        del model
+        torch.cuda.empty_cache()
+        GB = args.gen_batch
+        gmodel = S.SequentialVAE(ds, GB, netname, device=local_rank, operand_dtype=operand, restore=False, seed=0,
+                                 train=False, **over)
+        gmodel.use_torch_stream(stream)
+        with torch.cuda.stream(stream):
+            out = torch.empty([T, GB, H, W, C], device="cuda", dtype=torch.float32)
+        for i in range(2):
+            gmodel.generate_async(GB, out, None, seed=i)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gsteps = 3
+        gl0 = gmodel.launch_count
+        g0.record(stream)
+        for i in range(gsteps):
+            gmodel.generate_async(GB, out, None, seed=10 + i)
+        g1.record(stream)
+        barrier()
+        gms = g0.elapsed_time(g1) / gsteps
+        t = torch.tensor([gms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
+        gval = world * GB / (gms * 1e-3)
+        generation = {"metric": "sample img/s (generation-mode chain, all %d steps)" % T, "value": gval, "unit": "img/s",
+                      "batch_per_gpu": GB, "ms_per_chain": gms, "scaling": "replicas only",
+                      "gpu_launches": gmodel.launch_count - gl0,
+                      "tensor_frac": gval / world * algo["gen_flops"] / (peaks["tf_sustained"] * 1e12),
+                      "hbm_frac": gval / world * algo["gen_bytes"] / (peaks["hbm"] * 1e9)}
+        gmodel.close()
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample) -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_arm(args.workload, 2, 1)
+        cpu = {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "ms_per_step": r["ms_per_step"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if operand_used == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "netname": netname, "image": [H, W, C], "batch_per_gpu": B,
+                       "global_batch": B * world, "mc_steps": T, "latent_dim": Z,
+                       "parallelism": "dp%d (per-replica BN, NCCL grad all-reduce per chain step)" % world,
+                       "operands": "bf16 tcgen05 + fp32 accumulate" if operand_used == "bf16" else "fp32 SIMT",
+                       "l2": "per-step working set (activations+weights+Adam state, >3 GB) exceeds the 126 MB L2",
+                       "eps": "in-kernel Philox"},
+            "roofline": roof, "path_roofline": path_roof, "kernels": table, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "generation": generation,
+        }
+        print(json.dumps(line), flush=True)
+        if args.profile_json:
+            with open(args.profile_json, "w") as f:
+                json.dump(line, f, indent=1)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

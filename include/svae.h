@@ -179,6 +179,19 @@ int64_t svae_launch_count(const svae_handle* h);   /* kernels launched by this h
 int64_t svae_activation_bytes(const svae_handle* h);
 int svae_tc_layers(const svae_handle* h);          /* number of contractions per train step routed to tcgen05 kernels */
 
+/* Per-kernel-class CUDA-event profile (what bench.py's roofline numbers are computed from): while enabled, every
+ * kernel launch is bracketed by events on the handle's stream and its algorithmic flops / bytes are accumulated.
+ * svae_profile_read synchronises, fills up to `capacity` classes, resets the counters and returns the class count. */
+typedef struct svae_kernel_stats {
+  char name[32];
+  int64_t launches;
+  double total_ms;   /* sum of per-launch event durations */
+  double flops;      /* algorithmic flops of those launches */
+  double bytes;      /* algorithmic HBM bytes of those launches */
+} svae_kernel_stats;
+int svae_profile_enable(svae_handle* h, int on);
+int svae_profile_read(svae_handle* h, svae_kernel_stats* out, int capacity);
+
 /* ---- layer-level entry points (unit parity against abstract_network.py:12-71; tests and micro-benchmarks only) ----
  * All pointers are device pointers; weights in the reference layout.  `operand_dtype` selects the kernel family. */
 /* convolution2d data path (abstract_network.py:18): x [B,H,W,Ci], w [4,4,Ci,Co] -> y [B,H/s,W/s,Co], SAME padding.

@@ -100,8 +100,18 @@ class Scope:
 # Layer blocks (abstract_network.py:8-71) with the TF-contrib defaults of SURVEY App. B
 # --------------------------------------------------------------------------------------------------------------
 
+PREACT_HOOK = None  # tests may set a callable(tensor): called with every pre-activation (input of lrelu / relu)
+
+
+def _probe(x):
+    if PREACT_HOOK is not None:
+        PREACT_HOOK(x.detach())
+    return x
+
+
 def lrelu(x, rate=0.1):
     """abstract_network.py:8-10: max(min(rate*x, 0), x)."""
+    _probe(x)
     return torch.maximum(torch.clamp(x * rate, max=0.0), x)
 
 
@@ -160,7 +170,7 @@ def _conv_block(sc: Scope, x, cin, cout, stride, act, transpose=False, dead=Fals
     if act == "lrelu":
         y = lrelu(y)
     elif act == "relu":
-        y = torch.relu(y)
+        y = torch.relu(_probe(y))
     return y
 
 
@@ -279,7 +289,7 @@ def generator_ladder(hp, sc: Scope, enc, z, first_step: bool, declare_only=False
         if run:
             if not first_step:
                 d = d + enc[level + 1]                                               # :1713
-            d = torch.relu(d)                                                        # :1714
+            d = torch.relu(_probe(d))                                                # :1714
             d = torch.cat([d, planes[level]], 3)                                     # :1716
         cur = _conv_block(sc, d if run else None, 2 * Fs[level + 1], Fs[level + 1], 1, "relu", transpose=True)  # :1717
         cin = Fs[level + 1]

@@ -42,6 +42,11 @@ class ParamInfo(C.Structure):
                 ("offset", C.c_int64), ("step", C.c_int32), ("flags", C.c_int32)]
 
 
+class KernelStats(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 _P = C.c_void_p
 _F = C.POINTER(C.c_float)
 
@@ -81,6 +86,8 @@ PROTOTYPES = {
     "svae_launch_count": (C.c_int64, [_P]),
     "svae_activation_bytes": (C.c_int64, [_P]),
     "svae_tc_layers": (C.c_int, [_P]),
+    "svae_profile_enable": (C.c_int, [_P, C.c_int]),
+    "svae_profile_read": (C.c_int, [_P, C.POINTER(KernelStats), C.c_int]),
     "svae_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 7),
     "svae_op_conv2d_transpose": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 7),
     "svae_op_conv2d_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 7),

@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #define SVAE_BN_EPS 1e-3f     // tf.contrib.layers.batch_norm default epsilon (abstract_network.py:22)
 #define SVAE_LRELU_SLOPE 0.1f // lrelu rate (abstract_network.py:8)
@@ -48,10 +49,53 @@ struct Geom {
   int KH, KW, stride, pad, mode, w_out_major, accumulate;
 };
 
+// ---- per-kernel-class event profiler (bench.py's live roofline numbers) -------------------------------------------
+enum KClass {
+  KC_GEMM_SIMT = 0, KC_WGRAD_SIMT, KC_SKINNY, KC_BN_FWD, KC_BN_BWD_REDUCE, KC_BN_BWD_APPLY, KC_OUT_MIX, KC_REPARAM,
+  KC_ADAM, KC_MISC, KC_GEMM_TC, KC_WGRAD_TC, KC_PACK, KC_COUNT
+};
+static const char* const kKClassNames[KC_COUNT] = {
+    "gather_gemm_simt", "wgrad_simt", "skinny_fc", "bn_act_fwd", "bn_bwd_reduce", "bn_bwd_apply", "out_mix",
+    "reparam_kl", "adam_clip", "misc", "gather_gemm_tcgen05", "wgrad_tcgen05", "pack_weights"};
+
+struct Profiler {
+  bool enabled = false;
+  struct Rec { cudaEvent_t a, b; int kc; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_used = 0;
+  int64_t launches[KC_COUNT] = {0};
+  double flops[KC_COUNT] = {0}, bytes[KC_COUNT] = {0}, ms[KC_COUNT] = {0};
+  cudaEvent_t get() {
+    if (pool_used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[pool_used++];
+  }
+};
+
 struct LaunchCtx {
   cudaStream_t stream;
   int64_t* launches;
   int sm_count;
+  Profiler* prof;
+};
+
+// RAII: brackets one kernel launch with events when profiling is on, and counts the launch either way.
+struct ProfScope {
+  const LaunchCtx& lc;
+  cudaEvent_t b = nullptr;
+  int kc;
+  ProfScope(const LaunchCtx& lc_, int kc_, double flops, double bytes) : lc(lc_), kc(kc_) {
+    ++*lc.launches;
+    Profiler* p = lc.prof;
+    if (p && p->enabled) {
+      cudaEvent_t a = p->get();
+      b = p->get();
+      cudaEventRecord(a, lc.stream);
+      p->recs.push_back({a, b, kc});
+      p->launches[kc]++; p->flops[kc] += flops; p->bytes[kc] += bytes;
+    }
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, lc.stream); }
 };
 
 #define CUDA_TRY(expr)                                                                        \

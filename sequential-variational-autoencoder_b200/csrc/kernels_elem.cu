@@ -370,8 +370,8 @@ static inline unsigned flat_blocks(int64_t n, int sm_count, int threads = 256) {
 
 int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats) {
   ColGrid cg = col_grid(rows, C, lc.sm_count);
+  ProfScope ps(lc, KC_MISC, 3.0 * rows * C, 4.0 * rows * C);
   col_stats_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, rows, C, stats);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -379,8 +379,8 @@ int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* 
 int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const float* beta, int64_t rows, int feats,
                int act, FeatView residual, FeatView out) {
   ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  ProfScope ps(lc, KC_BN_FWD, 4.0 * rows * feats, 4.0 * rows * feats * (residual.p ? 3 : 2));
   bn_act_fwd_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, stats, beta, rows, feats, act, residual, out);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -389,9 +389,10 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
                   int64_t rows, int feats, int act, FeatView residual, float* dyhat, double* S, float* dres,
                   int dres_accumulate) {
   ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  ProfScope ps(lc, KC_BN_BWD_REDUCE, 8.0 * rows * feats,
+               4.0 * rows * feats * (3 + (residual.p ? 1 : 0) + (dres ? 1 : 0)));
   bn_bwd_reduce_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(da, y, stats, beta, rows, feats, act, residual, dyhat, S,
                                                             dres, dres_accumulate);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -399,8 +400,8 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
 int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
                  int feats, float* dbeta) {
   ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  ProfScope ps(lc, KC_BN_BWD_APPLY, 5.0 * rows * feats, 12.0 * rows * feats);
   bn_bwd_apply_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(dyhat, y, stats, S, rows, feats, dbeta);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -408,9 +409,10 @@ int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double
 int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
                 const float* xprev, const float* tgt, float* xt, double* recon_sum) {
   if (p.C > MAXC) return -1;
+  ProfScope ps(lc, KC_OUT_MIX, 20.0 * p.pixels * p.C,
+               4.0 * p.pixels * (p.C + p.has_gate + p.C * (1 + (p.has_gate ? 1 : 0) + (tgt ? 1 : 0))));
   out_mix_fwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
                                                                                recon_sum);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -419,9 +421,10 @@ int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
                 const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
                 float* gx_prev, float* db_out, float* db_gate) {
   if (p.C > MAXC) return -1;
+  ProfScope ps(lc, KC_OUT_MIX, 30.0 * p.pixels * p.C,
+               4.0 * p.pixels * (2 * (p.C + p.has_gate) + p.C * (2 + (gx_in ? 1 : 0) + (p.has_gate ? 2 : 0))));
   out_mix_bwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
                                                                                gx_in, coef, du, gx_prev, db_out, db_gate);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -429,18 +432,18 @@ int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
 int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre, const float* sd_pre, const float* eps,
                 uint64_t seed, uint64_t counter_base, float* eps_store, float* mu, float* sd, float* z,
                 double* kl_sum) {
+  ProfScope ps(lc, KC_REPARAM, 20.0 * p.B * p.Z, 28.0 * p.B * p.Z);
   reparam_fwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(
       p, mu_pre, sd_pre, eps, seed, counter_base, eps_store, mu, sd, z, kl_sum);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, const float* mu_pre, const float* mu,
                 const float* sd, const float* eps, float kl_coef, float* dmu_pre, float* dsd_pre) {
+  ProfScope ps(lc, KC_REPARAM, 12.0 * p.B * p.Z, 28.0 * p.B * p.Z);
   reparam_bwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(p, dz, mu_pre, mu, sd, eps,
                                                                                         kl_coef, dmu_pre, dsd_pre);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -449,23 +452,23 @@ int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* 
                 float beta2, float eps, float clip, float grad_scale) {
   const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
   const int64_t n4 = aligned ? n / 4 : 0;
+  ProfScope ps(lc, KC_ADAM, 12.0 * n, 28.0 * n);   // read p,g,m,v + write p,m,v
   adam_kernel<<<flat_blocks(n4 > 0 ? n4 : n, lc.sm_count), 256, 0, lc.stream>>>(p, g, m, v, n4, n, lr_t, beta1, beta2,
                                                                                eps, clip, grad_scale);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base) {
+  ProfScope ps(lc, KC_MISC, 60.0 * n, 4.0 * n);
   fill_normal_kernel<<<flat_blocks(n, lc.sm_count), 256, 0, lc.stream>>>(dst, n, seed, counter_base);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n) {
+  ProfScope ps(lc, KC_MISC, 1.0 * n, 12.0 * n);
   axpy_kernel<<<flat_blocks(n, lc.sm_count), 256, 0, lc.stream>>>(dst, src, n);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

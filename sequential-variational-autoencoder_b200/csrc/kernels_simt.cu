@@ -352,6 +352,9 @@ skinny_wgrad_kernel(View a, View dout, int B, int K, int N, float* __restrict__ 
 int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w, View out, double* stats) {
   const int64_t M = (int64_t)g.B * g.Hout * g.Wout;
   if (M <= 0) return 0;
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_GEMM_SIMT, 2.0 * pix * g.KH * g.KW * g.Cin * g.Cout,
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)M * g.Cout + (double)g.KH * g.KW * g.Cin * g.Cout));
   if (g.Cout > 32) {
     dim3 grid((unsigned)((M + 63) / 64), (g.Cout + 63) / 64);
     gather_gemm_kernel<64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g, in, w, out, stats);
@@ -362,7 +365,6 @@ int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w
     dim3 grid((unsigned)((M + 255) / 256), 1);
     gather_gemm_kernel<256, 8, 4, 2><<<grid, 256, 0, lc.stream>>>(g, in, w, out, stats);
   }
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -379,8 +381,10 @@ int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
   int64_t rows_per_split = ((M + ksplit - 1) / ksplit + BK - 1) / BK * BK;
   ksplit = (M + rows_per_split - 1) / rows_per_split;
   dim3 grid((unsigned)base, (unsigned)ksplit);
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_WGRAD_SIMT, 2.0 * pix * taps * g.Cin * g.Cout,
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)M * g.Cout + (double)taps * g.Cin * g.Cout));
   wgrad_kernel<64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g, x, dy, dw, tilesA, tilesB, rows_per_split);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -388,16 +392,16 @@ int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
 int skinny_fwd(const LaunchCtx& lc, View a, int B, int K, const float* w, int w_n_major, const float* bias, View out,
                int N) {
   dim3 grid(B, (N + SK_NMAX - 1) / SK_NMAX);
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * N, 4.0 * ((double)B * K + (double)K * N + (double)B * N));
   skinny_fwd_kernel<<<grid, 256, 0, lc.stream>>>(a, K, w, w_n_major, bias, out, N);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int skinny_dgrad(const LaunchCtx& lc, View dout, int B, int N, const float* w, int K, View din, int accumulate) {
   dim3 grid((K + 255) / 256, B);
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * N, 4.0 * ((double)B * K + (double)K * N + (double)B * N));
   skinny_dgrad_kernel<<<grid, 256, N * sizeof(float), lc.stream>>>(dout, B, N, w, K, din, accumulate);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -405,8 +409,8 @@ int skinny_dgrad(const LaunchCtx& lc, View dout, int B, int N, const float* w, i
 int skinny_wgrad(const LaunchCtx& lc, View a, View dout, int B, int K, int N, float* dw, float* dbias,
                  int thread_over_n) {
   int span = thread_over_n ? N : K;
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * N, 4.0 * ((double)B * K + (double)K * N + (double)B * N));
   skinny_wgrad_kernel<<<(span + 255) / 256, 256, 0, lc.stream>>>(a, dout, B, K, N, dw, dbias, thread_over_n);
-  ++*lc.launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -165,7 +165,8 @@ struct svae_handle {
   NcclApi* nccl = nullptr; void* comm = nullptr; int rank = 0, nranks = 1;
   std::vector<cudaEvent_t> bucket_ev; cudaEvent_t comm_done = nullptr;
 
-  LaunchCtx lc() { return LaunchCtx{stream, &launches, sm_count}; }
+  Profiler prof;
+  LaunchCtx lc() { return LaunchCtx{stream, &launches, sm_count, &prof}; }
   float* pw(int idx) { return P + params[idx].offset; }
   float* pg(int idx) { return G + params[idx].offset; }
 };
@@ -1231,6 +1232,36 @@ int svae_comm_destroy(svae_handle* h) {
 }
 
 int64_t svae_launch_count(const svae_handle* h) { return h ? h->launches : 0; }
+
+int svae_profile_enable(svae_handle* h, int on) {
+  if (!h) return SVAE_EINVAL;
+  h->prof.enabled = on != 0;
+  return SVAE_OK;
+}
+int svae_profile_read(svae_handle* h, svae_kernel_stats* out, int capacity) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  Profiler& p = h->prof;
+  for (const Profiler::Rec& r : p.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) p.ms[r.kc] += ms;
+  }
+  cudaGetLastError();
+  p.recs.clear();
+  p.pool_used = 0;
+  int n = 0;
+  for (int k = 0; k < KC_COUNT; ++k) {
+    if (out && n < capacity) {
+      memset(&out[n], 0, sizeof out[n]);
+      snprintf(out[n].name, sizeof out[n].name, "%s", kKClassNames[k]);
+      out[n].launches = p.launches[k]; out[n].total_ms = p.ms[k]; out[n].flops = p.flops[k]; out[n].bytes = p.bytes[k];
+    }
+    ++n;
+    p.launches[k] = 0; p.ms[k] = 0; p.flops[k] = 0; p.bytes[k] = 0;
+  }
+  return n;
+}
 int64_t svae_activation_bytes(const svae_handle* h) { return h ? (int64_t)(h->act_bytes + h->grad_bytes) : 0; }
 int svae_tc_layers(const svae_handle* h) { return h ? h->tc_layers : 0; }
 

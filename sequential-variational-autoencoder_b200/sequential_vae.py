@@ -359,6 +359,20 @@ class SequentialVAE:
     def launch_count(self):
         return int(self._L.svae_launch_count(self._h))
 
+    def profile(self, on):
+        """Bracket every kernel launch with CUDA events (per-kernel-class totals via ``profile_read``)."""
+        self._chk(self._L.svae_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """{class name: dict(launches, ms, flops, bytes)} since the last read; synchronises and resets."""
+        arr = (_cabi.KernelStats * 32)()
+        n = self._L.svae_profile_read(self._h, arr, 32)
+        if n < 0:
+            self._chk(n)
+        return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=float(arr[i].total_ms),
+                                          flops=float(arr[i].flops), bytes=float(arr[i].bytes))
+                for i in range(n) if arr[i].launches}
+
     @property
     def tc_layers(self):
         return int(self._L.svae_tc_layers(self._h))

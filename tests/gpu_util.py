@@ -16,7 +16,10 @@ def ptr(t):
 
 
 def dev(a, dtype=torch.float32):
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda().contiguous()
+    """Upload on torch's stream and wait: libsvae runs on its own stream, so the copy must be complete first."""
+    t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda().contiguous()
+    torch.cuda.synchronize()
+    return t
 
 
 _handle_model = {}

@@ -44,7 +44,9 @@ def test_conv2d_forward_and_stats(B, H, Ci, Co, stride, operand):
     ref = O.conv2d_same(x, w, stride)
     y = torch.empty(B, H // stride, H // stride, Co, device="cuda")
     stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
-    rc = L.svae_op_conv2d(h, ptr(dev(x)), ptr(dev(w)), ptr(y), ptr(stats), B, H, H, Ci, Co, stride, operand)
+    torch.cuda.synchronize()
+    dx_, dw_ = dev(x), dev(w)          # keep the uploads alive: a temporary's block would be reused by the next upload
+    rc = L.svae_op_conv2d(h, ptr(dx_), ptr(dw_), ptr(y), ptr(stats), B, H, H, Ci, Co, stride, operand)
     _maybe_skip_tc(rc, L, h)
     m.sync()
     assert rel_err(y.cpu().numpy(), ref.numpy()) < _tol(operand)
@@ -69,7 +71,8 @@ def test_conv2d_transpose_forward(B, H, Ci, Co, stride, operand):
     w = torch.randn(4, 4, Co, Ci, generator=g, dtype=torch.float64) * 0.1
     ref = O.conv2d_transpose_same(x, w, stride)
     y = torch.empty(B, H * stride, H * stride, Co, device="cuda")
-    rc = L.svae_op_conv2d_transpose(h, ptr(dev(x)), ptr(dev(w)), ptr(y), None, B, H, H, Ci, Co, stride, operand)
+    dx_, dw_ = dev(x), dev(w)
+    rc = L.svae_op_conv2d_transpose(h, ptr(dx_), ptr(dw_), ptr(y), None, B, H, H, Ci, Co, stride, operand)
     _maybe_skip_tc(rc, L, h)
     m.sync()
     assert rel_err(y.cpu().numpy(), ref.numpy()) < _tol(operand)
@@ -87,8 +90,9 @@ def test_conv2d_backward(B, H, Ci, Co, stride, operand):
     O.conv2d_same(x, w, stride).backward(dy)
     dx = torch.empty(B, H, H, Ci, device="cuda")
     dw = torch.empty(4, 4, Ci, Co, device="cuda")
-    rc = L.svae_op_conv2d_backward(h, ptr(dev(x.detach())), ptr(dev(w.detach())), ptr(dev(dy)), ptr(dx), ptr(dw), B, H,
-                                   H, Ci, Co, stride, operand)
+    ux, uw, udy = dev(x.detach()), dev(w.detach()), dev(dy)
+    torch.cuda.synchronize()
+    rc = L.svae_op_conv2d_backward(h, ptr(ux), ptr(uw), ptr(udy), ptr(dx), ptr(dw), B, H, H, Ci, Co, stride, operand)
     _maybe_skip_tc(rc, L, h)
     m.sync()
     assert rel_err(dx.cpu().numpy(), x.grad.numpy()) < _tol(operand)
@@ -107,8 +111,10 @@ def test_conv2d_transpose_backward(B, H, Ci, Co, stride, operand):
     O.conv2d_transpose_same(x, w, stride).backward(dy)
     dx = torch.empty(B, H, H, Ci, device="cuda")
     dw = torch.empty(4, 4, Co, Ci, device="cuda")
-    rc = L.svae_op_conv2d_transpose_backward(h, ptr(dev(x.detach())), ptr(dev(w.detach())), ptr(dev(dy)), ptr(dx),
-                                             ptr(dw), B, H, H, Ci, Co, stride, operand)
+    ux, uw, udy = dev(x.detach()), dev(w.detach()), dev(dy)
+    torch.cuda.synchronize()
+    rc = L.svae_op_conv2d_transpose_backward(h, ptr(ux), ptr(uw), ptr(udy), ptr(dx), ptr(dw), B, H, H, Ci, Co, stride,
+                                             operand)
     _maybe_skip_tc(rc, L, h)
     m.sync()
     assert rel_err(dx.cpu().numpy(), x.grad.numpy()) < _tol(operand)
@@ -125,7 +131,8 @@ def test_bn_act(rows, C, act):
     ref = O.batch_norm(y, beta)
     ref = O.lrelu(ref) if act == 1 else torch.relu(ref) if act == 2 else ref
     out = torch.empty(rows, C, device="cuda")
-    assert L.svae_op_bn_act(h, ptr(dev(y)), ptr(dev(beta)), ptr(out), rows, C, act) == 0
+    uy, ub = dev(y), dev(beta)
+    assert L.svae_op_bn_act(h, ptr(uy), ptr(ub), ptr(out), rows, C, act) == 0
     m.sync()
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-5)
 

@@ -167,6 +167,7 @@ def test_oracle_reproduces_golden(case):
     blob = np.load(os.path.join(GOLD, case + ".npz"))
     c = mg.CASES[case]
     hp = O.hyperparams(c["netname"], c["dims"], c["rng"], **c["overrides"])
+    assert float(blob["preact_margin"]) > mg.MIN_MARGIN            # fixtures are sign-flip free by construction
     P = {k[2:]: torch.tensor(blob[k], dtype=torch.float64) for k in blob.files if k.startswith("P:")}
     assert list(P.keys()) == [s["name"] for s in O.param_specs(hp)]
     x, tgt, eps = (torch.tensor(blob[k]) for k in ("x", "tgt", "eps"))
