@@ -1,10 +1,455 @@
-// kernels_tc.cu - tcgen05 / TMEM contractions (placeholder until the shifted-window kernels land in this file).
+// kernels_tc.cu - tcgen05 / TMEM "shifted-window" implicit-GEMM kernels for the 4x4 convolutions and transposed
+// convolutions of the chain (bf16 operands, fp32 accumulation in tensor memory).
+//
+// Idea (B200-first, not a cuDNN-style im2col): for a 4x4 window every tap reads the SAME input pixels, only shifted.
+// The kernel walks the batch in a zero-padded linear pixel space q = (n*Hp + r)*Wp + c whose padding columns / rows are
+// shared between neighbouring rows / images (wrap-around), so that every tap is a constant offset "q + shift".  A CTA
+//   1. loads the halo [q0 - lo, q0 + 128 + hi) of its 128-row tile ONCE (fp32 NHWC -> bf16, zero fill), into a planar
+//      shared-memory layout  [8-channel chunk][pixel][16 B]  - exactly the canonical no-swizzle K-major UMMA layout with
+//      SBO = 128 B, LBO = plane pitch - in which "shift by s pixels" is "start address + 16*s";
+//   2. streams the pre-packed bf16 weights of each (channel chunk, tap) with one cp.async.bulk (TMA 1-D bulk copy) per
+//      stage through an mbarrier ring;
+//   3. issues tcgen05.mma (M=128, N=Cout, K=16) per tap and 16-channel slice from ONE thread, accumulating in TMEM;
+//   4. drains TMEM with tcgen05.ld, writes fp32 NHWC (channel-window aware, optional accumulate) and reduces the
+//      per-channel batch-norm statistics (sum, sum of squares) in the epilogue.
+// Stride-2 convs read four parity planes; stride-2 transposed convs are four output phases = four accumulators.
+//
+// Reference ops replaced: Conv2D / Conv2DBackpropInput as launched for conv2d_bn_lrelu, conv2d_t_bn(_relu) and their
+// input gradients (abstract_network.py:18,37,56; sequential_vae.py:1273).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
-bool tc_supported(const Geom&) { return false; }
-size_t tc_packed_bytes(const Geom&) { return 0; }
-int tc_pack_weights(const LaunchCtx&, const Geom&, const float*, void*) { return -1; }
-int tc_gather_gemm(const LaunchCtx&, const Geom&, View, const void*, View, double*) {
-  svae_global_error() = "tcgen05 path not built";
-  return -1;
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int MAX_STAGES = 4;
+
+struct TcParams {
+  const float* in; int in_ld, in_coff;
+  const __nv_bfloat16* wp;
+  float* out; int out_ld, out_coff;
+  double* stats;
+  int B, Hin, Win, Cin, Hout, Wout, N;
+  int mode;         // 0: stride-1 window, 1: stride-2 gather (4 parity planes), 2: stride-2 phases (4 accumulators)
+  int Hp, Wp, Hv, Wv;
+  int lo, HL, HLpad;
+  int KC, NC, JC;   // channels per chunk, number of chunks, 8-channel groups per chunk
+  int nplanes, nacc;
+  int accumulate;
+  long long Q;      // padded positions
+  int stages, a_bufs;
+  unsigned a_buf_bytes, b_stage_bytes, tmem_cols;
+  signed char acc[16], plane[16];
+  int shift[16];
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must become a trap (reported CUDA error), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, unsigned cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, canonical K-major layout without swizzle (cute::UMMA::SmemDescriptor):
+//   bits [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (between the two 8-element K groups of one MMA) ;
+//   [32,46) stride byte offset >> 4 (between 8-row groups) ; [46,48) version = 1 (sm_100) ; [61,64) layout type 0.
+__device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
+  d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1) at [7,10) /
+// [10,13), a/b K-major (0) at 15 / 16, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr unsigned make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+// warp-level transpose-reduction: on return lane l holds the sum over the 32 lanes of v[l]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = up ? v[i] : v[i + off];
+      float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+struct SmemHeader {
+  unsigned long long full_b[MAX_STAGES], empty_b[MAX_STAGES], a_ready[2], a_free[2], acc_done;
+  unsigned tmem_base;
+  unsigned pad;
+  float s_sum[4][128], s_sq[4][128];   // per-warp partial column statistics of one accumulator
+};
+
+// 6 warps: 0-3 halo producers then epilogue, 4 weight loader (TMA bulk), 5 MMA issuer + TMEM allocator
+__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+  unsigned char* b_smem = smem_raw + ((sizeof(SmemHeader) + 127) & ~127u);
+  unsigned char* a_smem = b_smem + (size_t)P.stages * P.b_stage_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long q0 = (long long)blockIdx.x * TILE_M;
+
+  if (tid == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(smem_u32(&hdr->full_b[s]), 1); mbar_init(smem_u32(&hdr->empty_b[s]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->a_ready[i]), 128); mbar_init(smem_u32(&hdr->a_free[i]), 1); }
+    mbar_init(smem_u32(&hdr->acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(&hdr->tmem_base), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = hdr->tmem_base;
+  const unsigned LBO_A = (unsigned)P.HLpad * 16u;   // bytes between consecutive 8-channel planes of the halo
+
+  if (warp < 4) {
+    // ================= halo producers: fp32 NHWC global -> bf16 planar smem (once per channel chunk) =================
+    const int per_plane = P.HL * P.JC;              // (pixel, 8-channel group) items per parity plane
+    const int items = per_plane * P.nplanes;
+    const int sm = P.mode == 1 ? 2 : 1;
+    for (int c = 0; c < P.NC; ++c) {
+      const int buf = c % P.a_bufs;
+      if (c >= P.a_bufs) mbar_wait(smem_u32(&hdr->a_free[buf]), ((c / P.a_bufs) - 1) & 1);
+      unsigned char* abuf = a_smem + (size_t)buf * P.a_buf_bytes;
+      for (int it = tid; it < items; it += 128) {
+        const int pl = it / per_plane;
+        const int rem = it - pl * per_plane;
+        const int i = rem / P.JC, j = rem - i * P.JC;
+        const long long q = q0 - P.lo + i;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (q >= 0 && q < P.Q) {
+          const int cc = (int)(q % P.Wp);
+          const long long t = q / P.Wp;
+          const int r = (int)(t % P.Hp);
+          const int n = (int)(t / P.Hp);
+          if (r < P.Hv && cc < P.Wv) {
+            const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
+            const float* src = P.in + (((size_t)n * P.Hin + ih) * P.Win + iw) * P.in_ld + P.in_coff + c * P.KC + j * 8;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(v0.x, v0.y), b1 = __floats2bfloat162_rn(v0.z, v0.w);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v1.x, v1.y), b3 = __floats2bfloat162_rn(v1.z, v1.w);
+            packed.x = *reinterpret_cast<unsigned*>(&b0); packed.y = *reinterpret_cast<unsigned*>(&b1);
+            packed.z = *reinterpret_cast<unsigned*>(&b2); packed.w = *reinterpret_cast<unsigned*>(&b3);
+          }
+        }
+        *reinterpret_cast<uint4*>(abuf + (size_t)(pl * P.JC + j) * LBO_A + (size_t)i * 16) = packed;
+      }
+      fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&hdr->a_ready[buf]));
+    }
+
+    // ================= epilogue: TMEM -> registers -> global (+ batch-norm statistics) =================
+    mbar_wait(smem_u32(&hdr->acc_done), 0);
+    tc_fence_after();
+    const int m = warp * 32 + lane;                 // accumulator row == TMEM lane
+    const long long q = q0 + m;
+    bool valid = q < P.Q;
+    int n = 0, r = 0, cc = 0;
+    if (valid) {
+      cc = (int)(q % P.Wp);
+      const long long t = q / P.Wp;
+      r = (int)(t % P.Hp);
+      n = (int)(t / P.Hp);
+      valid = r < P.Hv && cc < P.Wv;
+    }
+    for (int a = 0; a < P.nacc; ++a) {
+      int oh = r, ow = cc;
+      if (P.mode == 2) { oh = 2 * r + (a >> 1); ow = 2 * cc + (a & 1); }
+      float* orow = P.out + (((size_t)n * P.Hout + oh) * P.Wout + ow) * P.out_ld + P.out_coff;
+      for (int n0 = 0; n0 < P.N; n0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(a * P.N + n0), v);
+        const int ncols = min(32, P.N - n0);
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            if (k < ncols) {
+              float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+              float4* dst = reinterpret_cast<float4*>(orow + n0 + k);
+              if (P.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *dst = o;
+              v[k] = o.x; v[k + 1] = o.y; v[k + 2] = o.z; v[k + 3] = o.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0.f;
+        }
+        if (P.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { if (k >= ncols) v[k] = 0.f; sq[k] = v[k] * v[k]; }
+          const float cs = warp_colsum32(v, lane);
+          const float cq = warp_colsum32(sq, lane);
+          // accumulate this warp's column totals over accumulators (phases share channels)
+          if (a == 0) { hdr->s_sum[warp][n0 + lane] = cs; hdr->s_sq[warp][n0 + lane] = cq; }
+          else { hdr->s_sum[warp][n0 + lane] += cs; hdr->s_sq[warp][n0 + lane] += cq; }
+        }
+      }
+    }
+    tc_fence_before();
+    if (P.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      for (int col = tid; col < P.N; col += 128) {
+        const float s = hdr->s_sum[0][col] + hdr->s_sum[1][col] + hdr->s_sum[2][col] + hdr->s_sum[3][col];
+        const float s2 = hdr->s_sq[0][col] + hdr->s_sq[1][col] + hdr->s_sq[2][col] + hdr->s_sq[3][col];
+        atomicAdd(&P.stats[col], (double)s);
+        atomicAdd(&P.stats[P.N + col], (double)s2);
+      }
+    }
+  } else if (warp == 4) {
+    // ================= weight loader: one bulk copy per (channel chunk, tap) through the stage ring =================
+    if (lane == 0) {
+      int stage = 0; unsigned phase = 0;
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp);
+      for (int c = 0; c < P.NC; ++c)
+        for (int s = 0; s < 16; ++s) {
+          mbar_wait(smem_u32(&hdr->empty_b[stage]), phase ^ 1);
+          mbar_expect_tx(smem_u32(&hdr->full_b[stage]), P.b_stage_bytes);
+          bulk_g2s(smem_u32(b_smem + (size_t)stage * P.b_stage_bytes), wsrc + ((size_t)c * 16 + s) * P.b_stage_bytes,
+                   P.b_stage_bytes, smem_u32(&hdr->full_b[stage]));
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const unsigned idesc = make_idesc(TILE_M, P.N);
+      const unsigned LBO_B = (unsigned)P.N * 16u;
+      int stage = 0; unsigned phase = 0;
+      unsigned started = 0;                           // bit a set once accumulator a has been written
+      for (int c = 0; c < P.NC; ++c) {
+        const int buf = c % P.a_bufs;
+        mbar_wait(smem_u32(&hdr->a_ready[buf]), (c / P.a_bufs) & 1);
+        const unsigned abase = smem_u32(a_smem + (size_t)buf * P.a_buf_bytes);
+        for (int s = 0; s < 16; ++s) {
+          mbar_wait(smem_u32(&hdr->full_b[stage]), phase);
+          tc_fence_after();
+          const unsigned bbase = smem_u32(b_smem + (size_t)stage * P.b_stage_bytes);
+          const int a = P.acc[s];
+          const unsigned d_tmem = tmem_base + (unsigned)(a * P.N);
+          const unsigned arow = abase + (unsigned)(P.plane[s] * P.JC) * LBO_A + (unsigned)(P.lo + P.shift[s]) * 16u;
+          for (int kk = 0; kk < P.KC / 16; ++kk) {
+            const unsigned long long adesc = make_desc(arow + (unsigned)(2 * kk) * LBO_A, LBO_A, 128u);
+            const unsigned long long bdesc = make_desc(bbase + (unsigned)(2 * kk) * LBO_B, LBO_B, 128u);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (started >> a) & 1u);
+            started |= 1u << a;
+          }
+          umma_commit(smem_u32(&hdr->empty_b[stage]));   // frees the weight stage once these MMAs have read it
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&hdr->a_free[buf]));         // halo buffer reusable
+      }
+      umma_commit(smem_u32(&hdr->acc_done));
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+// weights -> bf16 [chunk c][tap slot s][8-channel group j][n][8]  (canonical K-major, no swizzle: LBO = N*16, SBO = 128)
+__global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KC) {
+  const int JC = KC / 8;
+  const long long total = (long long)16 * g.Cin * g.Cout;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long t = e;
+    const int k8 = (int)(t % 8); t /= 8;
+    const int n = (int)(t % g.Cout); t /= g.Cout;
+    const int j = (int)(t % JC); t /= JC;
+    const int s = (int)(t % 16); t /= 16;
+    const int c = (int)t;
+    const int ci = c * KC + j * 8 + k8;
+    const float v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + n] : w[((size_t)s * g.Cout + n) * g.Cin + ci];
+    out[e] = __float2bfloat16_rn(v);
+  }
+}
+
+int chunk_channels(const Geom& g) { return g.Cin <= 128 ? g.Cin : 128; }
+
+bool build_params(const Geom& g, TcParams& P) {
+  memset(&P, 0, sizeof P);
+  P.B = g.B; P.Hin = g.Hin; P.Win = g.Win; P.Cin = g.Cin; P.Hout = g.Hout; P.Wout = g.Wout; P.N = g.Cout;
+  P.accumulate = g.accumulate;
+  P.KC = chunk_channels(g); P.NC = g.Cin / P.KC; P.JC = P.KC / 8;
+  int hi;
+  if (g.stride == 1) {
+    P.mode = 0; P.nplanes = 1; P.nacc = 1;
+    P.Hp = g.Hin + 2; P.Wp = g.Win + 2; P.Hv = g.Hin; P.Wv = g.Win;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int s = kh * 4 + kw;
+        const int dh = g.mode == 0 ? kh - 1 : 1 - kh, dw = g.mode == 0 ? kw - 1 : 1 - kw;
+        P.acc[s] = 0; P.plane[s] = 0; P.shift[s] = dh * P.Wp + dw;
+      }
+    P.lo = g.mode == 0 ? P.Wp + 1 : 2 * P.Wp + 2;
+    hi = g.mode == 0 ? 2 * P.Wp + 2 : P.Wp + 1;
+  } else if (g.mode == 0) {   // stride-2 conv: parity planes of the input, output grid
+    P.mode = 1; P.nplanes = 4; P.nacc = 1;
+    P.Hp = g.Hout + 1; P.Wp = g.Wout + 1; P.Hv = g.Hout; P.Wv = g.Wout;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int s = kh * 4 + kw;
+        const int dh = kh == 0 ? -1 : kh == 3 ? 1 : 0, dw = kw == 0 ? -1 : kw == 3 ? 1 : 0;
+        P.acc[s] = 0; P.plane[s] = (signed char)((((kh + 1) & 1) << 1) | ((kw + 1) & 1)); P.shift[s] = dh * P.Wp + dw;
+      }
+    P.lo = P.Wp + 1; hi = P.Wp + 1;
+  } else {                    // stride-2 transposed conv: input grid, four output phases
+    P.mode = 2; P.nplanes = 1; P.nacc = 4;
+    P.Hp = g.Hin + 1; P.Wp = g.Win + 1; P.Hv = g.Hin; P.Wv = g.Win;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int s = kh * 4 + kw;
+        const int ph = (kh + 1) & 1, pw = (kw + 1) & 1;
+        const int dh = kh == 3 ? -1 : kh == 0 ? 1 : 0, dw = kw == 3 ? -1 : kw == 0 ? 1 : 0;
+        P.acc[s] = (signed char)(ph * 2 + pw); P.plane[s] = 0; P.shift[s] = dh * P.Wp + dw;
+      }
+    P.lo = P.Wp + 1; hi = P.Wp + 1;
+  }
+  P.HL = TILE_M + P.lo + hi;
+  P.HLpad = P.HL | 1;                               // odd plane pitch (in 16-byte units): conflict-free producer stores
+  P.Q = (long long)g.B * P.Hp * P.Wp;
+  P.a_buf_bytes = (unsigned)(P.nplanes * P.JC * P.HLpad * 16);
+  P.a_bufs = P.NC > 1 ? 2 : 1;
+  P.b_stage_bytes = (unsigned)(P.KC * P.N * 2);
+  // as many weight stages as fit next to the halo buffers (at least 2)
+  P.stages = MAX_STAGES;
+  {
+    const size_t fixed = ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.a_bufs * P.a_buf_bytes + 128;
+    while (P.stages > 2 && fixed + (size_t)P.stages * P.b_stage_bytes > 227 * 1024) --P.stages;
+  }
+  unsigned cols = (unsigned)(P.nacc * P.N), t = 32;
+  while (t < cols) t <<= 1;
+  P.tmem_cols = t;
+  return t <= 512;
+}
+
+size_t smem_bytes(const TcParams& P) {
+  return ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.stages * P.b_stage_bytes + (size_t)P.a_bufs * P.a_buf_bytes + 128;
+}
+
+}  // namespace
+
+bool tc_supported(const Geom& g) {
+  if (g.KH != 4 || g.KW != 4 || g.pad != 1) return false;
+  if (g.stride != 1 && g.stride != 2) return false;
+  if (g.Cin % 16 != 0 || g.Cin < 16) return false;
+  if (g.Cin > 128 && g.Cin % 128 != 0) return false;
+  if (g.Cout % 16 != 0 || g.Cout < 16 || g.Cout > 128) return false;
+  TcParams P;
+  if (!build_params(g, P)) return false;
+  return smem_bytes(P) <= 227 * 1024;
+}
+
+size_t tc_packed_bytes(const Geom& g) { return (size_t)16 * g.Cin * g.Cout * 2; }
+
+int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed) {
+  const long long total = (long long)16 * g.Cin * g.Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > lc.sm_count * 8) blocks = lc.sm_count * 8;
+  ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total);
+  tc_pack_kernel<<<blocks, 256, 0, lc.stream>>>(g, w, reinterpret_cast<__nv_bfloat16*>(w_packed), chunk_channels(g));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats) {
+  TcParams P;
+  if (!build_params(g, P)) { svae_global_error() = "tcgen05: unsupported geometry"; return -1; }
+  if ((in.ld % 4) || (in.coff % 4) || (out.ld % 4) || (out.coff % 4) || ((uintptr_t)in.p & 15) || ((uintptr_t)out.p & 15)) {
+    svae_global_error() = "tcgen05: tensors must be 16-byte aligned channel windows";
+    return -1;
+  }
+  P.in = in.p; P.in_ld = in.ld; P.in_coff = in.coff;
+  P.wp = reinterpret_cast<const __nv_bfloat16*>(w_packed);
+  P.out = out.p; P.out_ld = out.ld; P.out_coff = out.coff;
+  P.stats = stats;
+  const size_t smem = smem_bytes(P);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  const long long tiles = (P.Q + TILE_M - 1) / TILE_M;
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_GEMM_TC, 2.0 * pix * 16 * g.Cin * g.Cout,
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout) + 2.0 * 16 * g.Cin * g.Cout);
+  tc_conv_kernel<<<(unsigned)tiles, 192, smem, lc.stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
