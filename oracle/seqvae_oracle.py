@@ -122,8 +122,7 @@ def same_pads(size: int, k: int, s: int):
     return total // 2, total - total // 2
 
 
-def conv2d_same(x, w_hwio, stride: int):
-    """tf.contrib.layers.convolution2d data path (abstract_network.py:18): NHWC, HWIO weights, SAME padding."""
+def _conv2d_same_exact(x, w_hwio, stride: int):
     kh, kw = w_hwio.shape[0], w_hwio.shape[1]
     pt, pb = same_pads(x.shape[1], kh, stride)
     pl, pr = same_pads(x.shape[2], kw, stride)
@@ -132,10 +131,7 @@ def conv2d_same(x, w_hwio, stride: int):
     return y.permute(0, 2, 3, 1)
 
 
-def conv2d_transpose_same(x, w_hwoi, stride: int):
-    """tf.contrib.layers.convolution2d_transpose data path (abstract_network.py:37,56; sequential_vae.py:1720,1727):
-    weights [kh,kw,Cout,Cin]; computed by TF as conv2d_backprop_input, i.e. the exact adjoint of the SAME conv that
-    maps [N,H*s,W*s,Cout] -> [N,H,W,Cin] (SURVEY Q8)."""
+def _conv2d_transpose_same_exact(x, w_hwoi, stride: int):
     kh, kw = w_hwoi.shape[0], w_hwoi.shape[1]
     H, W = x.shape[1], x.shape[2]
     pt, _ = same_pads(H * stride, kh, stride)
@@ -144,6 +140,67 @@ def conv2d_transpose_same(x, w_hwoi, stride: int):
     y = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, stride=stride, padding=0)
     y = y[:, :, pt:pt + H * stride, pl:pl + W * stride]  # crop the forward conv's (before) padding
     return y.permute(0, 2, 3, 1)
+
+
+# ---- operand-rounding emulation (verification of the bf16 tensor-core kernels only) -----------------------------------
+# The CUDA library's SVAE_OPERAND_BF16 mode rounds the operands of the tensor-core contractions to bf16 (fp32
+# accumulation).  OPERAND_EMULATION = dict(fwd=pred, dgrad=pred, wgrad=pred) makes the oracle round exactly those
+# operands (pred(kind, h, w, cin, cout, stride) -> bool says whether the CUDA path runs that contraction on tensor cores) while
+# keeping its own accumulation precision, so that the kernels can be checked tightly inside the full chain.  None (the
+# default) is the reference semantics.
+OPERAND_EMULATION = None
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _EmulatedContraction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, transpose, rf, rd, rw):
+        fn = _conv2d_transpose_same_exact if transpose else _conv2d_same_exact
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, transpose, rd, rw)
+        return fn(_bf16(x) if rf else x, _bf16(w) if rf else w, stride)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, transpose, rd, rw = ctx.cfg
+        fn = _conv2d_transpose_same_exact if transpose else _conv2d_same_exact
+        with torch.enable_grad():
+            xd = x.detach().requires_grad_(True)
+            dx, = torch.autograd.grad(fn(xd, (_bf16(w) if rd else w).detach(), stride), xd, _bf16(dy) if rd else dy)
+            wd = w.detach().requires_grad_(True)
+            dw, = torch.autograd.grad(fn((_bf16(x) if rw else x).detach(), wd, stride), wd, _bf16(dy) if rw else dy)
+        return dx, dw, None, None, None, None, None
+
+
+def _contract(x, w, stride, transpose):
+    fn = _conv2d_transpose_same_exact if transpose else _conv2d_same_exact
+    em = OPERAND_EMULATION
+    if em is None:
+        return fn(x, w, stride)
+    cin = x.shape[-1]
+    cout = w.shape[2] if transpose else w.shape[3]
+    kind = "deconv" if transpose else "conv"
+    rf, rd, rw = (bool(em[k](kind, int(x.shape[1]), int(x.shape[2]), int(cin), int(cout), stride))
+                  for k in ("fwd", "dgrad", "wgrad"))
+    if not (rf or rd or rw):
+        return fn(x, w, stride)
+    return _EmulatedContraction.apply(x, w, stride, transpose, rf, rd, rw)
+
+
+def conv2d_same(x, w_hwio, stride: int):
+    """tf.contrib.layers.convolution2d data path (abstract_network.py:18): NHWC, HWIO weights, SAME padding."""
+    return _contract(x, w_hwio, stride, False)
+
+
+def conv2d_transpose_same(x, w_hwoi, stride: int):
+    """tf.contrib.layers.convolution2d_transpose data path (abstract_network.py:37,56; sequential_vae.py:1720,1727):
+    weights [kh,kw,Cout,Cin]; computed by TF as conv2d_backprop_input, i.e. the exact adjoint of the SAME conv that
+    maps [N,H*s,W*s,Cout] -> [N,H,W,Cin] (SURVEY Q8)."""
+    return _contract(x, w_hwoi, stride, True)
 
 
 def batch_norm(x, beta, eps=1e-3):

@@ -161,6 +161,9 @@ int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n); 
 // ---- tcgen05 contractions (kernels_tc.cu) ----------------------------------------------------------------------
 struct TcPlan;  // opaque per-layer packed-weight + schedule state
 bool tc_supported(const Geom& g);
+bool tc_wgrad_supported(const Geom& fwd);
+// g: conv-gather geometry (X = conv input side, dY = conv output side); accumulates into dw[(tap*Cin + a)*Cout + b]
+int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw);
 int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats);
 size_t tc_packed_bytes(const Geom& g);
 int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed);

@@ -340,6 +340,224 @@ __global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+
+// =====================================================================================================================
+// Weight gradient:  dW[tap][a][b] = sum_q X[q + shift(tap)][a] * dY[q][b]   (conv-gather geometry, q = padded positions)
+// Both operands live in the same planar shared-memory layout as above, now consumed as MN-major matrices (the reduction
+// dimension K is the pixel index): D[a, b] += A[a x 16 px] * B[16 px x b] with M = 128 input channels (rows beyond the
+// real channel count read neighbouring planes and are ignored), N = output-channel block, one TMEM accumulator per tap
+// of the CTA's tap group.  A CTA walks its share of the 128-pixel tiles, accumulating in TMEM the whole time, and
+// flushes once with red.global.add.f32.
+struct TwParams {
+  const float* x; int x_ld, x_coff;
+  const float* dy; int dy_ld, dy_coff;
+  float* dw;
+  int B, Hx, Wx, Ca, Hy, Wy, Cb;
+  int mode;                 // 0 stride 1 (one plane), 1 stride 2 (four parity planes of X)
+  int Hp, Wp, Hv, Wv, lo, HL, HLpad, YLpad;
+  int CaB, JA, N, JN;       // channels of X per CTA (<=128), CaB/8, channels of dY per CTA (<=128), N/8
+  int nplanes, taps_per_cta, ngroups, mblocks, nblocks, bufs;
+  long long Q, tiles;
+  unsigned x_buf_bytes, y_buf_bytes, tmem_cols;
+  signed char plane[16];
+  int shift[16];
+};
+
+struct SmemHeaderW {
+  unsigned long long ready[2], free_[2], acc_done;
+  unsigned tmem_base, pad;
+};
+
+__host__ __device__ constexpr unsigned make_idesc_mn(int M, int N) {   // both operands MN-major (bits 15, 16)
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ TwParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemHeaderW* hdr = reinterpret_cast<SmemHeaderW*>(smem_raw);
+  unsigned char* bufs = smem_raw + 128;
+  const unsigned stage_bytes = P.x_buf_bytes + P.y_buf_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int by = blockIdx.y;
+  const int nb = by % P.nblocks; by /= P.nblocks;
+  const int mb = by % P.mblocks; by /= P.mblocks;
+  const int grp = by;
+  const int a0 = mb * P.CaB, b0 = nb * P.N;
+  const long long my_tiles = (P.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->ready[i]), 128); mbar_init(smem_u32(&hdr->free_[i]), 1); }
+    mbar_init(smem_u32(&hdr->acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&hdr->tmem_base), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = hdr->tmem_base;
+  const unsigned PITCH_X = (unsigned)P.HLpad * 16u, PITCH_Y = (unsigned)P.YLpad * 16u;
+
+  if (warp < 4) {
+    const int sm = P.mode == 1 ? 2 : 1;
+    const int per_plane = P.HL * P.JA;
+    const int x_items = per_plane * P.nplanes;
+    const int y_items = TILE_M * P.JN;
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it % P.bufs);
+      if (it >= P.bufs) mbar_wait(smem_u32(&hdr->free_[buf]), (unsigned)((it / P.bufs) - 1) & 1u);
+      unsigned char* xb = bufs + (size_t)buf * stage_bytes;
+      unsigned char* yb = xb + P.x_buf_bytes;
+      const long long q0 = ((long long)blockIdx.x + it * gridDim.x) * TILE_M;
+      for (int e = tid; e < x_items; e += 128) {
+        const int pl = e / per_plane;
+        const int rem = e - pl * per_plane;
+        const int i = rem / P.JA, j = rem - i * P.JA;
+        const long long q = q0 - P.lo + i;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (q >= 0 && q < P.Q) {
+          const int cc = (int)(q % P.Wp);
+          const long long t = q / P.Wp;
+          const int r = (int)(t % P.Hp);
+          const int n = (int)(t / P.Hp);
+          if (r < P.Hv && cc < P.Wv) {
+            const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
+            const float* src = P.x + (((size_t)n * P.Hx + ih) * P.Wx + iw) * P.x_ld + P.x_coff + a0 + j * 8;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            __nv_bfloat162 c0 = __floats2bfloat162_rn(v0.x, v0.y), c1 = __floats2bfloat162_rn(v0.z, v0.w);
+            __nv_bfloat162 c2 = __floats2bfloat162_rn(v1.x, v1.y), c3 = __floats2bfloat162_rn(v1.z, v1.w);
+            packed.x = *reinterpret_cast<unsigned*>(&c0); packed.y = *reinterpret_cast<unsigned*>(&c1);
+            packed.z = *reinterpret_cast<unsigned*>(&c2); packed.w = *reinterpret_cast<unsigned*>(&c3);
+          }
+        }
+        *reinterpret_cast<uint4*>(xb + (size_t)(pl * P.JA + j) * PITCH_X + (size_t)i * 16) = packed;
+      }
+      for (int e = tid; e < y_items; e += 128) {
+        const int i = e / P.JN, j = e - i * P.JN;
+        const long long q = q0 + i;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (q < P.Q) {
+          const int cc = (int)(q % P.Wp);
+          const long long t = q / P.Wp;
+          const int r = (int)(t % P.Hp);
+          const int n = (int)(t / P.Hp);
+          if (r < P.Hv && cc < P.Wv) {
+            const float* src = P.dy + (((size_t)n * P.Hy + r) * P.Wy + cc) * P.dy_ld + P.dy_coff + b0 + j * 8;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            __nv_bfloat162 c0 = __floats2bfloat162_rn(v0.x, v0.y), c1 = __floats2bfloat162_rn(v0.z, v0.w);
+            __nv_bfloat162 c2 = __floats2bfloat162_rn(v1.x, v1.y), c3 = __floats2bfloat162_rn(v1.z, v1.w);
+            packed.x = *reinterpret_cast<unsigned*>(&c0); packed.y = *reinterpret_cast<unsigned*>(&c1);
+            packed.z = *reinterpret_cast<unsigned*>(&c2); packed.w = *reinterpret_cast<unsigned*>(&c3);
+          }
+        }
+        *reinterpret_cast<uint4*>(yb + (size_t)j * PITCH_Y + (size_t)i * 16) = packed;
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&hdr->ready[buf]));
+    }
+    // ---- epilogue: D row = X channel (TMEM lane), columns = dY channels; one accumulator per tap of the group ----
+    mbar_wait(smem_u32(&hdr->acc_done), 0);
+    tc_fence_after();
+    const int a = warp * 32 + lane;
+    for (int tl = 0; tl < P.taps_per_cta; ++tl) {
+      const int tap = grp * P.taps_per_cta + tl;
+      for (int n0 = 0; n0 < P.N; n0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tl * P.N + n0), v);
+        if (a < P.CaB && my_tiles > 0) {
+          float* dst = P.dw + ((size_t)tap * P.Ca + a0 + a) * P.Cb + b0 + n0;
+          const int ncols = min(32, P.N - n0);
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k < ncols) atomicAdd(dst + k, v[k]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    if (lane == 0) {
+      const unsigned idesc = make_idesc_mn(TILE_M, P.N);
+      unsigned started = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const int buf = (int)(it % P.bufs);
+        mbar_wait(smem_u32(&hdr->ready[buf]), (unsigned)(it / P.bufs) & 1u);
+        tc_fence_after();
+        const unsigned xb = smem_u32(bufs + (size_t)buf * stage_bytes);
+        const unsigned yb = xb + P.x_buf_bytes;
+        for (int tl = 0; tl < P.taps_per_cta; ++tl) {
+          const int tap = grp * P.taps_per_cta + tl;
+          const unsigned d_tmem = tmem_base + (unsigned)(tl * P.N);
+          const unsigned xrow = xb + (unsigned)(P.plane[tap] * P.JA) * PITCH_X + (unsigned)(P.lo + P.shift[tap]) * 16u;
+          for (int k = 0; k < TILE_M / 16; ++k) {
+            // MN-major canonical layout: 8 pixels (K) at 16 B, next K group at LBO = 128 B, next 8 channels at SBO = pitch
+            const unsigned long long adesc = make_desc(xrow + (unsigned)k * 256u, 128u, PITCH_X);
+            const unsigned long long bdesc = make_desc(yb + (unsigned)k * 256u, 128u, PITCH_Y);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (started >> tl) & 1u);
+            started |= 1u << tl;
+          }
+        }
+        umma_commit(smem_u32(&hdr->free_[buf]));
+      }
+      umma_commit(smem_u32(&hdr->acc_done));
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
+  // g: conv-gather geometry (mode 0) with X = [B,Hin,Win,Cin], dY = [B,Hout,Wout,Cout]
+  memset(&P, 0, sizeof P);
+  if (g.mode != 0 || g.KH != 4 || g.KW != 4 || g.pad != 1) return false;
+  if (g.Cin % 16 || g.Cout % 16 || g.Cin < 16 || g.Cout < 16) return false;
+  if ((g.Cin > 128 && g.Cin % 128) || (g.Cout > 128 && g.Cout % 128)) return false;
+  P.B = g.B; P.Hx = g.Hin; P.Wx = g.Win; P.Ca = g.Cin; P.Hy = g.Hout; P.Wy = g.Wout; P.Cb = g.Cout;
+  P.CaB = g.Cin < 128 ? g.Cin : 128; P.JA = P.CaB / 8; P.mblocks = g.Cin / P.CaB;
+  P.N = g.Cout < 128 ? g.Cout : 128; P.JN = P.N / 8; P.nblocks = g.Cout / P.N;
+  int hi;
+  if (g.stride == 1) {
+    P.mode = 0; P.nplanes = 1;
+    P.Hp = g.Hin + 2; P.Wp = g.Win + 2; P.Hv = g.Hin; P.Wv = g.Win;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) { P.plane[kh * 4 + kw] = 0; P.shift[kh * 4 + kw] = (kh - 1) * P.Wp + (kw - 1); }
+    P.lo = P.Wp + 1; hi = 2 * P.Wp + 2;
+  } else if (g.stride == 2) {
+    P.mode = 1; P.nplanes = 4;
+    P.Hp = g.Hout + 1; P.Wp = g.Wout + 1; P.Hv = g.Hout; P.Wv = g.Wout;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int dh = kh == 0 ? -1 : kh == 3 ? 1 : 0, dw = kw == 0 ? -1 : kw == 3 ? 1 : 0;
+        P.plane[kh * 4 + kw] = (signed char)((((kh + 1) & 1) << 1) | ((kw + 1) & 1));
+        P.shift[kh * 4 + kw] = dh * P.Wp + dw;
+      }
+    P.lo = P.Wp + 1; hi = P.Wp + 1;
+  } else {
+    return false;
+  }
+  P.HL = TILE_M + P.lo + hi;
+  P.HLpad = P.HL | 1;
+  P.YLpad = TILE_M | 1;
+  P.Q = (long long)g.B * P.Hp * P.Wp;
+  P.tiles = (P.Q + TILE_M - 1) / TILE_M;
+  P.taps_per_cta = 512 / P.N; if (P.taps_per_cta > 16) P.taps_per_cta = 16;
+  P.ngroups = 16 / P.taps_per_cta;
+  unsigned cols = (unsigned)(P.taps_per_cta * P.N), t = 32;
+  while (t < cols) t <<= 1;
+  P.tmem_cols = t;
+  // X buffer: every MMA reads 16 consecutive 8-channel planes starting at its parity plane's first one
+  P.x_buf_bytes = (unsigned)(((P.nplanes - 1) * P.JA + 16) * P.HLpad * 16);
+  P.y_buf_bytes = (unsigned)(P.JN * P.YLpad * 16);
+  P.bufs = 2;
+  if (128 + 2 * (size_t)(P.x_buf_bytes + P.y_buf_bytes) > 227 * 1024) P.bufs = 1;
+  if (128 + (size_t)P.bufs * (P.x_buf_bytes + P.y_buf_bytes) > 227 * 1024) return false;
+  (void)sm_count;
+  return true;
+}
+
 int chunk_channels(const Geom& g) { return g.Cin <= 128 ? g.Cin : 128; }
 
 bool build_params(const Geom& g, TcParams& P) {
@@ -414,6 +632,52 @@ bool tc_supported(const Geom& g) {
   TcParams P;
   if (!build_params(g, P)) return false;
   return smem_bytes(P) <= 227 * 1024;
+}
+
+static Geom wgrad_conv_geom(const Geom& fwd) {
+  // conv-gather geometry whose "input" side is X and "output" side is dY (for a transposed conv the roles swap)
+  Geom g = fwd;
+  if (fwd.mode == 1) {
+    g.Hin = fwd.Hout; g.Win = fwd.Wout; g.Cin = fwd.Cout;
+    g.Hout = fwd.Hin; g.Wout = fwd.Win; g.Cout = fwd.Cin;
+    g.mode = 0;
+  }
+  return g;
+}
+
+bool tc_wgrad_supported(const Geom& fwd) {
+  TwParams P;
+  Geom g = wgrad_conv_geom(fwd);
+  if (g.B < 1) g.B = 1;
+  return build_wparams(g, P, 148);
+}
+
+int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
+  TwParams P;
+  if (!build_wparams(g, P, lc.sm_count)) { svae_global_error() = "tcgen05 wgrad: unsupported geometry"; return -1; }
+  if ((x.ld % 4) || (x.coff % 4) || (dy.ld % 4) || (dy.coff % 4) || ((uintptr_t)x.p & 15) || ((uintptr_t)dy.p & 15)) {
+    svae_global_error() = "tcgen05 wgrad: tensors must be 16-byte aligned channel windows";
+    return -1;
+  }
+  P.x = x.p; P.x_ld = x.ld; P.x_coff = x.coff;
+  P.dy = dy.p; P.dy_ld = dy.ld; P.dy_coff = dy.coff;
+  P.dw = dw;
+  const size_t smem = 128 + (size_t)P.bufs * (P.x_buf_bytes + P.y_buf_bytes);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int gy = P.ngroups * P.mblocks * P.nblocks;
+  long long splits = (2LL * lc.sm_count + gy - 1) / gy;
+  if (splits > P.tiles) splits = P.tiles;
+  if (splits < 1) splits = 1;
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_WGRAD_TC, 2.0 * pix * 16 * g.Cin * g.Cout,
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout + 16.0 * g.Cin * g.Cout));
+  tc_wgrad_kernel<<<dim3((unsigned)splits, (unsigned)gy), 160, smem, lc.stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 size_t tc_packed_bytes(const Geom& g) { return (size_t)16 * g.Cin * g.Cout * 2; }

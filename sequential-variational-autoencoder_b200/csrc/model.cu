@@ -50,7 +50,7 @@ struct Block {
   FeatView res{};            // residual added before the activation (ladder shortcut)
   void* w_packed = nullptr;      // tcgen05 packed weights (forward form)
   void* w_packed_d = nullptr;    // tcgen05 packed weights (dgrad form)
-  bool tc_fwd = false, tc_dgrad = false;
+  bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false;
 };
 
 struct Head {  // layers.fully_connected head (sequential_vae.py:1592,1594,1607,1609)
@@ -507,10 +507,10 @@ int block_bwd(svae_handle* h, Block& b, int B, FeatView da, View in, float* dres
   // weight gradient
   if (b.g.mode == 0) {
     Geom g = b.g; g.B = B;
-    H_TRY(simt_wgrad(lc, g, in, dyv, h->pg(b.w)));
+    if (b.tc_wgrad) H_TRY(tc_wgrad(lc, g, in, dyv, h->pg(b.w))); else H_TRY(simt_wgrad(lc, g, in, dyv, h->pg(b.w)));
   } else {
     Geom g = dgrad_geom(b.g); g.B = B; g.mode = 0;  // conv geometry from the deconv's output grid to its input grid
-    H_TRY(simt_wgrad(lc, g, dyv, in, h->pg(b.w)));
+    if (b.tc_wgrad) H_TRY(tc_wgrad(lc, g, dyv, in, h->pg(b.w))); else H_TRY(simt_wgrad(lc, g, dyv, in, h->pg(b.w)));
   }
   if (din != nullptr) {
     Geom g = dgrad_geom(b.g);
@@ -837,6 +837,10 @@ void plan_pack(svae_handle* h, Block& b, void* ctx) {
   if (tc_supported(f)) {
     b.tc_fwd = true;
     b.w_packed = a->get<char>(tc_packed_bytes(f));
+    if (a->base) h->tc_layers++;
+  }
+  if (tc_wgrad_supported(f)) {
+    b.tc_wgrad = true;
     if (a->base) h->tc_layers++;
   }
   Geom d = dgrad_geom(b.g); d.B = h->cfg.max_batch;
@@ -1310,7 +1314,10 @@ int svae_op_conv2d_backward(svae_handle* h, const float* x, const float* w, cons
     LaunchCtx lc = h->lc();
     H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * Ci * Co, h->stream));
     Geom g = f; g.B = B;
-    H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(x), Ci, 0), mkview(const_cast<float*>(dy), Co, 0), dw));
+    if (operand == SVAE_OPERAND_BF16 && tc_wgrad_supported(f))
+      H_TRY(tc_wgrad(lc, g, mkview(const_cast<float*>(x), Ci, 0), mkview(const_cast<float*>(dy), Co, 0), dw));
+    else
+      H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(x), Ci, 0), mkview(const_cast<float*>(dy), Co, 0), dw));
   }
   return 0;
 }
@@ -1324,9 +1331,19 @@ int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const floa
     LaunchCtx lc = h->lc();
     H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * Ci * Co, h->stream));
     Geom g = dgrad_geom(f); g.B = B; g.mode = 0;
-    H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(dy), Co, 0), mkview(const_cast<float*>(x), Ci, 0), dw));
+    if (operand == SVAE_OPERAND_BF16 && tc_wgrad_supported(f))
+      H_TRY(tc_wgrad(lc, g, mkview(const_cast<float*>(dy), Co, 0), mkview(const_cast<float*>(x), Ci, 0), dw));
+    else
+      H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(dy), Co, 0), mkview(const_cast<float*>(x), Ci, 0), dw));
   }
   return 0;
+}
+int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int stride, int direction) {
+  Geom f = transposed ? deconv_geom(H, W, Ci, Co, stride) : conv_geom(H, W, Ci, Co, stride);
+  f.B = 1;
+  if (direction == 0) return tc_supported(f) ? 1 : 0;
+  if (direction == 1) { Geom d = dgrad_geom(f); d.B = 1; return tc_supported(d) ? 1 : 0; }
+  return tc_wgrad_supported(f) ? 1 : 0;
 }
 int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act) {
   if (!h) return SVAE_EINVAL;

@@ -61,3 +61,34 @@ def make_inputs(hp, B, seed=1):
     x = (torch.rand([B] + hp["data_dims"], generator=g, dtype=torch.float64) * (hi - lo) + lo).float().double()
     eps = torch.randn(hp["mc_steps"], B, hp["latent_dim"], generator=g, dtype=torch.float64).float().double()
     return x, eps
+
+
+class bf16_emulation:
+    """Context manager: make the oracle round the operands of exactly those contractions that libsvae's
+    SVAE_OPERAND_BF16 family runs on tensor cores (queried from the library, so the two cannot drift apart)."""
+
+    def __enter__(self):
+        L = _cabi.lib()
+
+        def pred(direction):
+            return lambda kind, h, w, cin, cout, stride: bool(
+                L.svae_op_tc_supported(1 if kind == "deconv" else 0, h, w, cin, cout, stride, direction))
+
+        O.OPERAND_EMULATION = dict(fwd=pred(0), dgrad=pred(1), wgrad=pred(2))
+        return self
+
+    def __exit__(self, *a):
+        O.OPERAND_EMULATION = None
+        return False
+
+
+class no_emulation:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def oracle_mode(operand):
+    return bf16_emulation() if operand == "bf16" else no_emulation()

@@ -15,12 +15,19 @@ import torch
 import seqvae_b200 as S
 from seqvae_b200 import _cabi
 from oracle import seqvae_oracle as O
-from gpu_util import TINY, make_inputs, make_pair, rel_err
+from gpu_util import TINY, make_inputs, make_pair, oracle_mode, rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-FWD_TOL = {"fp32": 1e-3, "bf16": 5e-2}
+# bf16 operands (SVAE_OPERAND_BF16): rounding the operands of the tensor-core contractions to bf16 (2^-9) flips ~0.1% of
+# the near-zero pre-activations per layer; on this chain at random init that alone moves gradients by median 0.5 / max 1.9
+# relative (measured on the fp64 CPU oracle with the rounding emulated, B=4, T=2) - no implementation with bf16 operands
+# can match fp64 gradients to 1e-3.  The bf16 KERNELS are therefore verified against the oracle with the same operand
+# rounding emulated (gpu_util.bf16_emulation: same layers rounded, fp64 accumulation) at the same bounds as the fp32
+# family, and the deviation from the unrounded fp64 oracle is bounded loosely (BF16_VS_EXACT) on forward quantities.
+FWD_TOL = {"fp32": 1e-3, "bf16": 1e-3}
+BF16_VS_EXACT = 8e-2
 # Gradients.  Two facts about ANY fp32 evaluation of this graph (measured with scripts/diag_grads.py and the fp32 CPU
 # oracle, i.e. independent of the CUDA kernels):
 #  (1) the chain at random init amplifies rounding noise ~3.5x per step: the fp32 CPU oracle's x_t deviates from the fp64
@@ -30,9 +37,9 @@ FWD_TOL = {"fp32": 1e-3, "bf16": 5e-2}
 #      from fp64 by 3e-3 .. 3e-2 on the small-batch cases below, and which implementation flips is a coin toss.
 # So: the golden fixtures (generated with a verified pre-activation margin, i.e. flip free) hold GRAD_TOL = 2e-3 on EVERY
 # tensor; the architecture-sized cases hold max(stated bound, 4x the fp32 CPU oracle's own deviation from fp64).
-GRAD_TOL = {"fp32": 2e-3, "bf16": 2e-1}
-GRAD_TOL_MED = {"fp32": 1e-3, "bf16": 6e-2}
-GRAD_TOL_MAX = {"fp32": 1e-2, "bf16": 3e-1}
+GRAD_TOL = {"fp32": 2e-3, "bf16": 2e-3}
+GRAD_TOL_MED = {"fp32": 1e-3, "bf16": 1e-3}
+GRAD_TOL_MAX = {"fp32": 1e-2, "bf16": 1e-2}
 
 
 def _oracle_pair(hp, P, x, tgt, eps, reg):
@@ -114,28 +121,39 @@ def test_golden_fixture(case, operand):
     model = S.SequentialVAE(ds, c["B"], c["netname"], operand_dtype=operand, restore=False, **c["overrides"])
     model.set_params({k[2:]: blob[k] for k in blob.files if k.startswith("P:")})
     out = model.forward(blob["x"], blob["tgt"], blob["eps"], float(blob["reg"]))
-    tol = FWD_TOL[operand]
-    np.testing.assert_allclose(out["mu"], blob["mu"], rtol=tol, atol=tol)
-    np.testing.assert_allclose(out["sigma"], blob["sigma"], rtol=tol, atol=tol)
-    np.testing.assert_allclose(out["x"], blob["xs"], rtol=tol, atol=tol)
-    np.testing.assert_allclose(out["recon"], blob["recon"], rtol=tol, atol=tol * 1e-1)
-    np.testing.assert_allclose(out["kl"], blob["kl"], rtol=tol, atol=tol * 1e-1)
-    assert math.isclose(out["loss"], float(blob["loss"]), rel_tol=tol)
-    model.backward()
-    G = model.gradients()
     hp = O.hyperparams(c["netname"], c["dims"], c["rng"], **c["overrides"])
-    inert = {s_["name"] for s_ in O.param_specs(hp) if s_["inert"]}
-    checked = 0
-    for k in blob.files:
-        if k.startswith("G:") and k[2:] not in inert:
-            ref = blob[k]
-            if np.linalg.norm(ref) > 1e-9:
-                assert rel_err(G[k[2:]], ref) < GRAD_TOL[operand], k
-                checked += 1
-    assert checked > 50
+    model.backward()
+    if operand == "fp32":
+        # flip-free fixture: every tensor at the strict bounds, against the committed golden values
+        tol = FWD_TOL[operand]
+        np.testing.assert_allclose(out["mu"], blob["mu"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(out["sigma"], blob["sigma"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(out["x"], blob["xs"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(out["recon"], blob["recon"], rtol=tol, atol=tol * 1e-1)
+        np.testing.assert_allclose(out["kl"], blob["kl"], rtol=tol, atol=tol * 1e-1)
+        assert math.isclose(out["loss"], float(blob["loss"]), rel_tol=tol)
+        G = model.gradients()
+        inert = {s_["name"] for s_ in O.param_specs(hp) if s_["inert"]}
+        checked = 0
+        for k in blob.files:
+            if k.startswith("G:") and k[2:] not in inert:
+                ref = blob[k]
+                if np.linalg.norm(ref) > 1e-9:
+                    assert rel_err(G[k[2:]], ref) < GRAD_TOL[operand], k
+                    checked += 1
+        assert checked > 50
+    else:
+        P = {k[2:]: torch.tensor(blob[k], dtype=torch.float64) for k in blob.files if k.startswith("P:")}
+        x, tgt, eps = (torch.tensor(blob[k]) for k in ("x", "tgt", "eps"))
+        with oracle_mode(operand):
+            fw, grads, fw32, g32 = _oracle_pair(hp, P, x, tgt, eps, float(blob["reg"]))
+        _check_forward(out, fw, operand, fw32)
+        _check_grads(model, grads, hp, operand, g32)
+        assert np.abs(out["x"] - blob["xs"]).max() < BF16_VS_EXACT
     gen = model.generate_mc_samples(None, c["B"], z=blob["z"])
     assert len(gen) == model.mc_steps + 1
-    np.testing.assert_allclose(np.stack(gen[1:]), blob["gen"], rtol=tol, atol=tol)
+    gtol = 1e-3 if operand == "fp32" else BF16_VS_EXACT
+    np.testing.assert_allclose(np.stack(gen[1:]), blob["gen"], rtol=gtol, atol=gtol)
     model.close()
 
 
@@ -151,11 +169,17 @@ def test_forward_and_gradients_match_oracle(netname, dims, rng, B, over, operand
     model, hp, P = make_pair(netname, dims, rng, B, operand, **over)
     x, eps = make_inputs(hp, B)
     tgt = (x * 0.9).float().double()
-    fw, grads, fw32, g32 = _oracle_pair(hp, P, x, tgt, eps, 0.6)
+    with oracle_mode(operand):
+        fw, grads, fw32, g32 = _oracle_pair(hp, P, x, tgt, eps, 0.6)
     out = model.forward(x.numpy(), tgt.numpy(), eps.numpy(), 0.6)
     _check_forward(out, fw, operand, fw32)
     model.backward()
     _check_grads(model, grads, hp, operand, g32)
+    if operand == "bf16":
+        with torch.no_grad():
+            exact = O.forward_chain(hp, P, x, tgt, eps, 0.6)
+        assert np.abs(out["x"] - torch.stack(exact["x"]).numpy()).max() < BF16_VS_EXACT
+        assert abs(out["loss"] - float(exact["loss"])) < BF16_VS_EXACT * abs(float(exact["loss"]))
     model.close()
 
 
