@@ -208,7 +208,8 @@ int svae_op_conv2d_backward(svae_handle* h, const float* x, const float* w, cons
 int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx,
                                       float* dw, int B, int H, int W, int Ci, int Co, int stride, int operand_dtype);
 /* 1 when the SVAE_OPERAND_BF16 kernel family runs this contraction on tensor cores (operands rounded to bf16), else 0
- * (it then runs on the fp32 SIMT kernels).  direction: 0 forward, 1 input gradient, 2 weight gradient. */
+ * (it then runs on the fp32 SIMT kernels).  transposed: 0 conv, 1 transposed conv, 2 fully connected (Ci -> Co, H = W = 1);
+ * direction: 0 forward, 1 input gradient, 2 weight gradient. */
 int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int stride, int direction);
 /* batch_norm (training mode, no gamma, eps 1e-3) + activation (0 none, 1 lrelu(0.1), 2 relu), rows x channels */
 int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act);

@@ -157,8 +157,14 @@ def _bf16(t):
 
 class _EmulatedContraction(torch.autograd.Function):
     @staticmethod
+    def _fn(transpose):
+        if transpose == "fc":
+            return lambda x, w, stride: x @ w
+        return _conv2d_transpose_same_exact if transpose else _conv2d_same_exact
+
+    @staticmethod
     def forward(ctx, x, w, stride, transpose, rf, rd, rw):
-        fn = _conv2d_transpose_same_exact if transpose else _conv2d_same_exact
+        fn = _EmulatedContraction._fn(transpose)
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, transpose, rd, rw)
         return fn(_bf16(x) if rf else x, _bf16(w) if rf else w, stride)
@@ -167,7 +173,7 @@ class _EmulatedContraction(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         stride, transpose, rd, rw = ctx.cfg
-        fn = _conv2d_transpose_same_exact if transpose else _conv2d_same_exact
+        fn = _EmulatedContraction._fn(transpose)
         with torch.enable_grad():
             xd = x.detach().requires_grad_(True)
             dx, = torch.autograd.grad(fn(xd, (_bf16(w) if rd else w).detach(), stride), xd, _bf16(dy) if rd else dy)
@@ -189,6 +195,17 @@ def _contract(x, w, stride, transpose):
     if not (rf or rd or rw):
         return fn(x, w, stride)
     return _EmulatedContraction.apply(x, w, stride, transpose, rf, rd, rw)
+
+
+def _fc(x, w):
+    """x @ w (tf.contrib.layers.fully_connected data path), with the operand-rounding emulation when enabled."""
+    em = OPERAND_EMULATION
+    if em is None:
+        return x @ w
+    rf, rd, rw = (bool(em[k]("fc", 1, 1, int(w.shape[0]), int(w.shape[1]), 1)) for k in ("fwd", "dgrad", "wgrad"))
+    if not (rf or rd or rw):
+        return x @ w
+    return _EmulatedContraction.apply(x, w, 1, "fc", rf, rd, rw)
 
 
 def conv2d_same(x, w_hwio, stride: int):
@@ -240,7 +257,7 @@ def _fc_bn_lrelu(sc: Scope, x, nin, nout, dead=False):
     beta = sc.get(bname + "/beta", (nout,), "zeros", dead=dead)
     if x is None:
         return None
-    return lrelu(batch_norm(x @ w + b, beta))
+    return lrelu(batch_norm(_fc(x, w) + b, beta))
 
 
 def _fc_head(sc: Scope, x, nin, nout):

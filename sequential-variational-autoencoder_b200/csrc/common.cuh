@@ -60,7 +60,7 @@ static const char* const kKClassNames[KC_COUNT] = {
 
 struct Profiler {
   bool enabled = false;
-  struct Rec { cudaEvent_t a, b; int kc; };
+  struct Rec { cudaEvent_t a, b; int kc; int geo[8]; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> pool;
   size_t pool_used = 0;
@@ -84,14 +84,17 @@ struct ProfScope {
   const LaunchCtx& lc;
   cudaEvent_t b = nullptr;
   int kc;
-  ProfScope(const LaunchCtx& lc_, int kc_, double flops, double bytes) : lc(lc_), kc(kc_) {
+  ProfScope(const LaunchCtx& lc_, int kc_, double flops, double bytes, const Geom* g = nullptr) : lc(lc_), kc(kc_) {
     ++*lc.launches;
     Profiler* p = lc.prof;
     if (p && p->enabled) {
       cudaEvent_t a = p->get();
       b = p->get();
       cudaEventRecord(a, lc.stream);
-      p->recs.push_back({a, b, kc});
+      Profiler::Rec r{a, b, kc, {0, 0, 0, 0, 0, 0, 0, 0}};
+      if (g) { r.geo[0] = g->B; r.geo[1] = g->Hin; r.geo[2] = g->Cin; r.geo[3] = g->Hout; r.geo[4] = g->Cout;
+               r.geo[5] = g->KH; r.geo[6] = g->stride; r.geo[7] = g->mode; }
+      p->recs.push_back(r);
       p->launches[kc]++; p->flops[kc] += flops; p->bytes[kc] += bytes;
     }
   }

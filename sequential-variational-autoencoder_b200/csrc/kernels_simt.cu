@@ -354,7 +354,7 @@ int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w
   if (M <= 0) return 0;
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
   ProfScope ps(lc, KC_GEMM_SIMT, 2.0 * pix * g.KH * g.KW * g.Cin * g.Cout,
-               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)M * g.Cout + (double)g.KH * g.KW * g.Cin * g.Cout));
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)M * g.Cout + (double)g.KH * g.KW * g.Cin * g.Cout), &g);
   if (g.Cout > 32) {
     dim3 grid((unsigned)((M + 63) / 64), (g.Cout + 63) / 64);
     gather_gemm_kernel<64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g, in, w, out, stats);
@@ -383,7 +383,7 @@ int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
   dim3 grid((unsigned)base, (unsigned)ksplit);
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
   ProfScope ps(lc, KC_WGRAD_SIMT, 2.0 * pix * taps * g.Cin * g.Cout,
-               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)M * g.Cout + (double)taps * g.Cin * g.Cout));
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)M * g.Cout + (double)taps * g.Cin * g.Cout), &g);
   wgrad_kernel<64, 64, 4, 4><<<grid, 256, 0, lc.stream>>>(g, x, dy, dw, tilesA, tilesB, rows_per_split);
   CUDA_TRY(cudaGetLastError());
   return 0;

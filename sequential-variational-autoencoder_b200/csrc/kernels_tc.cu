@@ -26,20 +26,21 @@ constexpr int TILE_M = 128;
 constexpr int MAX_STAGES = 4;
 
 struct TcParams {
-  const float* in; int in_ld, in_coff;
+  const float* in; int in_ld, in_coff, cin_valid, in_vec;
   const __nv_bfloat16* wp;
-  float* out; int out_ld, out_coff;
+  float* out; int out_ld, out_coff, n_valid, out_vec;
   double* stats;
-  int B, Hin, Win, Cin, Hout, Wout, N;
-  int mode;         // 0: stride-1 window, 1: stride-2 gather (4 parity planes), 2: stride-2 phases (4 accumulators)
+  int B, Hin, Win, Hout, Wout;
+  int Cin_p, N_p;   // channel counts padded to multiples of 16 (zero weights / zero activations in the padding)
+  int mode;         // 0: stride-1 window (or 1x1 = fully connected), 1: stride-2 gather (4 parity planes), 2: stride-2 phases
   int Hp, Wp, Hv, Wv;
   int lo, HL, HLpad;
   int KC, NC, JC;   // channels per chunk, number of chunks, 8-channel groups per chunk
-  int nplanes, nacc;
+  int nplanes, nacc, ntaps;
   int accumulate;
   long long Q;      // padded positions
   int stages, a_bufs;
-  unsigned a_buf_bytes, b_stage_bytes, tmem_cols;
+  unsigned a_buf_bytes, b_stage_max, tmem_cols;
   signed char acc[16], plane[16];
   int shift[16];
 };
@@ -151,15 +152,41 @@ struct SmemHeader {
   float s_sum[4][128], s_sq[4][128];   // per-warp partial column statistics of one accumulator
 };
 
-// 6 warps: 0-3 halo producers then epilogue, 4 weight loader (TMA bulk), 5 MMA issuer + TMEM allocator
+__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+  uint4 r;
+  r.x = *reinterpret_cast<unsigned*>(&b0); r.y = *reinterpret_cast<unsigned*>(&b1);
+  r.z = *reinterpret_cast<unsigned*>(&b2); r.w = *reinterpret_cast<unsigned*>(&b3);
+  return r;
+}
+// 8 consecutive channels [ch0, ch0+8) of one pixel -> 8 bf16; channels >= valid are zero (channel padding)
+__device__ __forceinline__ uint4 load8(const float* __restrict__ px, int ch0, int valid, int vec) {
+  float f[8];
+  if (vec) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(px + ch0));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(px + ch0) + 1);
+    f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (ch0 + e < valid) ? __ldg(px + ch0 + e) : 0.f;
+  }
+  return pack8_bf16(f);
+}
+
+// 6 warps: 0-3 halo producers then epilogue, 4 weight loader (TMA bulk), 5 MMA issuer + TMEM allocator.
+// blockIdx.x = 128-row tile of the padded pixel space, blockIdx.y = 128-column tile of the output channels.
 __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
   unsigned char* b_smem = smem_raw + ((sizeof(SmemHeader) + 127) & ~127u);
-  unsigned char* a_smem = b_smem + (size_t)P.stages * P.b_stage_bytes;
+  unsigned char* a_smem = b_smem + (size_t)P.stages * P.b_stage_max;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long q0 = (long long)blockIdx.x * TILE_M;
+  const int n0 = blockIdx.y * 128;
+  const int Nt = min(128, P.N_p - n0);               // this CTA's MMA N (multiple of 16)
+  const unsigned b_stage_bytes = (unsigned)(P.KC * Nt * 2);
 
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(smem_u32(&hdr->full_b[s]), 1); mbar_init(smem_u32(&hdr->empty_b[s]), 1); }
@@ -196,13 +223,8 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
           const int n = (int)(t / P.Hp);
           if (r < P.Hv && cc < P.Wv) {
             const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
-            const float* src = P.in + (((size_t)n * P.Hin + ih) * P.Win + iw) * P.in_ld + P.in_coff + c * P.KC + j * 8;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(v0.x, v0.y), b1 = __floats2bfloat162_rn(v0.z, v0.w);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(v1.x, v1.y), b3 = __floats2bfloat162_rn(v1.z, v1.w);
-            packed.x = *reinterpret_cast<unsigned*>(&b0); packed.y = *reinterpret_cast<unsigned*>(&b1);
-            packed.z = *reinterpret_cast<unsigned*>(&b2); packed.w = *reinterpret_cast<unsigned*>(&b3);
+            const float* px = P.in + (((size_t)n * P.Hin + ih) * P.Win + iw) * P.in_ld + P.in_coff;
+            packed = load8(px, c * P.KC + j * 8, P.cin_valid, P.in_vec);
           }
         }
         *reinterpret_cast<uint4*>(abuf + (size_t)(pl * P.JC + j) * LBO_A + (size_t)i * 16) = packed;
@@ -228,20 +250,32 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
     for (int a = 0; a < P.nacc; ++a) {
       int oh = r, ow = cc;
       if (P.mode == 2) { oh = 2 * r + (a >> 1); ow = 2 * cc + (a & 1); }
-      float* orow = P.out + (((size_t)n * P.Hout + oh) * P.Wout + ow) * P.out_ld + P.out_coff;
-      for (int n0 = 0; n0 < P.N; n0 += 32) {
+      float* orow = P.out + (((size_t)n * P.Hout + oh) * P.Wout + ow) * P.out_ld + P.out_coff + n0;
+      for (int nn = 0; nn < Nt; nn += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(a * P.N + n0), v);
-        const int ncols = min(32, P.N - n0);
+        tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(a * Nt + nn), v);
+        const int ncols = max(0, min(min(32, Nt - nn), P.n_valid - (n0 + nn)));   // real (unpadded) columns of this group
         if (valid) {
+          if (P.out_vec) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            if (k < ncols) {
-              float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-              float4* dst = reinterpret_cast<float4*>(orow + n0 + k);
-              if (P.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              *dst = o;
-              v[k] = o.x; v[k + 1] = o.y; v[k + 2] = o.z; v[k + 3] = o.w;
+            for (int k = 0; k < 32; k += 4) {
+              if (k < ncols) {
+                float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                float4* dst = reinterpret_cast<float4*>(orow + nn + k);
+                if (P.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *dst = o;
+                v[k] = o.x; v[k + 1] = o.y; v[k + 2] = o.z; v[k + 3] = o.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              if (k < ncols) {
+                float o = v[k];
+                if (P.accumulate) o += orow[nn + k];
+                orow[nn + k] = o;
+                v[k] = o;
+              }
             }
           }
         } else {
@@ -255,52 +289,55 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
           const float cs = warp_colsum32(v, lane);
           const float cq = warp_colsum32(sq, lane);
           // accumulate this warp's column totals over accumulators (phases share channels)
-          if (a == 0) { hdr->s_sum[warp][n0 + lane] = cs; hdr->s_sq[warp][n0 + lane] = cq; }
-          else { hdr->s_sum[warp][n0 + lane] += cs; hdr->s_sq[warp][n0 + lane] += cq; }
+          if (a == 0) { hdr->s_sum[warp][nn + lane] = cs; hdr->s_sq[warp][nn + lane] = cq; }
+          else { hdr->s_sum[warp][nn + lane] += cs; hdr->s_sq[warp][nn + lane] += cq; }
         }
       }
     }
     tc_fence_before();
     if (P.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-      for (int col = tid; col < P.N; col += 128) {
-        const float s = hdr->s_sum[0][col] + hdr->s_sum[1][col] + hdr->s_sum[2][col] + hdr->s_sum[3][col];
-        const float s2 = hdr->s_sq[0][col] + hdr->s_sq[1][col] + hdr->s_sq[2][col] + hdr->s_sq[3][col];
-        atomicAdd(&P.stats[col], (double)s);
-        atomicAdd(&P.stats[P.N + col], (double)s2);
+      for (int col = tid; col < Nt; col += 128) {
+        if (n0 + col < P.n_valid) {
+          const float s = hdr->s_sum[0][col] + hdr->s_sum[1][col] + hdr->s_sum[2][col] + hdr->s_sum[3][col];
+          const float s2 = hdr->s_sq[0][col] + hdr->s_sq[1][col] + hdr->s_sq[2][col] + hdr->s_sq[3][col];
+          atomicAdd(&P.stats[n0 + col], (double)s);
+          atomicAdd(&P.stats[P.n_valid + n0 + col], (double)s2);
+        }
       }
     }
   } else if (warp == 4) {
     // ================= weight loader: one bulk copy per (channel chunk, tap) through the stage ring =================
     if (lane == 0) {
       int stage = 0; unsigned phase = 0;
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp);
+      // packed weights: [n tile][chunk][tap][8-channel group][n][8]; every full tile holds 128*Cin_p*ntaps elements
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2;
       for (int c = 0; c < P.NC; ++c)
-        for (int s = 0; s < 16; ++s) {
+        for (int s = 0; s < P.ntaps; ++s) {
           mbar_wait(smem_u32(&hdr->empty_b[stage]), phase ^ 1);
-          mbar_expect_tx(smem_u32(&hdr->full_b[stage]), P.b_stage_bytes);
-          bulk_g2s(smem_u32(b_smem + (size_t)stage * P.b_stage_bytes), wsrc + ((size_t)c * 16 + s) * P.b_stage_bytes,
-                   P.b_stage_bytes, smem_u32(&hdr->full_b[stage]));
+          mbar_expect_tx(smem_u32(&hdr->full_b[stage]), b_stage_bytes);
+          bulk_g2s(smem_u32(b_smem + (size_t)stage * P.b_stage_max), wsrc + ((size_t)c * P.ntaps + s) * b_stage_bytes,
+                   b_stage_bytes, smem_u32(&hdr->full_b[stage]));
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
     }
   } else {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      const unsigned idesc = make_idesc(TILE_M, P.N);
-      const unsigned LBO_B = (unsigned)P.N * 16u;
+      const unsigned idesc = make_idesc(TILE_M, Nt);
+      const unsigned LBO_B = (unsigned)Nt * 16u;
       int stage = 0; unsigned phase = 0;
       unsigned started = 0;                           // bit a set once accumulator a has been written
       for (int c = 0; c < P.NC; ++c) {
         const int buf = c % P.a_bufs;
         mbar_wait(smem_u32(&hdr->a_ready[buf]), (c / P.a_bufs) & 1);
         const unsigned abase = smem_u32(a_smem + (size_t)buf * P.a_buf_bytes);
-        for (int s = 0; s < 16; ++s) {
+        for (int s = 0; s < P.ntaps; ++s) {
           mbar_wait(smem_u32(&hdr->full_b[stage]), phase);
           tc_fence_after();
-          const unsigned bbase = smem_u32(b_smem + (size_t)stage * P.b_stage_bytes);
+          const unsigned bbase = smem_u32(b_smem + (size_t)stage * P.b_stage_max);
           const int a = P.acc[s];
-          const unsigned d_tmem = tmem_base + (unsigned)(a * P.N);
+          const unsigned d_tmem = tmem_base + (unsigned)(a * Nt);
           const unsigned arow = abase + (unsigned)(P.plane[s] * P.JC) * LBO_A + (unsigned)(P.lo + P.shift[s]) * 16u;
           for (int kk = 0; kk < P.KC / 16; ++kk) {
             const unsigned long long adesc = make_desc(arow + (unsigned)(2 * kk) * LBO_A, LBO_A, 128u);
@@ -323,23 +360,104 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
   }
 }
 
-// weights -> bf16 [chunk c][tap slot s][8-channel group j][n][8]  (canonical K-major, no swizzle: LBO = N*16, SBO = 128)
-__global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KC) {
+static inline int round16(int v) { return (v + 15) / 16 * 16; }
+static inline int pick_kc(int cin_p) { return cin_p % 128 == 0 ? 128 : cin_p % 64 == 0 ? 64 : cin_p % 32 == 0 ? 32 : 16; }
+
+// weights -> bf16 [n tile][chunk c][tap s][8-channel group j][n][8]  (canonical K-major, no swizzle: LBO = Nt*16, SBO = 128);
+// zero in the channel padding
+__global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KC, int Cin_p,
+                               int N_p) {
   const int JC = KC / 8;
-  const long long total = (long long)16 * g.Cin * g.Cout;
+  const int ntaps = g.KH * g.KW;
+  const long long per_tile = (long long)128 * Cin_p * ntaps;
+  const long long total = (long long)N_p * Cin_p * ntaps;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    long long t = e;
+    const int tile = (int)(e / per_tile);
+    long long t = e - tile * per_tile;
+    const int Nt = min(128, N_p - tile * 128);
     const int k8 = (int)(t % 8); t /= 8;
-    const int n = (int)(t % g.Cout); t /= g.Cout;
+    const int n = (int)(t % Nt); t /= Nt;
     const int j = (int)(t % JC); t /= JC;
-    const int s = (int)(t % 16); t /= 16;
+    const int s = (int)(t % ntaps); t /= ntaps;
     const int c = (int)t;
-    const int ci = c * KC + j * 8 + k8;
-    const float v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + n] : w[((size_t)s * g.Cout + n) * g.Cin + ci];
+    const int ci = c * KC + j * 8 + k8, co = tile * 128 + n;
+    float v = 0.f;
+    if (ci < g.Cin && co < g.Cout)
+      v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + co] : w[((size_t)s * g.Cout + co) * g.Cin + ci];
     out[e] = __float2bfloat16_rn(v);
   }
 }
 
+bool build_params(const Geom& g, TcParams& P) {
+  memset(&P, 0, sizeof P);
+  P.B = g.B; P.Hin = g.Hin; P.Win = g.Win; P.Hout = g.Hout; P.Wout = g.Wout;
+  P.cin_valid = g.Cin; P.n_valid = g.Cout;
+  P.Cin_p = round16(g.Cin); P.N_p = round16(g.Cout);
+  P.accumulate = g.accumulate;
+  P.KC = pick_kc(P.Cin_p); P.NC = P.Cin_p / P.KC; P.JC = P.KC / 8;
+  int hi;
+  if (g.KH == 1) {            // fully connected = 1x1 window over a 1x1 "image"
+    if (g.KW != 1 || g.Hin != 1 || g.Win != 1 || g.Hout != 1 || g.Wout != 1) return false;
+    P.mode = 0; P.nplanes = 1; P.nacc = 1; P.ntaps = 1;
+    P.Hp = P.Wp = P.Hv = P.Wv = 1;
+    P.acc[0] = 0; P.plane[0] = 0; P.shift[0] = 0;
+    P.lo = 0; hi = 0;
+  } else if (g.stride == 1) {
+    P.mode = 0; P.nplanes = 1; P.nacc = 1; P.ntaps = 16;
+    P.Hp = g.Hin + 2; P.Wp = g.Win + 2; P.Hv = g.Hin; P.Wv = g.Win;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int s = kh * 4 + kw;
+        const int dh = g.mode == 0 ? kh - 1 : 1 - kh, dw = g.mode == 0 ? kw - 1 : 1 - kw;
+        P.acc[s] = 0; P.plane[s] = 0; P.shift[s] = dh * P.Wp + dw;
+      }
+    P.lo = g.mode == 0 ? P.Wp + 1 : 2 * P.Wp + 2;
+    hi = g.mode == 0 ? 2 * P.Wp + 2 : P.Wp + 1;
+  } else if (g.mode == 0) {   // stride-2 conv: parity planes of the input, output grid
+    P.mode = 1; P.nplanes = 4; P.nacc = 1; P.ntaps = 16;
+    P.Hp = g.Hout + 1; P.Wp = g.Wout + 1; P.Hv = g.Hout; P.Wv = g.Wout;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int s = kh * 4 + kw;
+        const int dh = kh == 0 ? -1 : kh == 3 ? 1 : 0, dw = kw == 0 ? -1 : kw == 3 ? 1 : 0;
+        P.acc[s] = 0; P.plane[s] = (signed char)((((kh + 1) & 1) << 1) | ((kw + 1) & 1)); P.shift[s] = dh * P.Wp + dw;
+      }
+    P.lo = P.Wp + 1; hi = P.Wp + 1;
+  } else {                    // stride-2 transposed conv: input grid, four output phases
+    P.mode = 2; P.nplanes = 1; P.nacc = 4; P.ntaps = 16;
+    P.Hp = g.Hin + 1; P.Wp = g.Win + 1; P.Hv = g.Hin; P.Wv = g.Win;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        const int s = kh * 4 + kw;
+        const int ph = (kh + 1) & 1, pw = (kw + 1) & 1;
+        const int dh = kh == 3 ? -1 : kh == 0 ? 1 : 0, dw = kw == 3 ? -1 : kw == 0 ? 1 : 0;
+        P.acc[s] = (signed char)(ph * 2 + pw); P.plane[s] = 0; P.shift[s] = dh * P.Wp + dw;
+      }
+    P.lo = P.Wp + 1; hi = P.Wp + 1;
+    if (P.N_p > 128) return false;                 // four accumulators of one N tile
+  }
+  P.HL = TILE_M + P.lo + hi;
+  P.HLpad = P.HL | 1;                               // odd plane pitch (in 16-byte units): conflict-free producer stores
+  P.Q = (long long)g.B * P.Hp * P.Wp;
+  P.a_buf_bytes = (unsigned)(P.nplanes * P.JC * P.HLpad * 16);
+  P.a_bufs = P.NC > 1 ? 2 : 1;
+  const int nt_max = P.N_p < 128 ? P.N_p : 128;
+  P.b_stage_max = (unsigned)(P.KC * nt_max * 2);
+  // as many weight stages as fit next to the halo buffers (at least 2)
+  P.stages = MAX_STAGES;
+  {
+    const size_t fixed = ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.a_bufs * P.a_buf_bytes + 128;
+    while (P.stages > 2 && fixed + (size_t)P.stages * P.b_stage_max > 227 * 1024) --P.stages;
+  }
+  unsigned cols = (unsigned)(P.nacc * nt_max), t = 32;
+  while (t < cols) t <<= 1;
+  P.tmem_cols = t;
+  return t <= 512;
+}
+
+size_t smem_bytes(const TcParams& P) {
+  return ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.stages * P.b_stage_max + (size_t)P.a_bufs * P.a_buf_bytes + 128;
+}
 
 // =====================================================================================================================
 // Weight gradient:  dW[tap][a][b] = sum_q X[q + shift(tap)][a] * dY[q][b]   (conv-gather geometry, q = padded positions)
@@ -349,10 +467,10 @@ __global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat1
 // of the CTA's tap group.  A CTA walks its share of the 128-pixel tiles, accumulating in TMEM the whole time, and
 // flushes once with red.global.add.f32.
 struct TwParams {
-  const float* x; int x_ld, x_coff;
-  const float* dy; int dy_ld, dy_coff;
-  float* dw;
-  int B, Hx, Wx, Ca, Hy, Wy, Cb;
+  const float* x; int x_ld, x_coff, x_vec;
+  const float* dy; int dy_ld, dy_coff, dy_vec;
+  float* dw; int dw_vec;
+  int B, Hx, Wx, Ca, Hy, Wy, Cb;   // Ca, Cb: real channel counts (dw is [16][Ca][Cb]); padded counts are mblocks*CaB, nblocks*N
   int mode;                 // 0 stride 1 (one plane), 1 stride 2 (four parity planes of X)
   int Hp, Wp, Hv, Wv, lo, HL, HLpad, YLpad;
   int CaB, JA, N, JN;       // channels of X per CTA (<=128), CaB/8, channels of dY per CTA (<=128), N/8
@@ -421,13 +539,8 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
           const int n = (int)(t / P.Hp);
           if (r < P.Hv && cc < P.Wv) {
             const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
-            const float* src = P.x + (((size_t)n * P.Hx + ih) * P.Wx + iw) * P.x_ld + P.x_coff + a0 + j * 8;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            __nv_bfloat162 c0 = __floats2bfloat162_rn(v0.x, v0.y), c1 = __floats2bfloat162_rn(v0.z, v0.w);
-            __nv_bfloat162 c2 = __floats2bfloat162_rn(v1.x, v1.y), c3 = __floats2bfloat162_rn(v1.z, v1.w);
-            packed.x = *reinterpret_cast<unsigned*>(&c0); packed.y = *reinterpret_cast<unsigned*>(&c1);
-            packed.z = *reinterpret_cast<unsigned*>(&c2); packed.w = *reinterpret_cast<unsigned*>(&c3);
+            const float* px = P.x + (((size_t)n * P.Hx + ih) * P.Wx + iw) * P.x_ld + P.x_coff;
+            packed = load8(px, a0 + j * 8, P.Ca, P.x_vec);
           }
         }
         *reinterpret_cast<uint4*>(xb + (size_t)(pl * P.JA + j) * PITCH_X + (size_t)i * 16) = packed;
@@ -442,13 +555,8 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
           const int r = (int)(t % P.Hp);
           const int n = (int)(t / P.Hp);
           if (r < P.Hv && cc < P.Wv) {
-            const float* src = P.dy + (((size_t)n * P.Hy + r) * P.Wy + cc) * P.dy_ld + P.dy_coff + b0 + j * 8;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            __nv_bfloat162 c0 = __floats2bfloat162_rn(v0.x, v0.y), c1 = __floats2bfloat162_rn(v0.z, v0.w);
-            __nv_bfloat162 c2 = __floats2bfloat162_rn(v1.x, v1.y), c3 = __floats2bfloat162_rn(v1.z, v1.w);
-            packed.x = *reinterpret_cast<unsigned*>(&c0); packed.y = *reinterpret_cast<unsigned*>(&c1);
-            packed.z = *reinterpret_cast<unsigned*>(&c2); packed.w = *reinterpret_cast<unsigned*>(&c3);
+            const float* px = P.dy + (((size_t)n * P.Hy + r) * P.Wy + cc) * P.dy_ld + P.dy_coff;
+            packed = load8(px, b0 + j * 8, P.Cb, P.dy_vec);
           }
         }
         *reinterpret_cast<uint4*>(yb + (size_t)j * PITCH_Y + (size_t)i * 16) = packed;
@@ -465,12 +573,18 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
       for (int n0 = 0; n0 < P.N; n0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tl * P.N + n0), v);
-        if (a < P.CaB && my_tiles > 0) {
+        if (a0 + a < P.Ca && my_tiles > 0) {
           float* dst = P.dw + ((size_t)tap * P.Ca + a0 + a) * P.Cb + b0 + n0;
-          const int ncols = min(32, P.N - n0);
+          const int ncols = max(0, min(min(32, P.N - n0), P.Cb - (b0 + n0)));
+          if (P.dw_vec) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (k < ncols) atomicAdd(dst + k, v[k]);
+            for (int k = 0; k < 32; k += 4)
+              if (k < ncols) atomicAdd(reinterpret_cast<float4*>(dst + k), make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < ncols) atomicAdd(dst + k, v[k]);
+          }
         }
       }
     }
@@ -513,11 +627,11 @@ bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
   // g: conv-gather geometry (mode 0) with X = [B,Hin,Win,Cin], dY = [B,Hout,Wout,Cout]
   memset(&P, 0, sizeof P);
   if (g.mode != 0 || g.KH != 4 || g.KW != 4 || g.pad != 1) return false;
-  if (g.Cin % 16 || g.Cout % 16 || g.Cin < 16 || g.Cout < 16) return false;
-  if ((g.Cin > 128 && g.Cin % 128) || (g.Cout > 128 && g.Cout % 128)) return false;
+  const int Ca_p = round16(g.Cin), Cb_p = round16(g.Cout);
+  if ((Ca_p > 128 && Ca_p % 128) || (Cb_p > 128 && Cb_p % 128)) return false;
   P.B = g.B; P.Hx = g.Hin; P.Wx = g.Win; P.Ca = g.Cin; P.Hy = g.Hout; P.Wy = g.Wout; P.Cb = g.Cout;
-  P.CaB = g.Cin < 128 ? g.Cin : 128; P.JA = P.CaB / 8; P.mblocks = g.Cin / P.CaB;
-  P.N = g.Cout < 128 ? g.Cout : 128; P.JN = P.N / 8; P.nblocks = g.Cout / P.N;
+  P.CaB = Ca_p < 128 ? Ca_p : 128; P.JA = P.CaB / 8; P.mblocks = Ca_p / P.CaB;
+  P.N = Cb_p < 128 ? Cb_p : 128; P.JN = P.N / 8; P.nblocks = Cb_p / P.N;
   int hi;
   if (g.stride == 1) {
     P.mode = 0; P.nplanes = 1;
@@ -558,80 +672,59 @@ bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
   return true;
 }
 
-int chunk_channels(const Geom& g) { return g.Cin <= 128 ? g.Cin : 128; }
-
-bool build_params(const Geom& g, TcParams& P) {
-  memset(&P, 0, sizeof P);
-  P.B = g.B; P.Hin = g.Hin; P.Win = g.Win; P.Cin = g.Cin; P.Hout = g.Hout; P.Wout = g.Wout; P.N = g.Cout;
-  P.accumulate = g.accumulate;
-  P.KC = chunk_channels(g); P.NC = g.Cin / P.KC; P.JC = P.KC / 8;
-  int hi;
-  if (g.stride == 1) {
-    P.mode = 0; P.nplanes = 1; P.nacc = 1;
-    P.Hp = g.Hin + 2; P.Wp = g.Win + 2; P.Hv = g.Hin; P.Wv = g.Win;
-    for (int kh = 0; kh < 4; ++kh)
-      for (int kw = 0; kw < 4; ++kw) {
-        const int s = kh * 4 + kw;
-        const int dh = g.mode == 0 ? kh - 1 : 1 - kh, dw = g.mode == 0 ? kw - 1 : 1 - kw;
-        P.acc[s] = 0; P.plane[s] = 0; P.shift[s] = dh * P.Wp + dw;
-      }
-    P.lo = g.mode == 0 ? P.Wp + 1 : 2 * P.Wp + 2;
-    hi = g.mode == 0 ? 2 * P.Wp + 2 : P.Wp + 1;
-  } else if (g.mode == 0) {   // stride-2 conv: parity planes of the input, output grid
-    P.mode = 1; P.nplanes = 4; P.nacc = 1;
-    P.Hp = g.Hout + 1; P.Wp = g.Wout + 1; P.Hv = g.Hout; P.Wv = g.Wout;
-    for (int kh = 0; kh < 4; ++kh)
-      for (int kw = 0; kw < 4; ++kw) {
-        const int s = kh * 4 + kw;
-        const int dh = kh == 0 ? -1 : kh == 3 ? 1 : 0, dw = kw == 0 ? -1 : kw == 3 ? 1 : 0;
-        P.acc[s] = 0; P.plane[s] = (signed char)((((kh + 1) & 1) << 1) | ((kw + 1) & 1)); P.shift[s] = dh * P.Wp + dw;
-      }
-    P.lo = P.Wp + 1; hi = P.Wp + 1;
-  } else {                    // stride-2 transposed conv: input grid, four output phases
-    P.mode = 2; P.nplanes = 1; P.nacc = 4;
-    P.Hp = g.Hin + 1; P.Wp = g.Win + 1; P.Hv = g.Hin; P.Wv = g.Win;
-    for (int kh = 0; kh < 4; ++kh)
-      for (int kw = 0; kw < 4; ++kw) {
-        const int s = kh * 4 + kw;
-        const int ph = (kh + 1) & 1, pw = (kw + 1) & 1;
-        const int dh = kh == 3 ? -1 : kh == 0 ? 1 : 0, dw = kw == 3 ? -1 : kw == 0 ? 1 : 0;
-        P.acc[s] = (signed char)(ph * 2 + pw); P.plane[s] = 0; P.shift[s] = dh * P.Wp + dw;
-      }
-    P.lo = P.Wp + 1; hi = P.Wp + 1;
-  }
-  P.HL = TILE_M + P.lo + hi;
-  P.HLpad = P.HL | 1;                               // odd plane pitch (in 16-byte units): conflict-free producer stores
-  P.Q = (long long)g.B * P.Hp * P.Wp;
-  P.a_buf_bytes = (unsigned)(P.nplanes * P.JC * P.HLpad * 16);
-  P.a_bufs = P.NC > 1 ? 2 : 1;
-  P.b_stage_bytes = (unsigned)(P.KC * P.N * 2);
-  // as many weight stages as fit next to the halo buffers (at least 2)
-  P.stages = MAX_STAGES;
-  {
-    const size_t fixed = ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.a_bufs * P.a_buf_bytes + 128;
-    while (P.stages > 2 && fixed + (size_t)P.stages * P.b_stage_bytes > 227 * 1024) --P.stages;
-  }
-  unsigned cols = (unsigned)(P.nacc * P.N), t = 32;
-  while (t < cols) t <<= 1;
-  P.tmem_cols = t;
-  return t <= 512;
-}
-
-size_t smem_bytes(const TcParams& P) {
-  return ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.stages * P.b_stage_bytes + (size_t)P.a_bufs * P.a_buf_bytes + 128;
-}
 
 }  // namespace
 
 bool tc_supported(const Geom& g) {
-  if (g.KH != 4 || g.KW != 4 || g.pad != 1) return false;
-  if (g.stride != 1 && g.stride != 2) return false;
-  if (g.Cin % 16 != 0 || g.Cin < 16) return false;
-  if (g.Cin > 128 && g.Cin % 128 != 0) return false;
-  if (g.Cout % 16 != 0 || g.Cout < 16 || g.Cout > 128) return false;
+  const bool conv = g.KH == 4 && g.KW == 4 && g.pad == 1 && (g.stride == 1 || g.stride == 2);
+  const bool fc = g.KH == 1 && g.KW == 1 && g.Hin == 1 && g.Win == 1;
+  if (!conv && !fc) return false;
+  if (g.Cin < 1 || g.Cout < 1) return false;
+  if (fc && (g.Cin < 64 || g.Cout < 64)) return false;   // skinny projections / heads stay on the fp32 row-dot kernels
   TcParams P;
-  if (!build_params(g, P)) return false;
+  Geom gg = g;
+  if (gg.B < 1) gg.B = 1;
+  if (!build_params(gg, P)) return false;
   return smem_bytes(P) <= 227 * 1024;
+}
+
+size_t tc_packed_bytes(const Geom& g) { return (size_t)g.KH * g.KW * round16(g.Cin) * round16(g.Cout) * 2; }
+
+int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed) {
+  const int Cin_p = round16(g.Cin), N_p = round16(g.Cout);
+  const long long total = (long long)g.KH * g.KW * Cin_p * N_p;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > lc.sm_count * 8) blocks = lc.sm_count * 8;
+  ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total);
+  tc_pack_kernel<<<blocks, 256, 0, lc.stream>>>(g, w, reinterpret_cast<__nv_bfloat16*>(w_packed), pick_kc(Cin_p), Cin_p, N_p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats) {
+  TcParams P;
+  if (!build_params(g, P)) { svae_global_error() = "tcgen05: unsupported geometry"; return -1; }
+  P.in = in.p; P.in_ld = in.ld; P.in_coff = in.coff;
+  P.in_vec = (in.ld % 4 == 0) && (in.coff % 4 == 0) && (((uintptr_t)in.p & 15) == 0) && (g.Cin % 8 == 0);
+  P.wp = reinterpret_cast<const __nv_bfloat16*>(w_packed);
+  P.out = out.p; P.out_ld = out.ld; P.out_coff = out.coff;
+  P.out_vec = (out.ld % 4 == 0) && (out.coff % 4 == 0) && (((uintptr_t)out.p & 15) == 0) && (g.Cout % 4 == 0);
+  P.stats = stats;
+  const size_t smem = smem_bytes(P);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const long long tiles = (P.Q + TILE_M - 1) / TILE_M;
+  const int ntiles = (P.N_p + 127) / 128;
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_GEMM_TC, 2.0 * pix * g.KH * g.KW * g.Cin * g.Cout,
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout) +
+                   2.0 * g.KH * g.KW * g.Cin * g.Cout, &g);
+  tc_conv_kernel<<<dim3((unsigned)tiles, (unsigned)ntiles), 192, smem, lc.stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 static Geom wgrad_conv_geom(const Geom& fwd) {
@@ -655,13 +748,12 @@ bool tc_wgrad_supported(const Geom& fwd) {
 int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
   TwParams P;
   if (!build_wparams(g, P, lc.sm_count)) { svae_global_error() = "tcgen05 wgrad: unsupported geometry"; return -1; }
-  if ((x.ld % 4) || (x.coff % 4) || (dy.ld % 4) || (dy.coff % 4) || ((uintptr_t)x.p & 15) || ((uintptr_t)dy.p & 15)) {
-    svae_global_error() = "tcgen05 wgrad: tensors must be 16-byte aligned channel windows";
-    return -1;
-  }
   P.x = x.p; P.x_ld = x.ld; P.x_coff = x.coff;
+  P.x_vec = (x.ld % 4 == 0) && (x.coff % 4 == 0) && (((uintptr_t)x.p & 15) == 0) && (g.Cin % 8 == 0);
   P.dy = dy.p; P.dy_ld = dy.ld; P.dy_coff = dy.coff;
+  P.dy_vec = (dy.ld % 4 == 0) && (dy.coff % 4 == 0) && (((uintptr_t)dy.p & 15) == 0) && (g.Cout % 8 == 0);
   P.dw = dw;
+  P.dw_vec = (g.Cout % 4 == 0) && (((uintptr_t)dw & 15) == 0);
   const size_t smem = 128 + (size_t)P.bufs * (P.x_buf_bytes + P.y_buf_bytes);
   static bool configured = false;
   if (!configured) {
@@ -669,51 +761,14 @@ int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
     configured = true;
   }
   const int gy = P.ngroups * P.mblocks * P.nblocks;
-  long long splits = (2LL * lc.sm_count + gy - 1) / gy;
+  long long splits = (lc.sm_count + gy - 1) / gy;    // about one CTA per SM: every extra split costs a full flush of atomics
   if (splits > P.tiles) splits = P.tiles;
   if (splits < 1) splits = 1;
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
   ProfScope ps(lc, KC_WGRAD_TC, 2.0 * pix * 16 * g.Cin * g.Cout,
-               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout + 16.0 * g.Cin * g.Cout));
+               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout + 16.0 * g.Cin * g.Cout), &g);
   tc_wgrad_kernel<<<dim3((unsigned)splits, (unsigned)gy), 160, smem, lc.stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-size_t tc_packed_bytes(const Geom& g) { return (size_t)16 * g.Cin * g.Cout * 2; }
-
-int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed) {
-  const long long total = (long long)16 * g.Cin * g.Cout;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > lc.sm_count * 8) blocks = lc.sm_count * 8;
-  ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total);
-  tc_pack_kernel<<<blocks, 256, 0, lc.stream>>>(g, w, reinterpret_cast<__nv_bfloat16*>(w_packed), chunk_channels(g));
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
-int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats) {
-  TcParams P;
-  if (!build_params(g, P)) { svae_global_error() = "tcgen05: unsupported geometry"; return -1; }
-  if ((in.ld % 4) || (in.coff % 4) || (out.ld % 4) || (out.coff % 4) || ((uintptr_t)in.p & 15) || ((uintptr_t)out.p & 15)) {
-    svae_global_error() = "tcgen05: tensors must be 16-byte aligned channel windows";
-    return -1;
-  }
-  P.in = in.p; P.in_ld = in.ld; P.in_coff = in.coff;
-  P.wp = reinterpret_cast<const __nv_bfloat16*>(w_packed);
-  P.out = out.p; P.out_ld = out.ld; P.out_coff = out.coff;
-  P.stats = stats;
-  const size_t smem = smem_bytes(P);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
-  const long long tiles = (P.Q + TILE_M - 1) / TILE_M;
-  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
-  ProfScope ps(lc, KC_GEMM_TC, 2.0 * pix * 16 * g.Cin * g.Cout,
-               4.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout) + 2.0 * 16 * g.Cin * g.Cout);
-  tc_conv_kernel<<<(unsigned)tiles, 192, smem, lc.stream>>>(P);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}

@@ -75,6 +75,7 @@ struct Step {
   int ncc;
   int w_out, b_out, w_gate, b_gate;       // output deconvs (live bias)
   Geom g_out, g_gate;
+  Block outb, gateb;                      // the same two deconvs as contraction blocks (no batch-norm) for TC routing
   float *u, *xt;
   int64_t p_begin, p_end;                 // parameter range (all-reduce bucket)
 };
@@ -336,12 +337,14 @@ void build_params(svae_handle* h) {
       s.w_out = add_param(h, o + "/weights", {4, 4, C, F[1]}, t, SVAE_PF_THETA | SVAE_PF_XAVIER);
       s.b_out = add_param(h, o + "/biases", {C}, t, SVAE_PF_THETA);
       s.g_out = deconv_geom(S[1], S[1], F[1], C, 2);
+      s.outb.g = s.g_out; s.outb.w = s.w_out;
       s.w_gate = s.b_gate = -1;
       if (t > 0) {
         std::string r = nm.next_convt();
         s.w_gate = add_param(h, r + "/weights", {4, 4, 1, F[1]}, t, SVAE_PF_THETA | SVAE_PF_XAVIER);
         s.b_gate = add_param(h, r + "/biases", {1}, t, SVAE_PF_THETA);
         s.g_gate = deconv_geom(S[1], S[1], F[1], 1, 2);
+        s.gateb.g = s.g_gate; s.gateb.w = s.w_gate;
       }
     }
     s.p_end = h->arena_numel;
@@ -568,8 +571,9 @@ int decoder_fwd(svae_handle* h, Step& s, int B, const float* z, const float* xpr
   }
   const int has_gate = s.t > 0 ? 1 : 0;
   const int ldu = C + has_gate;
-  H_TRY(contract(h, s.g_out, B, cur, h->pw(s.w_out), nullptr, false, mkview(s.u, ldu, 0), nullptr));
-  if (has_gate) H_TRY(contract(h, s.g_gate, B, cur, h->pw(s.w_gate), nullptr, false, mkview(s.u, ldu, C), nullptr));
+  H_TRY(contract(h, s.g_out, B, cur, h->pw(s.w_out), s.outb.w_packed, s.outb.tc_fwd, mkview(s.u, ldu, 0), nullptr));
+  if (has_gate)
+    H_TRY(contract(h, s.g_gate, B, cur, h->pw(s.w_gate), s.gateb.w_packed, s.gateb.tc_fwd, mkview(s.u, ldu, C), nullptr));
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
   H_TRY(out_mix_fwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, tgt, xt_out, recon_sum));
@@ -650,14 +654,16 @@ int decoder_bwd(svae_handle* h, Step& s, int B, const float* gx_in, float* gx_pr
   View dc0 = mkview(h->d_c[0], F[1], 0);
   {
     Geom g = dgrad_geom(s.g_out);
-    H_TRY(contract(h, g, B, mkview(h->d_u, ldu, 0), h->pw(s.w_out), nullptr, false, dc0, nullptr));
+    H_TRY(contract(h, g, B, mkview(h->d_u, ldu, 0), h->pw(s.w_out), s.outb.w_packed_d, s.outb.tc_dgrad, dc0, nullptr));
     Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
-    H_TRY(simt_wgrad(lc, gw, mkview(h->d_u, ldu, 0), c0, h->pg(s.w_out)));
+    if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lc, gw, mkview(h->d_u, ldu, 0), c0, h->pg(s.w_out)));
+    else H_TRY(simt_wgrad(lc, gw, mkview(h->d_u, ldu, 0), c0, h->pg(s.w_out)));
     if (has_gate) {
       Geom g2 = dgrad_geom(s.g_gate); g2.accumulate = 1;
-      H_TRY(contract(h, g2, B, mkview(h->d_u, ldu, C), h->pw(s.w_gate), nullptr, false, dc0, nullptr));
+      H_TRY(contract(h, g2, B, mkview(h->d_u, ldu, C), h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr));
       Geom gw2 = dgrad_geom(s.g_gate); gw2.B = B; gw2.mode = 0;
-      H_TRY(simt_wgrad(lc, gw2, mkview(h->d_u, ldu, C), c0, h->pg(s.w_gate)));
+      if (s.gateb.tc_wgrad) H_TRY(tc_wgrad(lc, gw2, mkview(h->d_u, ldu, C), c0, h->pg(s.w_gate)));
+      else H_TRY(simt_wgrad(lc, gw2, mkview(h->d_u, ldu, C), c0, h->pg(s.w_gate)));
     }
   }
   for (int l = 0; l <= L - 2; ++l) {
@@ -827,6 +833,8 @@ void for_each_block(svae_handle* h, void (*fn)(svae_handle*, Block&, void*), voi
     fn(h, s.decfc, ctx);
     for (Block& b : s.ta) fn(h, b, ctx);
     for (Block& b : s.tb) fn(h, b, ctx);
+    fn(h, s.outb, ctx);
+    if (s.t > 0) fn(h, s.gateb, ctx);
   }
 }
 
@@ -1247,9 +1255,13 @@ int svae_profile_read(svae_handle* h, svae_kernel_stats* out, int capacity) {
   H_CUDA(cudaSetDevice(h->device));
   H_CUDA(cudaStreamSynchronize(h->stream));
   Profiler& p = h->prof;
+  const char* trace = getenv("SVAE_TRACE");
   for (const Profiler::Rec& r : p.recs) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) p.ms[r.kc] += ms;
+    if (trace && trace[0] == '1' && r.geo[0] > 0)
+      fprintf(stderr, "TRACE %s B=%d Hin=%d Cin=%d Hout=%d Cout=%d k=%d s=%d mode=%d ms=%.4f\n", kKClassNames[r.kc],
+              r.geo[0], r.geo[1], r.geo[2], r.geo[3], r.geo[4], r.geo[5], r.geo[6], r.geo[7], ms);
   }
   cudaGetLastError();
   p.recs.clear();
@@ -1339,7 +1351,7 @@ int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const floa
   return 0;
 }
 int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int stride, int direction) {
-  Geom f = transposed ? deconv_geom(H, W, Ci, Co, stride) : conv_geom(H, W, Ci, Co, stride);
+  Geom f = transposed == 2 ? fc_geom(Ci, Co) : transposed ? deconv_geom(H, W, Ci, Co, stride) : conv_geom(H, W, Ci, Co, stride);
   f.B = 1;
   if (direction == 0) return tc_supported(f) ? 1 : 0;
   if (direction == 1) { Geom d = dgrad_geom(f); d.B = 1; return tc_supported(d) ? 1 : 0; }

@@ -72,7 +72,7 @@ class bf16_emulation:
 
         def pred(direction):
             return lambda kind, h, w, cin, cout, stride: bool(
-                L.svae_op_tc_supported(1 if kind == "deconv" else 0, h, w, cin, cout, stride, direction))
+                L.svae_op_tc_supported({"conv": 0, "deconv": 1, "fc": 2}[kind], h, w, cin, cout, stride, direction))
 
         O.OPERAND_EMULATION = dict(fwd=pred(0), dgrad=pred(1), wgrad=pred(2))
         return self
