@@ -118,11 +118,18 @@ int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w
 // dW(tap,a,b) = sum_rows X(gathered at tap, channel a) * dY(row, channel b); layout w[(tap*Ca + a)*Cb + b].
 // Geometry: X is [B,Hin,Win,Ca] (g.Cin = Ca), dY is [B,Hout,Wout,Cb] (g.Cout = Cb), conv-gather (mode 0) indexing.
 int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw);
-// skinny fully-connected helpers (heads, latent projections)
-int skinny_fwd(const LaunchCtx& lc, View a, int B, int K, const float* w, int w_n_major, const float* bias, View out,
-               int N);
-int skinny_dgrad(const LaunchCtx& lc, View dout, int B, int N, const float* w, int K, View din, int accumulate);
-int skinny_wgrad(const LaunchCtx& lc, View a, View dout, int B, int K, int N, float* dw, float* dbias, int w_n_major);
+// skinny fully-connected helpers (recognition heads, latent projections)
+struct HeadSet {   // all heads that read one flattened feature map (sequential_vae.py:1592-1609)
+  int nheads;
+  const float* w[4]; const float* b[4];
+  float* gw[4]; float* gb[4];
+  int n[4], col[4], is_sd[4];
+};
+int heads_fwd(const LaunchCtx& lc, const float* flat, int B, int K, const HeadSet& hs, float* mu_pre, float* sd_pre, int Z);
+int heads_dgrad(const LaunchCtx& lc, const HeadSet& hs, const float* dmu, const float* dsd, int B, int Z, int K, float* d_flat);
+int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const float* dmu, const float* dsd, int B, int Z, int K);
+int lat_wgrad(const LaunchCtx& lc, View z, const float* dy, int B, int KZ, int N, float* dw);
+int lat_dz(const LaunchCtx& lc, const float* dy, const float* w, int B, int KZ, int N, View dz);
 
 // ---- elementwise / reductions (kernels_elem.cu) ----------------------------------------------------------------
 int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats);
@@ -170,3 +177,6 @@ int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw);
 int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats);
 size_t tc_packed_bytes(const Geom& g);
 int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed);
+struct TcPackEntry { Geom g; const float* w; void* out; int KC, Cin_p, N_p; long long total; };
+TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed);
+int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double total_elems);

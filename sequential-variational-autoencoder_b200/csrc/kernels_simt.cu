@@ -234,116 +234,166 @@ wgrad_kernel(Geom g, View x, View dy, float* __restrict__ dw, int tilesA, int ti
   }
 }
 
-// ---- skinny fully-connected kernels ---------------------------------------------------------------------------
+// ---- skinny fully-connected kernels ------------------------------------------------------------------------------
+// Recognition heads (layers.fully_connected, sequential_vae.py:1592-1609): [B, K] x [K, n] with K = 8192..32768 and
+// n = latent_dims[l] <= 32 - GEMV-like, bound by reading the activation map once.  All heads that read the same feature
+// map run in ONE launch; K (forward) / the batch (weight gradient) is split across blocks and combined with atomics.
 constexpr int SK_NMAX = 32;
 
-// out[b, n] = bias[n] + sum_k a[b,k] * W(k,n) ; one block per (row b, group of SK_NMAX outputs)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mu_pre / sd_pre [B, Z] (pre-zeroed) += flat[b, kslice] . W_h[kslice, :]  (+ bias from the first K slice)
 __global__ void __launch_bounds__(256)
-skinny_fwd_kernel(View a, int K, const float* __restrict__ w, int w_n_major, const float* __restrict__ bias, View out,
-                  int N) {
-  const int b = blockIdx.x;
-  const int n0 = blockIdx.y * SK_NMAX;
-  const int nn = min(SK_NMAX, N - n0);
-  float acc[SK_NMAX];
-#pragma unroll
-  for (int n = 0; n < SK_NMAX; ++n) acc[n] = 0.f;
-  const float* arow = a.p + (size_t)b * a.ld + a.coff;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float av = __ldg(arow + k);
-    if (w_n_major) {
-#pragma unroll
-      for (int n = 0; n < SK_NMAX; ++n)
-        if (n < nn) acc[n] = fmaf(av, __ldg(w + (size_t)(n0 + n) * K + k), acc[n]);
-    } else {
-      const float* wr = w + (size_t)k * N + n0;
-#pragma unroll
-      for (int n = 0; n < SK_NMAX; ++n)
-        if (n < nn) acc[n] = fmaf(av, __ldg(wr + n), acc[n]);
-    }
-  }
+heads_fwd_kernel(const float* __restrict__ flat, int K, HeadSet hs, float* __restrict__ mu_pre, float* __restrict__ sd_pre,
+                 int Z) {
   __shared__ float red[8][SK_NMAX];
+  const int b = blockIdx.x;
+  const int kper = (K + gridDim.y - 1) / gridDim.y;
+  const int k0 = blockIdx.y * kper, k1 = min(K, k0 + kper);
+  const float* arow = flat + (size_t)b * K;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int n = 0; n < SK_NMAX; ++n) {
-    float v = acc[n];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[wid][n] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < nn) {
-    float v = bias ? bias[n0 + threadIdx.x] : 0.f;
-    for (int wi = 0; wi < 8; ++wi) v += red[wi][threadIdx.x];
-    out.p[(size_t)b * out.ld + out.coff + n0 + threadIdx.x] = v;
-  }
-}
-
-// din[b,k] (+)= sum_n dout[b,n] * w[k*N + n]      (w is [K,N])
-__global__ void __launch_bounds__(256)
-skinny_dgrad_kernel(View dout, int B, int N, const float* __restrict__ w, int K, View din, int accumulate) {
-  const int b = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  extern __shared__ float s_d[];
-  for (int n = threadIdx.x; n < N; n += blockDim.x) s_d[n] = dout.p[(size_t)b * dout.ld + dout.coff + n];
-  __syncthreads();
-  if (k >= K) return;
-  const float* wr = w + (size_t)k * N;
-  float v = 0.f;
-  for (int n = 0; n < N; ++n) v = fmaf(s_d[n], __ldg(wr + n), v);
-  float* dst = din.p + (size_t)b * din.ld + din.coff + k;
-  if (accumulate) v += *dst;
-  *dst = v;
-}
-
-// w_n_major == 0: dw[k*N + n] = sum_b a[b,k] * dout[b,n]   (thread per k; heads: K large, N small)
-// w_n_major == 1: dw[n*K + k] = same value, K small, N large (latent projections [lat, feats]): thread per n
-__global__ void __launch_bounds__(256)
-skinny_wgrad_kernel(View a, View dout, int B, int K, int N, float* __restrict__ dw, float* __restrict__ dbias,
-                    int thread_over_n) {
-  if (!thread_over_n) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < K) {
-      for (int n0 = 0; n0 < N; n0 += SK_NMAX) {
-        float acc[SK_NMAX];
-#pragma unroll
-        for (int n = 0; n < SK_NMAX; ++n) acc[n] = 0.f;
-        const int nn = min(SK_NMAX, N - n0);
-        for (int b = 0; b < B; ++b) {
-          float av = __ldg(a.p + (size_t)b * a.ld + a.coff + k);
-          const float* dr = dout.p + (size_t)b * dout.ld + dout.coff + n0;
-#pragma unroll
-          for (int n = 0; n < SK_NMAX; ++n)
-            if (n < nn) acc[n] = fmaf(av, __ldg(dr + n), acc[n]);
-        }
-#pragma unroll
-        for (int n = 0; n < SK_NMAX; ++n)
-          if (n < nn) dw[(size_t)k * N + n0 + n] = acc[n];
-      }
-    }
-    if (dbias != nullptr && blockIdx.x == 0) {
-      for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += dout.p[(size_t)b * dout.ld + dout.coff + n];
-        dbias[n] = s;
-      }
-    }
-  } else {
-    // thread per output feature n; K (<= SK_NMAX) latent inputs; dw laid out [K, N] (reference [in,out])
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+  for (int h = 0; h < hs.nheads; ++h) {
+    const int n = hs.n[h];
+    const float* __restrict__ w = hs.w[h];
     float acc[SK_NMAX];
 #pragma unroll
-    for (int k = 0; k < SK_NMAX; ++k) acc[k] = 0.f;
-    for (int b = 0; b < B; ++b) {
-      float dv = __ldg(dout.p + (size_t)b * dout.ld + dout.coff + n);
-      const float* ar = a.p + (size_t)b * a.ld + a.coff;
+    for (int i = 0; i < SK_NMAX; ++i) acc[i] = 0.f;
+    for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      const float av = __ldg(arow + k);
+      const float* wr = w + (size_t)k * n;
 #pragma unroll
-      for (int k = 0; k < SK_NMAX; ++k)
-        if (k < K) acc[k] = fmaf(__ldg(ar + k), dv, acc[k]);
+      for (int i = 0; i < SK_NMAX; ++i)
+        if (i < n) acc[i] = fmaf(av, __ldg(wr + i), acc[i]);
     }
 #pragma unroll
+    for (int i = 0; i < SK_NMAX; ++i) {
+      if (i < n) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[wid][i] = v;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < n) {
+      float v = blockIdx.y == 0 ? hs.b[h][threadIdx.x] : 0.f;
+      for (int wi = 0; wi < 8; ++wi) v += red[wi][threadIdx.x];
+      float* dst = (hs.is_sd[h] ? sd_pre : mu_pre) + (size_t)b * Z + hs.col[h] + threadIdx.x;
+      atomicAdd(dst, v);
+    }
+    __syncthreads();
+  }
+}
+
+// d_flat[b, k] = sum_h sum_n d_h[b, col_h + n] * W_h[k, n]   (overwrite)
+__global__ void __launch_bounds__(256)
+heads_dgrad_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int Z, int K,
+                   float* __restrict__ d_flat) {
+  __shared__ float s_d[4 * SK_NMAX];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < hs.nheads * SK_NMAX; i += blockDim.x) {
+    const int h = i / SK_NMAX, n = i % SK_NMAX;
+    s_d[i] = n < hs.n[h] ? (hs.is_sd[h] ? dsd : dmu)[(size_t)b * Z + hs.col[h] + n] : 0.f;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float v = 0.f;
+  for (int h = 0; h < hs.nheads; ++h) {
+    const int n = hs.n[h];
+    const float* wr = hs.w[h] + (size_t)k * n;
+    for (int i = 0; i < n; ++i) v = fmaf(s_d[h * SK_NMAX + i], __ldg(wr + i), v);
+  }
+  d_flat[(size_t)b * K + k] = v;
+}
+
+// gw_h[k, n] += sum_{b in slice} flat[b, k] * d_h[b, col_h + n] ; gb_h[n] += sum_b d_h[b, col_h + n]   (grads pre-zeroed)
+__global__ void __launch_bounds__(256)
+heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd,
+                   int B, int Z, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bper = (B + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * bper, r1 = min(B, r0 + bper);
+  for (int h = 0; h < hs.nheads; ++h) {
+    const int n = hs.n[h];
+    const float* __restrict__ d = (hs.is_sd[h] ? dsd : dmu) + hs.col[h];
+    if (k < K) {
+      float acc[SK_NMAX];
+#pragma unroll
+      for (int i = 0; i < SK_NMAX; ++i) acc[i] = 0.f;
+      for (int b = r0; b < r1; ++b) {
+        const float av = __ldg(flat + (size_t)b * K + k);
+        const float* dr = d + (size_t)b * Z;
+#pragma unroll
+        for (int i = 0; i < SK_NMAX; ++i)
+          if (i < n) acc[i] = fmaf(av, __ldg(dr + i), acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < SK_NMAX; ++i)
+        if (i < n) atomicAdd(hs.gw[h] + (size_t)k * n + i, acc[i]);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < n) {
+      float sum = 0.f;
+      for (int b = 0; b < B; ++b) sum += d[(size_t)b * Z + threadIdx.x];
+      hs.gb[h][threadIdx.x] = sum;
+    }
+  }
+}
+
+// Latent projections (split_latent, sequential_vae.py:1801-1806): [B, kz<=32] x [kz, N] with N up to 32768.
+// dW[k, f] += sum_{b in slice} z[b, k] * dy[b, f]      (grid: f tiles x batch slices, grads pre-zeroed)
+__global__ void __launch_bounds__(256)
+lat_wgrad_kernel(View z, const float* __restrict__ dy, int B, int KZ, int N, float* __restrict__ dw) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= N) return;
+  const int bper = (B + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * bper, r1 = min(B, r0 + bper);
+  float acc[SK_NMAX];
+#pragma unroll
+  for (int k = 0; k < SK_NMAX; ++k) acc[k] = 0.f;
+  for (int b = r0; b < r1; ++b) {
+    const float dv = __ldg(dy + (size_t)b * N + f);
+    const float* zr = z.p + (size_t)b * z.ld + z.coff;
+#pragma unroll
     for (int k = 0; k < SK_NMAX; ++k)
-      if (k < K) dw[(size_t)k * N + n] = acc[k];
+      if (k < KZ) acc[k] = fmaf(__ldg(zr + k), dv, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < SK_NMAX; ++k)
+    if (k < KZ) atomicAdd(dw + (size_t)k * N + f, acc[k]);
+}
+
+// dz[b, k] (pre-zeroed window) += sum_{f in slice} dy[b, f] * W[k, f]
+__global__ void __launch_bounds__(256)
+lat_dz_kernel(const float* __restrict__ dy, const float* __restrict__ w, int KZ, int N, View dz) {
+  __shared__ float red[8][SK_NMAX];
+  const int b = blockIdx.x;
+  const int fper = (N + gridDim.y - 1) / gridDim.y;
+  const int f0 = blockIdx.y * fper, f1 = min(N, f0 + fper);
+  float acc[SK_NMAX];
+#pragma unroll
+  for (int k = 0; k < SK_NMAX; ++k) acc[k] = 0.f;
+  for (int f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+    const float dv = __ldg(dy + (size_t)b * N + f);
+#pragma unroll
+    for (int k = 0; k < SK_NMAX; ++k)
+      if (k < KZ) acc[k] = fmaf(dv, __ldg(w + (size_t)k * N + f), acc[k]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < SK_NMAX; ++k) {
+    if (k < KZ) {
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) red[wid][k] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < KZ) {
+    float v = 0.f;
+    for (int wi = 0; wi < 8; ++wi) v += red[wi][threadIdx.x];
+    atomicAdd(dz.p + (size_t)b * dz.ld + dz.coff + threadIdx.x, v);
   }
 }
 
@@ -389,28 +439,58 @@ int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
   return 0;
 }
 
-int skinny_fwd(const LaunchCtx& lc, View a, int B, int K, const float* w, int w_n_major, const float* bias, View out,
-               int N) {
-  dim3 grid(B, (N + SK_NMAX - 1) / SK_NMAX);
-  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * N, 4.0 * ((double)B * K + (double)K * N + (double)B * N));
-  skinny_fwd_kernel<<<grid, 256, 0, lc.stream>>>(a, K, w, w_n_major, bias, out, N);
+static int split_for(int rows_or_blocks, int sm_count, int max_split) {
+  int s = (2 * sm_count + rows_or_blocks - 1) / rows_or_blocks;
+  if (s < 1) s = 1;
+  if (s > max_split) s = max_split;
+  return s;
+}
+
+int heads_fwd(const LaunchCtx& lc, const float* flat, int B, int K, const HeadSet& hs, float* mu_pre, float* sd_pre, int Z) {
+  int ntot = 0;
+  for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
+  const int ks = split_for(B, lc.sm_count, (K + 2047) / 2048);
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
+  heads_fwd_kernel<<<dim3(B, ks), 256, 0, lc.stream>>>(flat, K, hs, mu_pre, sd_pre, Z);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int skinny_dgrad(const LaunchCtx& lc, View dout, int B, int N, const float* w, int K, View din, int accumulate) {
-  dim3 grid((K + 255) / 256, B);
-  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * N, 4.0 * ((double)B * K + (double)K * N + (double)B * N));
-  skinny_dgrad_kernel<<<grid, 256, N * sizeof(float), lc.stream>>>(dout, B, N, w, K, din, accumulate);
+int heads_dgrad(const LaunchCtx& lc, const HeadSet& hs, const float* dmu, const float* dsd, int B, int Z, int K,
+                float* d_flat) {
+  int ntot = 0;
+  for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
+  heads_dgrad_kernel<<<dim3((K + 255) / 256, B), 256, 0, lc.stream>>>(hs, dmu, dsd, Z, K, d_flat);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int skinny_wgrad(const LaunchCtx& lc, View a, View dout, int B, int K, int N, float* dw, float* dbias,
-                 int thread_over_n) {
-  int span = thread_over_n ? N : K;
-  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * N, 4.0 * ((double)B * K + (double)K * N + (double)B * N));
-  skinny_wgrad_kernel<<<(span + 255) / 256, 256, 0, lc.stream>>>(a, dout, B, K, N, dw, dbias, thread_over_n);
+int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const float* dmu, const float* dsd, int B, int Z,
+                int K) {
+  int ntot = 0;
+  for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
+  const int kb = (K + 255) / 256;
+  const int bs = split_for(kb, lc.sm_count, (B + 7) / 8);
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
+  heads_wgrad_kernel<<<dim3(kb, bs), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lat_wgrad(const LaunchCtx& lc, View z, const float* dy, int B, int KZ, int N, float* dw) {
+  const int fb = (N + 255) / 256;
+  const int bs = split_for(fb, lc.sm_count, (B + 7) / 8);
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * KZ * N, 4.0 * ((double)B * N + (double)KZ * N));
+  lat_wgrad_kernel<<<dim3(fb, bs), 256, 0, lc.stream>>>(z, dy, B, KZ, N, dw);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lat_dz(const LaunchCtx& lc, const float* dy, const float* w, int B, int KZ, int N, View dz) {
+  const int fs = split_for(B, lc.sm_count, (N + 2047) / 2048);
+  ProfScope ps(lc, KC_SKINNY, 2.0 * B * KZ * N, 4.0 * ((double)B * N + (double)KZ * N));
+  lat_dz_kernel<<<dim3(B, fs), 256, 0, lc.stream>>>(dy, w, KZ, N, dz);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -174,6 +174,74 @@ __device__ __forceinline__ uint4 load8(const float* __restrict__ px, int ch0, in
   return pack8_bf16(f);
 }
 
+// Raw (fp32) 8-channel group: loads are issued first for a whole batch of items so that several are in flight per thread.
+struct Raw8 { float4 a, b; };
+__device__ __forceinline__ Raw8 load8_raw(const float* __restrict__ px, int ch0, int valid, int vec) {
+  Raw8 r;
+  if (vec) {
+    r.a = __ldg(reinterpret_cast<const float4*>(px + ch0));
+    r.b = __ldg(reinterpret_cast<const float4*>(px + ch0) + 1);
+  } else {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (ch0 + e < valid) ? __ldg(px + ch0 + e) : 0.f;
+    r.a = make_float4(f[0], f[1], f[2], f[3]); r.b = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack_raw(const Raw8& r) {
+  const float f[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+  return pack8_bf16(f);
+}
+
+// Stage one halo (or plain 128-row tile when lo = hi = 0) of an NHWC fp32 tensor into the planar bf16 layout
+//   dst[(plane*J + j) * pitch + i*16]   for i in [0, HL), j in [0, J), plane in [0, nplanes)
+// q = q_first + i walks the padded pixel space (Hp x Wp per image, valid window Hv x Wv, `sm` = parity-plane stride).
+// 32-bit index math (Q < 2^31 is checked on the host) and 4 items per thread in flight.
+__device__ __forceinline__ void stage_halo(unsigned char* dst, unsigned pitch, const float* __restrict__ src, int ld, int coff,
+                                           int ch_base, int ch_valid, int vec, int HL, int J, int nplanes, int sm,
+                                           int q_first, int Q, int Hp, int Wp, int Hv, int Wv, int Hsrc, int Wsrc, int tid,
+                                           int nthreads) {
+  const int per_plane = HL * J;
+  const int items = per_plane * nplanes;
+  constexpr int U = 4;
+  for (int base = tid; base < items; base += nthreads * U) {
+    Raw8 raw[U];
+    unsigned off[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = base + u * nthreads;
+      ok[u] = false;
+      off[u] = 0;
+      if (it < items) {
+        const int pl = it / per_plane;
+        const int rem = it - pl * per_plane;
+        const int i = rem / J, j = rem - i * J;
+        off[u] = (unsigned)(pl * J + j) * pitch + (unsigned)i * 16u;
+        const int q = q_first + i;
+        if (q >= 0 && q < Q) {
+          const int t = q / Wp;
+          const int cc = q - t * Wp;
+          const int n = t / Hp;
+          const int r = t - n * Hp;
+          if (r < Hv && cc < Wv) {
+            const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
+            const float* px = src + ((size_t)(n * Hsrc + ih) * Wsrc + iw) * ld + coff;
+            raw[u] = load8_raw(px, ch_base + j * 8, ch_valid, vec);
+            ok[u] = true;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = base + u * nthreads;
+      if (it < items) *reinterpret_cast<uint4*>(dst + off[u]) = ok[u] ? pack_raw(raw[u]) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
 // 6 warps: 0-3 halo producers then epilogue, 4 weight loader (TMA bulk), 5 MMA issuer + TMEM allocator.
 // blockIdx.x = 128-row tile of the padded pixel space, blockIdx.y = 128-column tile of the output channels.
 __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ TcParams P) {
@@ -203,32 +271,13 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
 
   if (warp < 4) {
     // ================= halo producers: fp32 NHWC global -> bf16 planar smem (once per channel chunk) =================
-    const int per_plane = P.HL * P.JC;              // (pixel, 8-channel group) items per parity plane
-    const int items = per_plane * P.nplanes;
     const int sm = P.mode == 1 ? 2 : 1;
     for (int c = 0; c < P.NC; ++c) {
       const int buf = c % P.a_bufs;
       if (c >= P.a_bufs) mbar_wait(smem_u32(&hdr->a_free[buf]), ((c / P.a_bufs) - 1) & 1);
       unsigned char* abuf = a_smem + (size_t)buf * P.a_buf_bytes;
-      for (int it = tid; it < items; it += 128) {
-        const int pl = it / per_plane;
-        const int rem = it - pl * per_plane;
-        const int i = rem / P.JC, j = rem - i * P.JC;
-        const long long q = q0 - P.lo + i;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-        if (q >= 0 && q < P.Q) {
-          const int cc = (int)(q % P.Wp);
-          const long long t = q / P.Wp;
-          const int r = (int)(t % P.Hp);
-          const int n = (int)(t / P.Hp);
-          if (r < P.Hv && cc < P.Wv) {
-            const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
-            const float* px = P.in + (((size_t)n * P.Hin + ih) * P.Win + iw) * P.in_ld + P.in_coff;
-            packed = load8(px, c * P.KC + j * 8, P.cin_valid, P.in_vec);
-          }
-        }
-        *reinterpret_cast<uint4*>(abuf + (size_t)(pl * P.JC + j) * LBO_A + (size_t)i * 16) = packed;
-      }
+      stage_halo(abuf, LBO_A, P.in, P.in_ld, P.in_coff, c * P.KC, P.cin_valid, P.in_vec, P.HL, P.JC, P.nplanes, sm,
+                 (int)q0 - P.lo, (int)P.Q, P.Hp, P.Wp, P.Hv, P.Wv, P.Hin, P.Win, tid, 128);
       fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&hdr->a_ready[buf]));
     }
@@ -388,6 +437,33 @@ __global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat1
   }
 }
 
+__device__ __forceinline__ void pack_one(const Geom& g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                         int KC, int Cin_p, int N_p, long long e) {
+  const int JC = KC / 8;
+  const int ntaps = g.KH * g.KW;
+  const long long per_tile = (long long)128 * Cin_p * ntaps;
+  const int tile = (int)(e / per_tile);
+  long long t = e - tile * per_tile;
+  const int Nt = min(128, N_p - tile * 128);
+  const int k8 = (int)(t % 8); t /= 8;
+  const int n = (int)(t % Nt); t /= Nt;
+  const int j = (int)(t % JC); t /= JC;
+  const int s = (int)(t % ntaps); t /= ntaps;
+  const int c = (int)t;
+  const int ci = c * KC + j * 8 + k8, co = tile * 128 + n;
+  float v = 0.f;
+  if (ci < g.Cin && co < g.Cout)
+    v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + co] : w[((size_t)s * g.Cout + co) * g.Cin + ci];
+  out[e] = __float2bfloat16_rn(v);
+}
+
+// every tensor-core layer's operand copy in one launch: blockIdx.y = table entry
+__global__ void tc_pack_batched_kernel(const TcPackEntry* __restrict__ tab) {
+  const TcPackEntry E = tab[blockIdx.y];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E.total; e += (long long)gridDim.x * blockDim.x)
+    pack_one(E.g, E.w, reinterpret_cast<__nv_bfloat16*>(E.out), E.KC, E.Cin_p, E.N_p, e);
+}
+
 bool build_params(const Geom& g, TcParams& P) {
   memset(&P, 0, sizeof P);
   P.B = g.B; P.Hin = g.Hin; P.Win = g.Win; P.Hout = g.Hout; P.Wout = g.Wout;
@@ -439,6 +515,7 @@ bool build_params(const Geom& g, TcParams& P) {
   P.HL = TILE_M + P.lo + hi;
   P.HLpad = P.HL | 1;                               // odd plane pitch (in 16-byte units): conflict-free producer stores
   P.Q = (long long)g.B * P.Hp * P.Wp;
+  if (P.Q + TILE_M + P.HL >= (1ll << 31) || (long long)g.B * g.Hin * g.Win >= (1ll << 31)) return false;   // 32-bit pixel indices
   P.a_buf_bytes = (unsigned)(P.nplanes * P.JC * P.HLpad * 16);
   P.a_bufs = P.NC > 1 ? 2 : 1;
   const int nt_max = P.N_p < 128 ? P.N_p : 128;
@@ -517,50 +594,16 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
 
   if (warp < 4) {
     const int sm = P.mode == 1 ? 2 : 1;
-    const int per_plane = P.HL * P.JA;
-    const int x_items = per_plane * P.nplanes;
-    const int y_items = TILE_M * P.JN;
     for (long long it = 0; it < my_tiles; ++it) {
       const int buf = (int)(it % P.bufs);
       if (it >= P.bufs) mbar_wait(smem_u32(&hdr->free_[buf]), (unsigned)((it / P.bufs) - 1) & 1u);
       unsigned char* xb = bufs + (size_t)buf * stage_bytes;
       unsigned char* yb = xb + P.x_buf_bytes;
       const long long q0 = ((long long)blockIdx.x + it * gridDim.x) * TILE_M;
-      for (int e = tid; e < x_items; e += 128) {
-        const int pl = e / per_plane;
-        const int rem = e - pl * per_plane;
-        const int i = rem / P.JA, j = rem - i * P.JA;
-        const long long q = q0 - P.lo + i;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-        if (q >= 0 && q < P.Q) {
-          const int cc = (int)(q % P.Wp);
-          const long long t = q / P.Wp;
-          const int r = (int)(t % P.Hp);
-          const int n = (int)(t / P.Hp);
-          if (r < P.Hv && cc < P.Wv) {
-            const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
-            const float* px = P.x + (((size_t)n * P.Hx + ih) * P.Wx + iw) * P.x_ld + P.x_coff;
-            packed = load8(px, a0 + j * 8, P.Ca, P.x_vec);
-          }
-        }
-        *reinterpret_cast<uint4*>(xb + (size_t)(pl * P.JA + j) * PITCH_X + (size_t)i * 16) = packed;
-      }
-      for (int e = tid; e < y_items; e += 128) {
-        const int i = e / P.JN, j = e - i * P.JN;
-        const long long q = q0 + i;
-        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-        if (q < P.Q) {
-          const int cc = (int)(q % P.Wp);
-          const long long t = q / P.Wp;
-          const int r = (int)(t % P.Hp);
-          const int n = (int)(t / P.Hp);
-          if (r < P.Hv && cc < P.Wv) {
-            const float* px = P.dy + (((size_t)n * P.Hy + r) * P.Wy + cc) * P.dy_ld + P.dy_coff;
-            packed = load8(px, b0 + j * 8, P.Cb, P.dy_vec);
-          }
-        }
-        *reinterpret_cast<uint4*>(yb + (size_t)j * PITCH_Y + (size_t)i * 16) = packed;
-      }
+      stage_halo(xb, PITCH_X, P.x, P.x_ld, P.x_coff, a0, P.Ca, P.x_vec, P.HL, P.JA, P.nplanes, sm, (int)q0 - P.lo, (int)P.Q,
+                 P.Hp, P.Wp, P.Hv, P.Wv, P.Hx, P.Wx, tid, 128);
+      stage_halo(yb, PITCH_Y, P.dy, P.dy_ld, P.dy_coff, b0, P.Cb, P.dy_vec, TILE_M, P.JN, 1, 1, (int)q0, (int)P.Q, P.Hp, P.Wp,
+                 P.Hv, P.Wv, P.Hy, P.Wy, tid, 128);
       fence_proxy_async();
       mbar_arrive(smem_u32(&hdr->ready[buf]));
     }
@@ -656,6 +699,7 @@ bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
   P.HLpad = P.HL | 1;
   P.YLpad = TILE_M | 1;
   P.Q = (long long)g.B * P.Hp * P.Wp;
+  if (P.Q + TILE_M + P.HL >= (1ll << 31) || (long long)g.B * g.Hin * g.Win >= (1ll << 31)) return false;
   P.tiles = (P.Q + TILE_M - 1) / TILE_M;
   P.taps_per_cta = 512 / P.N; if (P.taps_per_cta > 16) P.taps_per_cta = 16;
   P.ngroups = 16 / P.taps_per_cta;
@@ -697,6 +741,22 @@ int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_
   if (blocks > lc.sm_count * 8) blocks = lc.sm_count * 8;
   ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total);
   tc_pack_kernel<<<blocks, 256, 0, lc.stream>>>(g, w, reinterpret_cast<__nv_bfloat16*>(w_packed), pick_kc(Cin_p), Cin_p, N_p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed) {
+  TcPackEntry e;
+  e.g = g; e.w = w; e.out = w_packed;
+  e.Cin_p = round16(g.Cin); e.N_p = round16(g.Cout); e.KC = pick_kc(e.Cin_p);
+  e.total = (long long)g.KH * g.KW * e.Cin_p * e.N_p;
+  return e;
+}
+
+int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double total_elems) {
+  if (n <= 0) return 0;
+  ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total_elems);
+  tc_pack_batched_kernel<<<dim3(32, (unsigned)n), 256, 0, lc.stream>>>(reinterpret_cast<const TcPackEntry*>(dev_entries));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

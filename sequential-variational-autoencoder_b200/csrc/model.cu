@@ -157,6 +157,7 @@ struct svae_handle {
   size_t io_steps_elems = 0;
   // tcgen05 packed weights
   char* pack_base = nullptr; size_t pack_bytes = 0;
+  void* pack_table = nullptr; int pack_entries = 0;
   int tc_layers = 0;
   // last forward
   int last_B = 0; float last_reg = 1.f; bool have_fwd = false;
@@ -396,7 +397,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       float* a = act.get<float>((size_t)B * b.rpi * b.feats);
       b.out = fv4(a, b.feats, 0, b.feats);
     }
-    s.mu_pre = act.get<float>((size_t)B * Z); s.sd_pre = act.get<float>((size_t)B * Z);
+    s.mu_pre = act.get<float>(2 * (size_t)B * Z); s.sd_pre = s.mu_pre + (size_t)B * Z;   // one block: zeroed together
     s.mu = act.get<float>((size_t)B * Z); s.sd = act.get<float>((size_t)B * Z);
     s.z = act.get<float>((size_t)B * Z); s.eps = act.get<float>((size_t)B * Z);
     // decoder concat buffers first (encoder / projections write into them)
@@ -530,8 +531,9 @@ int skinny_block_bwd(svae_handle* h, Block& b, int B, FeatView da, View zin, int
   H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, FeatView{}, dy, b.S, nullptr, 0));
   H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, B, b.feats, h->pg(b.beta)));
   View dyv = mkview(dy, b.feats, 0);
-  H_TRY(skinny_wgrad(lc, zin, dyv, B, K, b.feats, h->pg(b.w), nullptr, 1));
-  H_TRY(skinny_fwd(lc, dyv, B, b.feats, h->pw(b.w), 1, nullptr, dz_out, K));
+  (void)dyv;
+  H_TRY(lat_wgrad(lc, zin, dy, B, K, b.feats, h->pg(b.w)));
+  H_TRY(lat_dz(lc, dy, h->pw(b.w), B, K, b.feats, dz_out));   // d_z is zeroed at the start of the step's backward
   return 0;
 }
 
@@ -580,9 +582,23 @@ int decoder_fwd(svae_handle* h, Step& s, int B, const float* z, const float* xpr
   return 0;
 }
 
+HeadSet make_headset(svae_handle* h, Step& s, int l) {
+  HeadSet hs{};
+  hs.nheads = (int)s.heads[l].size();
+  for (int i = 0; i < hs.nheads; ++i) {
+    const Head& hd = s.heads[l][i];
+    hs.w[i] = h->pw(hd.w); hs.b[i] = h->pw(hd.b);
+    hs.gw[i] = h->G ? h->pg(hd.w) : nullptr; hs.gb[i] = h->G ? h->pg(hd.b) : nullptr;
+    hs.n[i] = hd.n; hs.col[i] = hd.col; hs.is_sd[i] = hd.is_sd;
+  }
+  return hs;
+}
+
 int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float* eps, uint64_t seed, double* kl_sum) {
   const int L = h->L;
   LaunchCtx lc = h->lc();
+  // the heads accumulate into mu_pre / sd_pre (adjacent in the arena) with atomics
+  H_CUDA(cudaMemsetAsync(s.mu_pre, 0, sizeof(float) * 2 * (size_t)h->cfg.max_batch * h->Z, h->stream));
   View cur = mkview(const_cast<float*>(x), h->C, 0);
   for (int k = 0; k < 2 * (L - 1); ++k) {
     H_TRY(block_fwd(h, s.inf[k], B, cur));
@@ -590,9 +606,8 @@ int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float*
     if (k & 1) {
       const int l = k / 2;
       const int K = s.inf[k].rpi * s.inf[k].feats;
-      for (const Head& hd : s.heads[l])
-        H_TRY(skinny_fwd(lc, mkview(cur.p, K, 0), B, K, h->pw(hd.w), 0, h->pw(hd.b),
-                         mkview(hd.is_sd ? s.sd_pre : s.mu_pre, h->Z, hd.col), hd.n));
+      HeadSet hs = make_headset(h, s, l);
+      H_TRY(heads_fwd(lc, cur.p, B, K, hs, s.mu_pre, s.sd_pre, h->Z));
     }
   }
   ReparamParams rp{B, h->Z, h->cfg.latent_mean_clip, h->cfg.prior_stddev};
@@ -647,6 +662,7 @@ int decoder_bwd(svae_handle* h, Step& s, int B, const float* gx_in, float* gx_pr
   (void)T;
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
+  H_CUDA(cudaMemsetAsync(h->d_z, 0, sizeof(float) * (size_t)B * h->Z, h->stream));   // lat_dz accumulates with atomics
   H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
                     coef, h->d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr));
   // output deconvs: dgrad into d_c[0], wgrads
@@ -730,15 +746,9 @@ int recognition_bwd(svae_handle* h, Step& s, int B, float reg) {
   for (int l = 0; l < L - 1; ++l) {
     const Block& fb = s.inf[2 * l + 1];
     const int K = fb.rpi * fb.feats;
-    View flat = mkview(fb.out.p, K, 0);
-    View d_flat = mkview(h->d_inf[2 * l + 1], K, 0);
-    int first = 1;
-    for (const Head& hd : s.heads[l]) {
-      View dout = mkview(hd.is_sd ? h->d_sd_pre : h->d_mu_pre, h->Z, hd.col);
-      H_TRY(skinny_dgrad(lc, dout, B, hd.n, h->pw(hd.w), K, d_flat, first ? 0 : 1));
-      H_TRY(skinny_wgrad(lc, flat, dout, B, K, hd.n, h->pg(hd.w), h->pg(hd.b), 0));
-      first = 0;
-    }
+    HeadSet hs = make_headset(h, s, l);
+    H_TRY(heads_dgrad(lc, hs, h->d_mu_pre, h->d_sd_pre, B, h->Z, K, h->d_inf[2 * l + 1]));
+    H_TRY(heads_wgrad(lc, fb.out.p, hs, h->d_mu_pre, h->d_sd_pre, B, h->Z, K));
   }
   for (int k = 2 * (L - 1) - 1; k >= 0; --k) {
     Block& b = s.inf[k];
@@ -859,21 +869,25 @@ void plan_pack(svae_handle* h, Block& b, void* ctx) {
   }
 }
 
-struct PackCtx { int rc; };
-void do_pack(svae_handle* h, Block& b, void* ctx) {
-  PackCtx* pc = (PackCtx*)ctx;
-  if (pc->rc != 0) return;
-  LaunchCtx lc = h->lc();
-  if (b.tc_fwd) { Geom f = b.g; f.B = 1; pc->rc = tc_pack_weights(lc, f, h->pw(b.w), b.w_packed); }
-  if (pc->rc == 0 && b.tc_dgrad) { Geom d = dgrad_geom(b.g); d.B = 1; pc->rc = tc_pack_weights(lc, d, h->pw(b.w), b.w_packed_d); }
+void collect_pack(svae_handle* h, Block& b, void* ctx) {
+  std::vector<TcPackEntry>* v = (std::vector<TcPackEntry>*)ctx;
+  if (b.tc_fwd) { Geom f = b.g; f.B = 1; v->push_back(tc_pack_entry(f, h->pw(b.w), b.w_packed)); }
+  if (b.tc_dgrad) { Geom d = dgrad_geom(b.g); d.B = 1; v->push_back(tc_pack_entry(d, h->pw(b.w), b.w_packed_d)); }
 }
 
+// fp32 master weights -> packed bf16 operand copies of every tensor-core layer, ONE launch
 int repack_if_dirty(svae_handle* h) {
   if (!h->weights_dirty) return 0;
   if (h->cfg.operand_dtype == SVAE_OPERAND_BF16 && h->pack_bytes > 0) {
-    PackCtx pc{0};
-    for_each_block(h, do_pack, &pc);
-    if (pc.rc != 0) { h->err = g_err; return pc.rc; }
+    if (h->pack_table == nullptr) {
+      std::vector<TcPackEntry> v;
+      for_each_block(h, collect_pack, &v);
+      h->pack_entries = (int)v.size();
+      H_CUDA(cudaMalloc(&h->pack_table, sizeof(TcPackEntry) * v.size()));
+      H_CUDA(cudaMemcpy(h->pack_table, v.data(), sizeof(TcPackEntry) * v.size(), cudaMemcpyHostToDevice));
+    }
+    LaunchCtx lc = h->lc();
+    H_TRY(tc_pack_batched(lc, h->pack_table, h->pack_entries, (double)h->pack_bytes / 2));
   }
   h->weights_dirty = false;
   return 0;
@@ -887,7 +901,7 @@ void destroy_impl(svae_handle* h) {
   for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
   if (h->comm_done) cudaEventDestroy(h->comm_done);
   cudaFree(h->P); cudaFree(h->G); cudaFree(h->M); cudaFree(h->V);
-  cudaFree(h->act_base); cudaFree(h->zf_base); cudaFree(h->zb_base); cudaFree(h->grad_base); cudaFree(h->pack_base);
+  cudaFree(h->act_base); cudaFree(h->zf_base); cudaFree(h->zb_base); cudaFree(h->grad_base); cudaFree(h->pack_base); cudaFree(h->pack_table);
   cudaFree(h->io_steps); cudaFree(h->loss_sums);
   if (h->loss_host) cudaFreeHost(h->loss_host);
   if (h->pin_x) cudaFreeHost(h->pin_x);

@@ -203,11 +203,11 @@ def test_loss_flags():
     model, hp, P = make_pair("c_inhomog", [16, 16, 3], (-1.0, 1.0), 4, "fp32", **over)
     hp["regularized_steps"] = [0, 2]
     x, eps = make_inputs(hp, 4)
-    fw, grads = O.loss_and_grads(hp, P, x, x, eps, 0.8)
+    fw, grads, fw32, g32 = _oracle_pair(hp, P, x, x, eps, 0.8)
     out = model.forward(x.numpy(), None, eps.numpy(), 0.8)
-    _check_forward(out, fw, "fp32")
+    _check_forward(out, fw, "fp32", fw32)
     model.backward()
-    _check_grads(model, grads, hp, "fp32")
+    _check_grads(model, grads, hp, "fp32", g32)
     model.close()
 
 
