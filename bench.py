@@ -155,6 +155,10 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL's version banner, ...) that write to fd 1 go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

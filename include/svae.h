@@ -211,6 +211,8 @@ int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const floa
  * (it then runs on the fp32 SIMT kernels).  transposed: 0 conv, 1 transposed conv, 2 fully connected (Ci -> Co, H = W = 1);
  * direction: 0 forward, 1 input gradient, 2 weight gradient. */
 int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int stride, int direction);
+/* Development aid: when non-NULL, the tcgen05 conv kernel writes per-CTA phase timestamps ([cta][8] uint64 ns) here. */
+int svae_debug_set_buffer(void* dev_buffer);
 /* batch_norm (training mode, no gamma, eps 1e-3) + activation (0 none, 1 lrelu(0.1), 2 relu), rows x channels */
 int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act);
 /* fused clip + TF-Adam on n elements (sequential_vae.py:1275-1276) */

@@ -30,6 +30,7 @@ struct TcParams {
   const __nv_bfloat16* wp;
   float* out; int out_ld, out_coff, n_valid, out_vec;
   double* stats;
+  unsigned long long* dbg;   // optional per-CTA phase timestamps (globaltimer ns): [cta][8]
   int B, Hin, Win, Hout, Wout;
   int Cin_p, N_p;   // channel counts padded to multiples of 16 (zero weights / zero activations in the padding)
   int mode;         // 0: stride-1 window (or 1x1 = fully connected), 1: stride-2 gather (4 parity planes), 2: stride-2 phases
@@ -37,6 +38,7 @@ struct TcParams {
   int lo, HL, HLpad;
   int KC, NC, JC;   // channels per chunk, number of chunks, 8-channel groups per chunk
   int nplanes, nacc, ntaps;
+  int tps;          // taps per weight stage (one bulk copy brings tps consecutive taps of one channel chunk)
   int accumulate;
   long long Q;      // padded positions
   int stages, a_bufs;
@@ -66,10 +68,25 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must become a trap (reported CUDA error), never a hung GPU.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+#ifdef SVAE_MBAR_POLL
+  for (unsigned it = 0; !mbar_test_wait(bar, parity); ++it) {
+    if (it > (1u << 28)) __trap();
+  }
+#else
   for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it)
     if (it > (1u << 26)) __trap();
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -150,7 +167,24 @@ struct SmemHeader {
   unsigned tmem_base;
   unsigned pad;
   float s_sum[4][128], s_sq[4][128];   // per-warp partial column statistics of one accumulator
+  volatile unsigned long long ts[16];  // debug timestamps
+  volatile unsigned long long tl[128]; // debug: per producer thread, time after its arrive
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+#ifdef SVAE_DBG_CLOCK64
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+#else
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#endif
+  return t;
+}
+// timestamps go to shared memory while the kernel runs (a global store ahead of fence.proxy.async would stall it) and are
+// flushed to global once at the very end
+// (executed by the whole warp, lane 0's store is predicated: an `if (tid == 0)` wrapper would split lane 0 from its warp
+//  and serialise the two groups through everything that follows)
+#define DBG_MARK(slot) do { if (P.dbg != nullptr) { const unsigned long long t_ = gtimer(); if ((threadIdx.x & 31) == 0) hdr->ts[slot] = t_; } } while (0)
 
 __device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
   __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -204,47 +238,46 @@ __device__ __forceinline__ void stage_halo(unsigned char* dst, unsigned pitch, c
                                            int nthreads) {
   const int per_plane = HL * J;
   const int items = per_plane * nplanes;
-  constexpr int U = 4;
+  // Branch-free body: every lane computes a (clamped, always legal) address and a validity flag, ALL loads of the batch
+  // are issued before the first use, invalid items are zeroed by a select.  Divergent "valid / zero" paths would make
+  // the two lane groups of a warp run the loop one after the other.
+  constexpr int U = 8;
   for (int base = tid; base < items; base += nthreads * U) {
     Raw8 raw[U];
     unsigned off[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int it = base + u * nthreads;
-      ok[u] = false;
-      off[u] = 0;
-      if (it < items) {
-        const int pl = it / per_plane;
-        const int rem = it - pl * per_plane;
-        const int i = rem / J, j = rem - i * J;
-        off[u] = (unsigned)(pl * J + j) * pitch + (unsigned)i * 16u;
-        const int q = q_first + i;
-        if (q >= 0 && q < Q) {
-          const int t = q / Wp;
-          const int cc = q - t * Wp;
-          const int n = t / Hp;
-          const int r = t - n * Hp;
-          if (r < Hv && cc < Wv) {
-            const int ih = r * sm + (pl >> 1), iw = cc * sm + (pl & 1);
-            const float* px = src + ((size_t)(n * Hsrc + ih) * Wsrc + iw) * ld + coff;
-            raw[u] = load8_raw(px, ch_base + j * 8, ch_valid, vec);
-            ok[u] = true;
-          }
-        }
-      }
+      const int it = min(base + u * nthreads, items - 1);
+      const int pl = it / per_plane;
+      const int rem = it - pl * per_plane;
+      const int i = rem / J, j = rem - i * J;
+      off[u] = (unsigned)(pl * J + j) * pitch + (unsigned)i * 16u;
+      const int q = q_first + i;
+      const int qc = min(max(q, 0), Q - 1);
+      const int t = qc / Wp;
+      const int cc = qc - t * Wp;
+      const int n = t / Hp;
+      const int r = t - n * Hp;
+      ok[u] = (q >= 0) & (q < Q) & (r < Hv) & (cc < Wv);
+      const int ih = min(r, Hv - 1) * sm + (pl >> 1), iw = min(cc, Wv - 1) * sm + (pl & 1);
+      const float* px = src + ((size_t)(n * Hsrc + ih) * Wsrc + iw) * ld + coff;
+      raw[u] = load8_raw(px, ch_base + j * 8, ch_valid, vec);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int it = base + u * nthreads;
-      if (it < items) *reinterpret_cast<uint4*>(dst + off[u]) = ok[u] ? pack_raw(raw[u]) : make_uint4(0u, 0u, 0u, 0u);
+      if (base + u * nthreads < items) {
+        uint4 v = pack_raw(raw[u]);
+        if (!ok[u]) v = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst + off[u]) = v;
+      }
     }
   }
 }
 
 // 6 warps: 0-3 halo producers then epilogue, 4 weight loader (TMA bulk), 5 MMA issuer + TMEM allocator.
 // blockIdx.x = 128-row tile of the padded pixel space, blockIdx.y = 128-column tile of the output channels.
-__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(192, 3) tc_conv_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
   unsigned char* b_smem = smem_raw + ((sizeof(SmemHeader) + 127) & ~127u);
@@ -253,8 +286,10 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long q0 = (long long)blockIdx.x * TILE_M;
   const int n0 = blockIdx.y * 128;
+  if (warp == 0) DBG_MARK(0);
   const int Nt = min(128, P.N_p - n0);               // this CTA's MMA N (multiple of 16)
-  const unsigned b_stage_bytes = (unsigned)(P.KC * Nt * 2);
+  const unsigned b_tap_bytes = (unsigned)(P.KC * Nt * 2);
+  const unsigned b_stage_bytes = b_tap_bytes * (unsigned)P.tps;
 
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(smem_u32(&hdr->full_b[s]), 1); mbar_init(smem_u32(&hdr->empty_b[s]), 1); }
@@ -268,6 +303,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
   tc_fence_after();
   const unsigned tmem_base = hdr->tmem_base;
   const unsigned LBO_A = (unsigned)P.HLpad * 16u;   // bytes between consecutive 8-channel planes of the halo
+  if (warp == 0) DBG_MARK(1);
 
   if (warp < 4) {
     // ================= halo producers: fp32 NHWC global -> bf16 planar smem (once per channel chunk) =================
@@ -278,13 +314,24 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
       unsigned char* abuf = a_smem + (size_t)buf * P.a_buf_bytes;
       stage_halo(abuf, LBO_A, P.in, P.in_ld, P.in_coff, c * P.KC, P.cin_valid, P.in_vec, P.HL, P.JC, P.nplanes, sm,
                  (int)q0 - P.lo, (int)P.Q, P.Hp, P.Wp, P.Hv, P.Wv, P.Hin, P.Win, tid, 128);
+      if (warp == 0) DBG_MARK(14);
+#ifndef SVAE_NO_PROXY_FENCE
       fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+#endif
+#ifdef SVAE_NAMED_BAR
+      asm volatile("bar.arrive 2, 160;" ::: "memory");   // producers (128) arrive, the MMA warp (32) syncs
+#else
       mbar_arrive(smem_u32(&hdr->a_ready[buf]));
+#endif
     }
+    if (warp == 0) DBG_MARK(2);
+    DBG_MARK(8 + warp);
+    if (P.dbg != nullptr) hdr->tl[tid] = gtimer();
 
     // ================= epilogue: TMEM -> registers -> global (+ batch-norm statistics) =================
     mbar_wait(smem_u32(&hdr->acc_done), 0);
     tc_fence_after();
+    if (warp == 0) DBG_MARK(3);
     const int m = warp * 32 + lane;                 // accumulator row == TMEM lane
     const long long q = q0 + m;
     bool valid = q < P.Q;
@@ -344,6 +391,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
       }
     }
     tc_fence_before();
+    if (warp == 0) DBG_MARK(4);
     if (P.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
       for (int col = tid; col < Nt; col += 128) {
@@ -357,56 +405,75 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
     }
   } else if (warp == 4) {
     // ================= weight loader: one bulk copy per (channel chunk, tap) through the stage ring =================
-    if (lane == 0) {
-      int stage = 0; unsigned phase = 0;
-      // packed weights: [n tile][chunk][tap][8-channel group][n][8]; every full tile holds 128*Cin_p*ntaps elements
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2;
-      for (int c = 0; c < P.NC; ++c)
-        for (int s = 0; s < P.ntaps; ++s) {
-          mbar_wait(smem_u32(&hdr->empty_b[stage]), phase ^ 1);
+    // (the whole warp walks the ring and waits converged; one lane issues - a lone lane spinning while its 31
+    //  siblings sit in the final bar.sync is scheduled poorly)
+    int stage = 0; unsigned phase = 0;
+    // packed weights: [n tile][chunk][tap][8-channel group][n][8]; every full tile holds 128*Cin_p*ntaps elements
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2;
+    for (int c = 0; c < P.NC; ++c)
+      for (int s = 0; s < P.ntaps; s += P.tps) {
+        mbar_wait(smem_u32(&hdr->empty_b[stage]), phase ^ 1);
+        if (lane == 0) {
           mbar_expect_tx(smem_u32(&hdr->full_b[stage]), b_stage_bytes);
-          bulk_g2s(smem_u32(b_smem + (size_t)stage * P.b_stage_max), wsrc + ((size_t)c * P.ntaps + s) * b_stage_bytes,
+          bulk_g2s(smem_u32(b_smem + (size_t)stage * P.b_stage_max), wsrc + ((size_t)c * P.ntaps + s) * b_tap_bytes,
                    b_stage_bytes, smem_u32(&hdr->full_b[stage]));
-          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-    }
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+      }
   } else {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      const unsigned idesc = make_idesc(TILE_M, Nt);
-      const unsigned LBO_B = (unsigned)Nt * 16u;
-      int stage = 0; unsigned phase = 0;
-      unsigned started = 0;                           // bit a set once accumulator a has been written
-      for (int c = 0; c < P.NC; ++c) {
-        const int buf = c % P.a_bufs;
-        mbar_wait(smem_u32(&hdr->a_ready[buf]), (c / P.a_bufs) & 1);
-        const unsigned abase = smem_u32(a_smem + (size_t)buf * P.a_buf_bytes);
-        for (int s = 0; s < P.ntaps; ++s) {
-          mbar_wait(smem_u32(&hdr->full_b[stage]), phase);
-          tc_fence_after();
-          const unsigned bbase = smem_u32(b_smem + (size_t)stage * P.b_stage_max);
-          const int a = P.acc[s];
-          const unsigned d_tmem = tmem_base + (unsigned)(a * Nt);
-          const unsigned arow = abase + (unsigned)(P.plane[s] * P.JC) * LBO_A + (unsigned)(P.lo + P.shift[s]) * 16u;
-          for (int kk = 0; kk < P.KC / 16; ++kk) {
-            const unsigned long long adesc = make_desc(arow + (unsigned)(2 * kk) * LBO_A, LBO_A, 128u);
-            const unsigned long long bdesc = make_desc(bbase + (unsigned)(2 * kk) * LBO_B, LBO_B, 128u);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (started >> a) & 1u);
-            started |= 1u << a;
+    // ================= MMA issuer (warp converged on the waits, one elected lane issues) =================
+    const unsigned idesc = make_idesc(TILE_M, Nt);
+    const unsigned LBO_B = (unsigned)Nt * 16u;
+    int stage = 0; unsigned phase = 0;
+    unsigned started = 0;                           // bit a set once accumulator a has been written
+    DBG_MARK(12);
+    for (int c = 0; c < P.NC; ++c) {
+      const int buf = c % P.a_bufs;
+#ifdef SVAE_NAMED_BAR
+      asm volatile("bar.sync 2, 160;" ::: "memory");
+#else
+      mbar_wait(smem_u32(&hdr->a_ready[buf]), (c / P.a_bufs) & 1);
+#endif
+      if (c == 0) DBG_MARK(6);
+      const unsigned abase = smem_u32(a_smem + (size_t)buf * P.a_buf_bytes);
+      for (int s0 = 0; s0 < P.ntaps; s0 += P.tps) {
+        mbar_wait(smem_u32(&hdr->full_b[stage]), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int tl = 0; tl < P.tps; ++tl) {
+            const int s = s0 + tl;
+            const unsigned bbase = smem_u32(b_smem + (size_t)stage * P.b_stage_max) + (unsigned)tl * b_tap_bytes;
+            const int a = P.acc[s];
+            const unsigned d_tmem = tmem_base + (unsigned)(a * Nt);
+            const unsigned arow = abase + (unsigned)(P.plane[s] * P.JC) * LBO_A + (unsigned)(P.lo + P.shift[s]) * 16u;
+            for (int kk = 0; kk < P.KC / 16; ++kk) {
+              const unsigned long long adesc = make_desc(arow + (unsigned)(2 * kk) * LBO_A, LBO_A, 128u);
+              const unsigned long long bdesc = make_desc(bbase + (unsigned)(2 * kk) * LBO_B, LBO_B, 128u);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (started >> a) & 1u);
+              started |= 1u << a;
+            }
           }
           umma_commit(smem_u32(&hdr->empty_b[stage]));   // frees the weight stage once these MMAs have read it
-          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&hdr->a_free[buf]));         // halo buffer reusable
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(smem_u32(&hdr->acc_done));
+      if (lane == 0) umma_commit(smem_u32(&hdr->a_free[buf]));   // halo buffer reusable
+      __syncwarp();
     }
+    if (lane == 0) umma_commit(smem_u32(&hdr->acc_done));
+    __syncwarp();
+    DBG_MARK(7);
   }
   __syncthreads();
+  if (warp == 0) DBG_MARK(5);
   if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, P.tmem_cols);
   }
+  if (P.dbg != nullptr && tid < 16) P.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + tid] = hdr->ts[tid];
+  if (P.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid < 128) P.dbg[8192 * 16 + tid] = hdr->tl[tid] - hdr->ts[1];
 }
 
 static inline int round16(int v) { return (v + 15) / 16 * 16; }
@@ -519,12 +586,22 @@ bool build_params(const Geom& g, TcParams& P) {
   P.a_buf_bytes = (unsigned)(P.nplanes * P.JC * P.HLpad * 16);
   P.a_bufs = P.NC > 1 ? 2 : 1;
   const int nt_max = P.N_p < 128 ? P.N_p : 128;
-  P.b_stage_max = (unsigned)(P.KC * nt_max * 2);
-  // as many weight stages as fit next to the halo buffers (at least 2)
-  P.stages = MAX_STAGES;
+  // Weight stages: one bulk copy brings `tps` consecutive taps (<= 32 KB), so that small layers get all their weights in
+  // one or two copies instead of 16 latency-bound round trips; <= 64 KB of weight stages keeps >= 2 CTAs per SM.
+  const unsigned tap_bytes = (unsigned)(P.KC * nt_max * 2);
+  P.tps = 1;
+  while (P.tps * 2 <= P.ntaps && (unsigned)(P.tps * 2) * tap_bytes <= 32 * 1024) P.tps *= 2;
+  P.b_stage_max = tap_bytes * (unsigned)P.tps;
   {
+    const int loads = P.NC * (P.ntaps / P.tps);
+    int st = (int)((64 * 1024) / P.b_stage_max);
+    if (st < 2) st = 2;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st > loads) st = loads;
+    P.stages = st;
     const size_t fixed = ((sizeof(SmemHeader) + 127) & ~(size_t)127) + (size_t)P.a_bufs * P.a_buf_bytes + 128;
-    while (P.stages > 2 && fixed + (size_t)P.stages * P.b_stage_max > 227 * 1024) --P.stages;
+    while (P.stages > 1 && fixed + (size_t)P.stages * P.b_stage_max > 227 * 1024) --P.stages;
+    if (fixed + (size_t)P.stages * P.b_stage_max > 227 * 1024) return false;
   }
   unsigned cols = (unsigned)(P.nacc * nt_max), t = 32;
   while (t < cols) t <<= 1;
@@ -633,13 +710,13 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
     }
     tc_fence_before();
   } else {
-    if (lane == 0) {
-      const unsigned idesc = make_idesc_mn(TILE_M, P.N);
-      unsigned started = 0;
-      for (long long it = 0; it < my_tiles; ++it) {
-        const int buf = (int)(it % P.bufs);
-        mbar_wait(smem_u32(&hdr->ready[buf]), (unsigned)(it / P.bufs) & 1u);
-        tc_fence_after();
+    const unsigned idesc = make_idesc_mn(TILE_M, P.N);
+    unsigned started = 0;
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it % P.bufs);
+      mbar_wait(smem_u32(&hdr->ready[buf]), (unsigned)(it / P.bufs) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
         const unsigned xb = smem_u32(bufs + (size_t)buf * stage_bytes);
         const unsigned yb = xb + P.x_buf_bytes;
         for (int tl = 0; tl < P.taps_per_cta; ++tl) {
@@ -656,8 +733,10 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
         }
         umma_commit(smem_u32(&hdr->free_[buf]));
       }
-      umma_commit(smem_u32(&hdr->acc_done));
+      __syncwarp();
     }
+    if (lane == 0) umma_commit(smem_u32(&hdr->acc_done));
+    __syncwarp();
   }
   __syncthreads();
   if (warp == 4) {
@@ -719,6 +798,8 @@ bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
 
 }  // namespace
 
+void* g_tc_debug_buffer = nullptr;   // set through svae_debug_set_buffer (scripts/diag_phases.py only)
+
 bool tc_supported(const Geom& g) {
   const bool conv = g.KH == 4 && g.KW == 4 && g.pad == 1 && (g.stride == 1 || g.stride == 2);
   const bool fc = g.KH == 1 && g.KW == 1 && g.Hin == 1 && g.Win == 1;
@@ -770,6 +851,7 @@ int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_pa
   P.out = out.p; P.out_ld = out.ld; P.out_coff = out.coff;
   P.out_vec = (out.ld % 4 == 0) && (out.coff % 4 == 0) && (((uintptr_t)out.p & 15) == 0) && (g.Cout % 4 == 0);
   P.stats = stats;
+  P.dbg = reinterpret_cast<unsigned long long*>(g_tc_debug_buffer);
   const size_t smem = smem_bytes(P);
   static bool configured = false;
   if (!configured) {

@@ -1364,6 +1364,9 @@ int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const floa
   }
   return 0;
 }
+extern void* g_tc_debug_buffer;
+int svae_debug_set_buffer(void* dev_buffer) { g_tc_debug_buffer = dev_buffer; return 0; }
+
 int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int stride, int direction) {
   Geom f = transposed == 2 ? fc_geom(Ci, Co) : transposed ? deconv_geom(H, W, Ci, Co, stride) : conv_geom(H, W, Ci, Co, stride);
   f.B = 1;
