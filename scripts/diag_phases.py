@@ -21,8 +21,6 @@ def run(kind, H, Ci, Co, stride):
         assert fn(h, ptr(x), ptr(w), ptr(y), ptr(stats), B, H, H, Ci, Co, stride, 1) == 0
         m.sync()
     L.svae_debug_set_buffer(None)
-    tl = dbg.cpu().numpy()[8192 * 16:]
-    print("   per-thread arrive times (CTA 0, us):", " ".join("%.1f" % (v / 1e3) for v in tl[:64]))
     d = dbg.cpu().numpy()[:8192 * 16].reshape(-1, 16)
     d = d[d[:, 0] > 0]
     t0 = d[:, 0].min()

@@ -168,7 +168,8 @@ struct SmemHeader {
   unsigned pad;
   float s_sum[4][128], s_sq[4][128];   // per-warp partial column statistics of one accumulator
   volatile unsigned long long ts[16];  // debug timestamps
-  volatile unsigned long long tl[128]; // debug: per producer thread, time after its arrive
+  unsigned tap_a_lo[16];               // per tap: low word of the A descriptor (start address of the shifted window >> 4)
+  unsigned tap_dtmem[16];              // per tap: TMEM address of its accumulator
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -326,7 +327,6 @@ __global__ void __launch_bounds__(192, 3) tc_conv_kernel(const __grid_constant__
     }
     if (warp == 0) DBG_MARK(2);
     DBG_MARK(8 + warp);
-    if (P.dbg != nullptr) hdr->tl[tid] = gtimer();
 
     // ================= epilogue: TMEM -> registers -> global (+ batch-norm statistics) =================
     mbar_wait(smem_u32(&hdr->acc_done), 0);
@@ -423,36 +423,52 @@ __global__ void __launch_bounds__(192, 3) tc_conv_kernel(const __grid_constant__
       }
   } else {
     // ================= MMA issuer (warp converged on the waits, one elected lane issues) =================
+    // The issue loop must be a handful of instructions per MMA (a single thread feeds the tensor core): everything
+    // that depends only on the tap is computed once, by 16 lanes in parallel, while the producers are still loading.
     const unsigned idesc = make_idesc(TILE_M, Nt);
     const unsigned LBO_B = (unsigned)Nt * 16u;
+    if (lane < P.ntaps) {
+      hdr->tap_a_lo[lane] = ((unsigned)(P.plane[lane] * P.JC) * LBO_A + (unsigned)(P.lo + P.shift[lane]) * 16u) >> 4;
+      hdr->tap_dtmem[lane] = tmem_base + (unsigned)(P.acc[lane] * Nt);
+    }
+    __syncwarp();
+    // descriptor high words are tap-independent: LBO | SBO | version
+    const unsigned long long a_hi = ((unsigned long long)((128u >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((LBO_A >> 4) & 0x3FFF) << 16);
+    const unsigned long long b_hi = ((unsigned long long)((128u >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((LBO_B >> 4) & 0x3FFF) << 16);
+    const unsigned a_kstep = (2u * LBO_A) >> 4, b_kstep = (2u * LBO_B) >> 4;   // one 16-channel slice further
+    const int nk = P.KC / 16;
     int stage = 0; unsigned phase = 0;
     unsigned started = 0;                           // bit a set once accumulator a has been written
     DBG_MARK(12);
     for (int c = 0; c < P.NC; ++c) {
       const int buf = c % P.a_bufs;
-#ifdef SVAE_NAMED_BAR
-      asm volatile("bar.sync 2, 160;" ::: "memory");
-#else
       mbar_wait(smem_u32(&hdr->a_ready[buf]), (c / P.a_bufs) & 1);
-#endif
       if (c == 0) DBG_MARK(6);
-      const unsigned abase = smem_u32(a_smem + (size_t)buf * P.a_buf_bytes);
+      const unsigned abase4 = smem_u32(a_smem + (size_t)buf * P.a_buf_bytes) >> 4;
       for (int s0 = 0; s0 < P.ntaps; s0 += P.tps) {
         mbar_wait(smem_u32(&hdr->full_b[stage]), phase);
         tc_fence_after();
         if (lane == 0) {
+          unsigned b_lo = smem_u32(b_smem + (size_t)stage * P.b_stage_max) >> 4;
           for (int tl = 0; tl < P.tps; ++tl) {
             const int s = s0 + tl;
-            const unsigned bbase = smem_u32(b_smem + (size_t)stage * P.b_stage_max) + (unsigned)tl * b_tap_bytes;
-            const int a = P.acc[s];
-            const unsigned d_tmem = tmem_base + (unsigned)(a * Nt);
-            const unsigned arow = abase + (unsigned)(P.plane[s] * P.JC) * LBO_A + (unsigned)(P.lo + P.shift[s]) * 16u;
-            for (int kk = 0; kk < P.KC / 16; ++kk) {
-              const unsigned long long adesc = make_desc(arow + (unsigned)(2 * kk) * LBO_A, LBO_A, 128u);
-              const unsigned long long bdesc = make_desc(bbase + (unsigned)(2 * kk) * LBO_B, LBO_B, 128u);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (started >> a) & 1u);
-              started |= 1u << a;
+            const unsigned d_tmem = hdr->tap_dtmem[s];
+            const unsigned a = (unsigned)P.acc[s];
+            unsigned a_lo = abase4 + hdr->tap_a_lo[s];
+            unsigned bk = b_lo;
+            unsigned acc_flag = (started >> a) & 1u;
+#pragma unroll 4
+            for (int kk = 0; kk < nk; ++kk) {
+              umma_bf16(d_tmem, a_hi | (unsigned long long)(a_lo & 0x3FFF), b_hi | (unsigned long long)(bk & 0x3FFF), idesc,
+                        acc_flag);
+              acc_flag = 1u;
+              a_lo += a_kstep;
+              bk += b_kstep;
             }
+            started |= 1u << a;
+            b_lo += b_tap_bytes >> 4;
           }
           umma_commit(smem_u32(&hdr->empty_b[stage]));   // frees the weight stage once these MMAs have read it
         }
@@ -473,7 +489,6 @@ __global__ void __launch_bounds__(192, 3) tc_conv_kernel(const __grid_constant__
     tmem_dealloc(tmem_base, P.tmem_cols);
   }
   if (P.dbg != nullptr && tid < 16) P.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + tid] = hdr->ts[tid];
-  if (P.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid < 128) P.dbg[8192 * 16 + tid] = hdr->tl[tid] - hdr->ts[1];
 }
 
 static inline int round16(int v) { return (v + 15) / 16 * 16; }
