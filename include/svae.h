@@ -207,6 +207,11 @@ int svae_op_conv2d_backward(svae_handle* h, const float* x, const float* w, cons
 /* gradients of the transposed conv: dy [B,H*s,W*s,Co] -> dx [B,H,W,Ci], dw [4,4,Co,Ci] */
 int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx,
                                       float* dw, int B, int H, int W, int Ci, int Co, int stride, int operand_dtype);
+/* fully_connected data path of fc_bn_lrelu (abstract_network.py:65): y[B,N] = x[B,K] . w[K,N]; gradients dx[B,K]
+ * (may be NULL), dw[K,N] (may be NULL).  SVAE_OPERAND_BF16 needs K, N >= 64 (svae_op_tc_supported(2, ...)). */
+int svae_op_fc(svae_handle* h, const float* x, const float* w, float* y, int B, int K, int N, int operand_dtype);
+int svae_op_fc_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx, float* dw, int B,
+                        int K, int N, int operand_dtype);
 /* 1 when the SVAE_OPERAND_BF16 kernel family runs this contraction on tensor cores (operands rounded to bf16), else 0
  * (it then runs on the fp32 SIMT kernels).  transposed: 0 conv, 1 transposed conv, 2 fully connected (Ci -> Co, H = W = 1);
  * direction: 0 forward, 1 input gradient, 2 weight gradient. */

@@ -92,6 +92,8 @@ PROTOTYPES = {
     "svae_op_conv2d_transpose": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 7),
     "svae_op_conv2d_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 7),
     "svae_op_conv2d_transpose_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 7),
+    "svae_op_fc": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 4),
+    "svae_op_fc_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 4),
     "svae_op_tc_supported": (C.c_int, [C.c_int] * 7),
     "svae_debug_set_buffer": (C.c_int, [_P]),
     "svae_op_bn_act": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int]),

@@ -159,12 +159,24 @@ struct ReparamParams {
   int B, Z;
   float clip, prior;
 };
+// Per-iteration scalars live in device memory so that a captured CUDA graph of the train step can be replayed with new
+// values (learning-rate schedule + Adam bias correction, KL warm-up coefficient, Philox key / counter).
+struct SvaeDyn {
+  float lr_t;                    // lr * sqrt(1 - b2^t) / (1 - b1^t)          sequential_vae.py:1267,1356
+  float reg;                     // reg_coeff                                 :1357
+  unsigned long long seed;       // Philox key of the in-kernel eps
+  unsigned long long iteration;  // Philox counter base = (iteration*T + t) * max_batch*Z
+};
+// eps == NULL: Philox N(0,1) keyed by dyn->seed at counter (dyn->iteration*T + t)*stride + i
 int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre, const float* sd_pre, const float* eps,
-                uint64_t seed, uint64_t counter_base, float* eps_store, float* mu, float* sd, float* z, double* kl_sum);
+                const SvaeDyn* dyn, int T, int t, uint64_t stride, float* eps_store, float* mu, float* sd, float* z,
+                double* kl_sum);
+// KL gradient coefficient = dyn->reg * kl_scale
 int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, const float* mu_pre, const float* mu,
-                const float* sd, const float* eps, float kl_coef, float* dmu_pre, float* dsd_pre);
-int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
-                float beta2, float eps, float clip, float grad_scale);
+                const float* sd, const float* eps, const SvaeDyn* dyn, float kl_scale, float* dmu_pre, float* dsd_pre);
+// dyn != NULL: the step size is read from dyn->lr_t (lr_t ignored)
+int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, const SvaeDyn* dyn, float lr_t,
+                float beta1, float beta2, float eps, float clip, float grad_scale);
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base);
 int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n);  // dst += src
 
@@ -180,3 +192,8 @@ int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_
 struct TcPackEntry { Geom g; const float* w; void* out; int KC, Cin_p, N_p; long long total; };
 TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed);
 int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double total_elems);
+// ---- tcgen05 fully-connected kernel (kernels_fc.cu): fp32 operands read directly, bf16 in shared memory -----------
+bool tc_fc_supported(int K, int N);
+// mode 0: out[M,N] = x[M,K] . w[K,N] ; 1: out[M,K] = x[M,N] . w[K,N]^T ; 2: out[K,N] = x[M,K]^T . w[M,N]
+int tc_fc(const LaunchCtx& lc, int mode, const float* x, int ldx, const float* w, int ldw, float* out, int ldo, int M, int K,
+          int N, int accumulate);

@@ -284,11 +284,13 @@ __global__ void fill_normal_kernel(float* __restrict__ dst, int64_t n, uint64_t 
 
 __global__ void __launch_bounds__(256)
 reparam_fwd_kernel(ReparamParams p, const float* __restrict__ mu_pre, const float* __restrict__ sd_pre,
-                   const float* __restrict__ eps, uint64_t seed, uint64_t base, float* __restrict__ eps_store,
-                   float* __restrict__ mu, float* __restrict__ sd, float* __restrict__ z,
+                   const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, int T, int t, uint64_t stride,
+                   float* __restrict__ eps_store, float* __restrict__ mu, float* __restrict__ sd, float* __restrict__ z,
                    double* __restrict__ kl_sum) {
   __shared__ float red[32];
   const int n = p.B * p.Z;
+  const uint64_t seed = dyn->seed;
+  const uint64_t base = (dyn->iteration * (uint64_t)T + (uint64_t)t) * stride;
   float kl = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float m = fminf(fmaxf(mu_pre[i], -p.clip), p.clip);                 // sequential_vae.py:1593
@@ -307,9 +309,10 @@ reparam_fwd_kernel(ReparamParams p, const float* __restrict__ mu_pre, const floa
 
 __global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz, const float* __restrict__ mu_pre,
                                    const float* __restrict__ mu, const float* __restrict__ sd,
-                                   const float* __restrict__ eps, float kl_coef, float* __restrict__ dmu_pre,
-                                   float* __restrict__ dsd_pre) {
+                                   const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, float kl_scale,
+                                   float* __restrict__ dmu_pre, float* __restrict__ dsd_pre) {
   const int n = p.B * p.Z;
+  const float kl_coef = dyn->reg * kl_scale;
   const float ip2 = 1.f / (p.prior * p.prior);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float g = dz[i];
@@ -324,7 +327,8 @@ __global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
-            int64_t n, float lr_t, float b1, float b2, float eps, float clip, float gscale) {
+            int64_t n, const SvaeDyn* __restrict__ dyn, float lr_t, float b1, float b2, float eps, float clip, float gscale) {
+  if (dyn != nullptr) lr_t = dyn->lr_t;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* p4 = reinterpret_cast<float4*>(p);
   float4* m4 = reinterpret_cast<float4*>(m);
@@ -430,31 +434,31 @@ int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
 }
 
 int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre, const float* sd_pre, const float* eps,
-                uint64_t seed, uint64_t counter_base, float* eps_store, float* mu, float* sd, float* z,
+                const SvaeDyn* dyn, int T, int t, uint64_t stride, float* eps_store, float* mu, float* sd, float* z,
                 double* kl_sum) {
   ProfScope ps(lc, KC_REPARAM, 20.0 * p.B * p.Z, 28.0 * p.B * p.Z);
   reparam_fwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(
-      p, mu_pre, sd_pre, eps, seed, counter_base, eps_store, mu, sd, z, kl_sum);
+      p, mu_pre, sd_pre, eps, dyn, T, t, stride, eps_store, mu, sd, z, kl_sum);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, const float* mu_pre, const float* mu,
-                const float* sd, const float* eps, float kl_coef, float* dmu_pre, float* dsd_pre) {
+                const float* sd, const float* eps, const SvaeDyn* dyn, float kl_scale, float* dmu_pre, float* dsd_pre) {
   ProfScope ps(lc, KC_REPARAM, 12.0 * p.B * p.Z, 28.0 * p.B * p.Z);
-  reparam_bwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(p, dz, mu_pre, mu, sd, eps,
-                                                                                        kl_coef, dmu_pre, dsd_pre);
+  reparam_bwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(p, dz, mu_pre, mu, sd, eps, dyn,
+                                                                                        kl_scale, dmu_pre, dsd_pre);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1,
-                float beta2, float eps, float clip, float grad_scale) {
+int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, const SvaeDyn* dyn, float lr_t,
+                float beta1, float beta2, float eps, float clip, float grad_scale) {
   const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
   const int64_t n4 = aligned ? n / 4 : 0;
   ProfScope ps(lc, KC_ADAM, 12.0 * n, 28.0 * n);   // read p,g,m,v + write p,m,v
-  adam_kernel<<<flat_blocks(n4 > 0 ? n4 : n, lc.sm_count), 256, 0, lc.stream>>>(p, g, m, v, n4, n, lr_t, beta1, beta2,
-                                                                               eps, clip, grad_scale);
+  adam_kernel<<<flat_blocks(n4 > 0 ? n4 : n, lc.sm_count), 256, 0, lc.stream>>>(p, g, m, v, n4, n, dyn, lr_t, beta1,
+                                                                               beta2, eps, clip, grad_scale);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

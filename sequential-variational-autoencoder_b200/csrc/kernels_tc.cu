@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -47,120 +48,8 @@ struct TcParams {
   int shift[16];
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+using namespace tcptx;
 
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must become a trap (reported CUDA error), never a hung GPU.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-#ifdef SVAE_MBAR_POLL
-  for (unsigned it = 0; !mbar_test_wait(bar, parity); ++it) {
-    if (it > (1u << 28)) __trap();
-  }
-#else
-  for (unsigned it = 0; !mbar_try_wait(bar, parity); ++it)
-    if (it > (1u << 26)) __trap();
-#endif
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, unsigned cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-  unsigned r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor, canonical K-major layout without swizzle (cute::UMMA::SmemDescriptor):
-//   bits [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (between the two 8-element K groups of one MMA) ;
-//   [32,46) stride byte offset >> 4 (between 8-row groups) ; [46,48) version = 1 (sm_100) ; [61,64) layout type 0.
-__device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
-  unsigned long long d = 0;
-  d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
-  d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1) at [7,10) /
-// [10,13), a/b K-major (0) at 15 / 16, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr unsigned make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
-}
-
-// warp-level transpose-reduction: on return lane l holds the sum over the 32 lanes of v[l]
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      float send = up ? v[i] : v[i + off];
-      float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
 
 struct SmemHeader {
   unsigned long long full_b[MAX_STAGES], empty_b[MAX_STAGES], a_ready[2], a_free[2], acc_done;
@@ -187,14 +76,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
 //  and serialise the two groups through everything that follows)
 #define DBG_MARK(slot) do { if (P.dbg != nullptr) { const unsigned long long t_ = gtimer(); if ((threadIdx.x & 31) == 0) hdr->ts[slot] = t_; } } while (0)
 
-__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
-  __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
-  __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
-  uint4 r;
-  r.x = *reinterpret_cast<unsigned*>(&b0); r.y = *reinterpret_cast<unsigned*>(&b1);
-  r.z = *reinterpret_cast<unsigned*>(&b2); r.w = *reinterpret_cast<unsigned*>(&b3);
-  return r;
-}
 // 8 consecutive channels [ch0, ch0+8) of one pixel -> 8 bf16; channels >= valid are zero (channel padding)
 __device__ __forceinline__ uint4 load8(const float* __restrict__ px, int ch0, int valid, int vec) {
   float f[8];
@@ -349,7 +230,7 @@ __global__ void __launch_bounds__(192, 3) tc_conv_kernel(const __grid_constant__
       float* orow = P.out + (((size_t)n * P.Hout + oh) * P.Wout + ow) * P.out_ld + P.out_coff + n0;
       for (int nn = 0; nn < Nt; nn += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(a * Nt + nn), v);
+        tmem_ld_upto32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(a * Nt + nn), v, Nt - nn);
         const int ncols = max(0, min(min(32, Nt - nn), P.n_valid - (n0 + nn)));   // real (unpadded) columns of this group
         if (valid) {
           if (P.out_vec) {
@@ -707,7 +588,7 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
       const int tap = grp * P.taps_per_cta + tl;
       for (int n0 = 0; n0 < P.N; n0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tl * P.N + n0), v);
+        tmem_ld_upto32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tl * P.N + n0), v, P.N - n0);
         if (a0 + a < P.Ca && my_tiles > 0) {
           float* dst = P.dw + ((size_t)tap * P.Ca + a0 + a) * P.Cb + b0 + n0;
           const int ncols = max(0, min(min(32, P.N - n0), P.Cb - (b0 + n0)));
@@ -820,7 +701,7 @@ bool tc_supported(const Geom& g) {
   const bool fc = g.KH == 1 && g.KW == 1 && g.Hin == 1 && g.Win == 1;
   if (!conv && !fc) return false;
   if (g.Cin < 1 || g.Cout < 1) return false;
-  if (fc && (g.Cin < 64 || g.Cout < 64)) return false;   // skinny projections / heads stay on the fp32 row-dot kernels
+  if (fc) return tc_fc_supported(g.Cin, g.Cout);   // kernels_fc.cu; skinny projections / heads stay on the fp32 row-dot kernels
   TcParams P;
   Geom gg = g;
   if (gg.B < 1) gg.B = 1;
@@ -858,6 +739,7 @@ int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double 
 }
 
 int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats) {
+  if (g.KH == 1) { svae_global_error() = "tcgen05 conv kernel: fully-connected layers run on tc_fc"; return -1; }
   TcParams P;
   if (!build_params(g, P)) { svae_global_error() = "tcgen05: unsupported geometry"; return -1; }
   P.in = in.p; P.in_ld = in.ld; P.in_coff = in.coff;
@@ -896,6 +778,7 @@ static Geom wgrad_conv_geom(const Geom& fwd) {
 }
 
 bool tc_wgrad_supported(const Geom& fwd) {
+  if (fwd.KH == 1 && fwd.KW == 1 && fwd.Hin == 1 && fwd.Win == 1) return tc_fc_supported(fwd.Cin, fwd.Cout);
   TwParams P;
   Geom g = wgrad_conv_geom(fwd);
   if (g.B < 1) g.B = 1;
@@ -903,6 +786,8 @@ bool tc_wgrad_supported(const Geom& fwd) {
 }
 
 int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
+  if (g.KH == 1)   // fully connected: dW[K,N] = X[B,K]^T . dY[B,N]
+    return tc_fc(lc, 2, x.p + x.coff, x.ld, dy.p + dy.coff, dy.ld, dw, g.Cout, g.B, g.Cin, g.Cout, 0);
   TwParams P;
   if (!build_wparams(g, P, lc.sm_count)) { svae_global_error() = "tcgen05 wgrad: unsupported geometry"; return -1; }
   P.x = x.p; P.x_ld = x.ld; P.x_coff = x.coff;

@@ -51,6 +51,21 @@ struct Block {
   void* w_packed = nullptr;      // tcgen05 packed weights (forward form)
   void* w_packed_d = nullptr;    // tcgen05 packed weights (dgrad form)
   bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false;
+  int dy_slot = -1;              // index of this block's d(pre-BN output) buffer inside a GradSet
+};
+
+// Gradient scratch of ONE chain step's backward.  Two sets (step parity) let the side streams (weight gradients,
+// recognition net) of step t still read their buffers while the main stream already runs step t-1.
+struct GradSet {
+  std::vector<float*> d_c, d_dcat, d_e, d_inf, dy;
+  float *d_fca = nullptr, *d_cc = nullptr, *d_z = nullptr, *d_mu_pre = nullptr, *d_sd_pre = nullptr, *d_u = nullptr;
+};
+
+struct GraphEntry {   // a captured train step, valid for exactly these arguments
+  const float *x, *tgt, *eps;
+  int B;
+  cudaGraphExec_t exec;
+  int64_t launches;   // kernels inside the graph (svae_launch_count keeps counting them)
 };
 
 struct Head {  // layers.fully_connected head (sequential_vae.py:1592,1594,1607,1609)
@@ -146,11 +161,22 @@ struct svae_handle {
   double* loss_sums = nullptr;  // [2T] recon_sum, kl_sum
   double* loss_host = nullptr;  // pinned
   // gradient scratch (one step's worth)
-  std::vector<float*> d_c, d_dcat, d_e, d_inf;
-  float *d_fca = nullptr, *d_cc = nullptr, *d_z = nullptr, *d_mu_pre = nullptr, *d_sd_pre = nullptr, *d_u = nullptr;
+  GradSet gs[2];
+  int n_dy_slots = 0;
+  std::vector<size_t> dy_slot_elems;
   float* gx[2] = {nullptr, nullptr};
-  float* dy_scratch = nullptr;
   char* grad_base = nullptr; size_t grad_bytes = 0;
+  // execution: main stream (`stream`) + side streams; `cur` is where the next launch goes
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // 0: chain weight gradients, 1: recognition / latent branch, 2: its weight gradients
+  cudaStream_t cur = nullptr;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  bool use_streams = true, use_graph = true, capturing = false;
+  int fork_mask = 15;   // debugging / ablation: 1 chain wgrads, 2 recognition branch, 4 its wgrads, 8 forward recognition
+  int eager_steps = 0;
+  std::vector<GraphEntry> graphs;
+  // per-iteration scalars (device copy + pinned ring)
+  SvaeDyn dyn_host{}; SvaeDyn* dyn_dev = nullptr; SvaeDyn* dyn_ring = nullptr; int dyn_slot = 0;
+  std::vector<cudaEvent_t> dyn_ev;
   // io staging
   float *in_x = nullptr, *in_tgt = nullptr, *in_eps = nullptr, *io_steps = nullptr, *gen_prev = nullptr;
   float *pin_x = nullptr, *pin_tgt = nullptr, *pin_eps = nullptr;
@@ -168,7 +194,7 @@ struct svae_handle {
   std::vector<cudaEvent_t> bucket_ev; cudaEvent_t comm_done = nullptr;
 
   Profiler prof;
-  LaunchCtx lc() { return LaunchCtx{stream, &launches, sm_count, &prof}; }
+  LaunchCtx lc() { return LaunchCtx{cur ? cur : stream, &launches, sm_count, &prof}; }
   float* pw(int idx) { return P + params[idx].offset; }
   float* pg(int idx) { return G + params[idx].offset; }
 };
@@ -447,34 +473,57 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
     s.u = act.get<float>((size_t)B * h->D * h->D * (C + 1));
     s.xt = act.get<float>((size_t)B * h->D * h->D * C);
   }
-  // gradient scratch: one step's worth, reused by every step's backward
+  // gradient scratch: two sets (step parity) of one step's worth; every block has its own d(pre-BN output) buffer so
+  // that its weight gradient can run on a side stream while the chain moves on
   if (c.train_capacity) {
-    const Step& s1 = h->steps[T > 1 ? 1 : 0];
-    h->d_c.resize(L - 1); h->d_dcat.resize(L - 1);
-    for (int l = 0; l < L - 1; ++l) {
-      h->d_c[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * F[l + 1]);
-      h->d_dcat[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * 2 * F[l + 1]);
+    const int NI = 2 * (L - 1), NE = 2 * (L - 1) + 1;
+    h->n_dy_slots = NI + NE + 2 + L + 2 * (L - 1);
+    h->dy_slot_elems.assign(h->n_dy_slots, 0);
+    auto slot = [&](Block& b, int id) {
+      b.dy_slot = id;
+      const size_t n = (size_t)B * b.rpi * b.feats;
+      if (n > h->dy_slot_elems[id]) h->dy_slot_elems[id] = n;
+    };
+    for (int t = 0; t < T; ++t) {
+      Step& s = h->steps[t];
+      for (int k = 0; k < (int)s.inf.size(); ++k) slot(s.inf[k], k);
+      for (int k = 0; k < (int)s.enc.size(); ++k) slot(s.enc[k], NI + k);
+      if (t > 0) slot(s.encfc, NI + NE - 1 + 1);
+      for (int i2 = 0; i2 < L; ++i2) slot(s.lat[i2], NI + NE + 1 + i2);
+      slot(s.decfc, NI + NE + 1 + L);
+      for (int l = 0; l < L - 1; ++l) { slot(s.ta[l], NI + NE + 2 + L + l); slot(s.tb[l], NI + NE + 2 + L + (L - 1) + l); }
     }
-    h->d_fca = gr.get<float>((size_t)B * S[L] * S[L] * F[L]);
-    h->d_cc = gr.get<float>((size_t)B * (F[L] + F[L + 1]));
-    h->d_z = gr.get<float>((size_t)B * Z);
-    h->d_mu_pre = gr.get<float>((size_t)B * Z);
-    h->d_sd_pre = gr.get<float>((size_t)B * Z);
-    h->d_u = gr.get<float>((size_t)B * h->D * h->D * (C + 1));
+    const Step& s1 = h->steps[T > 1 ? 1 : 0];
+    for (int p = 0; p < 2; ++p) {
+      GradSet& g = h->gs[p];
+      g.d_c.resize(L - 1); g.d_dcat.resize(L - 1);
+      for (int l = 0; l < L - 1; ++l) {
+        g.d_c[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * F[l + 1]);
+        g.d_dcat[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * 2 * F[l + 1]);
+      }
+      g.d_fca = gr.get<float>((size_t)B * S[L] * S[L] * F[L]);
+      g.d_cc = gr.get<float>((size_t)B * (F[L] + F[L + 1]));
+      g.d_z = gr.get<float>((size_t)B * Z);
+      g.d_mu_pre = gr.get<float>((size_t)B * Z);
+      g.d_sd_pre = gr.get<float>((size_t)B * Z);
+      g.d_u = gr.get<float>((size_t)B * h->D * h->D * (C + 1));
+      g.d_e.assign(2 * (L - 1) + 1, nullptr);
+      g.d_inf.assign(2 * (L - 1), nullptr);
+      for (int k = 0; k < 2 * (L - 1); ++k) {
+        const Block& b = h->steps[0].inf[k];
+        g.d_inf[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
+      }
+      if (T > 1)
+        for (int k = 0; k <= 2 * (L - 1); ++k) {
+          const Block& b = s1.enc[k];
+          g.d_e[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
+        }
+      g.dy.assign(h->n_dy_slots, nullptr);
+      for (int k = 0; k < h->n_dy_slots; ++k)
+        if (h->dy_slot_elems[k] > 0) g.dy[k] = gr.get<float>(h->dy_slot_elems[k]);
+    }
     h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * C);
     h->gx[1] = gr.get<float>((size_t)B * h->D * h->D * C);
-    h->d_e.assign(2 * (L - 1) + 1, nullptr);
-    h->d_inf.assign(2 * (L - 1), nullptr);
-    for (int k = 0; k < 2 * (L - 1); ++k) {
-      const Block& b = h->steps[0].inf[k];
-      h->d_inf[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
-    }
-    if (T > 1)
-      for (int k = 0; k <= 2 * (L - 1); ++k) {
-        const Block& b = s1.enc[k];
-        h->d_e[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
-      }
-    h->dy_scratch = gr.get<float>(max_y);
   }
   // io staging (host-buffer entry points)
   h->in_x = act.get<float>((size_t)B * h->D * h->D * C);
@@ -488,9 +537,46 @@ int contract(svae_handle* h, Geom g, int B, View in, const float* w, const void*
              double* stats) {
   g.B = B;
   LaunchCtx lc = h->lc();
+  if (use_tc && g.KH == 1) {
+    // fully connected: forward (w_out_major 0: w = [Cin, Cout]) or input gradient (w_out_major 1: w = [Cout, Cin])
+    int r = g.w_out_major == 0
+                ? tc_fc(lc, 0, in.p + in.coff, in.ld, w, g.Cout, out.p + out.coff, out.ld, B, g.Cin, g.Cout, g.accumulate)
+                : tc_fc(lc, 1, in.p + in.coff, in.ld, w, g.Cin, out.p + out.coff, out.ld, B, g.Cout, g.Cin, g.accumulate);
+    if (r == 0 && stats != nullptr) {
+      if (out.ld != g.Cout || out.coff != 0) { svae_global_error() = "fc statistics need a dense output"; return -1; }
+      r = col_stats(lc, out.p, B, g.Cout, stats);
+    }
+    return r;
+  }
   if (use_tc) return tc_gather_gemm(lc, g, in, w_packed, out, stats);
   return simt_gather_gemm(lc, g, in, w, out, stats);
 }
+
+// ---- streams: the main stream carries the chain; side streams carry work that is off the chain's critical path ------
+struct OnStream {   // RAII: route launches to `s` for the lifetime of the scope
+  svae_handle* h; cudaStream_t prev;
+  OnStream(svae_handle* h_, cudaStream_t s) : h(h_), prev(h_->cur) { h->cur = s; }
+  ~OnStream() { h->cur = prev; }
+};
+cudaStream_t cur_stream(svae_handle* h) { return h->cur ? h->cur : h->stream; }
+cudaEvent_t next_event(svae_handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+// work enqueued on `to` after this call waits for everything enqueued on `from` so far
+int link(svae_handle* h, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
+  cudaEvent_t e = next_event(h);
+  H_CUDA(cudaEventRecord(e, from));
+  H_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+// forked execution is used for training-capacity handles outside profiling (the profiler wants serialised kernels)
+bool forked(const svae_handle* h) { return h->use_streams && h->cfg.train_capacity && !h->prof.enabled && h->side[0] != nullptr; }
 
 int block_fwd(svae_handle* h, Block& b, int B, View in) {
   H_TRY(contract(h, b.g, B, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0), b.stats));
@@ -499,39 +585,43 @@ int block_fwd(svae_handle* h, Block& b, int B, View in) {
   return 0;
 }
 
-// backward of a block: da -> dy (in dy_scratch), weight/beta grads, optional input gradient
-int block_bwd(svae_handle* h, Block& b, int B, FeatView da, View in, float* dres, int dres_acc, const View* din,
-              int din_acc) {
+// backward of a block on the current stream: da -> dy, beta gradient, optional input gradient; the weight gradient goes
+// to `wst` (a side stream, or the current one)
+int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in, float* dres, int dres_acc, const View* din,
+              int din_acc, cudaStream_t wst) {
   LaunchCtx lc = h->lc();
   const int64_t rows = (int64_t)B * b.rpi;
-  float* dy = h->dy_scratch;
+  float* dy = gs.dy[b.dy_slot];
   H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
   H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta)));
   View dyv = mkview(dy, b.feats, 0);
-  // weight gradient
-  if (b.g.mode == 0) {
-    Geom g = b.g; g.B = B;
-    if (b.tc_wgrad) H_TRY(tc_wgrad(lc, g, in, dyv, h->pg(b.w))); else H_TRY(simt_wgrad(lc, g, in, dyv, h->pg(b.w)));
-  } else {
-    Geom g = dgrad_geom(b.g); g.B = B; g.mode = 0;  // conv geometry from the deconv's output grid to its input grid
-    if (b.tc_wgrad) H_TRY(tc_wgrad(lc, g, dyv, in, h->pg(b.w))); else H_TRY(simt_wgrad(lc, g, dyv, in, h->pg(b.w)));
-  }
+  // dy is final here: the weight gradient (side stream) depends on this point only, not on the input gradient below
+  H_TRY(link(h, cur_stream(h), wst));
   if (din != nullptr) {
     Geom g = dgrad_geom(b.g);
     g.accumulate = din_acc;
     H_TRY(contract(h, g, B, dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr));
   }
+  {
+    OnStream os(h, wst);
+    LaunchCtx lw = h->lc();
+    if (b.g.mode == 0) {
+      Geom g = b.g; g.B = B;
+      if (b.tc_wgrad) H_TRY(tc_wgrad(lw, g, in, dyv, h->pg(b.w))); else H_TRY(simt_wgrad(lw, g, in, dyv, h->pg(b.w)));
+    } else {
+      Geom g = dgrad_geom(b.g); g.B = B; g.mode = 0;  // conv geometry from the deconv's output grid to its input grid
+      if (b.tc_wgrad) H_TRY(tc_wgrad(lw, g, dyv, in, h->pg(b.w))); else H_TRY(simt_wgrad(lw, g, dyv, in, h->pg(b.w)));
+    }
+  }
   return 0;
 }
 
-int skinny_block_bwd(svae_handle* h, Block& b, int B, FeatView da, View zin, int K, View dz_out) {
+int skinny_block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View zin, int K, View dz_out) {
   // latent projection (K <= 32 inputs): dW via thread-per-feature, dz via row-wise dot with the [K,N] weights
   LaunchCtx lc = h->lc();
-  float* dy = h->dy_scratch;
+  float* dy = gs.dy[b.dy_slot];
   H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, FeatView{}, dy, b.S, nullptr, 0));
   H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, B, b.feats, h->pg(b.beta)));
-  View dyv = mkview(dy, b.feats, 0);
-  (void)dyv;
   H_TRY(lat_wgrad(lc, zin, dy, B, K, b.feats, h->pg(b.w)));
   H_TRY(lat_dz(lc, dy, h->pw(b.w), B, K, b.feats, dz_out));   // d_z is zeroed at the start of the step's backward
   return 0;
@@ -539,11 +629,25 @@ int skinny_block_bwd(svae_handle* h, Block& b, int B, FeatView da, View zin, int
 
 int zero_region(svae_handle* h, void* p, size_t bytes) {
   if (bytes == 0) return 0;
-  H_CUDA(cudaMemsetAsync(p, 0, bytes, h->stream));
+  H_CUDA(cudaMemsetAsync(p, 0, bytes, cur_stream(h)));
   return 0;
 }
 
 int repack_if_dirty(svae_handle* h);
+
+// per-iteration scalars -> device (pinned ring slot -> dyn_dev on the main stream).  Never captured into a graph: the
+// graph is replayed with whatever values the copy enqueued just before it delivered.
+int dyn_push(svae_handle* h) {
+  if (h->capturing) return 0;
+  const int slot = h->dyn_slot;
+  h->dyn_slot = (h->dyn_slot + 1) % (int)h->dyn_ev.size();
+  if (h->dyn_ev[slot] != nullptr) H_CUDA(cudaEventSynchronize(h->dyn_ev[slot]));   // the copy that last used this slot is done
+  else H_CUDA(cudaEventCreateWithFlags(&h->dyn_ev[slot], cudaEventDisableTiming));
+  h->dyn_ring[slot] = h->dyn_host;
+  H_CUDA(cudaMemcpyAsync(h->dyn_dev, &h->dyn_ring[slot], sizeof(SvaeDyn), cudaMemcpyHostToDevice, h->stream));
+  H_CUDA(cudaEventRecord(h->dyn_ev[slot], h->stream));
+  return 0;
+}
 
 // ---- forward of one chain step --------------------------------------------------------------------------------------
 int encoder_fwd(svae_handle* h, Step& s, int B, const float* xprev) {
@@ -558,12 +662,16 @@ int encoder_fwd(svae_handle* h, Step& s, int B, const float* xprev) {
   return 0;
 }
 
-int decoder_fwd(svae_handle* h, Step& s, int B, const float* z, const float* xprev, const float* tgt, float* xt_out,
-                double* recon_sum) {
+// latent projections P_i = fc_bn_lrelu(z_i) (split_latent, sequential_vae.py:1796-1806): depend on z_t only
+int latent_fwd(svae_handle* h, Step& s, int B, const float* z) {
+  for (int i = 0; i < h->L; ++i)
+    H_TRY(block_fwd(h, s.lat[i], B, mkview(const_cast<float*>(z), h->Z, h->zoff[i])));
+  return 0;
+}
+
+int decoder_fwd(svae_handle* h, Step& s, int B, const float* xprev, const float* tgt, float* xt_out, double* recon_sum) {
   const int L = h->L, C = h->C;
   LaunchCtx lc = h->lc();
-  for (int i = 0; i < L; ++i)
-    H_TRY(block_fwd(h, s.lat[i], B, mkview(const_cast<float*>(z), h->Z, h->zoff[i])));
   H_TRY(block_fwd(h, s.decfc, B, mkview(s.cc, s.ncc, 0)));
   View cur = mkview(s.decfc.out.p, s.ta[L - 2].g.Cin, 0);
   for (int l = L - 2; l >= 0; --l) {
@@ -594,11 +702,11 @@ HeadSet make_headset(svae_handle* h, Step& s, int l) {
   return hs;
 }
 
-int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float* eps, uint64_t seed, double* kl_sum) {
+int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float* eps, double* kl_sum) {
   const int L = h->L;
   LaunchCtx lc = h->lc();
   // the heads accumulate into mu_pre / sd_pre (adjacent in the arena) with atomics
-  H_CUDA(cudaMemsetAsync(s.mu_pre, 0, sizeof(float) * 2 * (size_t)h->cfg.max_batch * h->Z, h->stream));
+  H_CUDA(cudaMemsetAsync(s.mu_pre, 0, sizeof(float) * 2 * (size_t)h->cfg.max_batch * h->Z, cur_stream(h)));
   View cur = mkview(const_cast<float*>(x), h->C, 0);
   for (int k = 0; k < 2 * (L - 1); ++k) {
     H_TRY(block_fwd(h, s.inf[k], B, cur));
@@ -611,8 +719,8 @@ int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float*
     }
   }
   ReparamParams rp{B, h->Z, h->cfg.latent_mean_clip, h->cfg.prior_stddev};
-  uint64_t base = (h->iteration * (uint64_t)h->T + (uint64_t)s.t) * (uint64_t)(h->cfg.max_batch * h->Z);
-  H_TRY(reparam_fwd(lc, rp, s.mu_pre, s.sd_pre, eps, seed, base, s.eps, s.mu, s.sd, s.z, kl_sum));
+  H_TRY(reparam_fwd(lc, rp, s.mu_pre, s.sd_pre, eps, h->dyn_dev, h->T, s.t, (uint64_t)(h->cfg.max_batch * h->Z), s.eps, s.mu,
+                    s.sd, s.z, kl_sum));
   return 0;
 }
 
@@ -623,19 +731,40 @@ bool step_has_kl(const svae_handle* h, int t) { return (h->cfg.regularized_mask 
 int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float reg,
                  float* mu_out, float* sd_out, float* xs_out) {
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  h->cur = h->stream;
+  h->ev_used = 0;
+  h->dyn_host.reg = reg; h->dyn_host.seed = seed; h->dyn_host.iteration = h->iteration;
+  H_TRY(dyn_push(h));
   H_TRY(repack_if_dirty(h));
   H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
   H_TRY(zero_region(h, h->loss_sums, sizeof(double) * 2 * h->T));
   const size_t img = (size_t)B * h->D * h->D * h->C;
   const size_t bz = (size_t)B * h->Z;
+  const bool fork = forked(h) && h->act_sets == h->T && (h->fork_mask & 8);
+  std::vector<cudaEvent_t> rec_ev(h->T, nullptr);
+  if (fork) {
+    // The recognition nets read only x (sequential_vae.py:1011-1025) and the latent projections only z_t: all T of them
+    // run on the side streams, off the chain's critical path.
+    for (int t = 0; t < h->T; ++t) {
+      Step& s = h->steps[t];
+      cudaStream_t sd = h->side[t % 3];
+      if (t < 3) H_TRY(link(h, h->stream, sd));
+      OnStream os(h, sd);
+      H_TRY(recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, h->loss_sums + h->T + t));
+      H_TRY(latent_fwd(h, s, B, s.z));
+      rec_ev[t] = next_event(h);
+      H_CUDA(cudaEventRecord(rec_ev[t], sd));
+    }
+  }
   const float* prev = nullptr;
   for (int t = 0; t < h->T; ++t) {
     Step& s = h->steps[t];
     // forward-only handles alias steps >= 2 onto step 1's buffers: restart their batch-norm statistics
     if (t >= 2 && h->act_sets < h->T) H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
-    H_TRY(recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, seed, h->loss_sums + h->T + t));
+    if (!fork) H_TRY(recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, h->loss_sums + h->T + t));
     if (t > 0) H_TRY(encoder_fwd(h, s, B, prev));
-    H_TRY(decoder_fwd(h, s, B, s.z, prev, tgt, s.xt, h->loss_sums + t));
+    if (fork) H_CUDA(cudaStreamWaitEvent(h->stream, rec_ev[t], 0)); else H_TRY(latent_fwd(h, s, B, s.z));
+    H_TRY(decoder_fwd(h, s, B, prev, tgt, s.xt, h->loss_sums + t));
     if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out + t * img, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (mu_out) H_CUDA(cudaMemcpyAsync(mu_out + t * bz, s.mu, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (sd_out) H_CUDA(cudaMemcpyAsync(sd_out + t * bz, s.sd, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -651,123 +780,143 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------------
-int decoder_bwd(svae_handle* h, Step& s, int B, const float* gx_in, float* gx_prev, const float* xprev) {
-  const int L = h->L, C = h->C, T = h->T;
+// Streams of one step's backward: the chain (decoder, chain encoder: bn backward + input gradients) stays on the main
+// stream; weight gradients of the chain go to side[0]; the latent projections' backward and the whole recognition net go
+// to side[1] with its weight gradients on side[2].
+struct BwdStreams { cudaStream_t chain, w, rec, recw; };
+
+int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int B, const float* gx_in, float* gx_prev,
+                const float* xprev) {
+  const int L = h->L, C = h->C;
   const int* F = h->cfg.filter_sizes;
   LaunchCtx lc = h->lc();
   const int has_gate = s.t > 0 ? 1 : 0;
   const int ldu = C + has_gate;
   const float coef = step_has_recon(h, s.t)
                          ? 16.f * step_coef(h, s.t) * 2.f / ((float)B * h->D * h->D * C) : 0.f;   // :1146,1163,1168
-  (void)T;
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
-  H_CUDA(cudaMemsetAsync(h->d_z, 0, sizeof(float) * (size_t)B * h->Z, h->stream));   // lat_dz accumulates with atomics
+  H_CUDA(cudaMemsetAsync(gs.d_z, 0, sizeof(float) * (size_t)B * h->Z, st.chain));   // lat_dz accumulates with atomics
   H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
-                    coef, h->d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr));
+                    coef, gs.d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr));
   // output deconvs: dgrad into d_c[0], wgrads
   View c0 = mkview(s.tb[0].out.p, F[1], 0);
-  View dc0 = mkview(h->d_c[0], F[1], 0);
+  View dc0 = mkview(gs.d_c[0], F[1], 0);
   {
     Geom g = dgrad_geom(s.g_out);
-    H_TRY(contract(h, g, B, mkview(h->d_u, ldu, 0), h->pw(s.w_out), s.outb.w_packed_d, s.outb.tc_dgrad, dc0, nullptr));
-    Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
-    if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lc, gw, mkview(h->d_u, ldu, 0), c0, h->pg(s.w_out)));
-    else H_TRY(simt_wgrad(lc, gw, mkview(h->d_u, ldu, 0), c0, h->pg(s.w_out)));
+    H_TRY(contract(h, g, B, mkview(gs.d_u, ldu, 0), h->pw(s.w_out), s.outb.w_packed_d, s.outb.tc_dgrad, dc0, nullptr));
     if (has_gate) {
       Geom g2 = dgrad_geom(s.g_gate); g2.accumulate = 1;
-      H_TRY(contract(h, g2, B, mkview(h->d_u, ldu, C), h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr));
+      H_TRY(contract(h, g2, B, mkview(gs.d_u, ldu, C), h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr));
+    }
+    H_TRY(link(h, st.chain, st.w));
+    OnStream os(h, st.w);
+    LaunchCtx lw = h->lc();
+    Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
+    if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
+    else H_TRY(simt_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
+    if (has_gate) {
       Geom gw2 = dgrad_geom(s.g_gate); gw2.B = B; gw2.mode = 0;
-      if (s.gateb.tc_wgrad) H_TRY(tc_wgrad(lc, gw2, mkview(h->d_u, ldu, C), c0, h->pg(s.w_gate)));
-      else H_TRY(simt_wgrad(lc, gw2, mkview(h->d_u, ldu, C), c0, h->pg(s.w_gate)));
+      if (s.gateb.tc_wgrad) H_TRY(tc_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
+      else H_TRY(simt_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
     }
   }
   for (int l = 0; l <= L - 2; ++l) {
     const int Fl = F[l + 1];
     // c_l = relu(bn(deconv_s1(dcat_l)))
     View dcat_in = mkview(s.dcat[l], 2 * Fl, 0);
-    View d_dcat = mkview(h->d_dcat[l], 2 * Fl, 0);
-    H_TRY(block_bwd(h, s.tb[l], B, fv4(h->d_c[l], Fl, 0, Fl), dcat_in, nullptr, 0, &d_dcat, 0));
+    View d_dcat = mkview(gs.d_dcat[l], 2 * Fl, 0);
+    H_TRY(block_bwd(h, gs, s.tb[l], B, fv4(gs.d_c[l], Fl, 0, Fl), dcat_in, nullptr, 0, &d_dcat, 0, st.w));
+    // P_l = lrelu(bn(fc(z_l))): second channel window of d_dcat, on the recognition stream
+    {
+      H_TRY(link(h, st.chain, st.rec));
+      OnStream os(h, st.rec);
+      const Block& lb = s.lat[l];
+      FeatView da{gs.d_dcat[l], 2 * Fl, Fl, Fl, lb.out.ppr};
+      H_TRY(skinny_block_bwd(h, gs, s.lat[l], B, da, mkview(s.z, h->Z, h->zoff[l]), h->cfg.latent_dims[l],
+                             mkview(gs.d_z, h->Z, h->zoff[l])));
+    }
     // d = relu(bn(deconv_s2(c_{l+1})) + e[l+1])
     View ta_in = l < L - 2 ? mkview(s.tb[l + 1].out.p, F[l + 2], 0) : mkview(s.decfc.out.p, s.ta[l].g.Cin, 0);
-    View d_next = l < L - 2 ? mkview(h->d_c[l + 1], F[l + 2], 0) : mkview(h->d_fca, s.ta[l].g.Cin, 0);
-    H_TRY(block_bwd(h, s.ta[l], B, fv4(h->d_dcat[l], 2 * Fl, 0, Fl), ta_in, has_gate ? h->d_e[2 * l + 1] : nullptr, 0,
-                    &d_next, 0));
-    // P_l = lrelu(bn(fc(z_l)))
-    const Block& lb = s.lat[l];
-    FeatView da{h->d_dcat[l], 2 * Fl, Fl, Fl, lb.out.ppr};
-    H_TRY(skinny_block_bwd(h, s.lat[l], B, da, mkview(s.z, h->Z, h->zoff[l]), h->cfg.latent_dims[l],
-                           mkview(h->d_z, h->Z, h->zoff[l])));
+    View d_next = l < L - 2 ? mkview(gs.d_c[l + 1], F[l + 2], 0) : mkview(gs.d_fca, s.ta[l].g.Cin, 0);
+    H_TRY(block_bwd(h, gs, s.ta[l], B, fv4(gs.d_dcat[l], 2 * Fl, 0, Fl), ta_in, has_gate ? gs.d_e[2 * l + 1] : nullptr, 0,
+                    &d_next, 0, st.w));
   }
   // dec.fc
   {
-    View d_cc = mkview(h->d_cc, s.ncc, 0);
-    H_TRY(block_bwd(h, s.decfc, B, fv4(h->d_fca, s.decfc.feats, 0, s.decfc.feats), mkview(s.cc, s.ncc, 0), nullptr, 0,
-                    &d_cc, 0));
+    View d_cc = mkview(gs.d_cc, s.ncc, 0);
+    H_TRY(block_bwd(h, gs, s.decfc, B, fv4(gs.d_fca, s.decfc.feats, 0, s.decfc.feats), mkview(s.cc, s.ncc, 0), nullptr, 0,
+                    &d_cc, 0, st.w));
   }
   // P_{L-1}
   {
+    H_TRY(link(h, st.chain, st.rec));
+    OnStream os(h, st.rec);
     const int coffP = s.t > 0 ? F[L] : 0;
-    FeatView da{h->d_cc, s.ncc, coffP, F[L + 1], 1};
-    H_TRY(skinny_block_bwd(h, s.lat[L - 1], B, da, mkview(s.z, h->Z, h->zoff[L - 1]), h->cfg.latent_dims[L - 1],
-                           mkview(h->d_z, h->Z, h->zoff[L - 1])));
+    FeatView da{gs.d_cc, s.ncc, coffP, F[L + 1], 1};
+    H_TRY(skinny_block_bwd(h, gs, s.lat[L - 1], B, da, mkview(s.z, h->Z, h->zoff[L - 1]), h->cfg.latent_dims[L - 1],
+                           mkview(gs.d_z, h->Z, h->zoff[L - 1])));
   }
   return 0;
 }
 
-int encoder_bwd(svae_handle* h, Step& s, int B, float* gx_prev, const float* xprev) {
+int encoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int B, float* gx_prev, const float* xprev) {
   const int L = h->L;
   const int* F = h->cfg.filter_sizes;
   const int last = 2 * (L - 1);
   // e[L] = lrelu(bn(fc(flat)))
   {
     View flat = mkview(s.enc[last].out.p, s.encfc.g.Cin, 0);
-    View d_flat = mkview(h->d_e[last], s.encfc.g.Cin, 0);
-    H_TRY(block_bwd(h, s.encfc, B, fv4(h->d_cc, s.ncc, 0, F[L]), flat, nullptr, 0, &d_flat, 0));
+    View d_flat = mkview(gs.d_e[last], s.encfc.g.Cin, 0);
+    H_TRY(block_bwd(h, gs, s.encfc, B, fv4(gs.d_cc, s.ncc, 0, F[L]), flat, nullptr, 0, &d_flat, 0, st.w));
   }
   for (int k = last; k >= 0; --k) {
     Block& b = s.enc[k];
     View in = k > 0 ? mkview(s.enc[k - 1].out.p, s.enc[k - 1].feats, 0) : mkview(const_cast<float*>(xprev), h->C, 0);
-    View din = k > 0 ? mkview(h->d_e[k - 1], s.enc[k - 1].feats, 0) : mkview(gx_prev, h->C, 0);
+    View din = k > 0 ? mkview(gs.d_e[k - 1], s.enc[k - 1].feats, 0) : mkview(gx_prev, h->C, 0);
     // d_e[k-1] already holds the decoder shortcut gradient when k-1 is odd (e[l+1] = enc[2l+1]); gx_prev always holds
     // the highway gradient
     const int acc = k > 0 ? ((k - 1) & 1) : 1;
-    H_TRY(block_bwd(h, b, B, fv4(h->d_e[k], b.feats, 0, b.feats), in, nullptr, 0, &din, acc));
+    H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_e[k], b.feats, 0, b.feats), in, nullptr, 0, &din, acc, st.w));
   }
   return 0;
 }
 
-int recognition_bwd(svae_handle* h, Step& s, int B, float reg) {
+// runs on the current stream (the recognition stream when forked); weight gradients on `wst`
+int recognition_bwd(svae_handle* h, GradSet& gs, Step& s, int B, cudaStream_t wst) {
   const int L = h->L;
   LaunchCtx lc = h->lc();
   ReparamParams rp{B, h->Z, h->cfg.latent_mean_clip, h->cfg.prior_stddev};
-  const float kl_coef = step_has_kl(h, s.t) ? reg * step_coef(h, s.t) / ((float)B * h->Z) : 0.f;   // :1156-1164,1172
-  H_TRY(reparam_bwd(lc, rp, h->d_z, s.mu_pre, s.mu, s.sd, s.eps, kl_coef, h->d_mu_pre, h->d_sd_pre));
+  const float kl_scale = step_has_kl(h, s.t) ? step_coef(h, s.t) / ((float)B * h->Z) : 0.f;   // :1156-1164,1172
+  H_TRY(reparam_bwd(lc, rp, gs.d_z, s.mu_pre, s.mu, s.sd, s.eps, h->dyn_dev, kl_scale, gs.d_mu_pre, gs.d_sd_pre));
   for (int l = 0; l < L - 1; ++l) {
     const Block& fb = s.inf[2 * l + 1];
     const int K = fb.rpi * fb.feats;
     HeadSet hs = make_headset(h, s, l);
-    H_TRY(heads_dgrad(lc, hs, h->d_mu_pre, h->d_sd_pre, B, h->Z, K, h->d_inf[2 * l + 1]));
-    H_TRY(heads_wgrad(lc, fb.out.p, hs, h->d_mu_pre, h->d_sd_pre, B, h->Z, K));
+    H_TRY(heads_dgrad(lc, hs, gs.d_mu_pre, gs.d_sd_pre, B, h->Z, K, gs.d_inf[2 * l + 1]));
+    H_TRY(heads_wgrad(lc, fb.out.p, hs, gs.d_mu_pre, gs.d_sd_pre, B, h->Z, K));
   }
   for (int k = 2 * (L - 1) - 1; k >= 0; --k) {
     Block& b = s.inf[k];
     View in = k > 0 ? mkview(s.inf[k - 1].out.p, s.inf[k - 1].feats, 0) : mkview(const_cast<float*>(h->last_x), h->C, 0);
     if (k > 0) {
-      View din = mkview(h->d_inf[k - 1], s.inf[k - 1].feats, 0);
-      H_TRY(block_bwd(h, b, B, fv4(h->d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, &din, (k - 1) & 1));
+      View din = mkview(gs.d_inf[k - 1], s.inf[k - 1].feats, 0);
+      H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, &din, (k - 1) & 1, wst));
     } else {
-      H_TRY(block_bwd(h, b, B, fv4(h->d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, nullptr, 0));
+      H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, nullptr, 0, wst));
     }
   }
   return 0;
 }
 
-int allreduce_bucket(svae_handle* h, int t) {
+int allreduce_bucket(svae_handle* h, int t, const BwdStreams& st) {
   if (h->comm == nullptr) return 0;
   Step& s = h->steps[t];
-  H_CUDA(cudaEventRecord(h->bucket_ev[t], h->stream));
-  H_CUDA(cudaStreamWaitEvent(h->comm_stream, h->bucket_ev[t], 0));
+  // the bucket is complete when every stream that produced gradients of step t has finished its part
+  H_TRY(link(h, st.chain, h->comm_stream));
+  H_TRY(link(h, st.w, h->comm_stream));
+  H_TRY(link(h, st.rec, h->comm_stream));
+  H_TRY(link(h, st.recw, h->comm_stream));
   int r = h->nccl->AllReduce(h->G + s.p_begin, h->G + s.p_begin, (size_t)(s.p_end - s.p_begin), /*ncclFloat*/ 7,
                              /*ncclSum*/ 0, h->comm, h->comm_stream);
   if (r != 0) return fail(h, SVAE_ENCCL, std::string("ncclAllReduce failed: ") + h->nccl->GetErrorString(r));
@@ -778,20 +927,50 @@ int backward_impl(svae_handle* h) {
   if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "handle created without train_capacity");
   if (!h->have_fwd) return fail(h, SVAE_ESTATE, "svae_backward requires a preceding svae_forward");
   const int B = h->last_B, T = h->T;
+  h->cur = h->stream;
   H_TRY(zero_region(h, h->zb_base, h->zb_bytes));
   H_TRY(zero_region(h, h->G, (size_t)h->arena_numel * 4));
+  const bool fork = forked(h);
+  BwdStreams st{h->stream, h->stream, h->stream, h->stream};
+  if (fork) {
+    if (h->fork_mask & 1) st.w = h->side[0];
+    if (h->fork_mask & 2) st.rec = h->side[1];
+    st.recw = (h->fork_mask & 4) ? h->side[2] : st.rec;
+  }
+  // side_done[t][i]: side stream i has finished step t's work (its scratch set may be reused two steps later)
+  std::vector<cudaEvent_t> side_done((size_t)T * 3, nullptr);
   int cur = 0;
   const float* gx_in = nullptr;  // dL/dx_t from later steps
   for (int t = T - 1; t >= 0; --t) {
     Step& s = h->steps[t];
+    GradSet& gs = h->gs[t & 1];
+    if (fork && t + 2 < T)
+      for (int i = 0; i < 3; ++i) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + 2) * 3 + i], 0));
     const float* xprev = t > 0 ? h->steps[t - 1].xt : nullptr;
     float* gx_prev = h->gx[cur ^ 1];
-    H_TRY(decoder_bwd(h, s, B, gx_in, gx_prev, xprev));
-    if (t > 0) H_TRY(encoder_bwd(h, s, B, gx_prev, xprev));
-    H_TRY(recognition_bwd(h, s, B, h->last_reg));
-    H_TRY(allreduce_bucket(h, t));
+    H_TRY(decoder_bwd(h, gs, st, s, B, gx_in, gx_prev, xprev));
+    {
+      // recognition net of this step: needs d_z (complete once the last latent projection's backward has run on st.rec)
+      OnStream os(h, st.rec);
+      H_TRY(recognition_bwd(h, gs, s, B, st.recw));
+    }
+    if (t > 0) H_TRY(encoder_bwd(h, gs, st, s, B, gx_prev, xprev));
+    if (fork) {
+      cudaStream_t sd[3] = {st.w, st.rec, st.recw};
+      for (int i = 0; i < 3; ++i) {
+        side_done[(size_t)t * 3 + i] = next_event(h);
+        H_CUDA(cudaEventRecord(side_done[(size_t)t * 3 + i], sd[i]));
+      }
+    }
+    H_TRY(allreduce_bucket(h, t, st));
     gx_in = gx_prev;
     cur ^= 1;
+  }
+  if (fork)   // join: everything that follows on the main stream (Adam) sees all gradients
+  {
+    H_TRY(link(h, st.w, h->stream));
+    H_TRY(link(h, st.rec, h->stream));
+    H_TRY(link(h, st.recw, h->stream));
   }
   if (h->comm != nullptr) {
     H_CUDA(cudaEventRecord(h->comm_done, h->comm_stream));
@@ -805,8 +984,11 @@ int adam_impl(svae_handle* h, float lr) {
   h->adam_t += 1;
   const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)h->adam_t)) / (1.0 - pow(b1, (double)h->adam_t)));
+  h->cur = h->stream;
+  h->dyn_host.lr_t = lr_t;
+  H_TRY(dyn_push(h));
   LaunchCtx lc = h->lc();
-  H_TRY(adam_update(lc, h->P, h->G, h->M, h->V, h->arena_numel, lr_t, h->cfg.adam_beta1, h->cfg.adam_beta2,
+  H_TRY(adam_update(lc, h->P, h->G, h->M, h->V, h->arena_numel, h->dyn_dev, lr_t, h->cfg.adam_beta1, h->cfg.adam_beta2,
                     h->cfg.adam_eps, h->cfg.clip_value, 1.f / (float)h->nranks));
   h->weights_dirty = true;
   return 0;
@@ -852,9 +1034,10 @@ void plan_pack(svae_handle* h, Block& b, void* ctx) {
   Arena* a = (Arena*)ctx;
   if (h->cfg.operand_dtype != SVAE_OPERAND_BF16) return;
   Geom f = b.g; f.B = h->cfg.max_batch;
+  const bool is_fc = f.KH == 1;   // fc layers read the fp32 master weights directly (kernels_fc.cu): nothing to pack
   if (tc_supported(f)) {
     b.tc_fwd = true;
-    b.w_packed = a->get<char>(tc_packed_bytes(f));
+    if (!is_fc) b.w_packed = a->get<char>(tc_packed_bytes(f));
     if (a->base) h->tc_layers++;
   }
   if (tc_wgrad_supported(f)) {
@@ -864,15 +1047,15 @@ void plan_pack(svae_handle* h, Block& b, void* ctx) {
   Geom d = dgrad_geom(b.g); d.B = h->cfg.max_batch;
   if (tc_supported(d)) {
     b.tc_dgrad = true;
-    b.w_packed_d = a->get<char>(tc_packed_bytes(d));
+    if (!is_fc) b.w_packed_d = a->get<char>(tc_packed_bytes(d));
     if (a->base) h->tc_layers++;
   }
 }
 
 void collect_pack(svae_handle* h, Block& b, void* ctx) {
   std::vector<TcPackEntry>* v = (std::vector<TcPackEntry>*)ctx;
-  if (b.tc_fwd) { Geom f = b.g; f.B = 1; v->push_back(tc_pack_entry(f, h->pw(b.w), b.w_packed)); }
-  if (b.tc_dgrad) { Geom d = dgrad_geom(b.g); d.B = 1; v->push_back(tc_pack_entry(d, h->pw(b.w), b.w_packed_d)); }
+  if (b.tc_fwd && b.w_packed) { Geom f = b.g; f.B = 1; v->push_back(tc_pack_entry(f, h->pw(b.w), b.w_packed)); }
+  if (b.tc_dgrad && b.w_packed_d) { Geom d = dgrad_geom(b.g); d.B = 1; v->push_back(tc_pack_entry(d, h->pw(b.w), b.w_packed_d)); }
 }
 
 // fp32 master weights -> packed bf16 operand copies of every tensor-core layer, ONE launch
@@ -899,6 +1082,12 @@ void destroy_impl(svae_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
   for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
+  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->dyn_ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
+  cudaFree(h->dyn_dev);
+  if (h->dyn_ring) cudaFreeHost(h->dyn_ring);
   if (h->comm_done) cudaEventDestroy(h->comm_done);
   cudaFree(h->P); cudaFree(h->G); cudaFree(h->M); cudaFree(h->V);
   cudaFree(h->act_base); cudaFree(h->zf_base); cudaFree(h->zb_base); cudaFree(h->grad_base); cudaFree(h->pack_base); cudaFree(h->pack_table);
@@ -1012,6 +1201,19 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
   }
   C_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
+  {
+    const char* e1 = getenv("SVAE_STREAMS"); const char* e2 = getenv("SVAE_GRAPH");
+    h->use_streams = !(e1 && e1[0] == '0');
+    h->use_graph = !(e2 && e2[0] == '0');
+    const char* e3 = getenv("SVAE_FORK_MASK");
+    if (e3) h->fork_mask = atoi(e3);
+  }
+  if (cfg->train_capacity)
+    for (int i = 0; i < 3; ++i) C_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+  C_CUDA(cudaMalloc((void**)&h->dyn_dev, sizeof(SvaeDyn)));
+  C_CUDA(cudaMemset(h->dyn_dev, 0, sizeof(SvaeDyn)));
+  C_CUDA(cudaMallocHost((void**)&h->dyn_ring, sizeof(SvaeDyn) * 256));
+  h->dyn_ev.assign(256, nullptr);
   build_params(h);
   const size_t pbytes = (size_t)h->arena_numel * 4;
   C_CUDA(cudaMalloc(&h->P, pbytes));
@@ -1058,12 +1260,16 @@ int svae_destroy(svae_handle* h) { destroy_impl(h); return SVAE_OK; }
 int svae_set_stream(svae_handle* h, void* s) {
   if (!h) return SVAE_EINVAL;
   h->stream = s ? (cudaStream_t)s : h->own_stream;
+  h->cur = nullptr;
+  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);   // captured on the previous stream's dependencies
+  h->graphs.clear();
   return SVAE_OK;
 }
 int svae_sync(svae_handle* h) {
   if (!h) return SVAE_EINVAL;
   H_CUDA(cudaSetDevice(h->device));
   H_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 3; ++i) if (h->side[i]) H_CUDA(cudaStreamSynchronize(h->side[i]));
   if (h->comm_stream) H_CUDA(cudaStreamSynchronize(h->comm_stream));
   return SVAE_OK;
 }
@@ -1121,10 +1327,75 @@ int svae_adam_step(svae_handle* h, float lr) {
   H_CUDA(cudaSetDevice(h->device));
   return adam_impl(h, lr);
 }
+// One captured CUDA graph per (x, target, eps, batch) argument set: ~1300 kernel launches on four streams become one
+// graph launch.  Everything that changes between iterations (step size, KL coefficient, Philox key/counter) is read by
+// the kernels from h->dyn_dev, which a small copy enqueued just before the graph refreshes.
+static int train_step_graph(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float lr,
+                            float reg) {
+  GraphEntry* ge = nullptr;
+  for (GraphEntry& e : h->graphs)
+    if (e.x == x && e.tgt == tgt && e.eps == eps && e.B == B) ge = &e;
+  // host-side state the eager path would have updated
+  h->iteration += 1;
+  h->adam_t += 1;
+  const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+  h->dyn_host.lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)h->adam_t)) / (1.0 - pow(b1, (double)h->adam_t)));
+  h->dyn_host.reg = reg; h->dyn_host.seed = seed; h->dyn_host.iteration = h->iteration;
+  H_TRY(dyn_push(h));
+  if (ge == nullptr) {
+    if (h->graphs.size() >= 8) {   // callers that rotate many buffers: drop the oldest
+      cudaGraphExecDestroy(h->graphs.front().exec);
+      h->graphs.erase(h->graphs.begin());
+    }
+    const int64_t adam_t0 = h->adam_t, launches0 = h->launches;
+    h->adam_t -= 1;                 // adam_impl increments it again below
+    h->weights_dirty = true;        // the captured step always refreshes the packed operand copies
+    std::vector<cudaEvent_t> eager_pool;
+    eager_pool.swap(h->ev_pool);    // events recorded during capture are kept apart from the eager ones
+    h->capturing = true;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    int r = ce == cudaSuccess ? 0 : SVAE_ECUDA;
+    if (r == 0) r = forward_impl(h, x, tgt, B, eps, seed, reg, nullptr, nullptr, nullptr);
+    if (r == 0) r = backward_impl(h);
+    if (r == 0) r = adam_impl(h, lr);
+    cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
+    h->capturing = false;
+    h->ev_pool.swap(eager_pool);
+    for (cudaEvent_t e : eager_pool) cudaEventDestroy(e);
+    h->adam_t = adam_t0;
+    if (r != 0 || ee != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (r == 0) { svae_set_cuda_error(ee != cudaSuccess ? ee : ce, "stream capture of the train step", __FILE__, __LINE__); h->err = g_err; r = SVAE_ECUDA; }
+      return r;
+    }
+    GraphEntry e{x, tgt, eps, B, nullptr};
+    e.launches = h->launches - launches0;
+    h->launches = launches0;
+    cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { svae_set_cuda_error(ie, "cudaGraphInstantiate", __FILE__, __LINE__); h->err = g_err; return SVAE_ECUDA; }
+    h->graphs.push_back(e);
+    ge = &h->graphs.back();
+  }
+  H_CUDA(cudaGraphLaunch(ge->exec, h->stream));
+  h->launches += ge->launches;
+  h->last_B = B; h->last_reg = reg; h->last_x = x; h->last_tgt = tgt;
+  h->have_fwd = false;
+  h->weights_dirty = true;
+  return SVAE_OK;
+}
+
 int svae_train_step(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float lr,
                     float reg) {
   if (!h || !x || !tgt) return fail(h, SVAE_EINVAL, "null argument");
+  if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "handle created without train_capacity");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
   H_CUDA(cudaSetDevice(h->device));
+  // the first steps run eagerly (one-off allocations, function attributes); profiling needs per-kernel events
+  if (h->use_graph && !h->prof.enabled && h->eager_steps >= 1) return train_step_graph(h, x, tgt, B, eps, seed, lr, reg);
+  h->eager_steps += 1;
   h->iteration += 1;
   H_TRY(forward_impl(h, x, tgt, B, eps, seed, reg, nullptr, nullptr, nullptr));
   H_TRY(backward_impl(h));
@@ -1188,6 +1459,7 @@ int svae_generate(svae_handle* h, int B, const float* z, uint64_t seed, float* o
   if (!h || !out) return fail(h, SVAE_EINVAL, "null argument");
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
   H_CUDA(cudaSetDevice(h->device));
+  h->cur = h->stream;
   H_TRY(repack_if_dirty(h));
   H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
   LaunchCtx lc = h->lc();
@@ -1205,7 +1477,8 @@ int svae_generate(svae_handle* h, int B, const float* z, uint64_t seed, float* o
       H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
     }
     if (t > 0) H_TRY(encoder_fwd(h, s, B, prev));
-    H_TRY(decoder_fwd(h, s, B, z + t * bz, prev, nullptr, out + t * img, nullptr));
+    H_TRY(latent_fwd(h, s, B, z + t * bz));
+    H_TRY(decoder_fwd(h, s, B, prev, nullptr, out + t * img, nullptr));
     prev = out + t * img;
   }
   h->have_fwd = false;
@@ -1364,6 +1637,33 @@ int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const floa
   }
   return 0;
 }
+/* fully_connected data path (abstract_network.py:65; sequential_vae.py:1704,1775): y[B,N] = x[B,K] . w[K,N] */
+int svae_op_fc(svae_handle* h, const float* x, const float* w, float* y, int B, int K, int N, int operand) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  Geom g = fc_geom(K, N);
+  const bool tc = operand == SVAE_OPERAND_BF16;
+  if (tc && !tc_supported(g)) return fail(h, SVAE_EINVAL, "shape not supported by the tcgen05 kernels");
+  H_TRY(contract(h, g, B, mkview(const_cast<float*>(x), K, 0), w, nullptr, tc, mkview(y, N, 0), nullptr));
+  return 0;
+}
+int svae_op_fc_backward(svae_handle* h, const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int K,
+                        int N, int operand) {
+  if (!h) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  Geom f = fc_geom(K, N);
+  const bool tc = operand == SVAE_OPERAND_BF16;
+  if (tc && !tc_supported(f)) return fail(h, SVAE_EINVAL, "shape not supported by the tcgen05 kernels");
+  if (dx) H_TRY(contract(h, dgrad_geom(f), B, mkview(const_cast<float*>(dy), N, 0), w, nullptr, tc, mkview(dx, K, 0), nullptr));
+  if (dw) {
+    LaunchCtx lc = h->lc();
+    H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * N, h->stream));
+    Geom g = f; g.B = B;
+    if (tc) H_TRY(tc_wgrad(lc, g, mkview(const_cast<float*>(x), K, 0), mkview(const_cast<float*>(dy), N, 0), dw));
+    else H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(x), K, 0), mkview(const_cast<float*>(dy), N, 0), dw));
+  }
+  return 0;
+}
 extern void* g_tc_debug_buffer;
 int svae_debug_set_buffer(void* dev_buffer) { g_tc_debug_buffer = dev_buffer; return 0; }
 
@@ -1394,7 +1694,7 @@ int svae_op_adam(svae_handle* h, float* p, const float* g, float* m, float* v, i
   H_CUDA(cudaSetDevice(h->device));
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
   LaunchCtx lc = h->lc();
-  H_TRY(adam_update(lc, p, g, m, v, n, lr_t, b1, b2, eps, clip, gscale));
+  H_TRY(adam_update(lc, p, g, m, v, n, nullptr, lr_t, b1, b2, eps, clip, gscale));
   return 0;
 }
 

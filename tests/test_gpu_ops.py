@@ -132,6 +132,39 @@ def test_conv2d_transpose_backward(B, H, Ci, Co, stride, operand):
     assert rel_err(dw.cpu().numpy(), w.grad.numpy()) < _tol(operand)
 
 
+FC_CASES = [
+    # B, K, N  (enc.fc 2048->384, dec.fc 512|896->6144 at B=100; ragged sizes exercise the zero fill / scalar tails)
+    (100, 2048, 384), (100, 896, 6144), (100, 512, 6144), (4, 64, 64), (7, 200, 136), (130, 96, 72), (256, 320, 256),
+]
+
+
+@pytest.mark.parametrize("operand", [0, 1])
+@pytest.mark.parametrize("B,K,N", FC_CASES)
+def test_fc_forward_backward(B, K, N, operand):
+    """fully_connected data path of fc_bn_lrelu (abstract_network.py:65) and its gradients."""
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(B + K + N)
+    x = torch.randn(B, K, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(K, N, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    dy = torch.randn(B, N, generator=g, dtype=torch.float64)
+    with _mode(operand):
+        ref = O._fc(x, w)
+        ref.backward(dy)
+    y = torch.empty(B, N, device="cuda")
+    dx = torch.empty(B, K, device="cuda")
+    dw = torch.empty(K, N, device="cuda")
+    ux, uw, udy = dev(x.detach()), dev(w.detach()), dev(dy)
+    torch.cuda.synchronize()
+    rc = L.svae_op_fc(h, ptr(ux), ptr(uw), ptr(y), B, K, N, operand)
+    _maybe_skip_tc(rc, L, h)
+    rc = L.svae_op_fc_backward(h, ptr(ux), ptr(uw), ptr(udy), ptr(dx), ptr(dw), B, K, N, operand)
+    _maybe_skip_tc(rc, L, h)
+    m.sync()
+    assert rel_err(y.cpu().numpy(), ref.detach().numpy()) < _tol(operand)
+    assert rel_err(dx.cpu().numpy(), x.grad.numpy()) < _tol(operand)
+    assert rel_err(dw.cpu().numpy(), w.grad.numpy()) < _tol(operand)
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("rows,C", [(2 * 8 * 8, 16), (100, 6144), (7, 33), (4096, 32)])
 def test_bn_act(rows, C, act):
