@@ -1,5 +1,6 @@
 // common.cuh - shared declarations for libsvae (B200 / sm_100a).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -113,6 +114,44 @@ struct ProfScope {
 void svae_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 std::string& svae_global_error();
 
+// ---- bf16 activation copies for the TMA-fed kernels ------------------------------------------------------------------
+// A [B,H,W,C] tensor stored as bf16, PLANAR by 8-channel group, over the zero-padded linear pixel space of its consumer:
+//     element (n,h,w,c)  ->  p[ ((c/8) * group_rows + front + plane*plane_rows + q) * 8 + c%8 ]
+//   kind 0: q = (n*(H+2) + h)*(W+2) + w          (stride-1 windows)
+//   kind 1: q = (n*(H+1) + h)*(W+1) + w          (stride-2 transposed-conv input)
+//   kind 2: plane = (h&1)*2 + (w&1), q = (n*(H/2+1) + h/2)*(W/2+1) + w/2   (stride-2 conv input: four parity planes)
+// so that the halo of a 128-pixel tile is, per 8-channel group, ONE contiguous run of 16-byte pixels: a single
+// cp.async.bulk (TMA 1-D) brings it into exactly the canonical no-swizzle UMMA layout.  `front` zero rows before the
+// first pixel, a zero gap after every plane and a zero tail make every halo an in-bounds read; padding pixels are zero
+// and stay zero (producers only ever write valid pixels).
+struct BfAct {
+  __nv_bfloat16* p;
+  int kind, B, H, W, Cpad, Hp, Wp;
+  int front;              // zero rows before pixel 0 of the first plane
+  long long plane_rows;   // rows between parity planes (kind 2), = pixels + gap
+  long long group_rows;   // rows of one 8-channel group (front + planes + tail)
+};
+__host__ __device__ static inline size_t bf_index(const BfAct& d, int n, int h, int w, int c) {
+  long long q;
+  int pl = 0;
+  if (d.kind == 2) { q = ((long long)n * d.Hp + (h >> 1)) * d.Wp + (w >> 1); pl = (h & 1) * 2 + (w & 1); }
+  else q = ((long long)n * d.Hp + h) * d.Wp + w;
+  return (size_t)(((long long)(c >> 3) * d.group_rows + d.front + pl * d.plane_rows + q) * 8 + (c & 7));
+}
+// Where an elementwise producer writes the bf16 copy of (a channel window of) its output; p == nullptr: no copy.
+struct BfDst {
+  BfAct a;
+  int coff;        // first channel of the producer's window inside the copy (multiple of 8)
+  int inner, ppr;  // feature -> (pixel, channel) mapping of a 2-D batch norm whose output is a [.., S, S, inner] map
+                   // (0, 0: take the mapping of the fp32 output view)
+};
+BfAct bf_act_describe(int kind, int B, int H, int W, int C);
+size_t bf_act_bytes(const BfAct& d);
+int bf_act_fill(const LaunchCtx& lc, const BfAct& d, View src, int C);   // fp32 NHWC window -> padded bf16 copy (incl. zeros)
+bool tc2_supported(const Geom& g);
+int tc2_input_kind(const Geom& g);
+int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
+                    double* stats);
 // ---- SIMT fp32 contractions (kernels_simt.cu) ------------------------------------------------------------------
 int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w, View out, double* stats);
 // dW(tap,a,b) = sum_rows X(gathered at tap, channel a) * dY(row, channel b); layout w[(tap*Ca + a)*Cb + b].
@@ -133,15 +172,16 @@ int lat_dz(const LaunchCtx& lc, const float* dy, const float* w, int B, int KZ, 
 
 // ---- elementwise / reductions (kernels_elem.cu) ----------------------------------------------------------------
 int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats);
+// out.p may be NULL when only the bf16 copy is wanted; bf.a.p may be NULL
 int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const float* beta, int64_t rows, int feats,
-               int act, FeatView residual, FeatView out);
+               int act, FeatView residual, FeatView out, BfDst bf = BfDst{});
 // pass 1: dyhat = da * act'(bn(y)+res) ; S += (sum dyhat, sum dyhat*xhat) ; optional dres = dyhat (or += when acc)
 int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta,
                   int64_t rows, int feats, int act, FeatView residual, float* dyhat, double* S, float* dres,
                   int dres_accumulate);
 // pass 2: dy = rstd * (dyhat - S1/rows - xhat*S2/rows) in place ; dbeta = S1
 int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
-                 int feats, float* dbeta);
+                 int feats, float* dbeta, BfDst bf = BfDst{});
 struct OutMixParams {
   int64_t pixels;  // B*H*W
   int C;
@@ -150,11 +190,11 @@ struct OutMixParams {
 };
 // x_t = mix(sigmoid(u+bias)) ; accumulates sum (x_t - tgt)^2 into *recon_sum
 int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
-                const float* xprev, const float* tgt, float* xt, double* recon_sum);
+                const float* xprev, const float* tgt, float* xt, double* recon_sum, BfDst xt_bf = BfDst{});
 // g = gx_in (or 0) + coef*(x_t - tgt) ; du, gx_prev, bias grads
 int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
                 const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
-                float* gx_prev, float* db_out, float* db_gate);
+                float* gx_prev, float* db_out, float* db_gate, BfDst du_out_bf = BfDst{}, BfDst du_gate_bf = BfDst{});
 struct ReparamParams {
   int B, Z;
   float clip, prior;

@@ -7,6 +7,7 @@
 // tf.nn.relu / tf.concat / shortcut add (sequential_vae.py:1713-1716), output + highway mix (:1720-1729), loss
 // reductions (:1146-1164), reparameterisation (:1023), clip_by_value + AdamOptimizer (:18-25,1267-1276).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -74,9 +75,20 @@ __global__ void col_stats_kernel(const float* __restrict__ y, int64_t rows, int 
   }
 }
 
+// (pixel, channel) of feature f of row r for the bf16 copy: 4-D BN rows are pixels, 2-D BN rows are images
+__device__ __forceinline__ size_t bf_elem(const BfDst& bf, int64_t r, int f, int inner, int ppr) {
+  const int HW = bf.a.H * bf.a.W;
+  int64_t pix; int c;
+  { const int pf = f / inner; c = f - pf * inner; pix = r * ppr + pf; }   // 4-D: inner == feats, ppr == 1 -> (r, f)
+  const int n = (int)(pix / HW);
+  const int hw = (int)(pix - (int64_t)n * HW);
+  const int hh = hw / bf.a.W;
+  return bf_index(bf.a, n, hh, hw - hh * bf.a.W, bf.coff + c);
+}
+
 __global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                   const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
-                                  FeatView out) {
+                                  FeatView out, BfDst bf) {
   const int f = blockIdx.x * CX + threadIdx.x;
   if (f >= feats) return;
   float mean, rstd;
@@ -90,7 +102,56 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __r
   for (int64_t r = (int64_t)blockIdx.y * CY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * CY) {
     float v = fmaf(__ldg(y + (size_t)r * feats + f), rstd, sh);
     if (has_res) v += __ldg(res.p + r * rstride + roff);
-    out.p[r * ostride + ooff] = act_fwd(v, act);
+    v = act_fwd(v, act);
+    if (out.p != nullptr) out.p[r * ostride + ooff] = v;
+    if (bf.a.p != nullptr) bf.a.p[bf_elem(bf, r, f, bf.inner ? bf.inner : out.inner, bf.inner ? bf.ppr : out.ppr)] = __float2bfloat16_rn(v);
+  }
+}
+
+// Vectorised 4-D batch-norm apply (rows = pixels, C % 8 == 0): one thread per (pixel, 8-channel group) - two float4
+// loads of y (+ residual), optional fp32 NHWC store (channel window of a concat buffer), optional bf16 planar store
+// (one 16-byte write = exactly one pixel of one 8-channel plane of the consumer's TMA layout).
+__global__ void __launch_bounds__(256)
+bn_act_fwd_v8_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ beta,
+                     int64_t rows, int C, int act, const float* __restrict__ res, int res_ld, int res_coff,
+                     float* __restrict__ out, int out_ld, int out_coff, BfDst bf) {
+  extern __shared__ float s_coef[];   // [C] scale, [C] shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    bn_coeffs(stats, C, c, rows, mean, rstd);
+    s_coef[c] = rstd;
+    s_coef[C + c] = beta[c] - mean * rstd;
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  const int HW = bf.a.H * bf.a.W, W = bf.a.W;
+  const int64_t items = rows * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / G;
+    const int c0 = (int)(i - p * G) * 8;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0) + 1);
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_coef[c0 + e], s_coef[C + c0 + e]);
+    if (res != nullptr) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0) + 1);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = act_fwd(v[e], act);
+    if (out != nullptr) {
+      float4* o = reinterpret_cast<float4*>(out + p * out_ld + out_coff + c0);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (bf.a.p != nullptr) {
+      const int n = (int)(p / HW);
+      const int hw = (int)(p - (int64_t)n * HW);
+      const int hh = hw / W;
+      *reinterpret_cast<uint4*>(bf.a.p + bf_index(bf.a, n, hh, hw - hh * W, bf.coff + c0)) = tcptx::pack8_bf16(v);
+    }
   }
 }
 
@@ -135,7 +196,7 @@ __global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, c
 
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
                                     const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
-                                    int feats, float* __restrict__ dbeta) {
+                                    int feats, float* __restrict__ dbeta, BfDst bf) {
   const int f = blockIdx.x * CX + threadIdx.x;
   if (f >= feats) return;
   float mean, rstd;
@@ -146,7 +207,56 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __re
   for (int64_t r = (int64_t)blockIdx.y * CY + threadIdx.y; r < rows; r += (int64_t)gridDim.y * CY) {
     const size_t i = (size_t)r * feats + f;
     float xh = (__ldg(y + i) - mean) * rstd;
-    dyhat[i] = rstd * (dyhat[i] - m1 - xh * m2);
+    const float d = rstd * (dyhat[i] - m1 - xh * m2);
+    dyhat[i] = d;
+    if (bf.a.p != nullptr) bf.a.p[bf_elem(bf, r, f, feats, 1)] = __float2bfloat16_rn(d);
+  }
+}
+
+// Vectorised 4-D batch-norm backward, pass 2 (rows = pixels, C % 8 == 0): dy = rstd * (dyhat - S1/rows - xhat*S2/rows),
+// written in place (fp32, for the weight-gradient kernel) and as the bf16 planar copy the input-gradient kernel reads.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v8_kernel(float* __restrict__ dyhat, const float* __restrict__ y, const double* __restrict__ stats,
+                       const double* __restrict__ S, int64_t rows, int C, float* __restrict__ dbeta, int write_f32, BfDst bf) {
+  extern __shared__ float s_coef[];   // [C] mean, rstd, m1, m2
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    bn_coeffs(stats, C, c, rows, mean, rstd);
+    s_coef[c] = mean; s_coef[C + c] = rstd;
+    s_coef[2 * C + c] = (float)(S[c] / (double)rows);
+    s_coef[3 * C + c] = (float)(S[C + c] / (double)rows);
+    if (blockIdx.x == 0 && dbeta != nullptr) dbeta[c] = (float)S[c];
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  const int HW = bf.a.H * bf.a.W, W = bf.a.W;
+  const int64_t items = rows * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / G;
+    const int c0 = (int)(i - p * G) * 8;
+    float4* dp = reinterpret_cast<float4*>(dyhat + p * C + c0);
+    const float4 g0 = dp[0], g1 = dp[1];
+    const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0));
+    const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0) + 1);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    float d[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float rstd = s_coef[C + c0 + e];
+      const float xh = (yy[e] - s_coef[c0 + e]) * rstd;
+      d[e] = rstd * (g[e] - s_coef[2 * C + c0 + e] - xh * s_coef[3 * C + c0 + e]);
+    }
+    if (write_f32) {
+      dp[0] = make_float4(d[0], d[1], d[2], d[3]);
+      dp[1] = make_float4(d[4], d[5], d[6], d[7]);
+    }
+    if (bf.a.p != nullptr) {
+      const int n = (int)(p / HW);
+      const int hw = (int)(p - (int64_t)n * HW);
+      const int hh = hw / W;
+      *reinterpret_cast<uint4*>(bf.a.p + bf_index(bf.a, n, hh, hw - hh * W, bf.coff + c0)) = tcptx::pack8_bf16(d);
+    }
   }
 }
 
@@ -174,9 +284,10 @@ constexpr int MAXC = 4;  // image channels handled by the output-head kernels (1
 __global__ void __launch_bounds__(256)
 out_mix_fwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out,
                    const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
-                   float* __restrict__ xt, double* __restrict__ recon_sum) {
+                   float* __restrict__ xt, double* __restrict__ recon_sum, BfDst xbf) {
   __shared__ float red[32];
   const int ldu = p.C + p.has_gate;
+  const int HWb = xbf.a.H * xbf.a.W;
   float se = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.pixels; i += (int64_t)gridDim.x * blockDim.x) {
     const float* ur = u + (size_t)i * ldu;
@@ -189,6 +300,12 @@ out_mix_fwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
       float v = p.lo + (p.hi - p.lo) * o;                                             // :1721
       if (p.has_gate) v = r * v + (1.f - r) * xprev[(size_t)i * p.C + c];             // :1729
       xt[(size_t)i * p.C + c] = v;
+      if (xbf.a.p != nullptr) {   // bf16 copy for the next step's chain encoder (stride-2 conv input)
+        const int n = (int)(i / HWb);
+        const int hw = (int)(i - (int64_t)n * HWb);
+        const int hh = hw / xbf.a.W;
+        xbf.a.p[bf_index(xbf.a, n, hh, hw - hh * xbf.a.W, c)] = __float2bfloat16_rn(v);
+      }
       if (tgt != nullptr) {
         float d = v - tgt[(size_t)i * p.C + c];
         se += d * d;                                                                  // :1146
@@ -205,9 +322,11 @@ __global__ void __launch_bounds__(256)
 out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out,
                    const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
                    const float* __restrict__ xt, const float* __restrict__ gx_in, float coef, float* __restrict__ du,
-                   float* __restrict__ gx_prev, float* __restrict__ db_out, float* __restrict__ db_gate) {
+                   float* __restrict__ gx_prev, float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf) {
   __shared__ float red[32];
   const int ldu = p.C + p.has_gate;
+  const BfAct& la = obf.a.p != nullptr ? obf.a : gbf.a;
+  const int HWb = la.H * la.W, Wb = la.W;
   float bsum[MAXC + 1];
 #pragma unroll
   for (int c = 0; c <= MAXC; ++c) bsum[c] = 0.f;
@@ -220,6 +339,12 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
       r = p.minr + (p.maxr - p.minr) * s;
     }
     float dgate = 0.f;
+    int bn_ = 0, bh_ = 0, bw_ = 0;
+    if (obf.a.p != nullptr || gbf.a.p != nullptr) {
+      bn_ = (int)(i / HWb);
+      const int hw = (int)(i - (int64_t)bn_ * HWb);
+      bh_ = hw / Wb; bw_ = hw - bh_ * Wb;
+    }
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       if (c >= p.C) break;
@@ -230,6 +355,7 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
       float outv = p.lo + (p.hi - p.lo) * o;
       float d_u = g * r * (p.hi - p.lo) * o * (1.f - o);
       dr[c] = d_u;
+      if (obf.a.p != nullptr) obf.a.p[bf_index(obf.a, bn_, bh_, bw_, c)] = __float2bfloat16_rn(d_u);
       bsum[c] += d_u;
       if (p.has_gate) {
         dgate += g * (outv - xprev[ix]);
@@ -239,6 +365,7 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
     if (p.has_gate) {
       float d_g = dgate * (p.maxr - p.minr) * s * (1.f - s);
       dr[p.C] = d_g;
+      if (gbf.a.p != nullptr) gbf.a.p[bf_index(gbf.a, bn_, bh_, bw_, 0)] = __float2bfloat16_rn(d_g);
       bsum[MAXC] += d_g;
     }
   }
@@ -380,11 +507,27 @@ int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* 
   return 0;
 }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const float* beta, int64_t rows, int feats,
-               int act, FeatView residual, FeatView out) {
-  ColGrid cg = col_grid(rows, feats, lc.sm_count);
-  ProfScope ps(lc, KC_BN_FWD, 4.0 * rows * feats, 4.0 * rows * feats * (residual.p ? 3 : 2));
-  bn_act_fwd_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, stats, beta, rows, feats, act, residual, out);
+               int act, FeatView residual, FeatView out, BfDst bf) {
+  Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
+  const double bytes = 4.0 * rows * feats * (1 + (residual.p ? 1 : 0) + (out.p ? 1 : 0)) + (bf.a.p ? 2.0 * rows * feats : 0.0);
+  ProfScope ps(lc, KC_BN_FWD, 4.0 * rows * feats, bytes, &tg);
+  // 4-D batch norm (rows are pixels) with whole 8-channel groups: vectorised kernel
+  const bool v8 = out.ppr == 1 && out.inner == feats && feats % 8 == 0 && feats <= 2048 && aligned16(y) &&
+                  (out.p == nullptr || (out.ld % 4 == 0 && out.coff % 4 == 0 && aligned16(out.p))) &&
+                  (residual.p == nullptr || (residual.ppr == 1 && residual.inner == feats && residual.ld % 4 == 0 &&
+                                             residual.coff % 4 == 0 && aligned16(residual.p))) &&
+                  (bf.a.p == nullptr || (bf.coff % 8 == 0 && bf.inner == 0 && (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows));
+  if (v8) {
+    const int64_t items = rows * (feats / 8);
+    bn_act_fwd_v8_kernel<<<flat_blocks(items, lc.sm_count), 256, 2 * feats * sizeof(float), lc.stream>>>(
+        y, stats, beta, rows, feats, act, residual.p, residual.ld, residual.coff, out.p, out.ld, out.coff, bf);
+  } else {
+    ColGrid cg = col_grid(rows, feats, lc.sm_count);
+    bn_act_fwd_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, stats, beta, rows, feats, act, residual, out, bf);
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -393,8 +536,9 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
                   int64_t rows, int feats, int act, FeatView residual, float* dyhat, double* S, float* dres,
                   int dres_accumulate) {
   ColGrid cg = col_grid(rows, feats, lc.sm_count);
+  Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
   ProfScope ps(lc, KC_BN_BWD_REDUCE, 8.0 * rows * feats,
-               4.0 * rows * feats * (3 + (residual.p ? 1 : 0) + (dres ? 1 : 0)));
+               4.0 * rows * feats * (3 + (residual.p ? 1 : 0) + (dres ? 1 : 0)), &tg);
   bn_bwd_reduce_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(da, y, stats, beta, rows, feats, act, residual, dyhat, S,
                                                             dres, dres_accumulate);
   CUDA_TRY(cudaGetLastError());
@@ -402,33 +546,43 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
 }
 
 int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
-                 int feats, float* dbeta) {
-  ColGrid cg = col_grid(rows, feats, lc.sm_count);
-  ProfScope ps(lc, KC_BN_BWD_APPLY, 5.0 * rows * feats, 12.0 * rows * feats);
-  bn_bwd_apply_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(dyhat, y, stats, S, rows, feats, dbeta);
+                 int feats, float* dbeta, BfDst bf) {
+  Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
+  ProfScope ps(lc, KC_BN_BWD_APPLY, 5.0 * rows * feats, 12.0 * rows * feats + (bf.a.p ? 2.0 * rows * feats : 0.0), &tg);
+  const bool v8 = bf.a.p != nullptr && feats % 8 == 0 && feats <= 2048 && aligned16(dyhat) && aligned16(y) && bf.coff % 8 == 0 &&
+                  (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows;
+  if (v8) {
+    const int64_t items = rows * (feats / 8);
+    bn_bwd_apply_v8_kernel<<<flat_blocks(items, lc.sm_count), 256, 4 * feats * sizeof(float), lc.stream>>>(
+        dyhat, y, stats, S, rows, feats, dbeta, 1, bf);
+  } else {
+    ColGrid cg = col_grid(rows, feats, lc.sm_count);
+    bn_bwd_apply_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(dyhat, y, stats, S, rows, feats, dbeta, bf);
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
-                const float* xprev, const float* tgt, float* xt, double* recon_sum) {
+                const float* xprev, const float* tgt, float* xt, double* recon_sum, BfDst xt_bf) {
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 20.0 * p.pixels * p.C,
                4.0 * p.pixels * (p.C + p.has_gate + p.C * (1 + (p.has_gate ? 1 : 0) + (tgt ? 1 : 0))));
   out_mix_fwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
-                                                                               recon_sum);
+                                                                               recon_sum, xt_bf);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
                 const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
-                float* gx_prev, float* db_out, float* db_gate) {
+                float* gx_prev, float* db_out, float* db_gate, BfDst du_out_bf, BfDst du_gate_bf) {
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 30.0 * p.pixels * p.C,
                4.0 * p.pixels * (2 * (p.C + p.has_gate) + p.C * (2 + (gx_in ? 1 : 0) + (p.has_gate ? 2 : 0))));
   out_mix_bwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
-                                                                               gx_in, coef, du, gx_prev, db_out, db_gate);
+                                                                               gx_in, coef, du, gx_prev, db_out, db_gate,
+                                                                               du_out_bf, du_gate_bf);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

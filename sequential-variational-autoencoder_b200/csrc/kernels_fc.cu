@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(160) tc_fc_kernel(const __grid_constant__ FcPa
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FcSmem* hdr = reinterpret_cast<FcSmem*>(smem_raw);
   unsigned char* bufs = smem_raw + 128;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uniform_u32((unsigned)(tid >> 5));
   const int col0 = blockIdx.x * 128, row0 = blockIdx.y * 128;
   const int nchunks_total = (P.R + FC_RC - 1) / FC_RC;
   const int c_begin = blockIdx.z * P.chunks_per_split;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(160) tc_fc_kernel(const __grid_constant__ FcPa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const unsigned tmem_base = hdr->tmem_base;
+  const unsigned tmem_base = uniform_u32(hdr->tmem_base);
 
   if (warp < 4) {
     for (int it = 0; it < my_chunks; ++it) {
@@ -151,11 +152,12 @@ __global__ void __launch_bounds__(160) tc_fc_kernel(const __grid_constant__ FcPa
     // instruction descriptor: bf16 x bf16 -> fp32, M = 128, N = 128, major bits 15 (A) / 16 (B)
     const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(P.a.mn_major != 0) << 15) |
                            ((unsigned)(P.b.mn_major != 0) << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    const bool leader = elect_one();
     for (int it = 0; it < my_chunks; ++it) {
       const int buf = it % FC_STAGES;
       mbar_wait(smem_u32(&hdr->ready[buf]), (unsigned)(it / FC_STAGES) & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      if (leader) {
         const unsigned ab = smem_u32(bufs + (size_t)buf * 2 * FC_OP_BYTES);
         const unsigned bb = ab + FC_OP_BYTES;
 #pragma unroll
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(160) tc_fc_kernel(const __grid_constant__ FcPa
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(smem_u32(&hdr->acc_done));
+    if (leader) umma_commit(smem_u32(&hdr->acc_done));
     __syncwarp();
   }
   __syncthreads();

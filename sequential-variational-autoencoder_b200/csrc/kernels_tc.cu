@@ -49,6 +49,9 @@ struct TcParams {
 };
 
 using namespace tcptx;
+}
+extern void* g_tc_debug_buffer;
+namespace {
 
 
 struct SmemHeader {
@@ -545,7 +548,8 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
   SmemHeaderW* hdr = reinterpret_cast<SmemHeaderW*>(smem_raw);
   unsigned char* bufs = smem_raw + 128;
   const unsigned stage_bytes = P.x_buf_bytes + P.y_buf_bytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uniform_u32((unsigned)(tid >> 5));
   int by = blockIdx.y;
   const int nb = by % P.nblocks; by /= P.nblocks;
   const int mb = by % P.mblocks; by /= P.mblocks;
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const unsigned tmem_base = hdr->tmem_base;
+  const unsigned tmem_base = uniform_u32(hdr->tmem_base);
   const unsigned PITCH_X = (unsigned)P.HLpad * 16u, PITCH_Y = (unsigned)P.YLpad * 16u;
 
   if (warp < 4) {
@@ -606,32 +610,44 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
     }
     tc_fence_before();
   } else {
+    // issue loop on uniform operands (see tc2_conv_kernel): descriptor high words are loop invariants, the low words
+    // advance by 16 (= 256 bytes = 16 pixels) per MMA
     const unsigned idesc = make_idesc_mn(TILE_M, P.N);
-    unsigned started = 0;
-    for (long long it = 0; it < my_tiles; ++it) {
-      const int buf = (int)(it % P.bufs);
+    // MN-major canonical layout: 8 pixels (K) at 16 B, next K group at LBO = 128 B, next 8 channels at SBO = pitch
+    const unsigned long long a_hi = ((unsigned long long)((PITCH_X >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((128u >> 4) & 0x3FFF) << 16);
+    const unsigned long long b_hi = ((unsigned long long)((PITCH_Y >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((128u >> 4) & 0x3FFF) << 16);
+    const bool leader = elect_one();
+    const int my_tiles_i = (int)my_tiles;
+    unsigned first = 1u;
+    for (int it = 0; it < my_tiles_i; ++it) {
+      const int buf = it % P.bufs;
       mbar_wait(smem_u32(&hdr->ready[buf]), (unsigned)(it / P.bufs) & 1u);
       tc_fence_after();
-      if (lane == 0) {
-        const unsigned xb = smem_u32(bufs + (size_t)buf * stage_bytes);
-        const unsigned yb = xb + P.x_buf_bytes;
+      if (leader) {
+        const unsigned xb4 = smem_u32(bufs + (size_t)buf * stage_bytes) >> 4;
+        const unsigned yb4 = xb4 + (P.x_buf_bytes >> 4);
         for (int tl = 0; tl < P.taps_per_cta; ++tl) {
           const int tap = grp * P.taps_per_cta + tl;
           const unsigned d_tmem = tmem_base + (unsigned)(tl * P.N);
-          const unsigned xrow = xb + (unsigned)(P.plane[tap] * P.JA) * PITCH_X + (unsigned)(P.lo + P.shift[tap]) * 16u;
+          unsigned a_lo = xb4 + (unsigned)(P.plane[tap] * P.JA) * (PITCH_X >> 4) + (unsigned)(P.lo + P.shift[tap]);
+          unsigned b_lo = yb4;
+          unsigned acc_flag = first ^ 1u;
+#pragma unroll
           for (int k = 0; k < TILE_M / 16; ++k) {
-            // MN-major canonical layout: 8 pixels (K) at 16 B, next K group at LBO = 128 B, next 8 channels at SBO = pitch
-            const unsigned long long adesc = make_desc(xrow + (unsigned)k * 256u, 128u, PITCH_X);
-            const unsigned long long bdesc = make_desc(yb + (unsigned)k * 256u, 128u, PITCH_Y);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (started >> tl) & 1u);
-            started |= 1u << tl;
+            umma_bf16(d_tmem, a_hi | (unsigned long long)(a_lo & 0x3FFF), b_hi | (unsigned long long)(b_lo & 0x3FFF), idesc, acc_flag);
+            acc_flag = 1u;
+            a_lo += 16u;
+            b_lo += 16u;
           }
         }
         umma_commit(smem_u32(&hdr->free_[buf]));
       }
+      first = 0u;
       __syncwarp();
     }
-    if (lane == 0) umma_commit(smem_u32(&hdr->acc_done));
+    if (leader) umma_commit(smem_u32(&hdr->acc_done));
     __syncwarp();
   }
   __syncthreads();
@@ -693,6 +709,454 @@ bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
 
 
 }  // namespace
+
+
+// =====================================================================================================================
+// TMA-fed persistent variant of the shifted-window kernel ("tc2").
+// Activations arrive as bf16 copies in a zero-padded NHWC layout written by the producing elementwise kernel
+// (BfAct, common.cuh): the halo of a tile is then a contiguous pixel range of every 8-channel plane and one elected thread
+// stages it with cp.async.bulk.tensor (2-D box = 8 channels x <= 256 pixels, out-of-range pixels zero-filled by the
+// TMA unit) - no SIMT staging, no index math, no fp32 re-read.  The CTA is persistent: it walks tiles blockIdx.x,
+// +gridDim.x, ...; the packed weights of layers up to 144 KB stay resident in shared memory for all of them; the
+// accumulator is double-buffered in TMEM so that the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warps: 0 halo producer (TMA), 1 weight producer (bulk copies), 2 MMA issuer + TMEM owner, 3-6 epilogue.
+namespace {
+
+constexpr int A_STAGES_MAX = 4;
+constexpr unsigned W_RESIDENT_MAX = 144 * 1024;
+
+struct Tc2Params {
+  TcParams t;               // geometry (mode, padded space, taps, chunking) as for the SIMT-staged kernel
+  int tiles;
+  int nsplit, boxp;         // TMA boxes per 8-channel plane, pixels per box
+  unsigned a_pitch;         // bytes between planes in shared memory
+  unsigned a_bytes;         // one halo (all planes of one channel chunk)
+  int a_stages;
+  int w_resident;           // 1: all weights of the CTA's N tile live in shared memory
+  unsigned w_bytes_ntile;   // packed bytes of one full N tile (128 columns)
+  unsigned w_region;        // shared-memory bytes reserved for weights (resident copy or ring)
+  int w_stages;             // ring mode: stages of b_stage_max bytes
+  int acc_bufs;             // TMEM accumulator sets (2 = epilogue overlaps the next tile's MMAs)
+  unsigned acc_cols;        // columns per set (nacc * Nt rounded for the allocation)
+  unsigned tmem_cols;
+  const __nv_bfloat16* a_src;   // bf16 planar activation copy, pointing at (group chan0/8, pixel 0 of plane 0)
+  long long plane_rows;     // rows between parity planes
+  long long group_rows;     // rows between 8-channel groups
+};
+
+struct SmemHeader2 {
+  unsigned long long a_full[A_STAGES_MAX], a_empty[A_STAGES_MAX], w_full[MAX_STAGES], w_empty[MAX_STAGES];
+  unsigned long long acc_full[2], acc_empty[2];
+  unsigned tmem_base, pad;
+  float s_sum[4][128], s_sq[4][128];
+  unsigned tap_a_lo[16], tap_dcol[16];
+  volatile unsigned long long ts[16];   // debug timestamps (svae_debug_set_buffer)
+};
+#define DBG2(slot) do { if (P.dbg != nullptr) { const unsigned long long t_ = gtimer(); if ((threadIdx.x & 31) == 0) hdr->ts[slot] = t_; } } while (0)
+
+__global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const TcParams& P = PP.t;
+  SmemHeader2* hdr = reinterpret_cast<SmemHeader2*>(smem_raw);
+  unsigned char* w_smem = smem_raw + ((sizeof(SmemHeader2) + 127) & ~127u);
+  const int n0 = blockIdx.y * 128;
+  const int Nt = min(128, P.N_p - n0);
+  const unsigned b_tap_bytes = (unsigned)(P.KC * Nt * 2);
+  const unsigned b_stage_bytes = b_tap_bytes * (unsigned)P.tps;
+  unsigned char* a_smem = w_smem + PP.w_region;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uniform_u32((unsigned)(tid >> 5));   // warp-uniform for the compiler: role branches stay convergent
+  const int my_tiles = (PP.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (warp == 0) DBG2(0);
+
+  if (tid == 0) {
+    for (int s = 0; s < A_STAGES_MAX; ++s) { mbar_init(smem_u32(&hdr->a_full[s]), 1); mbar_init(smem_u32(&hdr->a_empty[s]), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(smem_u32(&hdr->w_full[s]), 1); mbar_init(smem_u32(&hdr->w_empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&hdr->acc_full[b]), 1); mbar_init(smem_u32(&hdr->acc_empty[b]), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&hdr->tmem_base), PP.tmem_cols);
+  if (warp >= 3) {
+    for (int i = tid - 96; i < 4 * 128; i += 128) { (&hdr->s_sum[0][0])[i] = 0.f; (&hdr->s_sq[0][0])[i] = 0.f; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = uniform_u32(hdr->tmem_base);
+  if (warp == 0) DBG2(1);
+
+  if (warp == 0) {
+    // ================= halo producer: one bulk copy (TMA 1-D) per (parity plane, 8-channel group) =================
+    int it = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int q0 = ((int)blockIdx.x + ti * (int)gridDim.x) * TILE_M;
+      for (int c = 0; c < P.NC; ++c, ++it) {
+        const int s = it % PP.a_stages;
+        if (it >= PP.a_stages) mbar_wait(smem_u32(&hdr->a_empty[s]), (unsigned)((it / PP.a_stages) - 1) & 1u);
+        if (lane == 0) {
+          const unsigned bar = smem_u32(&hdr->a_full[s]);
+          mbar_expect_tx(bar, PP.a_bytes);
+          const unsigned abase = smem_u32(a_smem + (size_t)s * PP.a_bytes);
+          for (int pl = 0; pl < P.nplanes; ++pl)
+            for (int j = 0; j < P.JC; ++j)
+              bulk_g2s(abase + (unsigned)(pl * P.JC + j) * PP.a_pitch,
+                       PP.a_src + ((long long)(c * P.JC + j) * PP.group_rows + pl * PP.plane_rows + (q0 - P.lo)) * 8,
+                       PP.a_pitch, bar);
+        }
+        __syncwarp();
+        if (it == 0) DBG2(2);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= weight producer =================
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2;
+    if (PP.w_resident) {
+      if (lane == 0 && my_tiles > 0) {
+        const unsigned total = (unsigned)(P.NC * P.ntaps) * b_tap_bytes;
+        const unsigned bar = smem_u32(&hdr->w_full[0]);
+        mbar_expect_tx(bar, total);
+        for (unsigned off = 0; off < total; off += 32768u)
+          bulk_g2s(smem_u32(w_smem + off), wsrc + off, min(32768u, total - off), bar);
+      }
+    } else {
+      int stage = 0; unsigned phase = 0;
+      for (int ti = 0; ti < my_tiles; ++ti)
+        for (int c = 0; c < P.NC; ++c)
+          for (int s = 0; s < P.ntaps; s += P.tps) {
+            mbar_wait(smem_u32(&hdr->w_empty[stage]), phase ^ 1);
+            if (lane == 0) {
+              mbar_expect_tx(smem_u32(&hdr->w_full[stage]), b_stage_bytes);
+              bulk_g2s(smem_u32(w_smem + (size_t)stage * P.b_stage_max), wsrc + ((size_t)c * P.ntaps + s) * b_tap_bytes,
+                       b_stage_bytes, smem_u32(&hdr->w_full[stage]));
+            }
+            __syncwarp();
+            if (++stage == PP.w_stages) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer =================
+    // Every operand of the issue loop is derived from kernel parameters, loop counters and the (uniform) shared-memory
+    // window, so that descriptors live in uniform registers: the loop is a handful of uniform ALU ops per tcgen05.mma.
+    const unsigned idesc = make_idesc(TILE_M, Nt);
+    const unsigned LBO_A = PP.a_pitch, LBO_B = (unsigned)Nt * 16u;
+    const unsigned long long a_hi = ((unsigned long long)((128u >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((LBO_A >> 4) & 0x3FFF) << 16);
+    const unsigned long long b_hi = ((unsigned long long)((128u >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((LBO_B >> 4) & 0x3FFF) << 16);
+    const unsigned a_kstep = (2u * LBO_A) >> 4, b_kstep = (2u * LBO_B) >> 4;
+    const unsigned plane4 = ((unsigned)P.JC * LBO_A) >> 4;     // one parity plane further (in 16-byte units)
+    const int nk = P.KC / 16;
+    const bool leader = elect_one();
+    int stage = 0; unsigned phase = 0;
+    int it = 0;
+    if (PP.w_resident && my_tiles > 0) mbar_wait(smem_u32(&hdr->w_full[0]), 0);
+    DBG2(3);
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int b = ti % PP.acc_bufs;
+      if (ti >= PP.acc_bufs) mbar_wait(smem_u32(&hdr->acc_empty[b]), (unsigned)((ti / PP.acc_bufs) - 1) & 1u);
+      tc_fence_after();
+      const unsigned acc_base = tmem_base + (unsigned)b * PP.acc_cols;
+      unsigned started = 0;
+      for (int c = 0; c < P.NC; ++c, ++it) {
+        const int s = it % PP.a_stages;
+        mbar_wait(smem_u32(&hdr->a_full[s]), (unsigned)(it / PP.a_stages) & 1u);
+        tc_fence_after();
+        if (it == 0) DBG2(4);
+        const unsigned abase4 = smem_u32(a_smem + (size_t)s * PP.a_bytes) >> 4;
+        for (int s0 = 0; s0 < P.ntaps; s0 += P.tps) {
+          unsigned b_lo;
+          if (PP.w_resident) {
+            b_lo = smem_u32(w_smem + ((size_t)c * P.ntaps + s0) * b_tap_bytes) >> 4;
+          } else {
+            mbar_wait(smem_u32(&hdr->w_full[stage]), phase);
+            tc_fence_after();
+            b_lo = smem_u32(w_smem + (size_t)stage * P.b_stage_max) >> 4;
+          }
+          if (leader) {
+            for (int tl = 0; tl < P.tps; ++tl) {
+              const int tp = s0 + tl;
+              const unsigned a = (unsigned)P.acc[tp];
+              const unsigned d_tmem = acc_base + a * (unsigned)Nt;
+              unsigned a_lo = abase4 + (unsigned)P.plane[tp] * plane4 + (unsigned)(P.lo + P.shift[tp]);
+              unsigned bk = b_lo;
+              unsigned acc_flag = (started >> a) & 1u;
+              for (int kk = 0; kk < nk; ++kk) {
+                umma_bf16(d_tmem, a_hi | (unsigned long long)(a_lo & 0x3FFF), b_hi | (unsigned long long)(bk & 0x3FFF), idesc,
+                          acc_flag);
+                acc_flag = 1u;
+                a_lo += a_kstep;
+                bk += b_kstep;
+              }
+              started |= 1u << a;
+              b_lo += b_tap_bytes >> 4;
+            }
+            if (!PP.w_resident) umma_commit(smem_u32(&hdr->w_empty[stage]));
+          }
+          __syncwarp();
+          if (!PP.w_resident) { if (++stage == PP.w_stages) { stage = 0; phase ^= 1; } }
+        }
+        if (leader) umma_commit(smem_u32(&hdr->a_empty[s]));
+        __syncwarp();
+      }
+      if (leader) umma_commit(smem_u32(&hdr->acc_full[b]));
+      __syncwarp();
+      if (ti == 0) DBG2(5);
+      if (ti == my_tiles - 1) DBG2(8);
+    }
+  } else {
+    // ================= epilogue warps 3..6: TMEM lane quarter = warp % 4 =================
+    const int quarter = warp & 3;
+    const int et = tid - 96;                          // 0..127 inside the epilogue group
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int b = ti % PP.acc_bufs;
+      mbar_wait(smem_u32(&hdr->acc_full[b]), (unsigned)(ti / PP.acc_bufs) & 1u);
+      tc_fence_after();
+      if (ti == 0 && warp == 3) DBG2(6);
+      const int q0 = ((int)blockIdx.x + ti * (int)gridDim.x) * TILE_M;
+      const int q = q0 + quarter * 32 + lane;
+      bool valid = q < (int)P.Q;
+      int n = 0, r = 0, cc = 0;
+      if (valid) {
+        const int t = q / P.Wp;
+        cc = q - t * P.Wp;
+        n = t / P.Hp;
+        r = t - n * P.Hp;
+        valid = r < P.Hv && cc < P.Wv;
+      }
+      const unsigned acc_base = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)b * PP.acc_cols;
+      for (int a = 0; a < P.nacc; ++a) {
+        int oh = r, ow = cc;
+        if (P.mode == 2) { oh = 2 * r + (a >> 1); ow = 2 * cc + (a & 1); }
+        float* orow = P.out + (((size_t)n * P.Hout + oh) * P.Wout + ow) * P.out_ld + P.out_coff + n0;
+        for (int nn = 0; nn < Nt; nn += 32) {
+          float v[32];
+          tmem_ld_upto32(acc_base + (unsigned)(a * Nt + nn), v, Nt - nn);
+          const int ncols = max(0, min(min(32, Nt - nn), P.n_valid - (n0 + nn)));
+          if (valid) {
+            if (P.out_vec) {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                if (k < ncols) {
+                  float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                  float4* dst = reinterpret_cast<float4*>(orow + nn + k);
+                  if (P.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                  *dst = o;
+                  v[k] = o.x; v[k + 1] = o.y; v[k + 2] = o.z; v[k + 3] = o.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                if (k < ncols) {
+                  float o = v[k];
+                  if (P.accumulate) o += orow[nn + k];
+                  orow[nn + k] = o;
+                  v[k] = o;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+          }
+          if (P.stats != nullptr) {
+            float sq[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { if (k >= ncols) v[k] = 0.f; sq[k] = v[k] * v[k]; }
+            const float cs = warp_colsum32(v, lane);
+            const float cq = warp_colsum32(sq, lane);
+            hdr->s_sum[quarter][nn + lane] += cs;      // this warp's slot: accumulated over phases and over the CTA's tiles
+            hdr->s_sq[quarter][nn + lane] += cq;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&hdr->acc_empty[b]));
+      if (ti == 0 && warp == 3) DBG2(7);
+      if (ti == my_tiles - 1 && warp == 3) DBG2(9);
+    }
+    if (P.stats != nullptr && my_tiles > 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = et; col < Nt; col += 128) {
+        if (n0 + col < P.n_valid) {
+          const float s = hdr->s_sum[0][col] + hdr->s_sum[1][col] + hdr->s_sum[2][col] + hdr->s_sum[3][col];
+          const float s2 = hdr->s_sq[0][col] + hdr->s_sq[1][col] + hdr->s_sq[2][col] + hdr->s_sq[3][col];
+          atomicAdd(&P.stats[n0 + col], (double)s);
+          atomicAdd(&P.stats[P.n_valid + n0 + col], (double)s2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) DBG2(10);
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, PP.tmem_cols);
+  }
+  if (P.dbg != nullptr) {
+    __syncthreads();
+    if (tid < 16) P.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + tid] = tid == 15 ? (unsigned long long)my_tiles : hdr->ts[tid];
+  }
+}
+
+bool build_params2(const Geom& g, Tc2Params& PP) {
+  memset(&PP, 0, sizeof PP);
+  TcParams& P = PP.t;
+  if (g.KH != 4) return false;
+  if (!build_params(g, P)) return false;
+  PP.tiles = (int)((P.Q + TILE_M - 1) / TILE_M);
+  PP.nsplit = 1;
+  PP.boxp = (P.HL + 7) & ~7;            // pixels per plane copy (16 B each); keeps every plane 128-byte aligned
+  PP.a_pitch = (unsigned)PP.boxp * 16u;
+  PP.a_bytes = (unsigned)(P.nplanes * P.JC) * PP.a_pitch;
+  const int nt_max = P.N_p < 128 ? P.N_p : 128;
+  PP.w_bytes_ntile = (unsigned)(P.NC * P.ntaps) * (unsigned)(P.KC * 128 * 2);
+  const unsigned w_need = (unsigned)(P.NC * P.ntaps) * (unsigned)(P.KC * nt_max * 2);
+  PP.w_resident = w_need <= W_RESIDENT_MAX ? 1 : 0;
+  const size_t hdr = (sizeof(SmemHeader2) + 127) & ~(size_t)127;
+  size_t w_region;
+  if (PP.w_resident) {
+    w_region = PP.w_bytes_ntile;        // region sized for a full tile; only w_need bytes are filled
+    if (nt_max < 128) w_region = w_need;
+  } else {
+    PP.w_stages = MAX_STAGES;
+    while (PP.w_stages > 2 && hdr + (size_t)PP.w_stages * P.b_stage_max + 2 * (size_t)PP.a_bytes + 256 > 227 * 1024) --PP.w_stages;
+    w_region = (size_t)PP.w_stages * P.b_stage_max;
+  }
+  w_region = (w_region + 127) & ~(size_t)127;
+  PP.w_region = (unsigned)w_region;
+  size_t left = 227 * 1024 - hdr - w_region - 256;
+  if (hdr + w_region + 256 > 227 * 1024 || left < PP.a_bytes) return false;
+  PP.a_stages = (int)(left / PP.a_bytes);
+  if (PP.a_stages > A_STAGES_MAX) PP.a_stages = A_STAGES_MAX;
+  const int want = P.NC > 1 ? 3 : 2;   // keep the footprint modest: two CTAs per SM help the short layers
+  if (PP.a_stages > want) PP.a_stages = want;
+  if (PP.a_stages < 1) return false;
+  unsigned cols = (unsigned)(P.nacc * nt_max), t = 32;
+  while (t < cols) t <<= 1;
+  PP.acc_cols = t;
+  PP.acc_bufs = 2 * t <= 512 ? 2 : 1;
+  PP.tmem_cols = t * (unsigned)PP.acc_bufs;
+  return PP.tmem_cols <= 512;
+}
+
+size_t smem_bytes2(const Tc2Params& PP) {
+  const TcParams& P = PP.t;
+  const size_t hdr = (sizeof(SmemHeader2) + 127) & ~(size_t)127;
+  return hdr + PP.w_region + (size_t)PP.a_stages * PP.a_bytes + 256;
+}
+
+// ---- bf16 padded activation copies ---------------------------------------------------------------------------------
+__global__ void bf_fill_kernel(BfAct d, const float* __restrict__ src, int ld, int coff, int C) {
+  // one thread per (row of a group, 8-channel group): zeros in the slack and the padding
+  const int G = d.Cpad / 8;
+  const int nplanes = d.kind == 2 ? 4 : 1;
+  const int Hv = d.kind == 2 ? d.H / 2 : d.H, Wv = d.kind == 2 ? d.W / 2 : d.W;
+  const long long Q = (long long)d.B * d.Hp * d.Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.group_rows * G; i += (long long)gridDim.x * blockDim.x) {
+    const int g8 = (int)(i / d.group_rows);
+    const long long row = i - (long long)g8 * d.group_rows;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long rr = row - d.front;
+    if (rr >= 0 && rr < nplanes * d.plane_rows) {
+      const int pl = (int)(rr / d.plane_rows);
+      const long long q = rr - (long long)pl * d.plane_rows;
+      if (q < Q) {
+        const int cc = (int)(q % d.Wp);
+        const long long t = q / d.Wp;
+        const int r = (int)(t % d.Hp), n = (int)(t / d.Hp);
+        if (r < Hv && cc < Wv) {
+          const int h = d.kind == 2 ? 2 * r + (pl >> 1) : r, w = d.kind == 2 ? 2 * cc + (pl & 1) : cc;
+          const float* px = src + (((size_t)n * d.H + h) * d.W + w) * ld + coff;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (g8 * 8 + e < C) ? px[g8 * 8 + e] : 0.f;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(d.p + (size_t)i * 8) = pack8_bf16(f);
+  }
+}
+
+}  // namespace
+
+BfAct bf_act_describe(int kind, int B, int H, int W, int C) {
+  BfAct d{};
+  d.kind = kind; d.B = B; d.H = H; d.W = W;
+  d.Cpad = (C + 15) / 16 * 16;           // the kernels chunk channels by 16: the padding channels are real zero planes
+  if (kind == 0) { d.Hp = H + 2; d.Wp = W + 2; }
+  else if (kind == 1) { d.Hp = H + 1; d.Wp = W + 1; }
+  else { d.Hp = H / 2 + 1; d.Wp = W / 2 + 1; }
+  const long long Q = (long long)B * d.Hp * d.Wp;
+  const int reach = 2 * d.Wp + 2;         // largest |tap shift| of any geometry that reads this layout
+  d.front = (reach + 7) & ~7;
+  d.plane_rows = kind == 2 ? ((Q + reach + 7) & ~7LL) : Q;
+  const long long tail = 128 + reach + 8;
+  d.group_rows = (d.front + (kind == 2 ? 4 : 1) * d.plane_rows + tail + 7) & ~7LL;
+  d.p = nullptr;
+  return d;
+}
+size_t bf_act_bytes(const BfAct& d) { return (size_t)d.group_rows * (d.Cpad / 8) * 16; }
+
+int bf_act_fill(const LaunchCtx& lc, const BfAct& d, View src, int C) {
+  const long long items = d.group_rows * (d.Cpad / 8);
+  long long blocks = (items + 255) / 256;
+  if (blocks > lc.sm_count * 16) blocks = lc.sm_count * 16;
+  ProfScope ps(lc, KC_MISC, 0.0, 6.0 * (double)items * 8);
+  bf_fill_kernel<<<(unsigned)blocks, 256, 0, lc.stream>>>(d, src.p, src.ld, src.coff, C);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+bool tc2_supported(const Geom& g) {
+  Tc2Params PP;
+  Geom gg = g; if (gg.B < 1) gg.B = 1;
+  if (!(g.KH == 4 && g.KW == 4 && g.pad == 1 && (g.stride == 1 || g.stride == 2))) return false;
+  return build_params2(gg, PP) && smem_bytes2(PP) <= 227 * 1024;
+}
+
+// layout kind the tc2 kernel wants for the INPUT of geometry g
+int tc2_input_kind(const Geom& g) { return g.stride == 1 ? 0 : (g.mode == 0 ? 2 : 1); }
+
+int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
+                    double* stats) {
+  Tc2Params PP;
+  if (!build_params2(g, PP)) { svae_global_error() = "tc2: unsupported geometry"; return -1; }
+  TcParams& P = PP.t;
+  if (in.kind != tc2_input_kind(g) || in.Hp != P.Hp || in.Wp != P.Wp || (chan0 & 7)) {
+    svae_global_error() = "tc2: activation copy is not in the layout this geometry reads";
+    return -1;
+  }
+  P.wp = reinterpret_cast<const __nv_bfloat16*>(w_packed);
+  P.out = out.p; P.out_ld = out.ld; P.out_coff = out.coff;
+  P.out_vec = (out.ld % 4 == 0) && (out.coff % 4 == 0) && (((uintptr_t)out.p & 15) == 0) && (g.Cout % 4 == 0);
+  P.stats = stats;
+  if (chan0 + P.Cin_p > in.Cpad || P.lo > in.front) { svae_global_error() = "tc2: channel window / slack of the activation copy too small"; return -1; }
+  P.dbg = reinterpret_cast<unsigned long long*>(g_tc_debug_buffer);
+  PP.a_src = in.p + ((long long)(chan0 / 8) * in.group_rows + in.front) * 8;
+  PP.plane_rows = in.plane_rows;
+  PP.group_rows = in.group_rows;
+  const size_t smem = smem_bytes2(PP);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int ntiles = (P.N_p + 127) / 128;
+  int per_sm = (int)((227 * 1024) / smem);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  if (PP.tmem_cols * (unsigned)per_sm > 512) per_sm = 1;
+  int ctas = lc.sm_count * per_sm / ntiles;
+  if (ctas < 1) ctas = 1;
+  if (ctas > PP.tiles) ctas = PP.tiles;
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_GEMM_TC, 2.0 * pix * g.KH * g.KW * g.Cin * g.Cout,
+               2.0 * (double)g.B * g.Hin * g.Win * g.Cin + 4.0 * (double)g.B * g.Hout * g.Wout * g.Cout +
+                   2.0 * g.KH * g.KW * g.Cin * g.Cout, &g);
+  tc2_conv_kernel<<<dim3((unsigned)ctas, (unsigned)ntiles), 224, smem, lc.stream>>>(PP);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 
 void* g_tc_debug_buffer = nullptr;   // set through svae_debug_set_buffer (scripts/diag_phases.py only)
 

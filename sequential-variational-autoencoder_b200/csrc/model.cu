@@ -52,12 +52,18 @@ struct Block {
   void* w_packed_d = nullptr;    // tcgen05 packed weights (dgrad form)
   bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false;
   int dy_slot = -1;              // index of this block's d(pre-BN output) buffer inside a GradSet
+  // TMA-fed kernels (tc2): bf16 planar copy of the block's input (written by whoever produces that tensor), and where
+  // this block's own activated output is additionally written for its consumer
+  BfAct in_bf{}; bool tc2_fwd = false, tc2_dgrad = false;
+  BfDst out_bf{};
 };
 
 // Gradient scratch of ONE chain step's backward.  Two sets (step parity) let the side streams (weight gradients,
 // recognition net) of step t still read their buffers while the main stream already runs step t-1.
 struct GradSet {
   std::vector<float*> d_c, d_dcat, d_e, d_inf, dy;
+  std::vector<BfAct> dy_bf;      // bf16 planar copies of dy for the TMA-fed input-gradient kernels (p == nullptr: none)
+  BfAct du_out_bf{}, du_gate_bf{};
   float *d_fca = nullptr, *d_cc = nullptr, *d_z = nullptr, *d_mu_pre = nullptr, *d_sd_pre = nullptr, *d_u = nullptr;
 };
 
@@ -92,6 +98,7 @@ struct Step {
   Geom g_out, g_gate;
   Block outb, gateb;                      // the same two deconvs as contraction blocks (no batch-norm) for TC routing
   float *u, *xt;
+  BfAct xt_bf{};                          // bf16 copy of x_t for the next step's chain encoder
   int64_t p_begin, p_end;                 // parameter range (all-reduce bucket)
 };
 
@@ -166,6 +173,9 @@ struct svae_handle {
   std::vector<size_t> dy_slot_elems;
   float* gx[2] = {nullptr, nullptr};
   char* grad_base = nullptr; size_t grad_bytes = 0;
+  char* bf_base = nullptr; size_t bf_bytes = 0;   // bf16 planar activation copies (zero-initialised once: the padding stays zero)
+  BfAct x_bf{};                                   // copy of the input batch for the recognition nets' first conv
+  bool use_tc2 = true;
   // execution: main stream (`stream`) + side streams; `cur` is where the next launch goes
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // 0: chain weight gradients, 1: recognition / latent branch, 2: its weight gradients
   cudaStream_t cur = nullptr;
@@ -389,7 +399,7 @@ void place_block(Block& b, Arena& act, Arena& zf, Arena& zb, int64_t maxB, bool 
 }
 FeatView fv4(float* p, int ld, int coff, int inner) { return FeatView{p, ld, coff, inner, 1}; }
 
-void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, size_t& max_y) {
+void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, Arena& bfa, size_t& max_y) {
   const svae_config& c = h->cfg;
   const int L = h->L, T = h->T, C = h->C, Z = h->Z;
   const int* F = c.filter_sizes;
@@ -403,6 +413,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       const Step& r = h->steps[1];
       auto alias = [](Block& b, const Block& q) {
         b.rpi = q.rpi; b.feats = q.feats; b.act = q.act; b.y = q.y; b.stats = q.stats; b.S = q.S; b.out = q.out; b.res = q.res;
+        b.in_bf = q.in_bf; b.tc2_fwd = q.tc2_fwd; b.out_bf = q.out_bf;
       };
       for (size_t i = 0; i < s.inf.size(); ++i) alias(s.inf[i], r.inf[i]);
       for (size_t i = 0; i < s.enc.size(); ++i) alias(s.enc[i], r.enc[i]);
@@ -473,6 +484,67 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
     s.u = act.get<float>((size_t)B * h->D * h->D * (C + 1));
     s.xt = act.get<float>((size_t)B * h->D * h->D * C);
   }
+  // ---- bf16 planar copies for the TMA-fed kernels: every tensor a tcgen05 conv reads gets one, in its consumer's layout
+  const bool tc2 = h->use_tc2 && c.operand_dtype == SVAE_OPERAND_BF16;
+  auto want = [&](Geom g) { g.B = (int)B; return tc2 && g.KH == 4 && tc_supported(g) && tc2_supported(g); };
+  auto mk = [&](const Geom& consumer, int H, int W, int Cc) {
+    BfAct a = bf_act_describe(tc2_input_kind(consumer), (int)B, H, W, Cc);
+    a.p = bfa.get<__nv_bfloat16>(bf_act_bytes(a) / 2);
+    return a;
+  };
+  // consumer `cb` reads the tensor produced by block `pb` (or by nobody: pb == nullptr) through a fresh copy
+  auto feed = [&](Block& cb, Block* pb) {
+    if (!want(cb.g)) return;
+    cb.in_bf = mk(cb.g, cb.g.Hin, cb.g.Win, cb.g.Cin);
+    cb.tc2_fwd = true;
+    if (pb) pb->out_bf = BfDst{cb.in_bf, 0, 0, 0};
+  };
+  if (tc2) {
+    Block& first = h->steps[0].inf[0];
+    if (want(first.g)) h->x_bf = mk(first.g, first.g.Hin, first.g.Win, first.g.Cin);
+    for (int t = 0; t < T; ++t) {
+      Step& s = h->steps[t];
+      if ((t >= h->act_sets) && t >= 2) continue;   // aliased onto step 1 above
+      for (int k = 0; k < (int)s.inf.size(); ++k) {
+        if (k == 0) { if (want(s.inf[0].g)) { s.inf[0].in_bf = h->x_bf; s.inf[0].tc2_fwd = true; } }
+        else feed(s.inf[k], &s.inf[k - 1]);
+      }
+      for (int k = 1; k < (int)s.enc.size(); ++k) feed(s.enc[k], &s.enc[k - 1]);
+      // x_t -> chain encoder of step t+1 (same geometry in every step >= 1)
+      if (T > 1 && want(h->steps[1].enc[0].g)) {
+        const Geom& eg = h->steps[1].enc[0].g;
+        s.xt_bf = mk(eg, eg.Hin, eg.Win, eg.Cin);
+      }
+      feed(s.ta[L - 2], &s.decfc);
+      if (s.ta[L - 2].tc2_fwd) { s.decfc.out_bf.inner = F[L]; s.decfc.out_bf.ppr = S[L] * S[L]; }   // [B, S_L*S_L*F_L] -> [B,S_L,S_L,F_L]
+      for (int l = L - 2; l >= 0; --l) {
+        feed(s.tb[l], &s.ta[l]);                                                  // dcat_l: [relu(bn(ta)+e), P_l]
+        if (s.tb[l].tc2_fwd) s.lat[l].out_bf = BfDst{s.tb[l].in_bf, F[l + 1], 0, 0};
+        if (l > 0) feed(s.ta[l - 1], &s.tb[l]);
+      }
+      // both output deconvs read c_0 = tb[0].out through one copy
+      if (want(s.outb.g) && (t == 0 || want(s.gateb.g))) {
+        feed(s.outb, &s.tb[0]);
+        if (t > 0) { s.gateb.in_bf = s.outb.in_bf; s.gateb.tc2_fwd = true; }
+      }
+    }
+    for (int t = 1; t < T; ++t) {   // enc[0] of step t reads the copy of x_{t-1}
+      Step& s = h->steps[t];
+      Step& pr = h->steps[t - 1];
+      if ((t >= h->act_sets) && t >= 2) {   // forward-only handles: steps >= 2 share step 1's buffers, copies included
+        const Step& r = h->steps[1];
+        auto alias_bf = [](Block& b, const Block& q) { b.in_bf = q.in_bf; b.tc2_fwd = q.tc2_fwd; b.out_bf = q.out_bf; };
+        for (size_t i = 0; i < s.inf.size(); ++i) alias_bf(s.inf[i], r.inf[i]);
+        for (size_t i = 0; i < s.enc.size(); ++i) alias_bf(s.enc[i], r.enc[i]);
+        alias_bf(s.encfc, r.encfc); alias_bf(s.decfc, r.decfc);
+        for (size_t i = 0; i < s.lat.size(); ++i) alias_bf(s.lat[i], r.lat[i]);
+        for (size_t i = 0; i < s.ta.size(); ++i) { alias_bf(s.ta[i], r.ta[i]); alias_bf(s.tb[i], r.tb[i]); }
+        alias_bf(s.outb, r.outb); alias_bf(s.gateb, r.gateb);
+        s.xt_bf = r.xt_bf;
+      }
+      if (want(s.enc[0].g)) { s.enc[0].in_bf = pr.xt_bf; s.enc[0].tc2_fwd = true; }
+    }
+  }
   // gradient scratch: two sets (step parity) of one step's worth; every block has its own d(pre-BN output) buffer so
   // that its weight gradient can run on a side stream while the chain moves on
   if (c.train_capacity) {
@@ -521,6 +593,27 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       g.dy.assign(h->n_dy_slots, nullptr);
       for (int k = 0; k < h->n_dy_slots; ++k)
         if (h->dy_slot_elems[k] > 0) g.dy[k] = gr.get<float>(h->dy_slot_elems[k]);
+      // bf16 copies of dy for the TMA-fed input-gradient kernels (one per slot: the geometry is the same in every step)
+      g.dy_bf.assign(h->n_dy_slots, BfAct{});
+      auto dyfeed = [&](Block& b, bool needs_din) {
+        if (b.dy_slot < 0 || !needs_din) return;
+        Geom dg = dgrad_geom(b.g);
+        if (!want(dg)) return;
+        if (g.dy_bf[b.dy_slot].Cpad == 0) g.dy_bf[b.dy_slot] = mk(dg, dg.Hin, dg.Win, dg.Cin);
+        b.tc2_dgrad = true;
+      };
+      for (int t = 0; t < T; ++t) {
+        Step& s = h->steps[t];
+        for (int k = 0; k < (int)s.inf.size(); ++k) dyfeed(s.inf[k], k > 0);
+        for (int k = 0; k < (int)s.enc.size(); ++k) dyfeed(s.enc[k], true);
+        for (int l = 0; l < L - 1; ++l) { dyfeed(s.ta[l], true); dyfeed(s.tb[l], true); }
+      }
+      {
+        Step& s1b = h->steps[T > 1 ? 1 : 0];
+        Geom dgo = dgrad_geom(s1b.g_out);
+        if (want(dgo)) g.du_out_bf = mk(dgo, dgo.Hin, dgo.Win, dgo.Cin);
+        if (T > 1) { Geom dgg = dgrad_geom(s1b.g_gate); if (want(dgg) && g.du_out_bf.Cpad) g.du_gate_bf = mk(dgg, dgg.Hin, dgg.Win, dgg.Cin); }
+      }
     }
     h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * C);
     h->gx[1] = gr.get<float>((size_t)B * h->D * h->D * C);
@@ -578,10 +671,21 @@ int link(svae_handle* h, cudaStream_t from, cudaStream_t to) {
 // forked execution is used for training-capacity handles outside profiling (the profiler wants serialised kernels)
 bool forked(const svae_handle* h) { return h->use_streams && h->cfg.train_capacity && !h->prof.enabled && h->side[0] != nullptr; }
 
+// contraction through the TMA-fed kernel when the input has a bf16 planar copy, else the SIMT-staged / fp32 kernels
+int contract_bf(svae_handle* h, Geom g, int B, bool tc2, const BfAct& in_bf, View in, const float* w, const void* w_packed,
+                bool use_tc, View out, double* stats) {
+  if (tc2) {
+    g.B = B;
+    LaunchCtx lc = h->lc();
+    return tc2_gather_gemm(lc, g, in_bf, 0, w_packed, out, stats);
+  }
+  return contract(h, g, B, in, w, w_packed, use_tc, out, stats);
+}
+
 int block_fwd(svae_handle* h, Block& b, int B, View in) {
-  H_TRY(contract(h, b.g, B, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0), b.stats));
+  H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0), b.stats));
   LaunchCtx lc = h->lc();
-  H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out));
+  H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out, b.out_bf));
   return 0;
 }
 
@@ -593,14 +697,16 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
   const int64_t rows = (int64_t)B * b.rpi;
   float* dy = gs.dy[b.dy_slot];
   H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
-  H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta)));
+  const bool tc2d = b.tc2_dgrad && din != nullptr && gs.dy_bf[b.dy_slot].p != nullptr;
+  H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta),
+                     tc2d ? BfDst{gs.dy_bf[b.dy_slot], 0, 0, 0} : BfDst{}));
   View dyv = mkview(dy, b.feats, 0);
   // dy is final here: the weight gradient (side stream) depends on this point only, not on the input gradient below
   H_TRY(link(h, cur_stream(h), wst));
   if (din != nullptr) {
     Geom g = dgrad_geom(b.g);
     g.accumulate = din_acc;
-    H_TRY(contract(h, g, B, dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr));
+    H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr));
   }
   {
     OnStream os(h, wst);
@@ -681,12 +787,15 @@ int decoder_fwd(svae_handle* h, Step& s, int B, const float* xprev, const float*
   }
   const int has_gate = s.t > 0 ? 1 : 0;
   const int ldu = C + has_gate;
-  H_TRY(contract(h, s.g_out, B, cur, h->pw(s.w_out), s.outb.w_packed, s.outb.tc_fwd, mkview(s.u, ldu, 0), nullptr));
+  H_TRY(contract_bf(h, s.g_out, B, s.outb.tc2_fwd, s.outb.in_bf, cur, h->pw(s.w_out), s.outb.w_packed, s.outb.tc_fwd,
+                    mkview(s.u, ldu, 0), nullptr));
   if (has_gate)
-    H_TRY(contract(h, s.g_gate, B, cur, h->pw(s.w_gate), s.gateb.w_packed, s.gateb.tc_fwd, mkview(s.u, ldu, C), nullptr));
+    H_TRY(contract_bf(h, s.g_gate, B, s.gateb.tc2_fwd, s.gateb.in_bf, cur, h->pw(s.w_gate), s.gateb.w_packed, s.gateb.tc_fwd,
+                      mkview(s.u, ldu, C), nullptr));
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
-  H_TRY(out_mix_fwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, tgt, xt_out, recon_sum));
+  H_TRY(out_mix_fwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, tgt, xt_out, recon_sum,
+                    s.xt_bf.p ? BfDst{s.xt_bf, 0, 0, 0} : BfDst{}));
   return 0;
 }
 
@@ -740,6 +849,12 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
   H_TRY(zero_region(h, h->loss_sums, sizeof(double) * 2 * h->T));
   const size_t img = (size_t)B * h->D * h->D * h->C;
   const size_t bz = (size_t)B * h->Z;
+  if (h->x_bf.p != nullptr) {   // bf16 planar copy of the batch for the recognition nets' first conv (all T steps read it)
+    LaunchCtx lc = h->lc();
+    BfAct xb = h->x_bf;
+    xb.B = B;                     // only the first B images exist in the caller's buffer; the rest of the copy is zeroed
+    H_TRY(bf_act_fill(lc, xb, mkview(const_cast<float*>(x), h->C, 0), h->C));
+  }
   const bool fork = forked(h) && h->act_sets == h->T && (h->fork_mask & 8);
   std::vector<cudaEvent_t> rec_ev(h->T, nullptr);
   if (fork) {
@@ -798,16 +913,20 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
                  h->cfg.max_highway};
   H_CUDA(cudaMemsetAsync(gs.d_z, 0, sizeof(float) * (size_t)B * h->Z, st.chain));   // lat_dz accumulates with atomics
   H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
-                    coef, gs.d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr));
+                    coef, gs.d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr,
+                    gs.du_out_bf.p ? BfDst{gs.du_out_bf, 0, 0, 0} : BfDst{},
+                    (has_gate && gs.du_gate_bf.p) ? BfDst{gs.du_gate_bf, 0, 0, 0} : BfDst{}));
   // output deconvs: dgrad into d_c[0], wgrads
   View c0 = mkview(s.tb[0].out.p, F[1], 0);
   View dc0 = mkview(gs.d_c[0], F[1], 0);
   {
     Geom g = dgrad_geom(s.g_out);
-    H_TRY(contract(h, g, B, mkview(gs.d_u, ldu, 0), h->pw(s.w_out), s.outb.w_packed_d, s.outb.tc_dgrad, dc0, nullptr));
+    H_TRY(contract_bf(h, g, B, gs.du_out_bf.p != nullptr && s.outb.tc_dgrad, gs.du_out_bf, mkview(gs.d_u, ldu, 0), h->pw(s.w_out),
+                      s.outb.w_packed_d, s.outb.tc_dgrad, dc0, nullptr));
     if (has_gate) {
       Geom g2 = dgrad_geom(s.g_gate); g2.accumulate = 1;
-      H_TRY(contract(h, g2, B, mkview(gs.d_u, ldu, C), h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr));
+      H_TRY(contract_bf(h, g2, B, gs.du_gate_bf.p != nullptr && s.gateb.tc_dgrad, gs.du_gate_bf, mkview(gs.d_u, ldu, C),
+                        h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr));
     }
     H_TRY(link(h, st.chain, st.w));
     OnStream os(h, st.w);
@@ -1090,7 +1209,7 @@ void destroy_impl(svae_handle* h) {
   if (h->dyn_ring) cudaFreeHost(h->dyn_ring);
   if (h->comm_done) cudaEventDestroy(h->comm_done);
   cudaFree(h->P); cudaFree(h->G); cudaFree(h->M); cudaFree(h->V);
-  cudaFree(h->act_base); cudaFree(h->zf_base); cudaFree(h->zb_base); cudaFree(h->grad_base); cudaFree(h->pack_base); cudaFree(h->pack_table);
+  cudaFree(h->bf_base); cudaFree(h->act_base); cudaFree(h->zf_base); cudaFree(h->zb_base); cudaFree(h->grad_base); cudaFree(h->pack_base); cudaFree(h->pack_table);
   cudaFree(h->io_steps); cudaFree(h->loss_sums);
   if (h->loss_host) cudaFreeHost(h->loss_host);
   if (h->pin_x) cudaFreeHost(h->pin_x);
@@ -1225,17 +1344,21 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
   }
   // two-pass bump allocation
   {
-    Arena act, zf, zb, gr; size_t max_y = 0;
-    build_buffers(h, act, zf, zb, gr, max_y);
+    Arena act, zf, zb, gr, bfa; size_t max_y = 0;
+    { const char* e = getenv("SVAE_TC2"); h->use_tc2 = !(e && e[0] == '0'); }
+    build_buffers(h, act, zf, zb, gr, bfa, max_y);
     h->act_bytes = act.off + 256; h->zf_bytes = zf.off + 256; h->zb_bytes = zb.off + 256; h->grad_bytes = gr.off + 256;
+    h->bf_bytes = bfa.off + 256;
+    C_CUDA(cudaMalloc(&h->bf_base, h->bf_bytes));
+    C_CUDA(cudaMemset(h->bf_base, 0, h->bf_bytes));
     C_CUDA(cudaMalloc(&h->act_base, h->act_bytes));
     C_CUDA(cudaMalloc(&h->zf_base, h->zf_bytes));
     C_CUDA(cudaMalloc(&h->zb_base, h->zb_bytes));
     C_CUDA(cudaMalloc(&h->grad_base, h->grad_bytes));
     C_CUDA(cudaMemset(h->act_base, 0, h->act_bytes));
-    Arena act2, zf2, zb2, gr2; size_t my2 = 0;
-    act2.base = h->act_base; zf2.base = h->zf_base; zb2.base = h->zb_base; gr2.base = h->grad_base;
-    build_buffers(h, act2, zf2, zb2, gr2, my2);
+    Arena act2, zf2, zb2, gr2, bfa2; size_t my2 = 0;
+    act2.base = h->act_base; zf2.base = h->zf_base; zb2.base = h->zb_base; gr2.base = h->grad_base; bfa2.base = h->bf_base;
+    build_buffers(h, act2, zf2, zb2, gr2, bfa2, my2);
   }
   {
     Arena pk;
@@ -1579,7 +1702,20 @@ static int op_contract(svae_handle* h, Geom g, int B, const float* x, int ldx, c
     void* packed = nullptr;
     H_CUDA(cudaMalloc(&packed, tc_packed_bytes(g)));
     int r = tc_pack_weights(lc, g, w, packed);
-    if (r == 0) r = tc_gather_gemm(lc, g, mkview(const_cast<float*>(x), ldx, 0), packed, mkview(y, ldy, 0), stats);
+    const char* e2 = getenv("SVAE_TC2");
+    if (r == 0 && !(e2 && e2[0] == '0') && tc2_supported(g)) {
+      // TMA-fed kernel: stage the fp32 input as a padded bf16 copy first (inside the chain the producing kernel writes it)
+      BfAct a = bf_act_describe(tc2_input_kind(g), B, g.Hin, g.Win, g.Cin);
+      void* abuf = nullptr;
+      H_CUDA(cudaMalloc(&abuf, bf_act_bytes(a)));
+      a.p = reinterpret_cast<__nv_bfloat16*>(abuf);
+      r = bf_act_fill(lc, a, mkview(const_cast<float*>(x), ldx, 0), g.Cin);
+      if (r == 0) r = tc2_gather_gemm(lc, g, a, 0, packed, mkview(y, ldy, 0), stats);
+      cudaStreamSynchronize(h->stream);
+      cudaFree(abuf);
+    } else if (r == 0) {
+      r = tc_gather_gemm(lc, g, mkview(const_cast<float*>(x), ldx, 0), packed, mkview(y, ldy, 0), stats);
+    }
     cudaStreamSynchronize(h->stream);
     cudaFree(packed);
     if (r != 0) { h->err = g_err; return r; }

@@ -110,6 +110,17 @@ __device__ __forceinline__ void tmem_ld_upto32(unsigned taddr, float (&v)[32], i
   if (avail >= 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 }
 
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded region runs on a single
+// lane and keeps warp-uniform operands (descriptors, TMEM addresses) in uniform registers instead of wrapping every
+// tcgen05.mma in a lane-election loop.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp-uniform broadcast of lane 0's value (also tells the compiler the result is uniform)
+__device__ __forceinline__ unsigned uniform_u32(unsigned v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Shared-memory matrix descriptor, canonical K-major layout without swizzle (cute::UMMA::SmemDescriptor):
 //   bits [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (between the two 8-element K groups of one MMA) ;
 //   [32,46) stride byte offset >> 4 (between 8-row groups) ; [46,48) version = 1 (sm_100) ; [61,64) layout type 0.
@@ -151,4 +162,18 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
   return r;
 }
 
+}  // namespace tcptx
+
+// ---- TMA tensor loads (cp.async.bulk.tensor, UTMALDG in SASS) -----------------------------------------------------------
+#include <cuda.h>
+namespace tcptx {
+// 2-D tiled load: box (dim0 = c0.., dim1 = c1..) of the tensor described by `tmap` -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tmap, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(tmap)) : "memory");
+}
 }  // namespace tcptx
