@@ -152,6 +152,8 @@ bool tc2_supported(const Geom& g);
 int tc2_input_kind(const Geom& g);
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
                     double* stats);
+bool tc2_wgrad_supported(const Geom& g);   // g: conv-gather geometry (see tc_wgrad)
+int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw);
 // ---- SIMT fp32 contractions (kernels_simt.cu) ------------------------------------------------------------------
 int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w, View out, double* stats);
 // dW(tap,a,b) = sum_rows X(gathered at tap, channel a) * dY(row, channel b); layout w[(tap*Ca + a)*Cb + b].

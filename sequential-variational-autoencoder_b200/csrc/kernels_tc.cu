@@ -1158,6 +1158,226 @@ int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int cha
   return 0;
 }
 
+
+// =====================================================================================================================
+// TMA-fed weight gradient ("tc2w"): the same contraction as tc_wgrad_kernel, with both operands arriving as bf16 planar
+// copies (BfAct).  X (shifted-window side) and dY live in the SAME padded pixel space, so a tile is
+//   X : nplanes * JA bulk copies of HL pixels x 16 B        dY : JN bulk copies of 128 pixels x 16 B
+// issued by one thread into a 3..4-deep ring; padding pixels of dY are zero, which is what masks the halo.
+// Warps: 0 producer, 1 MMA issuer + TMEM owner, 2-5 epilogue (once, at the end: red.global.add of the CTA's partial dW).
+namespace {
+
+constexpr int W_STAGES_MAX = 4;
+
+struct Tw2Params {
+  TwParams t;
+  const __nv_bfloat16* x_src;   // X copy at (group 0, pixel 0 of plane 0)
+  const __nv_bfloat16* y_src;   // dY copy at (group 0, pixel 0)
+  long long x_plane_rows, x_group_rows, y_group_rows;
+  unsigned x_pitch, y_pitch;    // bytes between 8-channel planes in shared memory
+  unsigned x_bytes, y_bytes;    // per stage
+  unsigned stage_bytes;
+  int stages;
+};
+
+struct SmemHeaderW2 {
+  unsigned long long full[W_STAGES_MAX], empty[W_STAGES_MAX], acc_done;
+  unsigned tmem_base, pad;
+};
+
+__global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant__ Tw2Params PP) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const TwParams& P = PP.t;
+  SmemHeaderW2* hdr = reinterpret_cast<SmemHeaderW2*>(smem_raw);
+  unsigned char* bufs = smem_raw + 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uniform_u32((unsigned)(tid >> 5));
+  int by = blockIdx.y;
+  const int nb = by % P.nblocks; by /= P.nblocks;
+  const int mb = by % P.mblocks; by /= P.mblocks;
+  const int grp = by;
+  const int a0 = mb * P.CaB, b0 = nb * P.N;
+  const int my_tiles = (int)((P.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(smem_u32(&hdr->full[i]), 1); mbar_init(smem_u32(&hdr->empty[i]), 1); }
+    mbar_init(smem_u32(&hdr->acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&hdr->tmem_base), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = uniform_u32(hdr->tmem_base);
+
+  if (warp == 0) {
+    // ---- producer ----
+    const __nv_bfloat16* xs = PP.x_src + (long long)(a0 / 8) * PP.x_group_rows * 8;
+    const __nv_bfloat16* ys = PP.y_src + (long long)(b0 / 8) * PP.y_group_rows * 8;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % PP.stages;
+      if (it >= PP.stages) mbar_wait(smem_u32(&hdr->empty[s]), (unsigned)((it / PP.stages) - 1) & 1u);
+      if (lane == 0) {
+        const long long q0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TILE_M;
+        const unsigned bar = smem_u32(&hdr->full[s]);
+        mbar_expect_tx(bar, PP.x_bytes + PP.y_bytes);
+        const unsigned xb = smem_u32(bufs + (size_t)s * PP.stage_bytes);
+        const unsigned yb = xb + PP.x_bytes;
+        for (int pl = 0; pl < P.nplanes; ++pl)
+          for (int j = 0; j < P.JA; ++j)
+            bulk_g2s(xb + (unsigned)(pl * P.JA + j) * PP.x_pitch, xs + ((long long)j * PP.x_group_rows + pl * PP.x_plane_rows + (q0 - P.lo)) * 8,
+                     PP.x_pitch, bar);
+        for (int j = 0; j < P.JN; ++j)
+          bulk_g2s(yb + (unsigned)j * PP.y_pitch, ys + ((long long)j * PP.y_group_rows + q0) * 8, PP.y_pitch, bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: D[a, b] (+)= X[a x 16 px] * dY[16 px x b], one accumulator per tap of the CTA's tap group ----
+    const unsigned idesc = make_idesc_mn(TILE_M, P.N);
+    const unsigned long long a_hi = ((unsigned long long)((PP.x_pitch >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((128u >> 4) & 0x3FFF) << 16);
+    const unsigned long long b_hi = ((unsigned long long)((PP.y_pitch >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+                                    ((unsigned long long)((128u >> 4) & 0x3FFF) << 16);
+    const bool leader = elect_one();
+    unsigned first = 1u;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % PP.stages;
+      mbar_wait(smem_u32(&hdr->full[s]), (unsigned)(it / PP.stages) & 1u);
+      tc_fence_after();
+      if (leader) {
+        const unsigned xb4 = smem_u32(bufs + (size_t)s * PP.stage_bytes) >> 4;
+        const unsigned yb4 = xb4 + (PP.x_bytes >> 4);
+        for (int tl = 0; tl < P.taps_per_cta; ++tl) {
+          const int tap = grp * P.taps_per_cta + tl;
+          const unsigned d_tmem = tmem_base + (unsigned)(tl * P.N);
+          unsigned a_lo = xb4 + (unsigned)(P.plane[tap] * P.JA) * (PP.x_pitch >> 4) + (unsigned)(P.lo + P.shift[tap]);
+          unsigned b_lo = yb4;
+          unsigned acc_flag = first ^ 1u;
+#pragma unroll
+          for (int k = 0; k < TILE_M / 16; ++k) {
+            umma_bf16(d_tmem, a_hi | (unsigned long long)(a_lo & 0x3FFF), b_hi | (unsigned long long)(b_lo & 0x3FFF), idesc, acc_flag);
+            acc_flag = 1u;
+            a_lo += 16u;
+            b_lo += 16u;
+          }
+        }
+        umma_commit(smem_u32(&hdr->empty[s]));
+      }
+      first = 0u;
+      __syncwarp();
+    }
+    if (leader) umma_commit(smem_u32(&hdr->acc_done));
+    __syncwarp();
+  } else {
+    // ---- epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1): row = X channel, columns = dY channels ----
+    mbar_wait(smem_u32(&hdr->acc_done), 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int a = quarter * 32 + lane;
+    for (int tl = 0; tl < P.taps_per_cta; ++tl) {
+      const int tap = grp * P.taps_per_cta + tl;
+      for (int n0 = 0; n0 < P.N; n0 += 32) {
+        float v[32];
+        tmem_ld_upto32(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(tl * P.N + n0), v, P.N - n0);
+        if (a < P.CaB && a0 + a < P.Ca && my_tiles > 0) {
+          float* dst = P.dw + ((size_t)tap * P.Ca + a0 + a) * P.Cb + b0 + n0;
+          const int ncols = max(0, min(min(32, P.N - n0), P.Cb - (b0 + n0)));
+          if (P.dw_vec) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              if (k < ncols) atomicAdd(reinterpret_cast<float4*>(dst + k), make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < ncols) atomicAdd(dst + k, v[k]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+bool build_wparams2(const Geom& g, Tw2Params& PP) {
+  memset(&PP, 0, sizeof PP);
+  TwParams& P = PP.t;
+  if (!build_wparams(g, P, 148)) return false;
+  const unsigned hl = (unsigned)((P.HL + 7) & ~7);
+  PP.x_pitch = hl * 16u;
+  PP.y_pitch = 128u * 16u;
+  PP.x_bytes = (unsigned)(P.nplanes * P.JA) * PP.x_pitch;
+  PP.y_bytes = (unsigned)P.JN * PP.y_pitch;
+  PP.stage_bytes = PP.x_bytes + PP.y_bytes;
+  // The A descriptor always spans 16 planes (M = 128 rows): planes beyond the JA real ones are never copied, they only have
+  // to be readable, i.e. inside the CTA's shared-memory window (their rows are ignored by the epilogue).
+  const size_t reach = 128 + (size_t)(W_STAGES_MAX - 1) * 0;   // header
+  (void)reach;
+  int st = W_STAGES_MAX;
+  while (st > 1 && 128 + (size_t)st * PP.stage_bytes > 200 * 1024) --st;
+  if (128 + (size_t)st * PP.stage_bytes > 200 * 1024) return false;
+  PP.stages = st;
+  return true;
+}
+
+size_t smem_bytes_w2(const Tw2Params& PP) {
+  const TwParams& P = PP.t;
+  // last stage's X buffer must see 16 readable planes from its highest parity-plane base
+  const size_t last_x = 128 + (size_t)(PP.stages - 1) * PP.stage_bytes;
+  const size_t need_read = last_x + (size_t)((P.nplanes - 1) * P.JA + 16) * PP.x_pitch;
+  size_t sz = 128 + (size_t)PP.stages * PP.stage_bytes;
+  if (need_read > sz) sz = need_read;
+  return sz + 128;
+}
+
+}  // namespace
+
+bool tc2_wgrad_supported(const Geom& g) {
+  Tw2Params PP;
+  Geom gg = g; if (gg.B < 1) gg.B = 1;
+  return build_wparams2(gg, PP) && smem_bytes_w2(PP) <= 227 * 1024;
+}
+
+// g: conv-gather geometry (X = conv input side in its tc2 input layout, dY = conv output side in the layout of the SAME
+// padded pixel space: kind 0 for stride 1, kind 1 for stride 2)
+int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw) {
+  Tw2Params PP;
+  if (!build_wparams2(g, PP)) { svae_global_error() = "tc2 wgrad: unsupported geometry"; return -1; }
+  TwParams& P = PP.t;
+  const int ykind = g.stride == 1 ? 0 : 1;
+  if (x.kind != tc2_input_kind(g) || x.Hp != P.Hp || x.Wp != P.Wp || dy.kind != ykind || dy.Hp != P.Hp || dy.Wp != P.Wp ||
+      P.lo > x.front || P.mblocks * P.CaB > x.Cpad || P.nblocks * P.N > dy.Cpad) {
+    svae_global_error() = "tc2 wgrad: operand copies are not in the layouts this geometry reads";
+    return -1;
+  }
+  PP.x_src = x.p + (long long)x.front * 8;
+  PP.y_src = dy.p + (long long)dy.front * 8;
+  PP.x_plane_rows = x.plane_rows; PP.x_group_rows = x.group_rows; PP.y_group_rows = dy.group_rows;
+  P.dw = dw;
+  P.dw_vec = (g.Cout % 4 == 0) && (((uintptr_t)dw & 15) == 0);
+  const size_t smem = smem_bytes_w2(PP);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tc2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int gy = P.ngroups * P.mblocks * P.nblocks;
+  long long splits = (lc.sm_count + gy - 1) / gy;
+  if (splits > P.tiles) splits = P.tiles;
+  if (splits < 1) splits = 1;
+  const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  ProfScope ps(lc, KC_WGRAD_TC, 2.0 * pix * 16 * g.Cin * g.Cout,
+               2.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout) + 4.0 * 16.0 * g.Cin * g.Cout, &g);
+  tc2_wgrad_kernel<<<dim3((unsigned)splits, (unsigned)gy), 192, smem, lc.stream>>>(PP);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 void* g_tc_debug_buffer = nullptr;   // set through svae_debug_set_buffer (scripts/diag_phases.py only)
 
 bool tc_supported(const Geom& g) {

@@ -54,7 +54,7 @@ struct Block {
   int dy_slot = -1;              // index of this block's d(pre-BN output) buffer inside a GradSet
   // TMA-fed kernels (tc2): bf16 planar copy of the block's input (written by whoever produces that tensor), and where
   // this block's own activated output is additionally written for its consumer
-  BfAct in_bf{}; bool tc2_fwd = false, tc2_dgrad = false;
+  BfAct in_bf{}; bool tc2_fwd = false, tc2_dgrad = false, tc2_wgrad = false;
   BfDst out_bf{};
 };
 
@@ -176,6 +176,7 @@ struct svae_handle {
   char* bf_base = nullptr; size_t bf_bytes = 0;   // bf16 planar activation copies (zero-initialised once: the padding stays zero)
   BfAct x_bf{};                                   // copy of the input batch for the recognition nets' first conv
   bool use_tc2 = true;
+  int bf_last_B = -1;                             // batch the copies were last written with (stale rows are zeroed on change)
   // execution: main stream (`stream`) + side streams; `cur` is where the next launch goes
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // 0: chain weight gradients, 1: recognition / latent branch, 2: its weight gradients
   cudaStream_t cur = nullptr;
@@ -595,12 +596,22 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
         if (h->dy_slot_elems[k] > 0) g.dy[k] = gr.get<float>(h->dy_slot_elems[k]);
       // bf16 copies of dy for the TMA-fed input-gradient kernels (one per slot: the geometry is the same in every step)
       g.dy_bf.assign(h->n_dy_slots, BfAct{});
+      auto wgeom = [&](const Block& b) {   // conv-gather geometry of the weight gradient (tc_wgrad convention)
+        Geom wg = b.g;
+        if (b.g.mode == 1) { wg = dgrad_geom(b.g); wg.mode = 0; }
+        wg.B = (int)B;
+        return wg;
+      };
       auto dyfeed = [&](Block& b, bool needs_din) {
-        if (b.dy_slot < 0 || !needs_din) return;
+        if (b.dy_slot < 0) return;
         Geom dg = dgrad_geom(b.g);
-        if (!want(dg)) return;
-        if (g.dy_bf[b.dy_slot].Cpad == 0) g.dy_bf[b.dy_slot] = mk(dg, dg.Hin, dg.Win, dg.Cin);
-        b.tc2_dgrad = true;
+        const bool for_dgrad = needs_din && want(dg);
+        // the weight gradient reads dy in the same layout as the input gradient does
+        const bool for_wgrad = tc2 && b.tc2_fwd && b.g.KH == 4 && tc_wgrad_supported(b.g) && tc2_wgrad_supported(wgeom(b));
+        if (!for_dgrad && !for_wgrad) return;
+        if (g.dy_bf[b.dy_slot].Cpad == 0) { Geom dk = dg; g.dy_bf[b.dy_slot] = mk(dk, dg.Hin, dg.Win, dg.Cin); }
+        if (for_dgrad) b.tc2_dgrad = true;
+        if (for_wgrad) b.tc2_wgrad = true;
       };
       for (int t = 0; t < T; ++t) {
         Step& s = h->steps[t];
@@ -613,6 +624,15 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
         Geom dgo = dgrad_geom(s1b.g_out);
         if (want(dgo)) g.du_out_bf = mk(dgo, dgo.Hin, dgo.Win, dgo.Cin);
         if (T > 1) { Geom dgg = dgrad_geom(s1b.g_gate); if (want(dgg) && g.du_out_bf.Cpad) g.du_gate_bf = mk(dgg, dgg.Hin, dgg.Win, dgg.Cin); }
+        for (int t = 0; t < T; ++t) {   // output deconvs: X = d_u copy, dY = copy of c_0
+          Step& s = h->steps[t];
+          Geom wo = dgrad_geom(s.g_out); wo.mode = 0; wo.B = (int)B;
+          s.outb.tc2_wgrad = g.du_out_bf.Cpad && s.outb.tc2_fwd && tc_wgrad_supported(s.outb.g) && tc2_wgrad_supported(wo);
+          if (t > 0) {
+            Geom wgt = dgrad_geom(s.g_gate); wgt.mode = 0; wgt.B = (int)B;
+            s.gateb.tc2_wgrad = g.du_gate_bf.Cpad && s.gateb.tc2_fwd && tc_wgrad_supported(s.gateb.g) && tc2_wgrad_supported(wgt);
+          }
+        }
       }
     }
     h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * C);
@@ -697,9 +717,11 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
   const int64_t rows = (int64_t)B * b.rpi;
   float* dy = gs.dy[b.dy_slot];
   H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
-  const bool tc2d = b.tc2_dgrad && din != nullptr && gs.dy_bf[b.dy_slot].p != nullptr;
+  const bool have_bf = gs.dy_bf[b.dy_slot].p != nullptr;
+  const bool tc2d = b.tc2_dgrad && din != nullptr && have_bf;
+  const bool tc2w = b.tc2_wgrad && have_bf && b.in_bf.p != nullptr;
   H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta),
-                     tc2d ? BfDst{gs.dy_bf[b.dy_slot], 0, 0, 0} : BfDst{}));
+                     (tc2d || tc2w) ? BfDst{gs.dy_bf[b.dy_slot], 0, 0, 0} : BfDst{}));
   View dyv = mkview(dy, b.feats, 0);
   // dy is final here: the weight gradient (side stream) depends on this point only, not on the input gradient below
   H_TRY(link(h, cur_stream(h), wst));
@@ -713,10 +735,12 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     LaunchCtx lw = h->lc();
     if (b.g.mode == 0) {
       Geom g = b.g; g.B = B;
-      if (b.tc_wgrad) H_TRY(tc_wgrad(lw, g, in, dyv, h->pg(b.w))); else H_TRY(simt_wgrad(lw, g, in, dyv, h->pg(b.w)));
+      if (tc2w) H_TRY(tc2_wgrad(lw, g, b.in_bf, gs.dy_bf[b.dy_slot], h->pg(b.w)));
+      else if (b.tc_wgrad) H_TRY(tc_wgrad(lw, g, in, dyv, h->pg(b.w))); else H_TRY(simt_wgrad(lw, g, in, dyv, h->pg(b.w)));
     } else {
       Geom g = dgrad_geom(b.g); g.B = B; g.mode = 0;  // conv geometry from the deconv's output grid to its input grid
-      if (b.tc_wgrad) H_TRY(tc_wgrad(lw, g, dyv, in, h->pg(b.w))); else H_TRY(simt_wgrad(lw, g, dyv, in, h->pg(b.w)));
+      if (tc2w) H_TRY(tc2_wgrad(lw, g, gs.dy_bf[b.dy_slot], b.in_bf, h->pg(b.w)));
+      else if (b.tc_wgrad) H_TRY(tc_wgrad(lw, g, dyv, in, h->pg(b.w))); else H_TRY(simt_wgrad(lw, g, dyv, in, h->pg(b.w)));
     }
   }
   return 0;
@@ -740,6 +764,16 @@ int zero_region(svae_handle* h, void* p, size_t bytes) {
 }
 
 int repack_if_dirty(svae_handle* h);
+
+// The bf16 copies are indexed by image: when the batch size changes, rows of images beyond the new batch would keep stale
+// values that the reductions over the padded pixel space (weight gradients) must not see.  Rare, so: wipe everything.
+int bf_guard(svae_handle* h, int B) {
+  if (h->bf_base != nullptr && h->bf_last_B != B) {
+    H_CUDA(cudaMemsetAsync(h->bf_base, 0, h->bf_bytes, h->stream));
+    h->bf_last_B = B;
+  }
+  return 0;
+}
 
 // per-iteration scalars -> device (pinned ring slot -> dyn_dev on the main stream).  Never captured into a graph: the
 // graph is replayed with whatever values the copy enqueued just before it delivered.
@@ -932,11 +966,13 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
     OnStream os(h, st.w);
     LaunchCtx lw = h->lc();
     Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
-    if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
+    if (s.outb.tc2_wgrad && gs.du_out_bf.p) H_TRY(tc2_wgrad(lw, gw, gs.du_out_bf, s.outb.in_bf, h->pg(s.w_out)));
+    else if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
     else H_TRY(simt_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
     if (has_gate) {
       Geom gw2 = dgrad_geom(s.g_gate); gw2.B = B; gw2.mode = 0;
-      if (s.gateb.tc_wgrad) H_TRY(tc_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
+      if (s.gateb.tc2_wgrad && gs.du_gate_bf.p) H_TRY(tc2_wgrad(lw, gw2, gs.du_gate_bf, s.gateb.in_bf, h->pg(s.w_gate)));
+      else if (s.gateb.tc_wgrad) H_TRY(tc_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
       else H_TRY(simt_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
     }
   }
@@ -1437,6 +1473,7 @@ int svae_forward(svae_handle* h, const float* x, const float* tgt, int B, const 
                  float* mu_out, float* sd_out, float* xs_out) {
   if (!h || !x || !tgt) return fail(h, SVAE_EINVAL, "null argument");
   H_CUDA(cudaSetDevice(h->device));
+  H_TRY(bf_guard(h, B));
   return forward_impl(h, x, tgt, B, eps, seed, reg, mu_out, sd_out, xs_out);
 }
 int svae_backward(svae_handle* h) {
@@ -1516,6 +1553,7 @@ int svae_train_step(svae_handle* h, const float* x, const float* tgt, int B, con
   if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "handle created without train_capacity");
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
   H_CUDA(cudaSetDevice(h->device));
+  H_TRY(bf_guard(h, B));
   // the first steps run eagerly (one-off allocations, function attributes); profiling needs per-kernel events
   if (h->use_graph && !h->prof.enabled && h->eager_steps >= 1) return train_step_graph(h, x, tgt, B, eps, seed, lr, reg);
   h->eager_steps += 1;
@@ -1563,6 +1601,7 @@ int svae_forward_host(svae_handle* h, const float* x, const float* tgt, int B, c
     H_TRY(ensure_io_steps(h, (size_t)h->T * (img + 2 * bz)));
     dxs = h->io_steps; dmu = h->io_steps + h->T * img; dsd = dmu + h->T * bz;
   }
+  H_TRY(bf_guard(h, B));
   H_TRY(forward_impl(h, h->in_x, dtgt, B, deps, seed, reg, mu_out ? dmu : nullptr, sd_out ? dsd : nullptr,
                      xs_out ? dxs : nullptr));
   if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out, dxs, h->T * img * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1583,6 +1622,7 @@ int svae_generate(svae_handle* h, int B, const float* z, uint64_t seed, float* o
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
   H_CUDA(cudaSetDevice(h->device));
   h->cur = h->stream;
+  H_TRY(bf_guard(h, B));
   H_TRY(repack_if_dirty(h));
   H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
   LaunchCtx lc = h->lc();
