@@ -204,7 +204,7 @@ def main():
         operand_used = "fp32"      # no contraction was routed to the tensor-core kernels
     else:
         operand_used = operand
-    stream = torch.cuda.Stream(device=local_rank)
+    stream = torch.cuda.Stream(device=local_rank, priority=-1)   # the chain runs on it: highest priority, side streams lowest
     model.use_torch_stream(stream)
     if world > 1:
         from seqvae_b200.dist import attach_communicator
@@ -368,7 +368,12 @@ def main():
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump(line, f, indent=1)
+    try:
+        model.close()                 # destroys the captured graphs and the library's communicator before torch's
+    except NameError:
+        pass
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

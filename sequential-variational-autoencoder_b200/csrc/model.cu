@@ -176,6 +176,10 @@ struct svae_handle {
   char* bf_base = nullptr; size_t bf_bytes = 0;   // bf16 planar activation copies (zero-initialised once: the padding stays zero)
   BfAct x_bf{};                                   // copy of the input batch for the recognition nets' first conv
   bool use_tc2 = true;
+  // SVAE_TIMELINE=1 (eager mode only): timing events at phase boundaries of every stream, printed by svae_sync
+  bool timeline = false;
+  struct Mark { cudaEvent_t e; const char* what; int t; };
+  std::vector<Mark> marks;
   int bf_last_B = -1;                             // batch the copies were last written with (stale rows are zeroed on change)
   // execution: main stream (`stream`) + side streams; `cur` is where the next launch goes
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // 0: chain weight gradients, 1: recognition / latent branch, 2: its weight gradients
@@ -680,6 +684,13 @@ cudaEvent_t next_event(svae_handle* h) {
   }
   return h->ev_pool[h->ev_used++];
 }
+void tl_mark(svae_handle* h, cudaStream_t s, const char* what, int t) {
+  if (!h->timeline || h->capturing) return;
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  h->marks.push_back(svae_handle::Mark{e, what, t});
+}
 // work enqueued on `to` after this call waits for everything enqueued on `from` so far
 int link(svae_handle* h, cudaStream_t from, cudaStream_t to) {
   if (from == to) return 0;
@@ -876,6 +887,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
   h->cur = h->stream;
   h->ev_used = 0;
+  tl_mark(h, h->stream, "main: step start", -1);
   h->dyn_host.reg = reg; h->dyn_host.seed = seed; h->dyn_host.iteration = h->iteration;
   H_TRY(dyn_push(h));
   H_TRY(repack_if_dirty(h));
@@ -903,6 +915,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
       H_TRY(latent_fwd(h, s, B, s.z));
       rec_ev[t] = next_event(h);
       H_CUDA(cudaEventRecord(rec_ev[t], sd));
+      tl_mark(h, sd, "side: recognition fwd done", t);
     }
   }
   const float* prev = nullptr;
@@ -914,6 +927,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
     if (t > 0) H_TRY(encoder_fwd(h, s, B, prev));
     if (fork) H_CUDA(cudaStreamWaitEvent(h->stream, rec_ev[t], 0)); else H_TRY(latent_fwd(h, s, B, s.z));
     H_TRY(decoder_fwd(h, s, B, prev, tgt, s.xt, h->loss_sums + t));
+    tl_mark(h, h->stream, "main: fwd chain step done", t);
     if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out + t * img, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (mu_out) H_CUDA(cudaMemcpyAsync(mu_out + t * bz, s.mu, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (sd_out) H_CUDA(cudaMemcpyAsync(sd_out + t * bz, s.sd, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -924,6 +938,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
       prev = h->gen_prev;
     }
   }
+  tl_mark(h, h->stream, "main: forward done", -1);
   h->last_B = B; h->last_reg = reg; h->have_fwd = true; h->last_x = x; h->last_tgt = tgt;
   return 0;
 }
@@ -1110,6 +1125,8 @@ int backward_impl(svae_handle* h) {
       H_TRY(recognition_bwd(h, gs, s, B, st.recw));
     }
     if (t > 0) H_TRY(encoder_bwd(h, gs, st, s, B, gx_prev, xprev));
+    tl_mark(h, st.chain, "main: bwd chain step done", t);
+    if (fork) { tl_mark(h, st.w, "W: chain wgrads done", t); tl_mark(h, st.rec, "R: recognition bwd done", t); tl_mark(h, st.recw, "W2: recognition wgrads done", t); }
     if (fork) {
       cudaStream_t sd[3] = {st.w, st.rec, st.recw};
       for (int i = 0; i < 3; ++i) {
@@ -1146,6 +1163,7 @@ int adam_impl(svae_handle* h, float lr) {
   H_TRY(adam_update(lc, h->P, h->G, h->M, h->V, h->arena_numel, h->dyn_dev, lr_t, h->cfg.adam_beta1, h->cfg.adam_beta2,
                     h->cfg.adam_eps, h->cfg.clip_value, 1.f / (float)h->nranks));
   h->weights_dirty = true;
+  tl_mark(h, h->stream, "main: adam done", -1);
   return 0;
 }
 
@@ -1235,9 +1253,13 @@ void destroy_impl(svae_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamSynchronize(h->side[i]);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  // captured graphs hold the communicator's collectives: they must go before the communicator does
+  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);
+  h->graphs.clear();
   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
   for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
-  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->dyn_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -1354,17 +1376,25 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     destroy_impl(h);
     return fail(nullptr, SVAE_ENODEVICE, "SVAE_OPERAND_BF16 needs an sm_100a (B200) device");
   }
-  C_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  // the chain (main stream) is the critical path: it gets the highest priority, the side streams the lowest, so that
+  // their kernels fill the SMs the chain leaves idle instead of competing with it
+  int prio_lo = 0, prio_hi = 0;
+  C_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  { const char* e = getenv("SVAE_PRIO"); if (e && e[0] == '0') prio_lo = prio_hi = 0; }
+  C_CUDA(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_hi));
   h->stream = h->own_stream;
   {
     const char* e1 = getenv("SVAE_STREAMS"); const char* e2 = getenv("SVAE_GRAPH");
     h->use_streams = !(e1 && e1[0] == '0');
     h->use_graph = !(e2 && e2[0] == '0');
+    const char* e4 = getenv("SVAE_TIMELINE");
+    h->timeline = e4 && e4[0] == '1';
+    if (h->timeline) h->use_graph = false;
     const char* e3 = getenv("SVAE_FORK_MASK");
     if (e3) h->fork_mask = atoi(e3);
   }
   if (cfg->train_capacity)
-    for (int i = 0; i < 3; ++i) C_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) C_CUDA(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio_lo));
   C_CUDA(cudaMalloc((void**)&h->dyn_dev, sizeof(SvaeDyn)));
   C_CUDA(cudaMemset(h->dyn_dev, 0, sizeof(SvaeDyn)));
   C_CUDA(cudaMallocHost((void**)&h->dyn_ring, sizeof(SvaeDyn) * 256));
@@ -1430,6 +1460,18 @@ int svae_sync(svae_handle* h) {
   H_CUDA(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < 3; ++i) if (h->side[i]) H_CUDA(cudaStreamSynchronize(h->side[i]));
   if (h->comm_stream) H_CUDA(cudaStreamSynchronize(h->comm_stream));
+  if (h->timeline && !h->marks.empty()) {
+    // print the most recent step only (marks since the last "step start")
+    size_t first = 0;
+    for (size_t i = 0; i < h->marks.size(); ++i) if (h->marks[i].t == -1 && h->marks[i].what[6] == 's' && h->marks[i].what[7] == 't') first = i;
+    for (size_t i = first; i < h->marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->marks[first].e, h->marks[i].e);
+      fprintf(stderr, "TIMELINE %8.3f ms  %s %d\n", ms, h->marks[i].what, h->marks[i].t);
+    }
+    for (auto& m : h->marks) cudaEventDestroy(m.e);
+    h->marks.clear();
+  }
   return SVAE_OK;
 }
 
@@ -1677,6 +1719,8 @@ int svae_comm_init(svae_handle* h, int rank, int nranks, const char id[128], con
   H_CUDA(cudaSetDevice(h->device));
   h->nccl = nccl_load(path);
   if (!h->nccl) return fail(h, SVAE_ENCCL, "libnccl not found: " + nccl_load_error());
+  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);   // captured without the all-reduces
+  h->graphs.clear();
   int r = h->nccl->CommInitRank(&h->comm, nranks, id, rank);
   if (r != 0) { h->comm = nullptr; return fail(h, SVAE_ENCCL, std::string("ncclCommInitRank: ") + h->nccl->GetErrorString(r)); }
   h->rank = rank; h->nranks = nranks;
@@ -1688,7 +1732,12 @@ int svae_comm_init(svae_handle* h, int rank, int nranks, const char id[128], con
 }
 int svae_comm_destroy(svae_handle* h) {
   if (!h) return SVAE_EINVAL;
-  if (h->comm && h->nccl) { svae_sync(h); h->nccl->CommDestroy(h->comm); }
+  if (h->comm && h->nccl) {
+    svae_sync(h);
+    for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);   // they contain this communicator's collectives
+    h->graphs.clear();
+    h->nccl->CommDestroy(h->comm);
+  }
   h->comm = nullptr; h->nranks = 1; h->rank = 0;
   return SVAE_OK;
 }

@@ -36,6 +36,9 @@ def inputs(hp):
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(150, exit=True)   # a hung collective must become a failed test, not a stuck box
     backend = sys.argv[1]
     out_path = sys.argv[2]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -121,6 +124,19 @@ def main():
                 if np.linalg.norm(upd_ref) > 1e-9:
                     err = max(err, float(np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref)))
             result = dict(all_same=bool(same.item()), err=err, loss=model.last_losses["loss"])
+        # three more steps: from the second step on the library replays a captured CUDA graph that contains the NCCL
+        # all-reduces; every rank must still hold bit-identical weights, and they must have moved
+        for _ in range(3):
+            model.train(xs.numpy().astype(np.float32), xs.numpy().astype(np.float32), es.numpy())
+        got2 = model.get_params(live_only=True)
+        flat2 = torch.from_numpy(np.concatenate([v.reshape(-1) for v in got2.values()])).cuda()
+        ref2 = flat2.clone()
+        dist.broadcast(ref2, 0)
+        same2 = torch.tensor([1 if (torch.equal(flat2, ref2) and not torch.equal(flat2, flat) and bool(torch.isfinite(flat2).all())) else 0],
+                             device="cuda")
+        dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            result["all_same_after_graph_steps"] = bool(same2.item())
         model.close()
     if rank == 0:
         with open(out_path, "w") as f:

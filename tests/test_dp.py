@@ -55,4 +55,5 @@ def test_dp_nccl_world2(tmp_path):
         pytest.skip("needs 2 GPUs")
     res = _launch("nccl", 2, tmp_path, 29542)
     assert res["all_same"]
+    assert res["all_same_after_graph_steps"], res
     assert res["err"] < 2e-2, res       # Adam's first step normalises gradient noise to ~lr: compare updates loosely
