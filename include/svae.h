@@ -220,6 +220,12 @@ int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int strid
 int svae_debug_set_buffer(void* dev_buffer);
 /* batch_norm (training mode, no gamma, eps 1e-3) + activation (0 none, 1 lrelu(0.1), 2 relu), rows x channels */
 int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act);
+/* backward of the same block (autodiff of abstract_network.py:22-23 / :41-42 / :69-70): da = dL/d(out) [rows,C], y = the
+ * pre-BN contraction output, residual = tensor added before the activation (ladder shortcut, sequential_vae.py:1713; may be
+ * NULL).  Writes dy = dL/dy [rows,C], dbeta[C] (may be NULL) and, when dres != NULL, the shortcut gradient
+ * (dres = or += da * act'). */
+int svae_op_bn_act_backward(svae_handle* h, const float* da, const float* y, const float* beta, const float* residual,
+                            float* dy, float* dbeta, float* dres, int dres_accumulate, int64_t rows, int C, int act);
 /* fused clip + TF-Adam on n elements (sequential_vae.py:1275-1276) */
 int svae_op_adam(svae_handle* h, float* p, const float* g, float* m, float* v, int64_t n, float lr, int64_t t,
                  float beta1, float beta2, float eps, float clip, float grad_scale);

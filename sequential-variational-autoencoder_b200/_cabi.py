@@ -97,6 +97,7 @@ PROTOTYPES = {
     "svae_op_tc_supported": (C.c_int, [C.c_int] * 7),
     "svae_debug_set_buffer": (C.c_int, [_P]),
     "svae_op_bn_act": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int]),
+    "svae_op_bn_act_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int]),
     "svae_op_adam": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_float]),
 }

@@ -172,6 +172,15 @@ int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const
 int lat_wgrad(const LaunchCtx& lc, View z, const float* dy, int B, int KZ, int N, float* dw);
 int lat_dz(const LaunchCtx& lc, const float* dy, const float* w, int B, int KZ, int N, View dz);
 
+// ---- fused latent projections (kernels_lat.cu): fc (K <= 32) + 2-D batch norm + activation in one kernel per direction --
+bool lat_fused_supported(int B, int KZ);
+// y[B,N] = z.W ; stats = (sum, sumsq) per feature ; act(bn(y)) -> out (fp32 concat slot, may be NULL) and bf (may be NULL)
+int lat_fwd_fused(const LaunchCtx& lc, View z, const float* w, const float* beta, int B, int KZ, int N, int act, float* y,
+                  double* stats, FeatView out, BfDst bf);
+// dw[KZ,N] += z^T dy ; dbeta = sum g ; dz[B, window] += dy.W^T  (dy never materialised)
+int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, View z,
+                  const float* w, int B, int KZ, int N, int act, float* dw, float* dbeta, View dz);
+
 // ---- elementwise / reductions (kernels_elem.cu) ----------------------------------------------------------------
 int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats);
 // out.p may be NULL when only the bf16 copy is wanted; bf.a.p may be NULL

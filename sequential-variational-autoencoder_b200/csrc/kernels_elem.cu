@@ -194,6 +194,78 @@ __global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, c
   }
 }
 
+// Vectorised 4-D batch-norm backward, pass 1 (rows = pixels, C % 8 == 0, C/8 divides the block): one thread per
+// (pixel, 8-channel group) with the group fixed per thread, so the two per-channel sums (sum g, sum g*xhat) stay in
+// registers across the grid-stride loop; one shared-memory reduction and one fp64 atomic per channel per block.
+// g = da * act'(xhat + beta + residual) is written for pass 2 and, when requested, (accumulated) into the shortcut gradient.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, const float* __restrict__ y,
+                        const double* __restrict__ stats, const float* __restrict__ beta, int64_t rows, int C, int act,
+                        const float* __restrict__ res, int res_ld, int res_coff, float* __restrict__ dyhat,
+                        double* __restrict__ S, float* __restrict__ dres, int dres_acc) {
+  extern __shared__ float s_buf[];   // [C] mean, [C] rstd, [C] beta, then the reduction scratch [blockDim][17]
+  float* s_red = s_buf + 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    bn_coeffs(stats, C, c, rows, mean, rstd);
+    s_buf[c] = mean; s_buf[C + c] = rstd; s_buf[2 * C + c] = beta[c];
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  const int c0 = (int)(threadIdx.x % G) * 8;
+  const int ppb = blockDim.x / G;                       // pixels per block per iteration
+  float mean[8], rstd[8], bt[8], a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mean[e] = s_buf[c0 + e]; rstd[e] = s_buf[C + c0 + e]; bt[e] = s_buf[2 * C + c0 + e]; a[e] = 0.f; b[e] = 0.f; }
+  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / G; p < rows; p += (int64_t)gridDim.x * ppb) {
+    const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0));
+    const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(da + p * da_ld + da_coff + c0));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(da + p * da_ld + da_coff + c0) + 1);
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float rr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (res != nullptr) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0) + 1);
+      rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+    }
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (yy[e] - mean[e]) * rstd[e];
+      const float pre = xh + bt[e] + rr[e];
+      g[e] = dd[e] * act_grad(pre, act);
+      a[e] += g[e];
+      b[e] += g[e] * xh;
+    }
+    float4* gp = reinterpret_cast<float4*>(dyhat + p * C + c0);
+    gp[0] = make_float4(g[0], g[1], g[2], g[3]);
+    gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+    if (dres != nullptr) {
+      float4* rp = reinterpret_cast<float4*>(dres + p * C + c0);
+      float4 o0 = make_float4(g[0], g[1], g[2], g[3]), o1 = make_float4(g[4], g[5], g[6], g[7]);
+      if (dres_acc) {
+        const float4 q0 = rp[0], q1 = rp[1];
+        o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w; o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+      }
+      rp[0] = o0; rp[1] = o1;
+    }
+  }
+  // block reduction: row t of the scratch holds thread t's 16 partial sums (pitch 17: conflict-free column reads)
+  float* mine = s_red + threadIdx.x * 17;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mine[e] = a[e]; mine[8 + e] = b[e]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;     // 0: sum g, 1: sum g*xhat
+    const int g8 = c >> 3, e = c & 7;
+    float tot = 0.f;
+    for (int t = g8; t < (int)blockDim.x; t += G) tot += s_red[t * 17 + which * 8 + e];
+    atomicAdd(&S[which * C + c], (double)tot);
+  }
+}
+
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
                                     const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
                                     int feats, float* __restrict__ dbeta, BfDst bf) {
@@ -535,10 +607,31 @@ int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const f
 int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta,
                   int64_t rows, int feats, int act, FeatView residual, float* dyhat, double* S, float* dres,
                   int dres_accumulate) {
-  ColGrid cg = col_grid(rows, feats, lc.sm_count);
   Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
   ProfScope ps(lc, KC_BN_BWD_REDUCE, 8.0 * rows * feats,
                4.0 * rows * feats * (3 + (residual.p ? 1 : 0) + (dres ? 1 : 0)), &tg);
+  // 4-D batch norm (rows are pixels) with whole 8-channel groups: vectorised kernel
+  const int G = feats / 8;
+  const bool v8 = da.ppr == 1 && da.inner == feats && feats % 8 == 0 && G <= 256 && rows >= 512 && aligned16(y) &&
+                  aligned16(dyhat) && aligned16(da.p) && da.ld % 4 == 0 && da.coff % 4 == 0 &&
+                  (residual.p == nullptr || (residual.ppr == 1 && residual.inner == feats && residual.ld % 4 == 0 &&
+                                             residual.coff % 4 == 0 && aligned16(residual.p))) &&
+                  (dres == nullptr || aligned16(dres));
+  if (v8) {
+    const int threads = (256 / G) * G;
+    const int ppb = threads / G;
+    int64_t blocks = (rows + ppb - 1) / ppb;
+    // enough blocks to fill the machine, few enough that the per-block reduction + atomics stay negligible
+    const int64_t cap = (int64_t)lc.sm_count * 2;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (3 * (size_t)feats + (size_t)threads * 17) * sizeof(float);
+    bn_bwd_reduce_v8_kernel<<<(unsigned)blocks, threads, smem, lc.stream>>>(
+        da.p, da.ld, da.coff, y, stats, beta, rows, feats, act, residual.p, residual.ld, residual.coff, dyhat, S, dres,
+        dres_accumulate);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  ColGrid cg = col_grid(rows, feats, lc.sm_count);
   bn_bwd_reduce_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(da, y, stats, beta, rows, feats, act, residual, dyhat, S,
                                                             dres, dres_accumulate);
   CUDA_TRY(cudaGetLastError());

@@ -247,6 +247,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // mu_pre / sd_pre [B, Z] (pre-zeroed) += flat[b, kslice] . W_h[kslice, :]  (+ bias from the first K slice)
+// NM: compile-time bound on the widths in this launch (the latent groups are 2-3 wide in the MNIST / CelebA nets, 20-30
+// in the LSUN one): the per-element inner loops are NM long, not SK_NMAX.
+template <int NM>
 __global__ void __launch_bounds__(256)
 heads_fwd_kernel(const float* __restrict__ flat, int K, HeadSet hs, float* __restrict__ mu_pre, float* __restrict__ sd_pre,
                  int Z) {
@@ -259,18 +262,19 @@ heads_fwd_kernel(const float* __restrict__ flat, int K, HeadSet hs, float* __res
   for (int h = 0; h < hs.nheads; ++h) {
     const int n = hs.n[h];
     const float* __restrict__ w = hs.w[h];
-    float acc[SK_NMAX];
+    float acc[NM];
 #pragma unroll
-    for (int i = 0; i < SK_NMAX; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NM; ++i) acc[i] = 0.f;
+#pragma unroll 4
     for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
       const float av = __ldg(arow + k);
       const float* wr = w + (size_t)k * n;
 #pragma unroll
-      for (int i = 0; i < SK_NMAX; ++i)
+      for (int i = 0; i < NM; ++i)
         if (i < n) acc[i] = fmaf(av, __ldg(wr + i), acc[i]);
     }
 #pragma unroll
-    for (int i = 0; i < SK_NMAX; ++i) {
+    for (int i = 0; i < NM; ++i) {
       if (i < n) {
         const float v = warp_sum(acc[i]);
         if (lane == 0) red[wid][i] = v;
@@ -310,6 +314,7 @@ heads_dgrad_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __res
 }
 
 // gw_h[k, n] += sum_{b in slice} flat[b, k] * d_h[b, col_h + n] ; gb_h[n] += sum_b d_h[b, col_h + n]   (grads pre-zeroed)
+template <int NM>
 __global__ void __launch_bounds__(256)
 heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd,
                    int B, int Z, int K) {
@@ -320,18 +325,18 @@ heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __re
     const int n = hs.n[h];
     const float* __restrict__ d = (hs.is_sd[h] ? dsd : dmu) + hs.col[h];
     if (k < K) {
-      float acc[SK_NMAX];
+      float acc[NM];
 #pragma unroll
-      for (int i = 0; i < SK_NMAX; ++i) acc[i] = 0.f;
+      for (int i = 0; i < NM; ++i) acc[i] = 0.f;
       for (int b = r0; b < r1; ++b) {
         const float av = __ldg(flat + (size_t)b * K + k);
         const float* dr = d + (size_t)b * Z;
 #pragma unroll
-        for (int i = 0; i < SK_NMAX; ++i)
+        for (int i = 0; i < NM; ++i)
           if (i < n) acc[i] = fmaf(av, __ldg(dr + i), acc[i]);
       }
 #pragma unroll
-      for (int i = 0; i < SK_NMAX; ++i)
+      for (int i = 0; i < NM; ++i)
         if (i < n) atomicAdd(hs.gw[h] + (size_t)k * n + i, acc[i]);
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < n) {
@@ -344,46 +349,49 @@ heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __re
 
 // Latent projections (split_latent, sequential_vae.py:1801-1806): [B, kz<=32] x [kz, N] with N up to 32768.
 // dW[k, f] += sum_{b in slice} z[b, k] * dy[b, f]      (grid: f tiles x batch slices, grads pre-zeroed)
+template <int NM>
 __global__ void __launch_bounds__(256)
 lat_wgrad_kernel(View z, const float* __restrict__ dy, int B, int KZ, int N, float* __restrict__ dw) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= N) return;
   const int bper = (B + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * bper, r1 = min(B, r0 + bper);
-  float acc[SK_NMAX];
+  float acc[NM];
 #pragma unroll
-  for (int k = 0; k < SK_NMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NM; ++k) acc[k] = 0.f;
   for (int b = r0; b < r1; ++b) {
     const float dv = __ldg(dy + (size_t)b * N + f);
     const float* zr = z.p + (size_t)b * z.ld + z.coff;
 #pragma unroll
-    for (int k = 0; k < SK_NMAX; ++k)
+    for (int k = 0; k < NM; ++k)
       if (k < KZ) acc[k] = fmaf(__ldg(zr + k), dv, acc[k]);
   }
 #pragma unroll
-  for (int k = 0; k < SK_NMAX; ++k)
+  for (int k = 0; k < NM; ++k)
     if (k < KZ) atomicAdd(dw + (size_t)k * N + f, acc[k]);
 }
 
 // dz[b, k] (pre-zeroed window) += sum_{f in slice} dy[b, f] * W[k, f]
+template <int NM>
 __global__ void __launch_bounds__(256)
 lat_dz_kernel(const float* __restrict__ dy, const float* __restrict__ w, int KZ, int N, View dz) {
   __shared__ float red[8][SK_NMAX];
   const int b = blockIdx.x;
   const int fper = (N + gridDim.y - 1) / gridDim.y;
   const int f0 = blockIdx.y * fper, f1 = min(N, f0 + fper);
-  float acc[SK_NMAX];
+  float acc[NM];
 #pragma unroll
-  for (int k = 0; k < SK_NMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NM; ++k) acc[k] = 0.f;
+#pragma unroll 4
   for (int f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
     const float dv = __ldg(dy + (size_t)b * N + f);
 #pragma unroll
-    for (int k = 0; k < SK_NMAX; ++k)
+    for (int k = 0; k < NM; ++k)
       if (k < KZ) acc[k] = fmaf(dv, __ldg(w + (size_t)k * N + f), acc[k]);
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < SK_NMAX; ++k) {
+  for (int k = 0; k < NM; ++k) {
     if (k < KZ) {
       const float v = warp_sum(acc[k]);
       if (lane == 0) red[wid][k] = v;
@@ -439,6 +447,21 @@ int simt_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw) {
   return 0;
 }
 
+// width class of a launch: the smallest of 4 / 8 / 16 / 32 that holds every head (or the latent group)
+static int width_class(int nmax) { return nmax <= 4 ? 4 : nmax <= 8 ? 8 : nmax <= 16 ? 16 : 32; }
+static int heads_nmax(const HeadSet& hs) {
+  int m = 0;
+  for (int h = 0; h < hs.nheads; ++h) m = hs.n[h] > m ? hs.n[h] : m;
+  return m;
+}
+#define SK_DISPATCH(NMAXV, CALL)                         \
+  switch (width_class(NMAXV)) {                          \
+    case 4: { constexpr int NM = 4; CALL; } break;       \
+    case 8: { constexpr int NM = 8; CALL; } break;       \
+    case 16: { constexpr int NM = 16; CALL; } break;     \
+    default: { constexpr int NM = 32; CALL; } break;     \
+  }
+
 static int split_for(int rows_or_blocks, int sm_count, int max_split) {
   int s = (2 * sm_count + rows_or_blocks - 1) / rows_or_blocks;
   if (s < 1) s = 1;
@@ -451,7 +474,7 @@ int heads_fwd(const LaunchCtx& lc, const float* flat, int B, int K, const HeadSe
   for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
   const int ks = split_for(B, lc.sm_count, (K + 2047) / 2048);
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
-  heads_fwd_kernel<<<dim3(B, ks), 256, 0, lc.stream>>>(flat, K, hs, mu_pre, sd_pre, Z);
+  SK_DISPATCH(heads_nmax(hs), (heads_fwd_kernel<NM><<<dim3(B, ks), 256, 0, lc.stream>>>(flat, K, hs, mu_pre, sd_pre, Z)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -473,7 +496,7 @@ int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const
   const int kb = (K + 255) / 256;
   const int bs = split_for(kb, lc.sm_count, (B + 7) / 8);
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
-  heads_wgrad_kernel<<<dim3(kb, bs), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K);
+  SK_DISPATCH(heads_nmax(hs), (heads_wgrad_kernel<NM><<<dim3(kb, bs), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -482,7 +505,7 @@ int lat_wgrad(const LaunchCtx& lc, View z, const float* dy, int B, int KZ, int N
   const int fb = (N + 255) / 256;
   const int bs = split_for(fb, lc.sm_count, (B + 7) / 8);
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * KZ * N, 4.0 * ((double)B * N + (double)KZ * N));
-  lat_wgrad_kernel<<<dim3(fb, bs), 256, 0, lc.stream>>>(z, dy, B, KZ, N, dw);
+  SK_DISPATCH(KZ, (lat_wgrad_kernel<NM><<<dim3(fb, bs), 256, 0, lc.stream>>>(z, dy, B, KZ, N, dw)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -490,7 +513,7 @@ int lat_wgrad(const LaunchCtx& lc, View z, const float* dy, int B, int KZ, int N
 int lat_dz(const LaunchCtx& lc, const float* dy, const float* w, int B, int KZ, int N, View dz) {
   const int fs = split_for(B, lc.sm_count, (N + 2047) / 2048);
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * KZ * N, 4.0 * ((double)B * N + (double)KZ * N));
-  lat_dz_kernel<<<dim3(B, fs), 256, 0, lc.stream>>>(dy, w, KZ, N, dz);
+  SK_DISPATCH(KZ, (lat_dz_kernel<NM><<<dim3(B, fs), 256, 0, lc.stream>>>(dy, w, KZ, N, dz)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -187,6 +187,7 @@ struct svae_handle {
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   bool use_streams = true, use_graph = true, capturing = false;
   int fork_mask = 15;   // debugging / ablation: 1 chain wgrads, 2 recognition branch, 4 its wgrads, 8 forward recognition
+  int ablate = 0;       // SVAE_ABLATE, TIMING EXPERIMENTS ONLY (results are wrong): 1 skip weight gradients, 2 skip the recognition / latent backward
   int eager_steps = 0;
   std::vector<GraphEntry> graphs;
   // per-iteration scalars (device copy + pinned ring)
@@ -741,7 +742,7 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     g.accumulate = din_acc;
     H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr));
   }
-  {
+  if (!(h->ablate & 1)) {
     OnStream os(h, wst);
     LaunchCtx lw = h->lc();
     if (b.g.mode == 0) {
@@ -759,7 +760,11 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
 
 int skinny_block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View zin, int K, View dz_out) {
   // latent projection (K <= 32 inputs): dW via thread-per-feature, dz via row-wise dot with the [K,N] weights
+  if (h->ablate & 2) return 0;
   LaunchCtx lc = h->lc();
+  if (lat_fused_supported(B, K))
+    return lat_bwd_fused(lc, da, b.y, b.stats, h->pw(b.beta), zin, h->pw(b.w), B, K, b.feats, b.act, h->pg(b.w), h->pg(b.beta),
+                         dz_out);
   float* dy = gs.dy[b.dy_slot];
   H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, FeatView{}, dy, b.S, nullptr, 0));
   H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, B, b.feats, h->pg(b.beta)));
@@ -815,8 +820,16 @@ int encoder_fwd(svae_handle* h, Step& s, int B, const float* xprev) {
 
 // latent projections P_i = fc_bn_lrelu(z_i) (split_latent, sequential_vae.py:1796-1806): depend on z_t only
 int latent_fwd(svae_handle* h, Step& s, int B, const float* z) {
-  for (int i = 0; i < h->L; ++i)
-    H_TRY(block_fwd(h, s.lat[i], B, mkview(const_cast<float*>(z), h->Z, h->zoff[i])));
+  for (int i = 0; i < h->L; ++i) {
+    Block& b = s.lat[i];
+    View zv = mkview(const_cast<float*>(z), h->Z, h->zoff[i]);
+    if (lat_fused_supported(B, b.g.Cin)) {
+      LaunchCtx lc = h->lc();
+      H_TRY(lat_fwd_fused(lc, zv, h->pw(b.w), h->pw(b.beta), B, b.g.Cin, b.feats, b.act, b.y, b.stats, b.out, b.out_bf));
+    } else {
+      H_TRY(block_fwd(h, b, B, zv));
+    }
+  }
   return 0;
 }
 
@@ -1122,7 +1135,7 @@ int backward_impl(svae_handle* h) {
     {
       // recognition net of this step: needs d_z (complete once the last latent projection's backward has run on st.rec)
       OnStream os(h, st.rec);
-      H_TRY(recognition_bwd(h, gs, s, B, st.recw));
+      if (!(h->ablate & 2)) H_TRY(recognition_bwd(h, gs, s, B, st.recw));
     }
     if (t > 0) H_TRY(encoder_bwd(h, gs, st, s, B, gx_prev, xprev));
     tl_mark(h, st.chain, "main: bwd chain step done", t);
@@ -1392,6 +1405,8 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     if (h->timeline) h->use_graph = false;
     const char* e3 = getenv("SVAE_FORK_MASK");
     if (e3) h->fork_mask = atoi(e3);
+    const char* e5 = getenv("SVAE_ABLATE");
+    if (e5) h->ablate = atoi(e5);
   }
   if (cfg->train_capacity)
     for (int i = 0; i < 3; ++i) C_CUDA(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio_lo));
@@ -1908,6 +1923,25 @@ int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out
   LaunchCtx lc = h->lc();
   int r = col_stats(lc, y, rows, C, stats);
   if (r == 0) r = bn_act_fwd(lc, y, stats, beta, rows, C, act, FeatView{}, FeatView{out, C, 0, C, 1});
+  cudaStreamSynchronize(h->stream);
+  cudaFree(stats);
+  if (r != 0) { h->err = g_err; return r; }
+  return 0;
+}
+int svae_op_bn_act_backward(svae_handle* h, const float* da, const float* y, const float* beta, const float* residual,
+                            float* dy, float* dbeta, float* dres, int dres_accumulate, int64_t rows, int C, int act) {
+  if (!h || !da || !y || !beta || !dy) return SVAE_EINVAL;
+  H_CUDA(cudaSetDevice(h->device));
+  double* stats = nullptr;   // [2C] forward statistics, [2C] backward sums
+  H_CUDA(cudaMalloc(&stats, sizeof(double) * 4 * C));
+  H_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * C, h->stream));
+  LaunchCtx lc = h->lc();
+  int r = col_stats(lc, y, rows, C, stats);
+  const FeatView resv = residual ? FeatView{const_cast<float*>(residual), C, 0, C, 1} : FeatView{};
+  if (r == 0)
+    r = bn_bwd_reduce(lc, FeatView{const_cast<float*>(da), C, 0, C, 1}, y, stats, beta, rows, C, act, resv, dy, stats + 2 * C,
+                      dres, dres_accumulate);
+  if (r == 0) r = bn_bwd_apply(lc, dy, y, stats, stats + 2 * C, rows, C, dbeta);
   cudaStreamSynchronize(h->stream);
   cudaFree(stats);
   if (r != 0) { h->err = g_err; return r; }

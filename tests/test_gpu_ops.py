@@ -181,6 +181,38 @@ def test_bn_act(rows, C, act):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("rows,C,res,acc", [(2 * 8 * 8, 16, 0, 0), (100, 6144, 0, 0), (7, 33, 1, 1), (4096, 32, 1, 1),
+                                            (1600, 128, 1, 0), (900, 384, 0, 0), (2048, 64, 0, 1)])
+def test_bn_act_backward(rows, C, res, acc, act):
+    """autodiff of batch_norm(+shortcut)+activation: the vectorised (rows >= 512, C % 8 == 0) and the generic kernels"""
+    m, L, h = op_handle()
+    g = torch.Generator().manual_seed(rows * 3 + C + act)
+    y = (torch.randn(rows, C, generator=g, dtype=torch.float64) * 2 + 0.5).requires_grad_(True)
+    beta = torch.randn(C, generator=g, dtype=torch.float64).requires_grad_(True)
+    r = torch.randn(rows, C, generator=g, dtype=torch.float64).requires_grad_(True) if res else None
+    da = torch.randn(rows, C, generator=g, dtype=torch.float64)
+    pre = O.batch_norm(y, beta)
+    if res:
+        pre = pre + r
+    out = O.lrelu(pre) if act == 1 else torch.relu(pre) if act == 2 else pre
+    (out * da).sum().backward()
+    uda, uy, ub = dev(da), dev(y.detach()), dev(beta.detach())
+    ur = dev(r.detach()) if res else None
+    dy = torch.empty(rows, C, device="cuda")
+    dbeta = torch.empty(C, device="cuda")
+    base = torch.randn(rows, C, generator=g, dtype=torch.float64)
+    dres = dev(base) if res else None
+    assert L.svae_op_bn_act_backward(h, ptr(uda), ptr(uy), ptr(ub), ptr(ur) if res else None, ptr(dy), ptr(dbeta),
+                                     ptr(dres) if res else None, acc, rows, C, act) == 0
+    m.sync()
+    assert rel_err(dy.cpu().numpy(), y.grad.numpy()) < 2e-4
+    assert rel_err(dbeta.cpu().numpy(), beta.grad.numpy()) < 2e-4
+    if res:
+        want = r.grad.numpy() + (base.numpy() if acc else 0.0)
+        assert rel_err(dres.cpu().numpy(), want) < 2e-5
+
+
 def test_adam_matches_tf_formulation():
     m, L, h = op_handle()
     from oracle import tf_semantics_np as TFNP
