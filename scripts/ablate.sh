@@ -4,8 +4,3 @@ for a in 0 1 2 3; do
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ablate=$a ms_per_step=%.3f'%d['ms_per_step'])"
 done
-for m in 0 ; do
-  SVAE_FORK_MASK=$m python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-generation 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fork_mask=$m ms_per_step=%.3f'%d['ms_per_step'])"
-done

@@ -32,5 +32,8 @@ def run(kind, H, Ci, Co, stride):
         seg(0, 1), seg(1, 2), seg(1, 3), seg(1, 4)))
     print("   tile0: mma issue+commit %.2f | epilogue sees acc +%.2f after commit | epilogue %.2f" % (seg(4, 5), seg(5, 6), seg(6, 7)))
     print("   last mma commit at %.2f, last epilogue done at %.2f, exit at %.2f (us after setup)" % (seg(1, 8), seg(1, 9), seg(1, 10)))
-for s in [("conv", 32, 32, 32, 1), ("deconv", 32, 64, 32, 1), ("conv", 8, 128, 128, 1), ("deconv", 16, 64, 32, 2), ("conv", 16, 64, 64, 1)]:
+cases = [("conv", 32, 32, 32, 1), ("deconv", 32, 64, 32, 1), ("conv", 8, 128, 128, 1), ("deconv", 16, 64, 32, 2), ("conv", 16, 64, 64, 1)]
+if len(sys.argv) > 2 and sys.argv[2] == "small":
+    cases = [("conv", 8, 128, 128, 2), ("deconv", 4, 128, 128, 2), ("deconv", 4, 384, 128, 2), ("deconv", 8, 256, 128, 1), ("conv", 8, 128, 128, 1)]
+for s in cases:
     run(*s)

@@ -78,6 +78,9 @@ struct LaunchCtx {
   int64_t* launches;
   int sm_count;
   Profiler* prof;
+  // Programmatic dependent launch (chain stream only, see launch_k): *pdl_state == 1 when the node enqueued last on this
+  // stream is a kernel; nullptr: never use it.  ProfScope sets it after every launch, non-kernel operations clear it.
+  int* pdl_state = nullptr;
 };
 
 // RAII: brackets one kernel launch with events when profiling is on, and counts the launch either way.
@@ -99,8 +102,37 @@ struct ProfScope {
       p->launches[kc]++; p->flops[kc] += flops; p->bytes[kc] += bytes;
     }
   }
-  ~ProfScope() { if (b) cudaEventRecord(b, lc.stream); }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, lc.stream);
+    if (lc.pdl_state) *lc.pdl_state = 1;
+  }
 };
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------
+// The chain (encoder -> decoder -> ... of step t, then t+1; the reverse in the backward) is ~600 short dependent kernels.
+// A kernel launched through launch_k on the chain stream right after another kernel carries the programmatic-stream-
+// serialization attribute: its CTAs are scheduled as soon as every CTA of the predecessor has passed pdl_trigger() (or
+// exited), run their prologue (barrier init, TMEM allocation, weight loads, index math) and block in pdl_wait() until the
+// predecessor has completed and flushed.  Rules every kernel launched this way follows: (1) pdl_wait() before the first
+// access to anything another kernel of the step writes, and before its own first global write; (2) pdl_trigger() only
+// after pdl_wait(), so that when a kernel's prologue runs, everything two or more kernels back is complete.
+// Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = lc.stream;
+  cudaLaunchAttribute at[1];
+  if (lc.pdl_state != nullptr && *lc.pdl_state == 1) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
@@ -145,13 +177,30 @@ struct BfDst {
   int inner, ppr;  // feature -> (pixel, channel) mapping of a 2-D batch norm whose output is a [.., S, S, inner] map
                    // (0, 0: take the mapping of the fp32 output view)
 };
+// Batch-norm backward pass 1 fused into the epilogue of the input-gradient kernel that PRODUCES da (= dL/d(activated
+// output) of the block described here): the first C output channels of that kernel are turned into
+// g = da * act'(xhat + beta + residual) before they are stored, sum g and sum g*xhat are reduced into S, and the shortcut
+// gradient is written (dres = or += g).  The block's backward is then one pass (bn_bwd_apply reading g where da was).
+struct BnBwdFuse {
+  const float* y;          // the block's pre-BN contraction output [rows, C]
+  const double* stats;     // its forward statistics [2C]
+  const float* beta;       // [C]
+  const float* res;        // residual added before the activation (4-D view) or nullptr
+  int res_ld, res_coff;
+  float* dres;             // shortcut gradient [rows, C] or nullptr
+  int dres_acc;
+  double* S;               // [2C] backward sums (pre-zeroed)
+  int C, act;
+  long long rows;
+};
 BfAct bf_act_describe(int kind, int B, int H, int W, int C);
 size_t bf_act_bytes(const BfAct& d);
 int bf_act_fill(const LaunchCtx& lc, const BfAct& d, View src, int C);   // fp32 NHWC window -> padded bf16 copy (incl. zeros)
 bool tc2_supported(const Geom& g);
 int tc2_input_kind(const Geom& g);
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
-                    double* stats);
+                    double* stats, const BnBwdFuse* fuse = nullptr);
+bool tc2_fuse_supported(const Geom& g, View out, int C);   // can this launch carry a BnBwdFuse over its first C output channels?
 bool tc2_wgrad_supported(const Geom& g);   // g: conv-gather geometry (see tc_wgrad)
 int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw);
 // ---- SIMT fp32 contractions (kernels_simt.cu) ------------------------------------------------------------------
@@ -181,6 +230,11 @@ int lat_fwd_fused(const LaunchCtx& lc, View z, const float* w, const float* beta
 int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, View z,
                   const float* w, int B, int KZ, int N, int act, float* dw, float* dbeta, View dz);
 
+// 2-D batch norm (per feature over the batch) of a fully-connected block, one launch per direction
+int bn2d_fwd(const LaunchCtx& lc, const float* y, const float* beta, int B, int N, int act, double* stats, FeatView out, BfDst bf);
+int bn2d_bwd(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, int B, int N, int act,
+             float* dy, float* dbeta);
+
 // ---- elementwise / reductions (kernels_elem.cu) ----------------------------------------------------------------
 int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats);
 // out.p may be NULL when only the bf16 copy is wanted; bf.a.p may be NULL
@@ -193,6 +247,10 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
 // pass 2: dy = rstd * (dyhat - S1/rows - xhat*S2/rows) in place ; dbeta = S1
 int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
                  int feats, float* dbeta, BfDst bf = BfDst{});
+// the same with g read through a 4-D channel window (where a fused input-gradient epilogue left it) and the fp32 dy
+// optional (dy == nullptr: only the bf16 copy is written)
+int bn_bwd_apply_from(const LaunchCtx& lc, View g, float* dy, const float* y, const double* stats, const double* S, int64_t rows,
+                      int feats, float* dbeta, BfDst bf);
 struct OutMixParams {
   int64_t pixels;  // B*H*W
   int C;

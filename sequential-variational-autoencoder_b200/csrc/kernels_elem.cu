@@ -55,6 +55,8 @@ __device__ __forceinline__ size_t fv_off(const FeatView& v, int f) {
 }
 
 __global__ void col_stats_kernel(const float* __restrict__ y, int64_t rows, int C, double* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s1[CY][CX], s2[CY][CX];
   const int f = blockIdx.x * CX + threadIdx.x;
   float a = 0.f, b = 0.f;
@@ -89,6 +91,8 @@ __device__ __forceinline__ size_t bf_elem(const BfDst& bf, int64_t r, int f, int
 __global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                   const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
                                   FeatView out, BfDst bf) {
+  pdl_wait();
+  pdl_trigger();
   const int f = blockIdx.x * CX + threadIdx.x;
   if (f >= feats) return;
   float mean, rstd;
@@ -115,6 +119,8 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_v8_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ beta,
                      int64_t rows, int C, int act, const float* __restrict__ res, int res_ld, int res_coff,
                      float* __restrict__ out, int out_ld, int out_coff, BfDst bf) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_coef[];   // [C] scale, [C] shift
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
@@ -159,6 +165,8 @@ __global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, c
                                      const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
                                      float* __restrict__ dyhat, double* __restrict__ S, float* __restrict__ dres,
                                      int dres_acc) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s1[CY][CX], s2[CY][CX];
   const int f = blockIdx.x * CX + threadIdx.x;
   float a = 0.f, b = 0.f;
@@ -203,6 +211,8 @@ bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, co
                         const double* __restrict__ stats, const float* __restrict__ beta, int64_t rows, int C, int act,
                         const float* __restrict__ res, int res_ld, int res_coff, float* __restrict__ dyhat,
                         double* __restrict__ S, float* __restrict__ dres, int dres_acc) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_buf[];   // [C] mean, [C] rstd, [C] beta, then the reduction scratch [blockDim][17]
   float* s_red = s_buf + 3 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -269,6 +279,8 @@ bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, co
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
                                     const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
                                     int feats, float* __restrict__ dbeta, BfDst bf) {
+  pdl_wait();
+  pdl_trigger();
   const int f = blockIdx.x * CX + threadIdx.x;
   if (f >= feats) return;
   float mean, rstd;
@@ -288,8 +300,11 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __re
 // Vectorised 4-D batch-norm backward, pass 2 (rows = pixels, C % 8 == 0): dy = rstd * (dyhat - S1/rows - xhat*S2/rows),
 // written in place (fp32, for the weight-gradient kernel) and as the bf16 planar copy the input-gradient kernel reads.
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_v8_kernel(float* __restrict__ dyhat, const float* __restrict__ y, const double* __restrict__ stats,
-                       const double* __restrict__ S, int64_t rows, int C, float* __restrict__ dbeta, int write_f32, BfDst bf) {
+bn_bwd_apply_v8_kernel(const float* g_in, int g_ld, int g_coff, float* dy_out, const float* __restrict__ y,
+                       const double* __restrict__ stats, const double* __restrict__ S, int64_t rows, int C,
+                       float* __restrict__ dbeta, BfDst bf) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_coef[];   // [C] mean, rstd, m1, m2
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
@@ -306,8 +321,8 @@ bn_bwd_apply_v8_kernel(float* __restrict__ dyhat, const float* __restrict__ y, c
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / G;
     const int c0 = (int)(i - p * G) * 8;
-    float4* dp = reinterpret_cast<float4*>(dyhat + p * C + c0);
-    const float4 g0 = dp[0], g1 = dp[1];
+    const float4* gp = reinterpret_cast<const float4*>(g_in + p * g_ld + g_coff + c0);   // may alias dy_out (in-place)
+    const float4 g0 = gp[0], g1 = gp[1];
     const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0));
     const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0) + 1);
     const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -319,7 +334,8 @@ bn_bwd_apply_v8_kernel(float* __restrict__ dyhat, const float* __restrict__ y, c
       const float xh = (yy[e] - s_coef[c0 + e]) * rstd;
       d[e] = rstd * (g[e] - s_coef[2 * C + c0 + e] - xh * s_coef[3 * C + c0 + e]);
     }
-    if (write_f32) {
+    if (dy_out != nullptr) {
+      float4* dp = reinterpret_cast<float4*>(dy_out + p * C + c0);
       dp[0] = make_float4(d[0], d[1], d[2], d[3]);
       dp[1] = make_float4(d[4], d[5], d[6], d[7]);
     }
@@ -357,6 +373,8 @@ __global__ void __launch_bounds__(256)
 out_mix_fwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out,
                    const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
                    float* __restrict__ xt, double* __restrict__ recon_sum, BfDst xbf) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int ldu = p.C + p.has_gate;
   const int HWb = xbf.a.H * xbf.a.W;
@@ -395,6 +413,8 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
                    const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
                    const float* __restrict__ xt, const float* __restrict__ gx_in, float coef, float* __restrict__ du,
                    float* __restrict__ gx_prev, float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int ldu = p.C + p.has_gate;
   const BfAct& la = obf.a.p != nullptr ? obf.a : gbf.a;
@@ -574,8 +594,7 @@ static inline unsigned flat_blocks(int64_t n, int sm_count, int threads = 256) {
 int col_stats(const LaunchCtx& lc, const float* y, int64_t rows, int C, double* stats) {
   ColGrid cg = col_grid(rows, C, lc.sm_count);
   ProfScope ps(lc, KC_MISC, 3.0 * rows * C, 4.0 * rows * C);
-  col_stats_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, rows, C, stats);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(lc, col_stats_kernel, cg.grid, cg.block, 0, y, rows, C, stats));
   return 0;
 }
 
@@ -594,11 +613,11 @@ int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const f
                   (bf.a.p == nullptr || (bf.coff % 8 == 0 && bf.inner == 0 && (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows));
   if (v8) {
     const int64_t items = rows * (feats / 8);
-    bn_act_fwd_v8_kernel<<<flat_blocks(items, lc.sm_count), 256, 2 * feats * sizeof(float), lc.stream>>>(
-        y, stats, beta, rows, feats, act, residual.p, residual.ld, residual.coff, out.p, out.ld, out.coff, bf);
+    CUDA_TRY(launch_k(lc, bn_act_fwd_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 2 * feats * sizeof(float), y, stats,
+                      beta, rows, feats, act, residual.p, residual.ld, residual.coff, out.p, out.ld, out.coff, bf));
   } else {
     ColGrid cg = col_grid(rows, feats, lc.sm_count);
-    bn_act_fwd_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(y, stats, beta, rows, feats, act, residual, out, bf);
+    CUDA_TRY(launch_k(lc, bn_act_fwd_kernel, cg.grid, cg.block, 0, y, stats, beta, rows, feats, act, residual, out, bf));
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -625,15 +644,13 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
     const int64_t cap = (int64_t)lc.sm_count * 2;
     if (blocks > cap) blocks = cap;
     const size_t smem = (3 * (size_t)feats + (size_t)threads * 17) * sizeof(float);
-    bn_bwd_reduce_v8_kernel<<<(unsigned)blocks, threads, smem, lc.stream>>>(
-        da.p, da.ld, da.coff, y, stats, beta, rows, feats, act, residual.p, residual.ld, residual.coff, dyhat, S, dres,
-        dres_accumulate);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_k(lc, bn_bwd_reduce_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
+                      rows, feats, act, residual.p, residual.ld, residual.coff, dyhat, S, dres, dres_accumulate));
     return 0;
   }
   ColGrid cg = col_grid(rows, feats, lc.sm_count);
-  bn_bwd_reduce_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(da, y, stats, beta, rows, feats, act, residual, dyhat, S,
-                                                            dres, dres_accumulate);
+  CUDA_TRY(launch_k(lc, bn_bwd_reduce_kernel, cg.grid, cg.block, 0, da, y, stats, beta, rows, feats, act, residual, dyhat, S, dres,
+                    dres_accumulate));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -646,13 +663,27 @@ int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double
                   (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows;
   if (v8) {
     const int64_t items = rows * (feats / 8);
-    bn_bwd_apply_v8_kernel<<<flat_blocks(items, lc.sm_count), 256, 4 * feats * sizeof(float), lc.stream>>>(
-        dyhat, y, stats, S, rows, feats, dbeta, 1, bf);
+    CUDA_TRY(launch_k(lc, bn_bwd_apply_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), dyhat,
+                      feats, 0, dyhat, y, stats, S, rows, feats, dbeta, bf));
   } else {
     ColGrid cg = col_grid(rows, feats, lc.sm_count);
-    bn_bwd_apply_kernel<<<cg.grid, cg.block, 0, lc.stream>>>(dyhat, y, stats, S, rows, feats, dbeta, bf);
+    CUDA_TRY(launch_k(lc, bn_bwd_apply_kernel, cg.grid, cg.block, 0, dyhat, y, stats, S, rows, feats, dbeta, bf));
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd_apply_from(const LaunchCtx& lc, View g, float* dy, const float* y, const double* stats, const double* S, int64_t rows,
+                      int feats, float* dbeta, BfDst bf) {
+  Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
+  ProfScope ps(lc, KC_BN_BWD_APPLY, 5.0 * rows * feats, (8.0 + (dy ? 4.0 : 0.0)) * rows * feats + (bf.a.p ? 2.0 * rows * feats : 0.0), &tg);
+  const bool ok = feats % 8 == 0 && feats <= 2048 && aligned16(g.p) && g.ld % 4 == 0 && g.coff % 4 == 0 && aligned16(y) &&
+                  (dy == nullptr || aligned16(dy)) && (dy != nullptr || bf.a.p != nullptr) &&
+                  (bf.a.p == nullptr || (bf.coff % 8 == 0 && (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows));
+  if (!ok) { svae_global_error() = "bn_bwd_apply_from: unsupported layout"; return -1; }
+  const int64_t items = rows * (feats / 8);
+  CUDA_TRY(launch_k(lc, bn_bwd_apply_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), g.p, g.ld,
+                    g.coff, dy, y, stats, S, rows, feats, dbeta, bf));
   return 0;
 }
 
@@ -661,8 +692,8 @@ int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 20.0 * p.pixels * p.C,
                4.0 * p.pixels * (p.C + p.has_gate + p.C * (1 + (p.has_gate ? 1 : 0) + (tgt ? 1 : 0))));
-  out_mix_fwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
-                                                                               recon_sum, xt_bf);
+  CUDA_TRY(launch_k(lc, out_mix_fwd_kernel, dim3(flat_blocks(p.pixels, lc.sm_count)), dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt,
+                    recon_sum, xt_bf));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -673,9 +704,8 @@ int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 30.0 * p.pixels * p.C,
                4.0 * p.pixels * (2 * (p.C + p.has_gate) + p.C * (2 + (gx_in ? 1 : 0) + (p.has_gate ? 2 : 0))));
-  out_mix_bwd_kernel<<<flat_blocks(p.pixels, lc.sm_count), 256, 0, lc.stream>>>(p, u, b_out, b_gate, xprev, tgt, xt,
-                                                                               gx_in, coef, du, gx_prev, db_out, db_gate,
-                                                                               du_out_bf, du_gate_bf);
+  CUDA_TRY(launch_k(lc, out_mix_bwd_kernel, dim3(flat_blocks(p.pixels, lc.sm_count)), dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt,
+                    gx_in, coef, du, gx_prev, db_out, db_gate, du_out_bf, du_gate_bf));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -221,6 +221,7 @@ int tc_fc(const LaunchCtx& lc, int mode, const float* x, int ldx, const float* w
   if (split > 1 && !accumulate) {
     if (ldo == cols) {
       CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows * cols, lc.stream));
+      if (lc.pdl_state) *lc.pdl_state = 0;   // a memset node now ends the stream: the next kernel takes a full dependency
     } else {
       zero_rows_kernel<<<lc.sm_count, 256, 0, lc.stream>>>(out, ldo, rows, cols);
       CUDA_TRY(cudaGetLastError());

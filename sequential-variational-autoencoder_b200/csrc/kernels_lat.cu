@@ -100,7 +100,8 @@ lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const fl
 }
 
 // RB rows of NM products are reduced across the warp (= 32 features of one row phase) at a time: 32 values per
-// transpose-reduction
+// transpose-reduction.  A block walks feature tiles blockIdx.x, +gridDim.x, ... and keeps its dz partial sums in shared
+// memory across them, so the global atomics on dz number gridDim.x per element, not N/32.
 template <int NM>
 __global__ void __launch_bounds__(LAT_THREADS)
 lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
@@ -120,15 +121,158 @@ lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __r
     s_dz[i] = 0.f;
   }
   __syncthreads();
-  const int f = blockIdx.x * 32 + threadIdx.x;
-  const bool live = f < N;          // dead lanes keep running: they take part in the warp reductions with zeros
   const int lane = threadIdx.x;
+  const size_t dstride = (size_t)da.ppr * da.ld;
+  const int tiles = (N + 31) / 32;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int f = tile * 32 + lane;
+    const bool live = f < N;        // dead lanes keep running: they take part in the warp reductions with zeros
+    float mean = 0.f, rstd = 0.f, bt = 0.f;
+    size_t doff = 0;
+    float wk[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) wk[k] = 0.f;
+    if (live) {
+      const double m = stats[f] / (double)B;
+      double var = stats[N + f] / (double)B - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)SVAE_BN_EPS));
+      bt = beta[f];
+      const int pix = f / da.inner;
+      doff = (size_t)pix * da.ld + da.coff + (f - pix * da.inner);
+#pragma unroll
+      for (int k = 0; k < NM; ++k) wk[k] = k < KZ ? __ldg(w + (size_t)k * N + f) : 0.f;
+    }
+    float S1 = 0.f, S2 = 0.f;
+    if (live) {
+#pragma unroll 4
+      for (int b = threadIdx.y; b < B; b += LAT_RY) {
+        const float xh = (__ldg(y + (size_t)b * N + f) - mean) * rstd;
+        const float g = __ldg(da.p + (size_t)b * dstride + doff) * lat_act_grad(xh + bt, act);
+        S1 += g;
+        S2 += g * xh;
+      }
+    }
+    s_a[threadIdx.y][lane] = S1;
+    s_b[threadIdx.y][lane] = S2;
+    __syncthreads();
+    S1 = 0.f; S2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LAT_RY; ++i) { S1 += s_a[i][lane]; S2 += s_b[i][lane]; }
+    const float m1 = S1 / (float)B, m2 = S2 / (float)B;
+    float aw[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) aw[k] = 0.f;
+    for (int b0 = threadIdx.y; b0 < B; b0 += LAT_RY * RB) {
+      float v[32];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int b = b0 + r * LAT_RY;
+        float d = 0.f;
+        if (live && b < B) {
+          const float xh = (__ldg(y + (size_t)b * N + f) - mean) * rstd;
+          const float g = __ldg(da.p + (size_t)b * dstride + doff) * lat_act_grad(xh + bt, act);
+          d = rstd * (g - m1 - xh * m2);
+        }
+#pragma unroll
+        for (int k = 0; k < NM; ++k) {
+          if (b < B) aw[k] = fmaf(s_z[b * NM + k], d, aw[k]);
+          v[r * NM + k] = d * wk[k];
+        }
+      }
+      const float tot = tcptx::warp_colsum32(v, lane);    // lane l: sum over the warp's features of value l = (row l/NM, k l%NM)
+      const int b = b0 + (lane / NM) * LAT_RY;
+      if (b < B) s_dz[b * NM + (lane % NM)] += tot;       // row b belongs to this warp alone (b % LAT_RY == threadIdx.y)
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k) s_w[threadIdx.y][k][lane] = aw[k];
+    __syncthreads();
+    if (live && threadIdx.y == 0) {
+#pragma unroll
+      for (int k = 0; k < NM; ++k) {
+        if (k < KZ) {
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < LAT_RY; ++i) t += s_w[i][k][lane];
+          dw[(size_t)k * N + f] += t;                      // this block owns columns f of the weight gradient
+        }
+      }
+      if (dbeta != nullptr) dbeta[f] = S1;
+    }
+    __syncthreads();                                       // s_a / s_b / s_w are reused by the next tile
+  }
+  for (int i = tid; i < B * NM; i += LAT_THREADS) {
+    const int b = i / NM, k = i - b * NM;
+    if (k < KZ) atomicAdd(dz + (size_t)b * dz_ld + dz_coff + k, s_dz[i]);
+  }
+}
+
+// ---- 2-D batch norm of a fully-connected block (fc_bn_lrelu, abstract_network.py:64-71: enc.fc, dec.fc) ------------------
+// rows = batch (<= a few hundred), feats = 384 .. 6144.  The same ownership as above - 32 features x LAT_RY row phases per
+// block - makes the statistics AND the normalisation one kernel (forward) and both backward passes one kernel.
+__global__ void __launch_bounds__(LAT_THREADS)
+bn2d_fwd_kernel(const float* __restrict__ y, const float* __restrict__ beta, int B, int N, int act,
+                double* __restrict__ stats, FeatView out, BfDst bf) {
+  __shared__ double s_s[LAT_RY][32], s_q[LAT_RY][32];
+  pdl_wait();
+  pdl_trigger();
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const bool live = f < N;
+  double s = 0.0, q = 0.0;
+  if (live) {
+#pragma unroll 4
+    for (int b = threadIdx.y; b < B; b += LAT_RY) {
+      const float v = __ldg(y + (size_t)b * N + f);
+      s += (double)v;
+      q += (double)v * (double)v;
+    }
+  }
+  s_s[threadIdx.y][threadIdx.x] = s;
+  s_q[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (!live) return;
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int i = 0; i < LAT_RY; ++i) { s += s_s[i][threadIdx.x]; q += s_q[i][threadIdx.x]; }
+  if (threadIdx.y == 0) { stats[f] = s; stats[N + f] = q; }
+  const double m = s / (double)B;
+  double var = q / (double)B - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)m;
+  const float rstd = (float)(1.0 / sqrt(var + (double)SVAE_BN_EPS));
+  const float sh = beta[f] - mean * rstd;
+  const int pix = f / out.inner, c = f - pix * out.inner;
+  const size_t ooff = (size_t)pix * out.ld + out.coff + c;
+  const size_t ostride = (size_t)out.ppr * out.ld;
+  const bool has_bf = bf.a.p != nullptr;
+  const int binner = bf.inner ? bf.inner : out.inner, bppr = bf.inner ? bf.ppr : out.ppr;
+  const int bpix = f / binner, bc = f - bpix * binner;
+  const int HW = has_bf ? bf.a.H * bf.a.W : 1, Wd = has_bf ? bf.a.W : 1;
+  for (int b = threadIdx.y; b < B; b += LAT_RY) {
+    const float v = lat_act(fmaf(__ldg(y + (size_t)b * N + f), rstd, sh), act);
+    if (out.p != nullptr) out.p[(size_t)b * ostride + ooff] = v;
+    if (has_bf) {
+      const int64_t p = (int64_t)b * bppr + bpix;
+      const int n = (int)(p / HW);
+      const int hw = (int)(p - (int64_t)n * HW);
+      const int hh = hw / Wd;
+      bf.a.p[bf_index(bf.a, n, hh, hw - hh * Wd, bf.coff + bc)] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LAT_THREADS)
+bn2d_bwd_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ beta,
+                int B, int N, int act, float* __restrict__ dy, float* __restrict__ dbeta) {
+  __shared__ float s_a[LAT_RY][32], s_b[LAT_RY][32];
+  pdl_wait();
+  pdl_trigger();
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const bool live = f < N;
   float mean = 0.f, rstd = 0.f, bt = 0.f;
   size_t doff = 0;
   const size_t dstride = (size_t)da.ppr * da.ld;
-  float wk[NM];
-#pragma unroll
-  for (int k = 0; k < NM; ++k) wk[k] = 0.f;
   if (live) {
     const double m = stats[f] / (double)B;
     double var = stats[N + f] / (double)B - m * m;
@@ -138,8 +282,6 @@ lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __r
     bt = beta[f];
     const int pix = f / da.inner;
     doff = (size_t)pix * da.ld + da.coff + (f - pix * da.inner);
-#pragma unroll
-    for (int k = 0; k < NM; ++k) wk[k] = k < KZ ? __ldg(w + (size_t)k * N + f) : 0.f;
   }
   float S1 = 0.f, S2 = 0.f;
   if (live) {
@@ -151,55 +293,20 @@ lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __r
       S2 += g * xh;
     }
   }
-  s_a[threadIdx.y][lane] = S1;
-  s_b[threadIdx.y][lane] = S2;
+  s_a[threadIdx.y][threadIdx.x] = S1;
+  s_b[threadIdx.y][threadIdx.x] = S2;
   __syncthreads();
+  if (!live) return;
   S1 = 0.f; S2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LAT_RY; ++i) { S1 += s_a[i][lane]; S2 += s_b[i][lane]; }
+  for (int i = 0; i < LAT_RY; ++i) { S1 += s_a[i][threadIdx.x]; S2 += s_b[i][threadIdx.x]; }
   const float m1 = S1 / (float)B, m2 = S2 / (float)B;
-  float aw[NM];
-#pragma unroll
-  for (int k = 0; k < NM; ++k) aw[k] = 0.f;
-  for (int b0 = threadIdx.y; b0 < B; b0 += LAT_RY * RB) {
-    float v[32];
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int b = b0 + r * LAT_RY;
-      float d = 0.f;
-      if (live && b < B) {
-        const float xh = (__ldg(y + (size_t)b * N + f) - mean) * rstd;
-        const float g = __ldg(da.p + (size_t)b * dstride + doff) * lat_act_grad(xh + bt, act);
-        d = rstd * (g - m1 - xh * m2);
-      }
-#pragma unroll
-      for (int k = 0; k < NM; ++k) {
-        if (b < B) aw[k] = fmaf(s_z[b * NM + k], d, aw[k]);
-        v[r * NM + k] = d * wk[k];
-      }
-    }
-    const float tot = tcptx::warp_colsum32(v, lane);      // lane l: sum over the warp's features of value l = (row l/NM, k l%NM)
-    const int b = b0 + (lane / NM) * LAT_RY;
-    if (b < B) atomicAdd(&s_dz[b * NM + (lane % NM)], tot);
-  }
-#pragma unroll
-  for (int k = 0; k < NM; ++k) s_w[threadIdx.y][k][lane] = aw[k];
-  __syncthreads();
-  if (live && threadIdx.y == 0) {
-#pragma unroll
-    for (int k = 0; k < NM; ++k) {
-      if (k < KZ) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < LAT_RY; ++i) t += s_w[i][k][lane];
-        dw[(size_t)k * N + f] += t;                        // this block owns columns f of the weight gradient
-      }
-    }
-    if (dbeta != nullptr) dbeta[f] = S1;
-  }
-  for (int i = tid; i < B * NM; i += LAT_THREADS) {
-    const int b = i / NM, k = i - b * NM;
-    if (k < KZ) atomicAdd(dz + (size_t)b * dz_ld + dz_coff + k, s_dz[i]);
+  if (threadIdx.y == 0 && dbeta != nullptr) dbeta[f] = S1;
+#pragma unroll 4
+  for (int b = threadIdx.y; b < B; b += LAT_RY) {
+    const float xh = (__ldg(y + (size_t)b * N + f) - mean) * rstd;
+    const float g = __ldg(da.p + (size_t)b * dstride + doff) * lat_act_grad(xh + bt, act);
+    dy[(size_t)b * N + f] = rstd * (g - m1 - xh * m2);
   }
 }
 
@@ -243,7 +350,8 @@ int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double
   if (!lat_fused_supported(B, KZ)) { svae_global_error() = "lat_bwd_fused: unsupported batch / latent width"; return -1; }
   Geom tg{}; tg.B = B; tg.Cin = KZ; tg.Cout = N;
   ProfScope ps(lc, KC_SKINNY, 8.0 * B * KZ * (double)N, 8.0 * B * (double)N, &tg);
-  const unsigned blocks = (unsigned)((N + 31) / 32);
+  unsigned blocks = (unsigned)((N + 31) / 32);
+  if (blocks > 2u * (unsigned)lc.sm_count) blocks = 2u * (unsigned)lc.sm_count;
   LAT_DISPATCH(KZ, {
     const size_t smem = 2 * (size_t)B * NM * sizeof(float);
     if (allow_smem(lat_bwd_fused_kernel<NM>, smem) != 0) return -3;
@@ -251,5 +359,22 @@ int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double
                                                                         dbeta, dz.p, dz.ld, dz.coff);
   });
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// statistics + normalisation + activation of a [B, N] fully-connected output in one launch (stats are left for the backward)
+int bn2d_fwd(const LaunchCtx& lc, const float* y, const float* beta, int B, int N, int act, double* stats, FeatView out, BfDst bf) {
+  Geom tg{}; tg.B = B; tg.Cout = N;
+  ProfScope ps(lc, KC_BN_FWD, 7.0 * B * (double)N, (double)B * N * (4.0 + (out.p ? 4.0 : 0.0) + (bf.a.p ? 2.0 : 0.0)), &tg);
+  CUDA_TRY(launch_k(lc, bn2d_fwd_kernel, dim3((unsigned)((N + 31) / 32)), dim3(32, LAT_RY), 0, y, beta, B, N, act, stats, out, bf));
+  return 0;
+}
+
+// both passes of the batch-norm backward of a [B, N] fully-connected output in one launch
+int bn2d_bwd(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, int B, int N, int act,
+             float* dy, float* dbeta) {
+  Geom tg{}; tg.B = B; tg.Cout = N;
+  ProfScope ps(lc, KC_BN_BWD_APPLY, 13.0 * B * (double)N, 12.0 * B * (double)N, &tg);
+  CUDA_TRY(launch_k(lc, bn2d_bwd_kernel, dim3((unsigned)((N + 31) / 32)), dim3(32, LAT_RY), 0, da, y, stats, beta, B, N, act, dy, dbeta));
   return 0;
 }

@@ -17,6 +17,7 @@
 // Reference ops replaced: Conv2D / Conv2DBackpropInput as launched for conv2d_bn_lrelu, conv2d_t_bn(_relu) and their
 // input gradients (abstract_network.py:18,37,56; sequential_vae.py:1273).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -732,6 +733,7 @@ struct Tc2Params {
   unsigned a_pitch;         // bytes between planes in shared memory
   unsigned a_bytes;         // one halo (all planes of one channel chunk)
   int a_stages;
+  int ntw;                  // output channels per CTA (blockIdx.z walks the sub-tiles of a 128-column packed tile; 128: whole tile)
   int w_resident;           // 1: all weights of the CTA's N tile live in shared memory
   unsigned w_bytes_ntile;   // packed bytes of one full N tile (128 columns)
   unsigned w_region;        // shared-memory bytes reserved for weights (resident copy or ring)
@@ -742,6 +744,7 @@ struct Tc2Params {
   const __nv_bfloat16* a_src;   // bf16 planar activation copy, pointing at (group chan0/8, pixel 0 of plane 0)
   long long plane_rows;     // rows between parity planes
   long long group_rows;     // rows between 8-channel groups
+  BnBwdFuse fz;             // fz.y != nullptr: batch-norm backward pass 1 of the consuming block fused into the epilogue
 };
 
 struct SmemHeader2 {
@@ -749,18 +752,30 @@ struct SmemHeader2 {
   unsigned long long acc_full[2], acc_empty[2];
   unsigned tmem_base, pad;
   float s_sum[4][128], s_sq[4][128];
+  // fused batch-norm backward: per channel of this CTA  f_mean = shift (-mean*rstd), f_rstd = scale, f_beta (read as float4)
+  alignas(16) float f_mean[128];
+  alignas(16) float f_rstd[128];
+  alignas(16) float f_beta[128];
   unsigned tap_a_lo[16], tap_dcol[16];
   volatile unsigned long long ts[16];   // debug timestamps (svae_debug_set_buffer)
 };
 #define DBG2(slot) do { if (P.dbg != nullptr) { const unsigned long long t_ = gtimer(); if ((threadIdx.x & 31) == 0) hdr->ts[slot] = t_; } } while (0)
 
-__global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
+// FUSED: the epilogue carries batch-norm backward pass 1 of the consuming block (BnBwdFuse); a separate instantiation so
+// that the plain kernel keeps its register budget.
+template <bool FUSED>
+__global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const TcParams& P = PP.t;
   SmemHeader2* hdr = reinterpret_cast<SmemHeader2*>(smem_raw);
   unsigned char* w_smem = smem_raw + ((sizeof(SmemHeader2) + 127) & ~127u);
-  const int n0 = blockIdx.y * 128;
-  const int Nt = min(128, P.N_p - n0);
+  // Output-channel tiling: blockIdx.y = 128-column tile of the packed weights, blockIdx.z = sub-tile of PP.ntw columns
+  // inside it.  Layers with few pixel tiles (4x4 / 8x8 maps, B = 100) are bound by streaming their weights into one CTA
+  // per tile; splitting the channels spreads that stream (and the MMAs) over up to 4x as many SMs.
+  const int tile_w = min(128, P.N_p - (int)blockIdx.y * 128);
+  const int n0 = blockIdx.y * 128 + blockIdx.z * PP.ntw;
+  const int Nt = min(PP.ntw, tile_w - (int)blockIdx.z * PP.ntw);
+  const bool w_sub = Nt != tile_w;     // sub-tile: one bulk copy per (chunk, tap, 8-channel group) row of Nt*16 bytes
   const unsigned b_tap_bytes = (unsigned)(P.KC * Nt * 2);
   const unsigned b_stage_bytes = b_tap_bytes * (unsigned)P.tps;
   unsigned char* a_smem = w_smem + PP.w_region;
@@ -784,6 +799,29 @@ __global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant_
   tc_fence_after();
   const unsigned tmem_base = uniform_u32(hdr->tmem_base);
   if (warp == 0) DBG2(1);
+  // Resident weights are fetched BEFORE the grid dependency is resolved: the packed operand copies are written once at the
+  // start of the step (>= 2 kernels back, see launch_k), so under programmatic dependent launch this load - like the barrier
+  // and TMEM setup above - overlaps the tail of the predecessor kernel.
+  const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2 +
+                              (size_t)blockIdx.z * PP.ntw * 16;
+  const unsigned src_row = (unsigned)tile_w * 16u, dst_row = (unsigned)Nt * 16u;   // one (chunk, tap, group) row: [n][8] bf16
+  if (warp == 1 && PP.w_resident && my_tiles > 0) {
+    const unsigned total = (unsigned)(P.NC * P.ntaps) * b_tap_bytes;
+    const unsigned bar = smem_u32(&hdr->w_full[0]);
+    if (lane == 0) mbar_expect_tx(bar, total);
+    __syncwarp();
+    if (!w_sub) {
+      if (lane == 0)
+        for (unsigned off = 0; off < total; off += 32768u)
+          bulk_g2s(smem_u32(w_smem + off), wsrc + off, min(32768u, total - off), bar);
+    } else {
+      const int rows = P.NC * P.ntaps * P.JC;
+      for (int r = lane; r < rows; r += 32)
+        bulk_g2s(smem_u32(w_smem) + (unsigned)r * dst_row, wsrc + (size_t)r * src_row, dst_row, bar);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= halo producer: one bulk copy (TMA 1-D) per (parity plane, 8-channel group) =================
@@ -809,25 +847,24 @@ __global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ================= weight producer =================
-    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2;
-    if (PP.w_resident) {
-      if (lane == 0 && my_tiles > 0) {
-        const unsigned total = (unsigned)(P.NC * P.ntaps) * b_tap_bytes;
-        const unsigned bar = smem_u32(&hdr->w_full[0]);
-        mbar_expect_tx(bar, total);
-        for (unsigned off = 0; off < total; off += 32768u)
-          bulk_g2s(smem_u32(w_smem + off), wsrc + off, min(32768u, total - off), bar);
-      }
-    } else {
+    if (!PP.w_resident) {
       int stage = 0; unsigned phase = 0;
       for (int ti = 0; ti < my_tiles; ++ti)
         for (int c = 0; c < P.NC; ++c)
           for (int s = 0; s < P.ntaps; s += P.tps) {
             mbar_wait(smem_u32(&hdr->w_empty[stage]), phase ^ 1);
-            if (lane == 0) {
-              mbar_expect_tx(smem_u32(&hdr->w_full[stage]), b_stage_bytes);
-              bulk_g2s(smem_u32(w_smem + (size_t)stage * P.b_stage_max), wsrc + ((size_t)c * P.ntaps + s) * b_tap_bytes,
-                       b_stage_bytes, smem_u32(&hdr->w_full[stage]));
+            if (lane == 0) mbar_expect_tx(smem_u32(&hdr->w_full[stage]), b_stage_bytes);
+            __syncwarp();
+            if (!w_sub) {
+              if (lane == 0)
+                bulk_g2s(smem_u32(w_smem + (size_t)stage * P.b_stage_max), wsrc + ((size_t)c * P.ntaps + s) * b_tap_bytes,
+                         b_stage_bytes, smem_u32(&hdr->w_full[stage]));
+            } else {
+              const int rows = P.tps * P.JC;
+              const size_t row0 = ((size_t)c * P.ntaps + s) * P.JC;
+              for (int r = lane; r < rows; r += 32)
+                bulk_g2s(smem_u32(w_smem + (size_t)stage * P.b_stage_max) + (unsigned)r * dst_row, wsrc + (row0 + r) * src_row, dst_row,
+                         smem_u32(&hdr->w_full[stage]));
             }
             __syncwarp();
             if (++stage == PP.w_stages) { stage = 0; phase ^= 1; }
@@ -907,6 +944,27 @@ __global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant_
     // ================= epilogue warps 3..6: TMEM lane quarter = warp % 4 =================
     const int quarter = warp & 3;
     const int et = tid - 96;                          // 0..127 inside the epilogue group
+    const BnBwdFuse& fz = PP.fz;
+    constexpr bool fused = FUSED;
+    if constexpr (FUSED) {
+      // xhat = y*scale + shift; channels outside the batch norm get scale = shift = 0 and beta = 1: xhat = 0, act' = 1, i.e.
+      // they pass through the same arithmetic unchanged and add nothing to the second sum - no per-element branches
+      for (int col = et; col < 128; col += 128) {
+        const int c = n0 + col;
+        float scale = 0.f, shift = 0.f, bt = 1.f;
+        if (col < Nt && c < fz.C) {
+          const double m = fz.stats[c] / (double)fz.rows;
+          double var = fz.stats[fz.C + c] / (double)fz.rows - m * m;
+          if (var < 0.0) var = 0.0;
+          const float mean = (float)m;
+          scale = (float)(1.0 / sqrt(var + (double)SVAE_BN_EPS));
+          shift = -mean * scale;
+          bt = fz.beta[c];
+        }
+        hdr->f_mean[col] = shift; hdr->f_rstd[col] = scale; hdr->f_beta[col] = bt;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int b = ti % PP.acc_bufs;
       mbar_wait(smem_u32(&hdr->acc_full[b]), (unsigned)(ti / PP.acc_bufs) & 1u);
@@ -932,6 +990,69 @@ __global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant_
           float v[32];
           tmem_ld_upto32(acc_base + (unsigned)(a * Nt + nn), v, Nt - nn);
           const int ncols = max(0, min(min(32, Nt - nn), P.n_valid - (n0 + nn)));
+          if constexpr (FUSED) {
+            // ---- da -> g = da * act'(xhat + beta + residual) for the consuming block's channels; sums of g and g*xhat ----
+            // Phase A issues every global load of the 32-column group (y, residual, previous value) before the first use, so
+            // that they are all in flight together; phase B computes and stores.  (Interleaved, each load would wait behind
+            // the preceding store: the compiler cannot prove that the output does not alias y.)
+            const size_t pix = ((size_t)n * P.Hout + oh) * P.Wout + ow;
+            const int cbase = n0 + nn;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* yp = reinterpret_cast<const float4*>(fz.y + pix * fz.C + cbase);
+            const float4* rp = reinterpret_cast<const float4*>(fz.res + pix * fz.res_ld + fz.res_coff + cbase);
+            float4* op = reinterpret_cast<float4*>(orow + nn);
+            const int nbn = valid ? min(ncols, fz.C - cbase) : 0;          // columns of this group inside the batch norm
+            const int nout = valid ? ncols : 0;
+            // one auxiliary operand per element: the residual (enters the activation derivative) OR the previous value of
+            // the output (accumulate) - the host never asks for both at once
+            const bool has_res = fz.res != nullptr, acc = P.accumulate != 0;
+            const float4* xp = has_res ? rp : op;
+            const int naux = has_res ? nbn : (acc ? nout : 0);
+            float4 yv[8], av[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              yv[j] = 4 * j < nbn ? __ldg(yp + j) : z4;
+              av[j] = 4 * j < naux ? xp[j] : z4;
+            }
+            if (!valid) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) v[k] = 0.f;
+            }
+            const float neg = fz.act == ACT_LRELU ? SVAE_LRELU_SLOPE : fz.act == ACT_RELU ? 0.f : 1.f;
+            const float rsel = has_res ? 1.f : 0.f, osel = has_res ? 0.f : 1.f;
+            float gy[32];     // g*y: sum g*xhat = scale * sum g*y + shift * sum g (applied per column at the end)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = 4 * j;
+              const float4 sc = *reinterpret_cast<const float4*>(&hdr->f_rstd[nn + k]);
+              const float4 sh = *reinterpret_cast<const float4*>(&hdr->f_mean[nn + k]);
+              const float4 bt = *reinterpret_cast<const float4*>(&hdr->f_beta[nn + k]);
+              const float yy[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w}, aa[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+              const float ss[4] = {sc.x, sc.y, sc.z, sc.w}, hh[4] = {sh.x, sh.y, sh.z, sh.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float pre = fmaf(yy[e], ss[e], hh[e]) + bb[e] + rsel * aa[e];
+                const float gval = fmaf(osel, aa[e], v[k + e]) * (pre > 0.f ? 1.f : neg);
+                v[k + e] = gval;
+                gy[k + e] = gval * yy[e];
+              }
+              if (k < nout) {
+                const float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                op[j] = o;
+                if (fz.dres != nullptr && k < nbn) {
+                  float4* dr = reinterpret_cast<float4*>(fz.dres + pix * fz.C + cbase) + j;
+                  float4 d = o;
+                  if (fz.dres_acc) { const float4 q4 = *dr; d.x += q4.x; d.y += q4.y; d.z += q4.z; d.w += q4.w; }
+                  *dr = d;
+                }
+              }
+            }
+            const float cs = warp_colsum32(v, lane);
+            const float cq = warp_colsum32(gy, lane);
+            hdr->s_sum[quarter][nn + lane] += cs;
+            hdr->s_sq[quarter][nn + lane] += cq;
+            continue;
+          }
           if (valid) {
             if (P.out_vec) {
 #pragma unroll
@@ -975,7 +1096,19 @@ __global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant_
       if (ti == 0 && warp == 3) DBG2(7);
       if (ti == my_tiles - 1 && warp == 3) DBG2(9);
     }
-    if (P.stats != nullptr && my_tiles > 0) {
+    if (fused) {
+      if (my_tiles > 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = et; col < Nt; col += 128) {
+        if (n0 + col < fz.C) {
+          const float s = hdr->s_sum[0][col] + hdr->s_sum[1][col] + hdr->s_sum[2][col] + hdr->s_sum[3][col];
+          const float s2 = hdr->s_sq[0][col] + hdr->s_sq[1][col] + hdr->s_sq[2][col] + hdr->s_sq[3][col];
+          atomicAdd(&fz.S[n0 + col], (double)s);
+          atomicAdd(&fz.S[fz.C + n0 + col], (double)hdr->f_rstd[col] * (double)s2 + (double)hdr->f_mean[col] * (double)s);   // sum g*xhat
+        }
+      }
+      }
+    } else if (P.stats != nullptr && my_tiles > 0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int col = et; col < Nt; col += 128) {
         if (n0 + col < P.n_valid) {
@@ -999,17 +1132,26 @@ __global__ void __launch_bounds__(224, 1) tc2_conv_kernel(const __grid_constant_
   }
 }
 
-bool build_params2(const Geom& g, Tc2Params& PP) {
+bool build_params2(const Geom& g, Tc2Params& PP, int ntw = 128) {
   memset(&PP, 0, sizeof PP);
   TcParams& P = PP.t;
   if (g.KH != 4) return false;
   if (!build_params(g, P)) return false;
+  PP.ntw = ntw;
+  if (ntw < 128) {
+    // sub-tiles must tile every 128-column packed tile exactly
+    if (ntw % 16 || ntw < 16 || (P.N_p >= 128 ? (P.N_p % 128 || 128 % ntw) : (P.N_p % ntw))) return false;
+    const unsigned tap_bytes = (unsigned)(P.KC * ntw * 2);     // weight stages as build_params sizes them, for the narrower tile
+    P.tps = 1;
+    while (P.tps * 2 <= P.ntaps && (unsigned)(P.tps * 2) * tap_bytes <= 32 * 1024) P.tps *= 2;
+    P.b_stage_max = tap_bytes * (unsigned)P.tps;
+  }
   PP.tiles = (int)((P.Q + TILE_M - 1) / TILE_M);
   PP.nsplit = 1;
   PP.boxp = (P.HL + 7) & ~7;            // pixels per plane copy (16 B each); keeps every plane 128-byte aligned
   PP.a_pitch = (unsigned)PP.boxp * 16u;
   PP.a_bytes = (unsigned)(P.nplanes * P.JC) * PP.a_pitch;
-  const int nt_max = P.N_p < 128 ? P.N_p : 128;
+  const int nt_max = min(P.N_p < 128 ? P.N_p : 128, ntw);
   PP.w_bytes_ntile = (unsigned)(P.NC * P.ntaps) * (unsigned)(P.KC * 128 * 2);
   const unsigned w_need = (unsigned)(P.NC * P.ntaps) * (unsigned)(P.KC * nt_max * 2);
   PP.w_resident = w_need <= W_RESIDENT_MAX ? 1 : 0;
@@ -1117,10 +1259,32 @@ bool tc2_supported(const Geom& g) {
 // layout kind the tc2 kernel wants for the INPUT of geometry g
 int tc2_input_kind(const Geom& g) { return g.stride == 1 ? 0 : (g.mode == 0 ? 2 : 1); }
 
+bool tc2_fuse_supported(const Geom& g, View out, int C) {
+  return C > 0 && C % 8 == 0 && C <= g.Cout && g.Cout % 4 == 0 && out.ld % 4 == 0 && out.coff % 4 == 0 &&
+         (((uintptr_t)out.p & 15) == 0) && tc2_supported(g);
+}
+
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
-                    double* stats) {
+                    double* stats, const BnBwdFuse* fuse) {
   Tc2Params PP;
   if (!build_params2(g, PP)) { svae_global_error() = "tc2: unsupported geometry"; return -1; }
+  {
+    // few pixel tiles (small feature maps): split the output channels over more CTAs (see the kernel's header comment)
+    const int tiles128 = (PP.t.N_p + 127) / 128;
+    const int ncap = PP.t.N_p < 128 ? PP.t.N_p : 128;
+    static const int force = getenv("SVAE_NTW") ? atoi(getenv("SVAE_NTW")) : 0;
+    int best = 128;
+    for (int split = 2; split <= 4; split *= 2) {
+      const int w = ncap / split;
+      if (w < 32 || ncap % split || (long long)PP.tiles * tiles128 * split > (long long)lc.sm_count) break;   // one wave, one CTA per SM
+      best = w;
+    }
+    if (force) best = force;
+    if (best < 128) {
+      Tc2Params Q2;
+      if (build_params2(g, Q2, best) && smem_bytes2(Q2) <= 227 * 1024) PP = Q2;
+    }
+  }
   TcParams& P = PP.t;
   if (in.kind != tc2_input_kind(g) || in.Hp != P.Hp || in.Wp != P.Wp || (chan0 & 7)) {
     svae_global_error() = "tc2: activation copy is not in the layout this geometry reads";
@@ -1130,6 +1294,10 @@ int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int cha
   P.out = out.p; P.out_ld = out.ld; P.out_coff = out.coff;
   P.out_vec = (out.ld % 4 == 0) && (out.coff % 4 == 0) && (((uintptr_t)out.p & 15) == 0) && (g.Cout % 4 == 0);
   P.stats = stats;
+  if (fuse != nullptr) {
+    if (stats != nullptr || !P.out_vec || fuse->C % 8 || fuse->C > g.Cout || (fuse->res != nullptr && g.accumulate)) { svae_global_error() = "tc2: fused batch-norm backward needs a vectorised output and no forward statistics"; return -1; }
+    PP.fz = *fuse;
+  }
   if (chan0 + P.Cin_p > in.Cpad || P.lo > in.front) { svae_global_error() = "tc2: channel window / slack of the activation copy too small"; return -1; }
   P.dbg = reinterpret_cast<unsigned long long*>(g_tc_debug_buffer);
   PP.a_src = in.p + ((long long)(chan0 / 8) * in.group_rows + in.front) * 8;
@@ -1138,23 +1306,25 @@ int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int cha
   const size_t smem = smem_bytes2(PP);
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
+  const int nsub = ((P.N_p < 128 ? P.N_p : 128) + PP.ntw - 1) / PP.ntw;
   const int ntiles = (P.N_p + 127) / 128;
   int per_sm = (int)((227 * 1024) / smem);
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   if (PP.tmem_cols * (unsigned)per_sm > 512) per_sm = 1;
-  int ctas = lc.sm_count * per_sm / ntiles;
+  int ctas = lc.sm_count * per_sm / (ntiles * nsub);
   if (ctas < 1) ctas = 1;
   if (ctas > PP.tiles) ctas = PP.tiles;
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
   ProfScope ps(lc, KC_GEMM_TC, 2.0 * pix * g.KH * g.KW * g.Cin * g.Cout,
                2.0 * (double)g.B * g.Hin * g.Win * g.Cin + 4.0 * (double)g.B * g.Hout * g.Wout * g.Cout +
                    2.0 * g.KH * g.KW * g.Cin * g.Cout, &g);
-  tc2_conv_kernel<<<dim3((unsigned)ctas, (unsigned)ntiles), 224, smem, lc.stream>>>(PP);
-  CUDA_TRY(cudaGetLastError());
+  if (fuse != nullptr) CUDA_TRY(launch_k(lc, tc2_conv_kernel<true>, dim3((unsigned)ctas, (unsigned)ntiles, (unsigned)nsub), dim3(224), smem, PP));
+  else CUDA_TRY(launch_k(lc, tc2_conv_kernel<false>, dim3((unsigned)ctas, (unsigned)ntiles, (unsigned)nsub), dim3(224), smem, PP));
   return 0;
 }
 

@@ -17,6 +17,12 @@
 #include "common.cuh"
 #include "nccl_dl.h"
 
+// Every non-kernel operation enqueued by this file ends the "previous node is a kernel" state that programmatic
+// dependent launch relies on (common.cuh, launch_k): the next kernel then takes an ordinary full dependency.
+#define cudaMemsetAsync(...) (h->pdl_prev = 0, cudaMemsetAsync(__VA_ARGS__))
+#define cudaMemcpyAsync(...) (h->pdl_prev = 0, cudaMemcpyAsync(__VA_ARGS__))
+#define cudaStreamWaitEvent(s_, e_, f_) ((void)(((s_) == h->stream) ? (h->pdl_prev = 0) : 0), cudaStreamWaitEvent(s_, e_, f_))
+
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 std::string& svae_global_error() { return g_err; }
@@ -56,6 +62,9 @@ struct Block {
   // this block's own activated output is additionally written for its consumer
   BfAct in_bf{}; bool tc2_fwd = false, tc2_dgrad = false, tc2_wgrad = false;
   BfDst out_bf{};
+  // set by the input-gradient kernel that produced this block's dL/d(activated output) when it already turned it into
+  // g = da * act' and reduced the two backward sums (BnBwdFuse): the block's backward then skips pass 1
+  bool g_fused = false;
 };
 
 // Gradient scratch of ONE chain step's backward.  Two sets (step parity) let the side streams (weight gradients,
@@ -187,6 +196,12 @@ struct svae_handle {
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   bool use_streams = true, use_graph = true, capturing = false;
   int fork_mask = 15;   // debugging / ablation: 1 chain wgrads, 2 recognition branch, 4 its wgrads, 8 forward recognition
+  int pdl_prev = 0;     // 1: the last node enqueued on the chain stream is a kernel (see launch_k)
+  bool use_pdl = true;  // SVAE_PDL=0 disables programmatic dependent launch
+  // SVAE_FUSE=1: batch-norm backward pass 1 inside the epilogue of the producing input-gradient kernel.  Correct (the GPU
+  // suite passes with it) but measured SLOWER on B200 (13.5 vs 12.7 ms/step): the epilogue has 4 warps per SM for work a
+  // standalone kernel spreads over 64, and it sits on the chain's critical path.  Off by default.
+  bool use_fuse = false;
   int ablate = 0;       // SVAE_ABLATE, TIMING EXPERIMENTS ONLY (results are wrong): 1 skip weight gradients, 2 skip the recognition / latent backward
   int eager_steps = 0;
   std::vector<GraphEntry> graphs;
@@ -210,7 +225,11 @@ struct svae_handle {
   std::vector<cudaEvent_t> bucket_ev; cudaEvent_t comm_done = nullptr;
 
   Profiler prof;
-  LaunchCtx lc() { return LaunchCtx{cur ? cur : stream, &launches, sm_count, &prof}; }
+  LaunchCtx lc() {
+    LaunchCtx c{cur ? cur : stream, &launches, sm_count, &prof};
+    if (use_pdl && !prof.enabled && (cur == nullptr || cur == stream)) c.pdl_state = &pdl_prev;
+    return c;
+  }
   float* pw(int idx) { return P + params[idx].offset; }
   float* pg(int idx) { return G + params[idx].offset; }
 };
@@ -705,42 +724,80 @@ bool forked(const svae_handle* h) { return h->use_streams && h->cfg.train_capaci
 
 // contraction through the TMA-fed kernel when the input has a bf16 planar copy, else the SIMT-staged / fp32 kernels
 int contract_bf(svae_handle* h, Geom g, int B, bool tc2, const BfAct& in_bf, View in, const float* w, const void* w_packed,
-                bool use_tc, View out, double* stats) {
+                bool use_tc, View out, double* stats, const BnBwdFuse* fuse = nullptr) {
   if (tc2) {
     g.B = B;
     LaunchCtx lc = h->lc();
-    return tc2_gather_gemm(lc, g, in_bf, 0, w_packed, out, stats);
+    return tc2_gather_gemm(lc, g, in_bf, 0, w_packed, out, stats, fuse);
   }
+  if (fuse != nullptr) { svae_global_error() = "fused batch-norm backward requested on a non-tc2 contraction"; return -1; }
   return contract(h, g, B, in, w, w_packed, use_tc, out, stats);
 }
 
+// Describe pass 1 of block `up`'s batch-norm backward for fusion into the input-gradient kernel (geometry dg, TMA-fed path)
+// that writes `din`, whose first up.feats channels are dL/d(up's activated output).  false: not fusable, run it separately.
+bool make_fuse(svae_handle* h, Block* up, int B, float* dres, int dres_acc, Geom dg, View din, BnBwdFuse& fz) {
+  if (up == nullptr || !h->use_fuse || up->g.KH != 4 || up->rpi <= 1) return false;   // 4-D batch norm only
+  if (up->res.p != nullptr && !(up->res.ppr == 1 && up->res.inner == up->feats && up->res.ld % 4 == 0 && up->res.coff % 4 == 0 &&
+                                ((uintptr_t)up->res.p & 15) == 0))
+    return false;
+  dg.B = B;
+  if (up->res.p != nullptr && dg.accumulate) return false;   // the fused epilogue carries one auxiliary operand per element
+  if ((int64_t)dg.Hout * dg.Wout != up->rpi || !tc2_fuse_supported(dg, din, up->feats)) return false;
+  if (((uintptr_t)up->y & 15) != 0 || (dres != nullptr && ((uintptr_t)dres & 15) != 0)) return false;
+  fz = BnBwdFuse{up->y, up->stats, h->pw(up->beta), up->res.p, up->res.ld, up->res.coff, dres, dres_acc, up->S, up->feats, up->act,
+                 (long long)B * up->rpi};
+  return true;
+}
+
+// fully-connected block with a 2-D batch norm (enc.fc, dec.fc): statistics + normalisation in one kernel (bn2d_fwd / bn2d_bwd)
+bool is_fc2d(const Block& b, int B) { return b.g.KH == 1 && b.rpi == 1 && b.res.p == nullptr && B <= 2048; }
+
 int block_fwd(svae_handle* h, Block& b, int B, View in) {
-  H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0), b.stats));
+  const bool fc2d = is_fc2d(b, B);
+  H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
+                    fc2d ? nullptr : b.stats));
   LaunchCtx lc = h->lc();
-  H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out, b.out_bf));
+  if (fc2d) H_TRY(bn2d_fwd(lc, b.y, h->pw(b.beta), B, b.feats, b.act, b.stats, b.out, b.out_bf));
+  else H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out, b.out_bf));
   return 0;
 }
 
 // backward of a block on the current stream: da -> dy, beta gradient, optional input gradient; the weight gradient goes
 // to `wst` (a side stream, or the current one)
 int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in, float* dres, int dres_acc, const View* din,
-              int din_acc, cudaStream_t wst) {
+              int din_acc, cudaStream_t wst, Block* up = nullptr, float* up_dres = nullptr, int up_dres_acc = 0) {
   LaunchCtx lc = h->lc();
   const int64_t rows = (int64_t)B * b.rpi;
   float* dy = gs.dy[b.dy_slot];
-  H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
   const bool have_bf = gs.dy_bf[b.dy_slot].p != nullptr;
   const bool tc2d = b.tc2_dgrad && din != nullptr && have_bf;
   const bool tc2w = b.tc2_wgrad && have_bf && b.in_bf.p != nullptr;
-  H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta),
-                     (tc2d || tc2w) ? BfDst{gs.dy_bf[b.dy_slot], 0, 0, 0} : BfDst{}));
+  const BfDst dy_bf = (tc2d || tc2w) ? BfDst{gs.dy_bf[b.dy_slot], 0, 0, 0} : BfDst{};
+  if (b.g_fused) {
+    // pass 1 ran inside the kernel that produced da (it holds g now); the fp32 dy is only written for consumers that are
+    // not TMA-fed
+    b.g_fused = false;
+    const bool need_f32 = !tc2w || (din != nullptr && !tc2d);
+    H_TRY(bn_bwd_apply_from(lc, mkview(da.p, da.ld, da.coff), need_f32 ? dy : nullptr, b.y, b.stats, b.S, rows, b.feats,
+                            h->pg(b.beta), dy_bf));
+  } else if (is_fc2d(b, B) && dres == nullptr && dy_bf.a.p == nullptr) {
+    H_TRY(bn2d_bwd(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, dy, h->pg(b.beta)));
+  } else {
+    H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
+    H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta), dy_bf));
+  }
   View dyv = mkview(dy, b.feats, 0);
   // dy is final here: the weight gradient (side stream) depends on this point only, not on the input gradient below
   H_TRY(link(h, cur_stream(h), wst));
   if (din != nullptr) {
     Geom g = dgrad_geom(b.g);
     g.accumulate = din_acc;
-    H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr));
+    BnBwdFuse fz;
+    const bool fuse = tc2d && make_fuse(h, up, B, up_dres, up_dres_acc, g, *din, fz);
+    H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr,
+                      fuse ? &fz : nullptr));
+    if (fuse) up->g_fused = true;
   }
   if (!(h->ablate & 1)) {
     OnStream os(h, wst);
@@ -982,13 +1039,21 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   View c0 = mkview(s.tb[0].out.p, F[1], 0);
   View dc0 = mkview(gs.d_c[0], F[1], 0);
   {
+    // d_c[0] is complete after the LAST of the two input gradients: that one carries pass 1 of tb[0]'s batch-norm backward
     Geom g = dgrad_geom(s.g_out);
-    H_TRY(contract_bf(h, g, B, gs.du_out_bf.p != nullptr && s.outb.tc_dgrad, gs.du_out_bf, mkview(gs.d_u, ldu, 0), h->pw(s.w_out),
-                      s.outb.w_packed_d, s.outb.tc_dgrad, dc0, nullptr));
+    const bool tc2o = gs.du_out_bf.p != nullptr && s.outb.tc_dgrad;
+    const bool tc2g = has_gate && gs.du_gate_bf.p != nullptr && s.gateb.tc_dgrad;
+    BnBwdFuse fz;
+    const bool fuse_o = !has_gate && tc2o && make_fuse(h, &s.tb[0], B, nullptr, 0, g, dc0, fz);
+    H_TRY(contract_bf(h, g, B, tc2o, gs.du_out_bf, mkview(gs.d_u, ldu, 0), h->pw(s.w_out), s.outb.w_packed_d, s.outb.tc_dgrad, dc0,
+                      nullptr, fuse_o ? &fz : nullptr));
+    if (fuse_o) s.tb[0].g_fused = true;
     if (has_gate) {
       Geom g2 = dgrad_geom(s.g_gate); g2.accumulate = 1;
+      const bool fuse_g = tc2g && make_fuse(h, &s.tb[0], B, nullptr, 0, g2, dc0, fz);
       H_TRY(contract_bf(h, g2, B, gs.du_gate_bf.p != nullptr && s.gateb.tc_dgrad, gs.du_gate_bf, mkview(gs.d_u, ldu, C),
-                        h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr));
+                        h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr, fuse_g ? &fz : nullptr));
+      if (fuse_g) s.tb[0].g_fused = true;
     }
     H_TRY(link(h, st.chain, st.w));
     OnStream os(h, st.w);
@@ -1009,7 +1074,8 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
     // c_l = relu(bn(deconv_s1(dcat_l)))
     View dcat_in = mkview(s.dcat[l], 2 * Fl, 0);
     View d_dcat = mkview(gs.d_dcat[l], 2 * Fl, 0);
-    H_TRY(block_bwd(h, gs, s.tb[l], B, fv4(gs.d_c[l], Fl, 0, Fl), dcat_in, nullptr, 0, &d_dcat, 0, st.w));
+    H_TRY(block_bwd(h, gs, s.tb[l], B, fv4(gs.d_c[l], Fl, 0, Fl), dcat_in, nullptr, 0, &d_dcat, 0, st.w, &s.ta[l],
+                    has_gate ? gs.d_e[2 * l + 1] : nullptr, 0));
     // P_l = lrelu(bn(fc(z_l))): second channel window of d_dcat, on the recognition stream
     {
       H_TRY(link(h, st.chain, st.rec));
@@ -1023,7 +1089,7 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
     View ta_in = l < L - 2 ? mkview(s.tb[l + 1].out.p, F[l + 2], 0) : mkview(s.decfc.out.p, s.ta[l].g.Cin, 0);
     View d_next = l < L - 2 ? mkview(gs.d_c[l + 1], F[l + 2], 0) : mkview(gs.d_fca, s.ta[l].g.Cin, 0);
     H_TRY(block_bwd(h, gs, s.ta[l], B, fv4(gs.d_dcat[l], 2 * Fl, 0, Fl), ta_in, has_gate ? gs.d_e[2 * l + 1] : nullptr, 0,
-                    &d_next, 0, st.w));
+                    &d_next, 0, st.w, l < L - 2 ? &s.tb[l + 1] : nullptr));
   }
   // dec.fc
   {
@@ -1060,7 +1126,7 @@ int encoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
     // d_e[k-1] already holds the decoder shortcut gradient when k-1 is odd (e[l+1] = enc[2l+1]); gx_prev always holds
     // the highway gradient
     const int acc = k > 0 ? ((k - 1) & 1) : 1;
-    H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_e[k], b.feats, 0, b.feats), in, nullptr, 0, &din, acc, st.w));
+    H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_e[k], b.feats, 0, b.feats), in, nullptr, 0, &din, acc, st.w, k > 0 ? &s.enc[k - 1] : nullptr));
   }
   return 0;
 }
@@ -1084,7 +1150,7 @@ int recognition_bwd(svae_handle* h, GradSet& gs, Step& s, int B, cudaStream_t ws
     View in = k > 0 ? mkview(s.inf[k - 1].out.p, s.inf[k - 1].feats, 0) : mkview(const_cast<float*>(h->last_x), h->C, 0);
     if (k > 0) {
       View din = mkview(gs.d_inf[k - 1], s.inf[k - 1].feats, 0);
-      H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, &din, (k - 1) & 1, wst));
+      H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, &din, (k - 1) & 1, wst, &s.inf[k - 1]));
     } else {
       H_TRY(block_bwd(h, gs, b, B, fv4(gs.d_inf[k], b.feats, 0, b.feats), in, nullptr, 0, nullptr, 0, wst));
     }
@@ -1100,6 +1166,7 @@ int allreduce_bucket(svae_handle* h, int t, const BwdStreams& st) {
   H_TRY(link(h, st.w, h->comm_stream));
   H_TRY(link(h, st.rec, h->comm_stream));
   H_TRY(link(h, st.recw, h->comm_stream));
+  h->pdl_prev = 0;
   int r = h->nccl->AllReduce(h->G + s.p_begin, h->G + s.p_begin, (size_t)(s.p_end - s.p_begin), /*ncclFloat*/ 7,
                              /*ncclSum*/ 0, h->comm, h->comm_stream);
   if (r != 0) return fail(h, SVAE_ENCCL, std::string("ncclAllReduce failed: ") + h->nccl->GetErrorString(r));
@@ -1405,6 +1472,10 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     if (h->timeline) h->use_graph = false;
     const char* e3 = getenv("SVAE_FORK_MASK");
     if (e3) h->fork_mask = atoi(e3);
+    const char* e7 = getenv("SVAE_FUSE");
+    h->use_fuse = e7 && e7[0] == '1';
+    const char* e6 = getenv("SVAE_PDL");
+    h->use_pdl = !(e6 && e6[0] == '0');
     const char* e5 = getenv("SVAE_ABLATE");
     if (e5) h->ablate = atoi(e5);
   }

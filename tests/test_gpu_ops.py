@@ -15,6 +15,8 @@ CONV_CASES = [
     (2, 16, 3, 8, 2), (3, 8, 8, 8, 1), (2, 8, 16, 16, 2), (5, 4, 16, 16, 1), (2, 2, 16, 24, 2),
     (2, 32, 32, 32, 1), (3, 16, 64, 64, 1), (2, 16, 32, 64, 2), (2, 8, 128, 128, 1), (1, 64, 3, 32, 2),
     (4, 4, 128, 128, 2), (100, 8, 64, 128, 2),
+    # few pixel tiles, wide layers: the tcgen05 kernel splits the output channels over blockIdx.z (sub-tiles of 32 / 64)
+    (100, 8, 128, 128, 2), (100, 8, 256, 128, 1), (100, 4, 384, 128, 2), (100, 8, 128, 384, 2),
 ]
 
 
