@@ -81,6 +81,7 @@ struct GraphEntry {   // a captured train step, valid for exactly these argument
   int B;
   cudaGraphExec_t exec;
   int64_t launches;   // kernels inside the graph (svae_launch_count keeps counting them)
+  bool bucket = false;   // captured with the per-chain-step Adam + repack (no repack at the start of the graph)
 };
 
 struct Head {  // layers.fully_connected head (sequential_vae.py:1592,1594,1607,1609)
@@ -196,6 +197,14 @@ struct svae_handle {
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   bool use_streams = true, use_graph = true, capturing = false;
   int fork_mask = 15;   // debugging / ablation: 1 chain wgrads, 2 recognition branch, 4 its wgrads, 8 forward recognition
+  // Bucketed update (svae_train_step only): the clipped-Adam update and the bf16 operand repack of chain step t's parameters
+  // run on `upd_stream` as soon as that step's gradients are final (after its all-reduce when data parallel), overlapped with
+  // the backward of the earlier steps - every step owns its parameters (inhomogeneous chain), so nothing still reads them.
+  cudaStream_t upd_stream = nullptr;
+  bool bucket_update = false;        // set by the train-step entry points around backward_impl
+  bool use_bucket_update = true;     // SVAE_BUCKET_UPDATE=0: one Adam launch + one repack launch after the backward
+  std::vector<int> pack_step_begin;  // pack-table entry range of every chain step (T + 1 offsets)
+  std::vector<double> pack_step_elems;
   int pdl_prev = 0;     // 1: the last node enqueued on the chain stream is a kernel (see launch_k)
   bool use_pdl = true;  // SVAE_PDL=0 disables programmatic dependent launch
   // SVAE_FUSE=1: batch-norm backward pass 1 inside the epilogue of the producing input-gradient kernel.  Correct (the GPU
@@ -1173,6 +1182,32 @@ int allreduce_bucket(svae_handle* h, int t, const BwdStreams& st) {
   return 0;
 }
 
+int ensure_pack_table(svae_handle* h);
+
+// clipped Adam + operand repack of chain step t's parameter slice (see svae_handle::upd_stream)
+int update_bucket(svae_handle* h, int t, const BwdStreams& st) {
+  if (!h->bucket_update) return 0;
+  Step& s = h->steps[t];
+  cudaStream_t us = h->comm != nullptr ? h->comm_stream : h->upd_stream;
+  if (h->comm == nullptr) {   // with a communicator the all-reduce of this bucket was just enqueued on the same stream
+    H_TRY(link(h, st.chain, us));
+    H_TRY(link(h, st.w, us));
+    H_TRY(link(h, st.rec, us));
+    H_TRY(link(h, st.recw, us));
+  }
+  OnStream os(h, us);
+  LaunchCtx lc = h->lc();
+  const int64_t n = s.p_end - s.p_begin;
+  H_TRY(adam_update(lc, h->P + s.p_begin, h->G + s.p_begin, h->M + s.p_begin, h->V + s.p_begin, n, h->dyn_dev, h->dyn_host.lr_t,
+                    h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->cfg.clip_value, 1.f / (float)h->nranks));
+  if (h->cfg.operand_dtype == SVAE_OPERAND_BF16 && h->pack_table != nullptr) {
+    const int b0 = h->pack_step_begin[t], b1 = h->pack_step_begin[t + 1];
+    if (b1 > b0)
+      H_TRY(tc_pack_batched(lc, reinterpret_cast<const TcPackEntry*>(h->pack_table) + b0, b1 - b0, h->pack_step_elems[t]));
+  }
+  return 0;
+}
+
 int backward_impl(svae_handle* h) {
   if (!h->cfg.train_capacity) return fail(h, SVAE_ESTATE, "handle created without train_capacity");
   if (!h->have_fwd) return fail(h, SVAE_ESTATE, "svae_backward requires a preceding svae_forward");
@@ -1215,6 +1250,7 @@ int backward_impl(svae_handle* h) {
       }
     }
     H_TRY(allreduce_bucket(h, t, st));
+    H_TRY(update_bucket(h, t, st));
     gx_in = gx_prev;
     cur ^= 1;
   }
@@ -1227,7 +1263,10 @@ int backward_impl(svae_handle* h) {
   if (h->comm != nullptr) {
     H_CUDA(cudaEventRecord(h->comm_done, h->comm_stream));
     H_CUDA(cudaStreamWaitEvent(h->stream, h->comm_done, 0));
+  } else if (h->bucket_update) {
+    H_TRY(link(h, h->upd_stream, h->stream));   // the next step reads the updated weights and operand copies
   }
+  if (h->bucket_update) h->weights_dirty = false;
   h->have_fwd = false;
   return 0;
 }
@@ -1311,17 +1350,38 @@ void collect_pack(svae_handle* h, Block& b, void* ctx) {
   if (b.tc_dgrad && b.w_packed_d) { Geom d = dgrad_geom(b.g); d.B = 1; v->push_back(tc_pack_entry(d, h->pw(b.w), b.w_packed_d)); }
 }
 
+int ensure_pack_table(svae_handle* h) {
+  if (h->pack_table != nullptr || h->pack_bytes == 0) return 0;
+  std::vector<TcPackEntry> v;
+  h->pack_step_begin.assign(h->T + 1, 0);
+  h->pack_step_elems.assign(h->T, 0.0);
+  for (int t = 0; t < h->T; ++t) {     // for_each_block order, one step at a time: every step's entries are contiguous
+    Step& s = h->steps[t];
+    h->pack_step_begin[t] = (int)v.size();
+    for (Block& b : s.inf) collect_pack(h, b, &v);
+    for (Block& b : s.enc) collect_pack(h, b, &v);
+    if (s.t > 0) collect_pack(h, s.encfc, &v);
+    for (Block& b : s.lat) collect_pack(h, b, &v);
+    collect_pack(h, s.decfc, &v);
+    for (Block& b : s.ta) collect_pack(h, b, &v);
+    for (Block& b : s.tb) collect_pack(h, b, &v);
+    collect_pack(h, s.outb, &v);
+    if (s.t > 0) collect_pack(h, s.gateb, &v);
+    for (int i = h->pack_step_begin[t]; i < (int)v.size(); ++i) h->pack_step_elems[t] += (double)v[i].total;
+  }
+  h->pack_step_begin[h->T] = (int)v.size();
+  h->pack_entries = (int)v.size();
+  if (v.empty()) return 0;
+  H_CUDA(cudaMalloc(&h->pack_table, sizeof(TcPackEntry) * v.size()));
+  H_CUDA(cudaMemcpy(h->pack_table, v.data(), sizeof(TcPackEntry) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 // fp32 master weights -> packed bf16 operand copies of every tensor-core layer, ONE launch
 int repack_if_dirty(svae_handle* h) {
   if (!h->weights_dirty) return 0;
   if (h->cfg.operand_dtype == SVAE_OPERAND_BF16 && h->pack_bytes > 0) {
-    if (h->pack_table == nullptr) {
-      std::vector<TcPackEntry> v;
-      for_each_block(h, collect_pack, &v);
-      h->pack_entries = (int)v.size();
-      H_CUDA(cudaMalloc(&h->pack_table, sizeof(TcPackEntry) * v.size()));
-      H_CUDA(cudaMemcpy(h->pack_table, v.data(), sizeof(TcPackEntry) * v.size(), cudaMemcpyHostToDevice));
-    }
+    H_TRY(ensure_pack_table(h));
     LaunchCtx lc = h->lc();
     H_TRY(tc_pack_batched(lc, h->pack_table, h->pack_entries, (double)h->pack_bytes / 2));
   }
@@ -1334,6 +1394,7 @@ void destroy_impl(svae_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamSynchronize(h->side[i]);
+  if (h->upd_stream) cudaStreamSynchronize(h->upd_stream);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
   // captured graphs hold the communicator's collectives: they must go before the communicator does
   for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);
@@ -1343,6 +1404,7 @@ void destroy_impl(svae_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->dyn_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
+  if (h->upd_stream) cudaStreamDestroy(h->upd_stream);
   cudaFree(h->dyn_dev);
   if (h->dyn_ring) cudaFreeHost(h->dyn_ring);
   if (h->comm_done) cudaEventDestroy(h->comm_done);
@@ -1479,8 +1541,12 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     const char* e5 = getenv("SVAE_ABLATE");
     if (e5) h->ablate = atoi(e5);
   }
-  if (cfg->train_capacity)
+  if (cfg->train_capacity) {
     for (int i = 0; i < 3; ++i) C_CUDA(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio_lo));
+    C_CUDA(cudaStreamCreateWithPriority(&h->upd_stream, cudaStreamNonBlocking, prio_lo));
+    const char* e8 = getenv("SVAE_BUCKET_UPDATE");
+    h->use_bucket_update = !(e8 && e8[0] == '0');
+  }
   C_CUDA(cudaMalloc((void**)&h->dyn_dev, sizeof(SvaeDyn)));
   C_CUDA(cudaMemset(h->dyn_dev, 0, sizeof(SvaeDyn)));
   C_CUDA(cudaMallocHost((void**)&h->dyn_ring, sizeof(SvaeDyn) * 256));
@@ -1636,8 +1702,12 @@ static int train_step_graph(svae_handle* h, const float* x, const float* tgt, in
       h->graphs.erase(h->graphs.begin());
     }
     const int64_t adam_t0 = h->adam_t, launches0 = h->launches;
-    h->adam_t -= 1;                 // adam_impl increments it again below
-    h->weights_dirty = true;        // the captured step always refreshes the packed operand copies
+    const bool bucket = h->use_bucket_update && h->upd_stream != nullptr;
+    if (!bucket) h->adam_t -= 1;    // adam_impl increments it again below
+    // one Adam + one repack at the end: the captured step starts by refreshing the packed operand copies.  Bucketed update:
+    // the copies are refreshed per chain step inside the backward, and are fresh when the graph starts (see below).
+    H_TRY(repack_if_dirty(h));
+    h->weights_dirty = !bucket;
     std::vector<cudaEvent_t> eager_pool;
     eager_pool.swap(h->ev_pool);    // events recorded during capture are kept apart from the eager ones
     h->capturing = true;
@@ -1645,8 +1715,10 @@ static int train_step_graph(svae_handle* h, const float* x, const float* tgt, in
     cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
     int r = ce == cudaSuccess ? 0 : SVAE_ECUDA;
     if (r == 0) r = forward_impl(h, x, tgt, B, eps, seed, reg, nullptr, nullptr, nullptr);
+    h->bucket_update = bucket;
     if (r == 0) r = backward_impl(h);
-    if (r == 0) r = adam_impl(h, lr);
+    h->bucket_update = false;
+    if (r == 0 && !bucket) r = adam_impl(h, lr);
     cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
     h->capturing = false;
     h->ev_pool.swap(eager_pool);
@@ -1659,6 +1731,7 @@ static int train_step_graph(svae_handle* h, const float* x, const float* tgt, in
       return r;
     }
     GraphEntry e{x, tgt, eps, B, nullptr};
+    e.bucket = bucket;
     e.launches = h->launches - launches0;
     h->launches = launches0;
     cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
@@ -1667,11 +1740,12 @@ static int train_step_graph(svae_handle* h, const float* x, const float* tgt, in
     h->graphs.push_back(e);
     ge = &h->graphs.back();
   }
+  if (ge->bucket) H_TRY(repack_if_dirty(h));   // e.g. after svae_set_params / svae_adam_step: this graph does not repack at its start
   H_CUDA(cudaGraphLaunch(ge->exec, h->stream));
   h->launches += ge->launches;
   h->last_B = B; h->last_reg = reg; h->last_x = x; h->last_tgt = tgt;
   h->have_fwd = false;
-  h->weights_dirty = true;
+  h->weights_dirty = !ge->bucket;
   return SVAE_OK;
 }
 
@@ -1686,9 +1760,19 @@ int svae_train_step(svae_handle* h, const float* x, const float* tgt, int B, con
   if (h->use_graph && !h->prof.enabled && h->eager_steps >= 1) return train_step_graph(h, x, tgt, B, eps, seed, lr, reg);
   h->eager_steps += 1;
   h->iteration += 1;
+  const bool bucket = h->use_bucket_update && h->upd_stream != nullptr && !h->prof.enabled;
+  if (bucket) {   // the step size must be on the device before the first bucket's update: pushed with the forward's scalars
+    h->adam_t += 1;
+    const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+    h->dyn_host.lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)h->adam_t)) / (1.0 - pow(b1, (double)h->adam_t)));
+    H_TRY(ensure_pack_table(h));
+  }
   H_TRY(forward_impl(h, x, tgt, B, eps, seed, reg, nullptr, nullptr, nullptr));
-  H_TRY(backward_impl(h));
-  H_TRY(adam_impl(h, lr));
+  h->bucket_update = bucket;
+  int rb = backward_impl(h);
+  h->bucket_update = false;
+  H_TRY(rb);
+  if (!bucket) H_TRY(adam_impl(h, lr));
   return SVAE_OK;
 }
 int svae_train_step_host(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed,
