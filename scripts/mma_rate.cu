@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // mma_rate.cu - microbenchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M=128, K=16) as a function of N, of the
 // shared-memory layout of the operands (no-swizzle K-major with a plane pitch = the "shifted window" layout of
 // kernels_tc.cu, no-swizzle MN-major = the wgrad layout, 128-byte swizzle K-major = the TMA layout) and of how many CTAs
@@ -85,6 +86,25 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const char* names[3] = {"K-major/noswz", "MN-major/noswz", "K-major/sw128"};
   const int iters = 2048;
+  // does the stride between the two K core matrices of A (LBO) matter?  (tc2 uses a 128-byte-multiple plane pitch)
+  for (unsigned lbo : {4096u, 4112u, 4160u, 3840u, 3856u, 2048u + 1024u})
+    for (int N : {32, 128}) {
+      Args a{N, iters, 0, 0, lbo, (unsigned)(N * 16), 1, out};
+      k<<<148, 128, 96 * 1024, 0>>>(a);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      printf("LBO_A=%u N=%3d rot=1 : issue %.1f cyc/mma, complete %.1f cyc/mma\n", lbo, N, (double)out[0] / iters, (double)out[1] / iters);
+    }
+  for (unsigned lbb : {512u, 528u, 2048u, 2064u})
+    for (int N : {32, 128}) {
+      Args a{N, iters, 0, 0, 4112u, lbb, 1, out};
+      if (lbb < (unsigned)N * 16) continue;
+      k<<<148, 128, 96 * 1024, 0>>>(a);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      printf("LBO_B=%u N=%3d rot=1 : issue %.1f cyc/mma, complete %.1f cyc/mma\n", lbb, N, (double)out[0] / iters, (double)out[1] / iters);
+    }
+  if (getenv("MMA_RATE_SHORT")) return 0;
   for (int ctas = 1; ctas <= 2; ++ctas)
     for (int la = 0; la < 3; ++la)
       for (int lb = 0; lb < 3; ++lb) {

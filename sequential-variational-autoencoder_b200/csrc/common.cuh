@@ -146,6 +146,19 @@ static inline cudaError_t launch_k(const LaunchCtx& lc, void (*kernel)(KArgs...)
 void svae_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 std::string& svae_global_error();
 
+// cooperative launch (all CTAs co-resident: the kernel may use a grid-wide barrier); never combined with the PDL attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_coop(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = lc.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- bf16 activation copies for the TMA-fed kernels ------------------------------------------------------------------
 // A [B,H,W,C] tensor stored as bf16, PLANAR by 8-channel group, over the zero-padded linear pixel space of its consumer:
 //     element (n,h,w,c)  ->  p[ ((c/8) * group_rows + front + plane*plane_rows + q) * 8 + c%8 ]
@@ -247,6 +260,13 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
 // pass 2: dy = rstd * (dyhat - S1/rows - xhat*S2/rows) in place ; dbeta = S1
 int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double* stats, const double* S, int64_t rows,
                  int feats, float* dbeta, BfDst bf = BfDst{});
+// Both passes in ONE cooperative kernel (4-D batch norm, C % 8 == 0): pass 1 reduces the two sums, a grid-wide barrier, pass 2
+// recomputes g from da / y (L2-resident) and writes dy - g is never materialised, dy fp32 only when `dy` != nullptr.
+// S must have 2C + 1 doubles, zeroed: the last one is the barrier counter.  Returns 1 when the layout is not supported
+// (the caller then runs bn_bwd_reduce + bn_bwd_apply).
+int bn_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, int64_t rows,
+                 int feats, int act, FeatView residual, float* dy, double* S, float* dres, int dres_accumulate, float* dbeta,
+                 BfDst bf);
 // the same with g read through a 4-D channel window (where a fused input-gradient epilogue left it) and the fp32 dy
 // optional (dy == nullptr: only the bf16 copy is written)
 int bn_bwd_apply_from(const LaunchCtx& lc, View g, float* dy, const float* y, const double* stats, const double* S, int64_t rows,

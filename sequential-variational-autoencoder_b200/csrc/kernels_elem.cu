@@ -276,6 +276,127 @@ bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, co
   }
 }
 
+// Both passes of the 4-D batch-norm backward in one cooperative kernel (see bn_bwd_fused in common.cuh).  Thread mapping as in
+// bn_bwd_reduce_v8_kernel: one (pixel, 8-channel group) per thread and iteration, the group fixed per thread.
+__global__ void __launch_bounds__(256)
+bn_bwd_fused_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, const float* __restrict__ y,
+                       const double* __restrict__ stats, const float* __restrict__ beta, int64_t rows, int C, int act,
+                       const float* __restrict__ res, int res_ld, int res_coff, float* __restrict__ dy_out,
+                       double* S, float* __restrict__ dres, int dres_acc, float* __restrict__ dbeta, BfDst bf) {
+  extern __shared__ float s_buf[];   // [C] mean, [C] rstd, [C] beta, [C] m1, [C] m2, then the reduction scratch [blockDim][17]
+  float* s_red = s_buf + 5 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    bn_coeffs(stats, C, c, rows, mean, rstd);
+    s_buf[c] = mean; s_buf[C + c] = rstd; s_buf[2 * C + c] = beta[c];
+  }
+  __syncthreads();
+  const int G = C >> 3;
+  const int c0 = (int)(threadIdx.x % G) * 8;
+  const int ppb = blockDim.x / G;
+  float mean[8], rstd[8], bt[8], a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mean[e] = s_buf[c0 + e]; rstd[e] = s_buf[C + c0 + e]; bt[e] = s_buf[2 * C + c0 + e]; a[e] = 0.f; b[e] = 0.f; }
+  const int64_t p_first = (int64_t)blockIdx.x * ppb + threadIdx.x / G, p_step = (int64_t)gridDim.x * ppb;
+  // ---- pass 1: sum g, sum g*xhat (+ the shortcut gradient) ----
+  for (int64_t p = p_first; p < rows; p += p_step) {
+    const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0));
+    const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(da + p * da_ld + da_coff + c0));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(da + p * da_ld + da_coff + c0) + 1);
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float rr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (res != nullptr) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0) + 1);
+      rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+    }
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (yy[e] - mean[e]) * rstd[e];
+      g[e] = dd[e] * act_grad(xh + bt[e] + rr[e], act);
+      a[e] += g[e];
+      b[e] += g[e] * xh;
+    }
+    if (dres != nullptr) {
+      float4* rp = reinterpret_cast<float4*>(dres + p * C + c0);
+      float4 o0 = make_float4(g[0], g[1], g[2], g[3]), o1 = make_float4(g[4], g[5], g[6], g[7]);
+      if (dres_acc) {
+        const float4 q0 = rp[0], q1 = rp[1];
+        o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w; o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+      }
+      rp[0] = o0; rp[1] = o1;
+    }
+  }
+  float* mine = s_red + threadIdx.x * 17;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mine[e] = a[e]; mine[8 + e] = b[e]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    const int g8 = c >> 3, e = c & 7;
+    float tot = 0.f;
+    for (int t = g8; t < (int)blockDim.x; t += G) tot += s_red[t * 17 + which * 8 + e];
+    atomicAdd(&S[which * C + c], (double)tot);
+  }
+  // ---- grid-wide barrier (cooperative launch: every block is resident); the counter lives behind the sums ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ctr = reinterpret_cast<unsigned*>(S + 2 * C);
+    atomicAdd(ctr, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(ctr) < gridDim.x) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- pass 2: dy = rstd * (g - S1/rows - xhat * S2/rows), g recomputed ----
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s1 = __ldcg(S + c), s2 = __ldcg(S + C + c);
+    s_buf[3 * C + c] = (float)(s1 / (double)rows);
+    s_buf[4 * C + c] = (float)(s2 / (double)rows);
+    if (blockIdx.x == 0 && dbeta != nullptr) dbeta[c] = (float)s1;
+  }
+  __syncthreads();
+  float m1[8], m2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { m1[e] = s_buf[3 * C + c0 + e]; m2[e] = s_buf[4 * C + c0 + e]; }
+  const int HW = bf.a.H * bf.a.W, W = bf.a.W;
+  for (int64_t p = p_first; p < rows; p += p_step) {
+    const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0));
+    const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + p * C + c0) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(da + p * da_ld + da_coff + c0));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(da + p * da_ld + da_coff + c0) + 1);
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float rr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (res != nullptr) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(res + p * res_ld + res_coff + c0) + 1);
+      rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+    }
+    float d[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (yy[e] - mean[e]) * rstd[e];
+      const float g = dd[e] * act_grad(xh + bt[e] + rr[e], act);
+      d[e] = rstd[e] * (g - m1[e] - xh * m2[e]);
+    }
+    if (dy_out != nullptr) {
+      float4* dp = reinterpret_cast<float4*>(dy_out + p * C + c0);
+      dp[0] = make_float4(d[0], d[1], d[2], d[3]);
+      dp[1] = make_float4(d[4], d[5], d[6], d[7]);
+    }
+    if (bf.a.p != nullptr) {
+      const int n = (int)(p / HW);
+      const int hw = (int)(p - (int64_t)n * HW);
+      const int hh = hw / W;
+      *reinterpret_cast<uint4*>(bf.a.p + bf_index(bf.a, n, hh, hw - hh * W, bf.coff + c0)) = tcptx::pack8_bf16(d);
+    }
+  }
+}
+
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
                                     const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
                                     int feats, float* __restrict__ dbeta, BfDst bf) {
@@ -670,6 +791,42 @@ int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double
     CUDA_TRY(launch_k(lc, bn_bwd_apply_kernel, cg.grid, cg.block, 0, dyhat, y, stats, S, rows, feats, dbeta, bf));
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bn_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, int64_t rows,
+                 int feats, int act, FeatView residual, float* dy, double* S, float* dres, int dres_accumulate, float* dbeta,
+                 BfDst bf) {
+  const int G = feats / 8;
+  const bool ok = da.ppr == 1 && da.inner == feats && feats % 8 == 0 && G <= 256 && rows >= 512 && aligned16(y) &&
+                  aligned16(da.p) && da.ld % 4 == 0 && da.coff % 4 == 0 && (dy == nullptr || aligned16(dy)) &&
+                  (dy != nullptr || bf.a.p != nullptr) &&
+                  (residual.p == nullptr || (residual.ppr == 1 && residual.inner == feats && residual.ld % 4 == 0 &&
+                                             residual.coff % 4 == 0 && aligned16(residual.p))) &&
+                  (dres == nullptr || aligned16(dres)) &&
+                  (bf.a.p == nullptr || (bf.coff % 8 == 0 && (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows));
+  if (!ok) return 1;
+  const int threads = (256 / G) * G;
+  const int ppb = threads / G;
+  const size_t smem = (5 * (size_t)feats + (size_t)threads * 17) * sizeof(float);
+  // every block must be resident at once: what the occupancy calculator allows, capped at two blocks per SM
+  static int per_sm_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int slot = smem > 40 * 1024 ? 1 : 0;
+  if (per_sm_cache[slot] == 0) {
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bn_bwd_fused_v8_kernel, 256, slot ? 64 * 1024 : 40 * 1024));
+    per_sm_cache[slot] = n < 1 ? -1 : (n > 2 ? 2 : n);
+    CUDA_TRY(cudaFuncSetAttribute(bn_bwd_fused_v8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  }
+  if (per_sm_cache[slot] < 0 || smem > 64 * 1024) return 1;
+  int64_t blocks = (rows + ppb - 1) / ppb;
+  const int64_t cap = (int64_t)lc.sm_count * per_sm_cache[slot];
+  if (blocks > cap) blocks = cap;
+  Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
+  ProfScope ps(lc, KC_BN_BWD_REDUCE, 13.0 * rows * feats,
+               rows * (double)feats * (8.0 + (residual.p ? 4.0 : 0.0) + (dres ? 4.0 : 0.0) + (dy ? 4.0 : 0.0) + (bf.a.p ? 2.0 : 0.0)), &tg);
+  CUDA_TRY(launch_coop(lc, bn_bwd_fused_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
+                       rows, feats, act, residual.p, residual.ld, residual.coff, dy, S, dres, dres_accumulate, dbeta, bf));
   return 0;
 }
 

@@ -351,7 +351,7 @@ int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double
   Geom tg{}; tg.B = B; tg.Cin = KZ; tg.Cout = N;
   ProfScope ps(lc, KC_SKINNY, 8.0 * B * KZ * (double)N, 8.0 * B * (double)N, &tg);
   unsigned blocks = (unsigned)((N + 31) / 32);
-  if (blocks > 2u * (unsigned)lc.sm_count) blocks = 2u * (unsigned)lc.sm_count;
+  if (blocks > 4u * (unsigned)lc.sm_count) blocks = 4u * (unsigned)lc.sm_count;
   LAT_DISPATCH(KZ, {
     const size_t smem = 2 * (size_t)B * NM * sizeof(float);
     if (allow_smem(lat_bwd_fused_kernel<NM>, smem) != 0) return -3;

@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(160) tc_wgrad_kernel(const __grid_constant__ T
   }
 }
 
-bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
+bool build_wparams(const Geom& g, TwParams& P, int sm_count, int tmem_cap = 512) {
   // g: conv-gather geometry (mode 0) with X = [B,Hin,Win,Cin], dY = [B,Hout,Wout,Cout]
   memset(&P, 0, sizeof P);
   if (g.mode != 0 || g.KH != 4 || g.KW != 4 || g.pad != 1) return false;
@@ -693,7 +693,9 @@ bool build_wparams(const Geom& g, TwParams& P, int sm_count) {
   P.Q = (long long)g.B * P.Hp * P.Wp;
   if (P.Q + TILE_M + P.HL >= (1ll << 31) || (long long)g.B * g.Hin * g.Win >= (1ll << 31)) return false;
   P.tiles = (P.Q + TILE_M - 1) / TILE_M;
-  P.taps_per_cta = 512 / P.N; if (P.taps_per_cta > 16) P.taps_per_cta = 16;
+  P.taps_per_cta = tmem_cap / P.N; if (P.taps_per_cta > 16) P.taps_per_cta = 16;
+  if (P.taps_per_cta < 1) return false;
+  while (16 % P.taps_per_cta) --P.taps_per_cta;     // the tap groups must tile the 16 taps exactly (N = 48, 80, ...)
   P.ngroups = 16 / P.taps_per_cta;
   unsigned cols = (unsigned)(P.taps_per_cta * P.N), t = 32;
   while (t < cols) t <<= 1;
@@ -1474,10 +1476,16 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
   }
 }
 
-bool build_wparams2(const Geom& g, Tw2Params& PP) {
+size_t smem_bytes_w2(const Tw2Params& PP);
+
+// two_per_sm: half the tensor memory (half the taps per CTA) and at most ~110 KB of shared memory, so that two CTAs share an
+// SM and interleave their MMAs - narrow layers (N <= 64) are paced by the per-CTA issue latency (59 cycles per MMA alone,
+// 40 with two CTAs, scripts/mma_rate.cu), not by the tensor pipe.
+bool build_wparams2(const Geom& g, Tw2Params& PP, bool two_per_sm = false) {
   memset(&PP, 0, sizeof PP);
   TwParams& P = PP.t;
-  if (!build_wparams(g, P, 148)) return false;
+  if (!build_wparams(g, P, 148, two_per_sm ? 256 : 512)) return false;
+  if (two_per_sm && (P.N > 64 || P.tmem_cols > 256)) return false;
   const unsigned hl = (unsigned)((P.HL + 7) & ~7);
   PP.x_pitch = hl * 16u;
   PP.y_pitch = 128u * 16u;
@@ -1489,6 +1497,12 @@ bool build_wparams2(const Geom& g, Tw2Params& PP) {
   const size_t reach = 128 + (size_t)(W_STAGES_MAX - 1) * 0;   // header
   (void)reach;
   int st = W_STAGES_MAX;
+  if (two_per_sm) {
+    const size_t cap = 110 * 1024;
+    PP.stages = st;
+    while (PP.stages > 2 && smem_bytes_w2(PP) > cap) --PP.stages;
+    return smem_bytes_w2(PP) <= cap;
+  }
   while (st > 1 && 128 + (size_t)st * PP.stage_bytes > 200 * 1024) --st;
   if (128 + (size_t)st * PP.stage_bytes > 200 * 1024) return false;
   PP.stages = st;
@@ -1518,6 +1532,12 @@ bool tc2_wgrad_supported(const Geom& g) {
 int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw) {
   Tw2Params PP;
   if (!build_wparams2(g, PP)) { svae_global_error() = "tc2 wgrad: unsupported geometry"; return -1; }
+  int per_sm = 1;
+  {
+    static const int mode = getenv("SVAE_WGRAD_2CTA") ? atoi(getenv("SVAE_WGRAD_2CTA")) : 0;   // measured neutral (4.94 vs 5.07 ms of wgrad per step): off
+    Tw2Params Q2;
+    if (mode && build_wparams2(g, Q2, true)) { PP = Q2; per_sm = 2; }
+  }
   TwParams& P = PP.t;
   const int ykind = g.stride == 1 ? 0 : 1;
   if (x.kind != tc2_input_kind(g) || x.Hp != P.Hp || x.Wp != P.Wp || dy.kind != ykind || dy.Hp != P.Hp || dy.Wp != P.Wp ||
@@ -1537,7 +1557,7 @@ int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& d
     configured = true;
   }
   const int gy = P.ngroups * P.mblocks * P.nblocks;
-  long long splits = (lc.sm_count + gy - 1) / gy;
+  long long splits = ((long long)lc.sm_count * per_sm + gy - 1) / gy;
   if (splits > P.tiles) splits = P.tiles;
   if (splits < 1) splits = 1;
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
@@ -1587,7 +1607,12 @@ TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed) {
 int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double total_elems) {
   if (n <= 0) return 0;
   ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total_elems);
-  tc_pack_batched_kernel<<<dim3(32, (unsigned)n), 256, 0, lc.stream>>>(reinterpret_cast<const TcPackEntry*>(dev_entries));
+  // blocks per entry: enough in total to fill the machine a few times over, whether the table holds every layer of the model
+  // (one launch after a full Adam step) or one chain step's layers (bucketed update)
+  int bx = (8 * lc.sm_count + n - 1) / n;
+  if (bx < 32) bx = 32;
+  if (bx > 256) bx = 256;
+  tc_pack_batched_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, lc.stream>>>(reinterpret_cast<const TcPackEntry*>(dev_entries));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -178,7 +178,13 @@ struct svae_handle {
   double* loss_sums = nullptr;  // [2T] recon_sum, kl_sum
   double* loss_host = nullptr;  // pinned
   // gradient scratch (one step's worth)
-  GradSet gs[2];
+  // Gradient scratch sets, used round-robin by the chain steps of a backward pass.  With NS sets the chain only has to wait
+  // for the side streams (weight gradients, recognition net) of step t + NS before it reuses their buffers; with 2 sets a
+  // timeline of the step showed the chain stalled ~0.4 ms per chain step on exactly that wait (the side streams lag behind
+  // under contention).  NS = min(T, SVAE_GRAD_SETS, default 8): no wait at all for the reference's T = 8.
+  static constexpr int MAX_GS = 8;
+  GradSet gs[MAX_GS];
+  int n_gs = 2;
   int n_dy_slots = 0;
   std::vector<size_t> dy_slot_elems;
   float* gx[2] = {nullptr, nullptr};
@@ -207,6 +213,10 @@ struct svae_handle {
   std::vector<double> pack_step_elems;
   int pdl_prev = 0;     // 1: the last node enqueued on the chain stream is a kernel (see launch_k)
   bool use_pdl = true;  // SVAE_PDL=0 disables programmatic dependent launch
+  // SVAE_COOP_BN=1: batch-norm backward as ONE cooperative kernel (reduce, grid barrier, apply) instead of two.  Correct and
+  // 1.2 ms/step less kernel time in isolation, but measured SLOWER inside the step (14.5 vs 12.6 ms): a cooperative grid has to
+  // become resident all at once, which drains the SMs the side streams were filling.  Off by default.
+  bool use_coop_bn = false;
   // SVAE_FUSE=1: batch-norm backward pass 1 inside the epilogue of the producing input-gradient kernel.  Correct (the GPU
   // suite passes with it) but measured SLOWER on B200 (13.5 vs 12.7 ms/step): the epilogue has 4 warps per SM for work a
   // standalone kernel spreads over 64, and it sits on the chain's critical path.  Off by default.
@@ -428,7 +438,7 @@ void place_block(Block& b, Arena& act, Arena& zf, Arena& zb, int64_t maxB, bool 
   size_t n = (size_t)maxB * b.rpi * b.feats;
   b.y = act.get<float>(n);
   b.stats = zf.get<double>(2 * (size_t)b.feats);
-  b.S = zb.get<double>(2 * (size_t)b.feats);
+  b.S = zb.get<double>(2 * (size_t)b.feats + 1);   // + the grid-barrier counter of the fused backward kernel
   if (n > max_y) max_y = n;
 }
 FeatView fv4(float* p, int ld, int coff, int inner) { return FeatView{p, ld, coff, inner, 1}; }
@@ -600,7 +610,15 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       for (int l = 0; l < L - 1; ++l) { slot(s.ta[l], NI + NE + 2 + L + l); slot(s.tb[l], NI + NE + 2 + L + (L - 1) + l); }
     }
     const Step& s1 = h->steps[T > 1 ? 1 : 0];
-    for (int p = 0; p < 2; ++p) {
+    {
+      int want = svae_handle::MAX_GS;
+      const char* e = getenv("SVAE_GRAD_SETS");
+      if (e) want = atoi(e);
+      if (want < 2) want = 2;
+      if (want > svae_handle::MAX_GS) want = svae_handle::MAX_GS;
+      h->n_gs = T < want ? (T < 2 ? 2 : T) : want;
+    }
+    for (int p = 0; p < h->n_gs; ++p) {
       GradSet& g = h->gs[p];
       g.d_c.resize(L - 1); g.d_dcat.resize(L - 1);
       for (int l = 0; l < L - 1; ++l) {
@@ -793,8 +811,17 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
   } else if (is_fc2d(b, B) && dres == nullptr && dy_bf.a.p == nullptr) {
     H_TRY(bn2d_bwd(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, dy, h->pg(b.beta)));
   } else {
-    H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
-    H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta), dy_bf));
+    int fr = 1;   // 1: not fused
+    if (h->use_coop_bn) {
+      const bool need_f32 = !tc2w || (din != nullptr && !tc2d);
+      fr = bn_bwd_fused(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, need_f32 ? dy : nullptr, b.S, dres,
+                        dres_acc, h->pg(b.beta), dy_bf);
+      if (fr < 0) { if (h->err.empty()) h->err = g_err; return fr; }
+    }
+    if (fr == 1) {
+      H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
+      H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta), dy_bf));
+    }
   }
   View dyv = mkview(dy, b.feats, 0);
   // dy is final here: the weight gradient (side stream) depends on this point only, not on the input gradient below
@@ -1228,9 +1255,10 @@ int backward_impl(svae_handle* h) {
   const float* gx_in = nullptr;  // dL/dx_t from later steps
   for (int t = T - 1; t >= 0; --t) {
     Step& s = h->steps[t];
-    GradSet& gs = h->gs[t & 1];
-    if (fork && t + 2 < T)
-      for (int i = 0; i < 3; ++i) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + 2) * 3 + i], 0));
+    const int NS = h->n_gs;
+    GradSet& gs = h->gs[t % NS];
+    if (fork && t + NS < T)
+      for (int i = 0; i < 3; ++i) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + NS) * 3 + i], 0));
     const float* xprev = t > 0 ? h->steps[t - 1].xt : nullptr;
     float* gx_prev = h->gx[cur ^ 1];
     H_TRY(decoder_bwd(h, gs, st, s, B, gx_in, gx_prev, xprev));
@@ -1536,6 +1564,8 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     if (e3) h->fork_mask = atoi(e3);
     const char* e7 = getenv("SVAE_FUSE");
     h->use_fuse = e7 && e7[0] == '1';
+    const char* e9 = getenv("SVAE_COOP_BN");
+    h->use_coop_bn = e9 && e9[0] == '1';
     const char* e6 = getenv("SVAE_PDL");
     h->use_pdl = !(e6 && e6[0] == '0');
     const char* e5 = getenv("SVAE_ABLATE");
