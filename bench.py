@@ -296,6 +296,17 @@ def main():
             roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": top["gbs"] / peaks["hbm"], "traffic": None, "share_of_step": top["share"],
                     "peak_source": peaks["source"]}
+    # DRAM traffic per launch of that kernel class, from the committed `ncu --set full` capture (profiles/traffic.json is
+    # written by scripts/ncu_raw_summary.py from the .ncu-rep of the same bench command)
+    if roof is not None:
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(roof["kernel"])
+            if ent:
+                roof["traffic"] = ent["dram_bytes_per_launch"]
+                roof["traffic_source"] = ent.get("source")
+        except (OSError, ValueError):
+            pass
     algo = ALGO.get(args.workload, {})
     path_roof = None
     if algo:

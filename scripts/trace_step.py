@@ -7,7 +7,7 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 import seqvae_b200 as S
 
-B = 100
+B = int(os.environ.get("TRACE_B", "100"))
 ds = S.SyntheticDataset("celebA", B, seed=1)
 model = S.SequentialVAE(ds, B, "c_inhomog", operand_dtype="bf16", restore=False, seed=0)
 st = torch.cuda.Stream(priority=-1)

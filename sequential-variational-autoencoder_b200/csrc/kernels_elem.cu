@@ -6,6 +6,8 @@
 // Reference ops replaced: tf.contrib.layers.batch_norm (training mode, abstract_network.py:22..79), lrelu (:8-10),
 // tf.nn.relu / tf.concat / shortcut add (sequential_vae.py:1713-1716), output + highway mix (:1720-1729), loss
 // reductions (:1146-1164), reparameterisation (:1023), clip_by_value + AdamOptimizer (:18-25,1267-1276).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -285,6 +287,8 @@ bn_bwd_fused_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, con
                        double* S, float* __restrict__ dres, int dres_acc, float* __restrict__ dbeta, BfDst bf) {
   extern __shared__ float s_buf[];   // [C] mean, [C] rstd, [C] beta, [C] m1, [C] m2, then the reduction scratch [blockDim][17]
   float* s_red = s_buf + 5 * C;
+  pdl_wait();
+  pdl_trigger();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     bn_coeffs(stats, C, c, rows, mean, rstd);
@@ -341,13 +345,22 @@ bn_bwd_fused_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, con
     for (int t = g8; t < (int)blockDim.x; t += G) tot += s_red[t * 17 + which * 8 + e];
     atomicAdd(&S[which * C + c], (double)tot);
   }
-  // ---- grid-wide barrier (cooperative launch: every block is resident); the counter lives behind the sums ----
+  // ---- grid-wide barrier; the counter lives behind the sums ----
+  // The grid is at most two blocks per SM (bn_bwd_fused), far below what the SMs can hold, so every block becomes resident
+  // as soon as the kernels of the other streams - none of which waits for this one - release their slots.  A cooperative
+  // launch would guarantee that formally but has to place the WHOLE grid at once, which was measured to cost more than the
+  // fusion saves (it drains the SMs the side streams fill).  The spin is bounded: after ~2 s the block gives up and poisons
+  // the result instead of hanging the device.
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned* ctr = reinterpret_cast<unsigned*>(S + 2 * C);
     atomicAdd(ctr, 1u);
-    while (*reinterpret_cast<volatile unsigned*>(ctr) < gridDim.x) __nanosleep(64);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned*>(ctr) < gridDim.x) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000ll) { S[0] = __longlong_as_double(0x7ff8000000000000ll); break; }   // NaN: the step fails loudly
+    }
     __threadfence();
   }
   __syncthreads();
@@ -704,7 +717,8 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
 
 static inline unsigned flat_blocks(int64_t n, int sm_count, int threads = 256) {
   int64_t b = (n + threads - 1) / threads;
-  int64_t cap = (int64_t)sm_count * 8;
+  static const int per_sm = getenv("SVAE_EW_CAP") ? atoi(getenv("SVAE_EW_CAP")) : 8;   // resident 256-thread blocks per SM
+  int64_t cap = (int64_t)sm_count * per_sm;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (unsigned)b;
@@ -825,8 +839,13 @@ int bn_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double*
   Geom tg{}; tg.B = (int)rows; tg.Cout = feats;
   ProfScope ps(lc, KC_BN_BWD_REDUCE, 13.0 * rows * feats,
                rows * (double)feats * (8.0 + (residual.p ? 4.0 : 0.0) + (dres ? 4.0 : 0.0) + (dy ? 4.0 : 0.0) + (bf.a.p ? 2.0 : 0.0)), &tg);
-  CUDA_TRY(launch_coop(lc, bn_bwd_fused_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
-                       rows, feats, act, residual.p, residual.ld, residual.coff, dy, S, dres, dres_accumulate, dbeta, bf));
+  static const bool coop = getenv("SVAE_COOP_LAUNCH") && getenv("SVAE_COOP_LAUNCH")[0] == '1';
+  if (coop)
+    CUDA_TRY(launch_coop(lc, bn_bwd_fused_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
+                         rows, feats, act, residual.p, residual.ld, residual.coff, dy, S, dres, dres_accumulate, dbeta, bf));
+  else
+    CUDA_TRY(launch_k(lc, bn_bwd_fused_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
+                      rows, feats, act, residual.p, residual.ld, residual.coff, dy, S, dres, dres_accumulate, dbeta, bf));
   return 0;
 }
 
