@@ -369,9 +369,10 @@ def main():
                        "operands": "bf16 tcgen05 + fp32 accumulate" if operand_used == "bf16" else "fp32 SIMT",
                        "l2": "per-step working set (activations+weights+Adam state, >3 GB) exceeds the 126 MB L2",
                        "eps": "in-kernel Philox",
-                       "execution": "CUDA graph of the whole step (4 streams: chain, weight gradients, recognition net, "
-                                    "its weight gradients); `kernels`/`roofline` come from %d extra serialised, "
-                                    "event-bracketed steps right after the timed region" % prof_steps},
+                       "execution": "CUDA graph of the whole step (5 streams: chain with programmatic dependent launch, its "
+                                    "weight gradients, recognition nets, their weight gradients, per-chain-step Adam + "
+                                    "repack); `kernels`/`roofline` come from %d extra serialised, event-bracketed steps "
+                                    "right after the timed region" % prof_steps},
             "roofline": roof, "path_roofline": path_roof, "kernels": table, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "generation": generation,
         }
