@@ -211,8 +211,10 @@ size_t bf_act_bytes(const BfAct& d);
 int bf_act_fill(const LaunchCtx& lc, const BfAct& d, View src, int C);   // fp32 NHWC window -> padded bf16 copy (incl. zeros)
 bool tc2_supported(const Geom& g);
 int tc2_input_kind(const Geom& g);
+// w_tile_width: tile width the weights were packed with (tc_pack_entry / tc_pack_weights): 128 or tc2_pick_ntw(g)
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
-                    double* stats, const BnBwdFuse* fuse = nullptr);
+                    double* stats, const BnBwdFuse* fuse = nullptr, int w_tile_width = 128);
+int tc2_pick_ntw(const Geom& g, int sm_count);
 bool tc2_fuse_supported(const Geom& g, View out, int C);   // can this launch carry a BnBwdFuse over its first C output channels?
 bool tc2_wgrad_supported(const Geom& g);   // g: conv-gather geometry (see tc_wgrad)
 int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw);
@@ -317,9 +319,9 @@ bool tc_wgrad_supported(const Geom& fwd);
 int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw);
 int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats);
 size_t tc_packed_bytes(const Geom& g);
-int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed);
-struct TcPackEntry { Geom g; const float* w; void* out; int KC, Cin_p, N_p; long long total; };
-TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed);
+int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed, int tile_width = 128);
+struct TcPackEntry { Geom g; const float* w; void* out; int KC, Cin_p, N_p, TW; long long total; };
+TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed, int tile_width = 128);
 int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double total_elems);
 // ---- tcgen05 fully-connected kernel (kernels_fc.cu): fp32 operands read directly, bf16 in shared memory -----------
 bool tc_fc_supported(int K, int N);

@@ -382,21 +382,21 @@ static inline int pick_kc(int cin_p) { return cin_p % 128 == 0 ? 128 : cin_p % 6
 // weights -> bf16 [n tile][chunk c][tap s][8-channel group j][n][8]  (canonical K-major, no swizzle: LBO = Nt*16, SBO = 128);
 // zero in the channel padding
 __global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KC, int Cin_p,
-                               int N_p) {
+                               int N_p, int TW) {
   const int JC = KC / 8;
   const int ntaps = g.KH * g.KW;
-  const long long per_tile = (long long)128 * Cin_p * ntaps;
+  const long long per_tile = (long long)TW * Cin_p * ntaps;
   const long long total = (long long)N_p * Cin_p * ntaps;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int tile = (int)(e / per_tile);
     long long t = e - tile * per_tile;
-    const int Nt = min(128, N_p - tile * 128);
+    const int Nt = min(TW, N_p - tile * TW);
     const int k8 = (int)(t % 8); t /= 8;
     const int n = (int)(t % Nt); t /= Nt;
     const int j = (int)(t % JC); t /= JC;
     const int s = (int)(t % ntaps); t /= ntaps;
     const int c = (int)t;
-    const int ci = c * KC + j * 8 + k8, co = tile * 128 + n;
+    const int ci = c * KC + j * 8 + k8, co = tile * TW + n;
     float v = 0.f;
     if (ci < g.Cin && co < g.Cout)
       v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + co] : w[((size_t)s * g.Cout + co) * g.Cin + ci];
@@ -405,19 +405,19 @@ __global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat1
 }
 
 __device__ __forceinline__ void pack_one(const Geom& g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                         int KC, int Cin_p, int N_p, long long e) {
+                                         int KC, int Cin_p, int N_p, int TW, long long e) {
   const int JC = KC / 8;
   const int ntaps = g.KH * g.KW;
-  const long long per_tile = (long long)128 * Cin_p * ntaps;
+  const long long per_tile = (long long)TW * Cin_p * ntaps;
   const int tile = (int)(e / per_tile);
   long long t = e - tile * per_tile;
-  const int Nt = min(128, N_p - tile * 128);
+  const int Nt = min(TW, N_p - tile * TW);
   const int k8 = (int)(t % 8); t /= 8;
   const int n = (int)(t % Nt); t /= Nt;
   const int j = (int)(t % JC); t /= JC;
   const int s = (int)(t % ntaps); t /= ntaps;
   const int c = (int)t;
-  const int ci = c * KC + j * 8 + k8, co = tile * 128 + n;
+  const int ci = c * KC + j * 8 + k8, co = tile * TW + n;
   float v = 0.f;
   if (ci < g.Cin && co < g.Cout)
     v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + co] : w[((size_t)s * g.Cout + co) * g.Cin + ci];
@@ -428,7 +428,7 @@ __device__ __forceinline__ void pack_one(const Geom& g, const float* __restrict_
 __global__ void tc_pack_batched_kernel(const TcPackEntry* __restrict__ tab) {
   const TcPackEntry E = tab[blockIdx.y];
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E.total; e += (long long)gridDim.x * blockDim.x)
-    pack_one(E.g, E.w, reinterpret_cast<__nv_bfloat16*>(E.out), E.KC, E.Cin_p, E.N_p, e);
+    pack_one(E.g, E.w, reinterpret_cast<__nv_bfloat16*>(E.out), E.KC, E.Cin_p, E.N_p, E.TW, e);
 }
 
 bool build_params(const Geom& g, TcParams& P) {
@@ -735,7 +735,8 @@ struct Tc2Params {
   unsigned a_pitch;         // bytes between planes in shared memory
   unsigned a_bytes;         // one halo (all planes of one channel chunk)
   int a_stages;
-  int ntw;                  // output channels per CTA (blockIdx.z walks the sub-tiles of a 128-column packed tile; 128: whole tile)
+  int ntw;                  // output channels per CTA (blockIdx.z walks the sub-tiles of a 128-column group; 128: whole group)
+  int wtw;                  // tile width the weights were packed with (128, or = ntw: the CTA's weights are then contiguous)
   int w_resident;           // 1: all weights of the CTA's N tile live in shared memory
   unsigned w_bytes_ntile;   // packed bytes of one full N tile (128 columns)
   unsigned w_region;        // shared-memory bytes reserved for weights (resident copy or ring)
@@ -747,6 +748,10 @@ struct Tc2Params {
   long long plane_rows;     // rows between parity planes
   long long group_rows;     // rows between 8-channel groups
   BnBwdFuse fz;             // fz.y != nullptr: batch-norm backward pass 1 of the consuming block fused into the epilogue
+  // per-tap issue table (host-built): A start offset inside a halo stage in 16-byte units (parity plane + lo + shift), and
+  // accumulator index | 0x80 when the tap is the first one that writes its accumulator
+  unsigned tap_a[16];
+  unsigned char tap_f[16];
 };
 
 struct SmemHeader2 {
@@ -774,9 +779,10 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
   // Output-channel tiling: blockIdx.y = 128-column tile of the packed weights, blockIdx.z = sub-tile of PP.ntw columns
   // inside it.  Layers with few pixel tiles (4x4 / 8x8 maps, B = 100) are bound by streaming their weights into one CTA
   // per tile; splitting the channels spreads that stream (and the MMAs) over up to 4x as many SMs.
-  const int tile_w = min(128, P.N_p - (int)blockIdx.y * 128);
   const int n0 = blockIdx.y * 128 + blockIdx.z * PP.ntw;
-  const int Nt = min(PP.ntw, tile_w - (int)blockIdx.z * PP.ntw);
+  const int Nt = min(PP.ntw, min(128, P.N_p - (int)blockIdx.y * 128) - (int)blockIdx.z * PP.ntw);
+  const int wtile = n0 / PP.wtw;                                  // packed tile holding this CTA's columns
+  const int tile_w = min(PP.wtw, P.N_p - wtile * PP.wtw);         // its width
   const bool w_sub = Nt != tile_w;     // sub-tile: one bulk copy per (chunk, tap, 8-channel group) row of Nt*16 bytes
   const unsigned b_tap_bytes = (unsigned)(P.KC * Nt * 2);
   const unsigned b_stage_bytes = b_tap_bytes * (unsigned)P.tps;
@@ -804,8 +810,8 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
   // Resident weights are fetched BEFORE the grid dependency is resolved: the packed operand copies are written once at the
   // start of the step (>= 2 kernels back, see launch_k), so under programmatic dependent launch this load - like the barrier
   // and TMEM setup above - overlaps the tail of the predecessor kernel.
-  const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)blockIdx.y * 128 * P.Cin_p * P.ntaps * 2 +
-                              (size_t)blockIdx.z * PP.ntw * 16;
+  const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(P.wp) + (size_t)wtile * PP.wtw * P.Cin_p * P.ntaps * 2 +
+                              (size_t)(n0 - wtile * PP.wtw) * 16;
   const unsigned src_row = (unsigned)tile_w * 16u, dst_row = (unsigned)Nt * 16u;   // one (chunk, tap, group) row: [n][8] bf16
   if (warp == 1 && PP.w_resident && my_tiles > 0) {
     const unsigned total = (unsigned)(P.NC * P.ntaps) * b_tap_bytes;
@@ -883,7 +889,6 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
     const unsigned long long b_hi = ((unsigned long long)((128u >> 4) & 0x3FFF) << 32) | (1ull << 46) |
                                     ((unsigned long long)((LBO_B >> 4) & 0x3FFF) << 16);
     const unsigned a_kstep = (2u * LBO_A) >> 4, b_kstep = (2u * LBO_B) >> 4;
-    const unsigned plane4 = ((unsigned)P.JC * LBO_A) >> 4;     // one parity plane further (in 16-byte units)
     const int nk = P.KC / 16;
     const bool leader = elect_one();
     int stage = 0; unsigned phase = 0;
@@ -895,7 +900,6 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
       if (ti >= PP.acc_bufs) mbar_wait(smem_u32(&hdr->acc_empty[b]), (unsigned)((ti / PP.acc_bufs) - 1) & 1u);
       tc_fence_after();
       const unsigned acc_base = tmem_base + (unsigned)b * PP.acc_cols;
-      unsigned started = 0;
       for (int c = 0; c < P.NC; ++c, ++it) {
         const int s = it % PP.a_stages;
         mbar_wait(smem_u32(&hdr->a_full[s]), (unsigned)(it / PP.a_stages) & 1u);
@@ -912,13 +916,18 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
             b_lo = smem_u32(w_smem + (size_t)stage * P.b_stage_max) >> 4;
           }
           if (leader) {
+            // The per-tap operands come from a host-built table in the parameter space; the NEXT tap's entry is fetched
+            // before the current tap's MMAs are issued, so the constant-load latency hides behind them (fetched on demand
+            // it made the issue loop, not the tensor pipe, the pace setter: ~118 instead of ~60 cycles per MMA).
+            unsigned na = PP.tap_a[s0], nf = PP.tap_f[s0];
             for (int tl = 0; tl < P.tps; ++tl) {
-              const int tp = s0 + tl;
-              const unsigned a = (unsigned)P.acc[tp];
-              const unsigned d_tmem = acc_base + a * (unsigned)Nt;
-              unsigned a_lo = abase4 + (unsigned)P.plane[tp] * plane4 + (unsigned)(P.lo + P.shift[tp]);
+              const unsigned ca = na, cf = nf;
+              const int nx = min(s0 + tl + 1, 15);
+              na = PP.tap_a[nx]; nf = PP.tap_f[nx];
+              const unsigned d_tmem = acc_base + (cf & 0x7Fu) * (unsigned)Nt;
+              unsigned a_lo = abase4 + ca;
               unsigned bk = b_lo;
-              unsigned acc_flag = (started >> a) & 1u;
+              unsigned acc_flag = (c > 0 || (cf & 0x80u) == 0u) ? 1u : 0u;
               for (int kk = 0; kk < nk; ++kk) {
                 umma_bf16(d_tmem, a_hi | (unsigned long long)(a_lo & 0x3FFF), b_hi | (unsigned long long)(bk & 0x3FFF), idesc,
                           acc_flag);
@@ -926,7 +935,6 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
                 a_lo += a_kstep;
                 bk += b_kstep;
               }
-              started |= 1u << a;
               b_lo += b_tap_bytes >> 4;
             }
             if (!PP.w_resident) umma_commit(smem_u32(&hdr->w_empty[stage]));
@@ -1181,6 +1189,17 @@ bool build_params2(const Geom& g, Tc2Params& PP, int ntw = 128) {
   PP.acc_cols = t;
   PP.acc_bufs = 2 * t <= 512 ? 2 : 1;
   PP.tmem_cols = t * (unsigned)PP.acc_bufs;
+  {
+    const unsigned plane4 = ((unsigned)P.JC * PP.a_pitch) >> 4;     // one parity plane further (in 16-byte units)
+    unsigned seen = 0;
+    for (int tp = 0; tp < 16; ++tp) {
+      const int tq = tp < P.ntaps ? tp : 0;
+      PP.tap_a[tp] = (unsigned)P.plane[tq] * plane4 + (unsigned)(P.lo + P.shift[tq]);
+      const unsigned a = (unsigned)P.acc[tq];
+      PP.tap_f[tp] = (unsigned char)(a | (((seen >> a) & 1u) ? 0u : 0x80u));
+      seen |= 1u << a;
+    }
+  }
   return PP.tmem_cols <= 512;
 }
 
@@ -1261,31 +1280,48 @@ bool tc2_supported(const Geom& g) {
 // layout kind the tc2 kernel wants for the INPUT of geometry g
 int tc2_input_kind(const Geom& g) { return g.stride == 1 ? 0 : (g.mode == 0 ? 2 : 1); }
 
+// Output channels per CTA for geometry g (B set): few pixel tiles (small feature maps) -> split the output channels over more
+// CTAs (see the kernel's header comment); 128 = no split.  The plan packs the weights with this tile width so that every
+// CTA's weights are one contiguous run (one large bulk copy per stage instead of 512-byte rows: 65 vs 18 GB/s per CTA).
+int tc2_pick_ntw(const Geom& g, int sm_count) {
+  Tc2Params PP;
+  if (!build_params2(g, PP)) return 128;
+  const int tiles128 = (PP.t.N_p + 127) / 128;
+  const int ncap = PP.t.N_p < 128 ? PP.t.N_p : 128;
+  static const int force = getenv("SVAE_NTW") ? atoi(getenv("SVAE_NTW")) : 0;
+  int best = 128;
+  for (int split = 2; split <= 4; split *= 2) {
+    const int w = ncap / split;
+    if (w < 32 || ncap % split || (long long)PP.tiles * tiles128 * split > (long long)sm_count) break;   // one wave, one CTA per SM
+    best = w;
+  }
+  if (force) best = force;
+  if (best < 128) {
+    Tc2Params Q2;
+    if (!(build_params2(g, Q2, best) && smem_bytes2(Q2) <= 227 * 1024)) best = 128;
+  }
+  return best;
+}
+
 bool tc2_fuse_supported(const Geom& g, View out, int C) {
   return C > 0 && C % 8 == 0 && C <= g.Cout && g.Cout % 4 == 0 && out.ld % 4 == 0 && out.coff % 4 == 0 &&
          (((uintptr_t)out.p & 15) == 0) && tc2_supported(g);
 }
 
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
-                    double* stats, const BnBwdFuse* fuse) {
+                    double* stats, const BnBwdFuse* fuse, int w_tile_width) {
   Tc2Params PP;
   if (!build_params2(g, PP)) { svae_global_error() = "tc2: unsupported geometry"; return -1; }
   {
-    // few pixel tiles (small feature maps): split the output channels over more CTAs (see the kernel's header comment)
-    const int tiles128 = (PP.t.N_p + 127) / 128;
-    const int ncap = PP.t.N_p < 128 ? PP.t.N_p : 128;
-    static const int force = getenv("SVAE_NTW") ? atoi(getenv("SVAE_NTW")) : 0;
-    int best = 128;
-    for (int split = 2; split <= 4; split *= 2) {
-      const int w = ncap / split;
-      if (w < 32 || ncap % split || (long long)PP.tiles * tiles128 * split > (long long)lc.sm_count) break;   // one wave, one CTA per SM
-      best = w;
-    }
-    if (force) best = force;
+    // weights packed with a narrower tile: that IS the CTA width; packed with 128: the heuristic may still split, the CTA
+    // then gathers its columns row by row
+    const int best = w_tile_width < 128 ? w_tile_width : tc2_pick_ntw(g, lc.sm_count);
     if (best < 128) {
       Tc2Params Q2;
       if (build_params2(g, Q2, best) && smem_bytes2(Q2) <= 227 * 1024) PP = Q2;
+      else if (w_tile_width < 128) { svae_global_error() = "tc2: weights packed for a tile width this launch cannot use"; return -1; }
     }
+    PP.wtw = w_tile_width < 128 ? w_tile_width : 128;
   }
   TcParams& P = PP.t;
   if (in.kind != tc2_input_kind(g) || in.Hp != P.Hp || in.Wp != P.Wp || (chan0 & 7)) {
@@ -1585,20 +1621,21 @@ bool tc_supported(const Geom& g) {
 
 size_t tc_packed_bytes(const Geom& g) { return (size_t)g.KH * g.KW * round16(g.Cin) * round16(g.Cout) * 2; }
 
-int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed) {
+int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed, int tile_width) {
   const int Cin_p = round16(g.Cin), N_p = round16(g.Cout);
   const long long total = (long long)g.KH * g.KW * Cin_p * N_p;
   int blocks = (int)((total + 255) / 256);
   if (blocks > lc.sm_count * 8) blocks = lc.sm_count * 8;
   ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total);
-  tc_pack_kernel<<<blocks, 256, 0, lc.stream>>>(g, w, reinterpret_cast<__nv_bfloat16*>(w_packed), pick_kc(Cin_p), Cin_p, N_p);
+  tc_pack_kernel<<<blocks, 256, 0, lc.stream>>>(g, w, reinterpret_cast<__nv_bfloat16*>(w_packed), pick_kc(Cin_p), Cin_p, N_p,
+                                                tile_width);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed) {
+TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed, int tile_width) {
   TcPackEntry e;
-  e.g = g; e.w = w; e.out = w_packed;
+  e.g = g; e.w = w; e.out = w_packed; e.TW = tile_width;
   e.Cin_p = round16(g.Cin); e.N_p = round16(g.Cout); e.KC = pick_kc(e.Cin_p);
   e.total = (long long)g.KH * g.KW * e.Cin_p * e.N_p;
   return e;

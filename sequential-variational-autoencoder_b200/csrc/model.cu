@@ -62,6 +62,7 @@ struct Block {
   // this block's own activated output is additionally written for its consumer
   BfAct in_bf{}; bool tc2_fwd = false, tc2_dgrad = false, tc2_wgrad = false;
   BfDst out_bf{};
+  int tw_f = 128, tw_d = 128;    // tile width of the packed forward / input-gradient weights (tc2_pick_ntw at plan time)
   // set by the input-gradient kernel that produced this block's dL/d(activated output) when it already turned it into
   // g = da * act' and reduced the two backward sums (BnBwdFuse): the block's backward then skips pass 1
   bool g_fused = false;
@@ -751,13 +752,14 @@ bool forked(const svae_handle* h) { return h->use_streams && h->cfg.train_capaci
 
 // contraction through the TMA-fed kernel when the input has a bf16 planar copy, else the SIMT-staged / fp32 kernels
 int contract_bf(svae_handle* h, Geom g, int B, bool tc2, const BfAct& in_bf, View in, const float* w, const void* w_packed,
-                bool use_tc, View out, double* stats, const BnBwdFuse* fuse = nullptr) {
+                bool use_tc, View out, double* stats, const BnBwdFuse* fuse = nullptr, int w_tile_width = 128) {
   if (tc2) {
     g.B = B;
     LaunchCtx lc = h->lc();
-    return tc2_gather_gemm(lc, g, in_bf, 0, w_packed, out, stats, fuse);
+    return tc2_gather_gemm(lc, g, in_bf, 0, w_packed, out, stats, fuse, w_tile_width);
   }
   if (fuse != nullptr) { svae_global_error() = "fused batch-norm backward requested on a non-tc2 contraction"; return -1; }
+  if (w_tile_width != 128 && use_tc) { svae_global_error() = "weights packed for the TMA-fed kernel reached the SIMT-staged one"; return -1; }
   return contract(h, g, B, in, w, w_packed, use_tc, out, stats);
 }
 
@@ -783,7 +785,7 @@ bool is_fc2d(const Block& b, int B) { return b.g.KH == 1 && b.rpi == 1 && b.res.
 int block_fwd(svae_handle* h, Block& b, int B, View in) {
   const bool fc2d = is_fc2d(b, B);
   H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
-                    fc2d ? nullptr : b.stats));
+                    fc2d ? nullptr : b.stats, nullptr, b.tw_f));
   LaunchCtx lc = h->lc();
   if (fc2d) H_TRY(bn2d_fwd(lc, b.y, h->pw(b.beta), B, b.feats, b.act, b.stats, b.out, b.out_bf));
   else H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out, b.out_bf));
@@ -832,7 +834,7 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     BnBwdFuse fz;
     const bool fuse = tc2d && make_fuse(h, up, B, up_dres, up_dres_acc, g, *din, fz);
     H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr,
-                      fuse ? &fz : nullptr));
+                      fuse ? &fz : nullptr, b.tw_d));
     if (fuse) up->g_fused = true;
   }
   if (!(h->ablate & 1)) {
@@ -1358,6 +1360,7 @@ void plan_pack(svae_handle* h, Block& b, void* ctx) {
   if (tc_supported(f)) {
     b.tc_fwd = true;
     if (!is_fc) b.w_packed = a->get<char>(tc_packed_bytes(f));
+    if (!is_fc && b.tc2_fwd) b.tw_f = tc2_pick_ntw(f, h->sm_count);
     if (a->base) h->tc_layers++;
   }
   if (tc_wgrad_supported(f)) {
@@ -1368,14 +1371,15 @@ void plan_pack(svae_handle* h, Block& b, void* ctx) {
   if (tc_supported(d)) {
     b.tc_dgrad = true;
     if (!is_fc) b.w_packed_d = a->get<char>(tc_packed_bytes(d));
+    if (!is_fc && b.tc2_dgrad) b.tw_d = tc2_pick_ntw(d, h->sm_count);
     if (a->base) h->tc_layers++;
   }
 }
 
 void collect_pack(svae_handle* h, Block& b, void* ctx) {
   std::vector<TcPackEntry>* v = (std::vector<TcPackEntry>*)ctx;
-  if (b.tc_fwd && b.w_packed) { Geom f = b.g; f.B = 1; v->push_back(tc_pack_entry(f, h->pw(b.w), b.w_packed)); }
-  if (b.tc_dgrad && b.w_packed_d) { Geom d = dgrad_geom(b.g); d.B = 1; v->push_back(tc_pack_entry(d, h->pw(b.w), b.w_packed_d)); }
+  if (b.tc_fwd && b.w_packed) { Geom f = b.g; f.B = 1; v->push_back(tc_pack_entry(f, h->pw(b.w), b.w_packed, b.tw_f)); }
+  if (b.tc_dgrad && b.w_packed_d) { Geom d = dgrad_geom(b.g); d.B = 1; v->push_back(tc_pack_entry(d, h->pw(b.w), b.w_packed_d, b.tw_d)); }
 }
 
 int ensure_pack_table(svae_handle* h) {
@@ -1990,16 +1994,18 @@ static int op_contract(svae_handle* h, Geom g, int B, const float* x, int ldx, c
     if (!tc_supported(g)) return fail(h, SVAE_EINVAL, "shape not supported by the tcgen05 kernels");
     void* packed = nullptr;
     H_CUDA(cudaMalloc(&packed, tc_packed_bytes(g)));
-    int r = tc_pack_weights(lc, g, w, packed);
     const char* e2 = getenv("SVAE_TC2");
-    if (r == 0 && !(e2 && e2[0] == '0') && tc2_supported(g)) {
+    const bool use2 = !(e2 && e2[0] == '0') && tc2_supported(g);
+    const int tw = use2 ? tc2_pick_ntw(g, h->sm_count) : 128;
+    int r = tc_pack_weights(lc, g, w, packed, tw);
+    if (r == 0 && use2) {
       // TMA-fed kernel: stage the fp32 input as a padded bf16 copy first (inside the chain the producing kernel writes it)
       BfAct a = bf_act_describe(tc2_input_kind(g), B, g.Hin, g.Win, g.Cin);
       void* abuf = nullptr;
       H_CUDA(cudaMalloc(&abuf, bf_act_bytes(a)));
       a.p = reinterpret_cast<__nv_bfloat16*>(abuf);
       r = bf_act_fill(lc, a, mkview(const_cast<float*>(x), ldx, 0), g.Cin);
-      if (r == 0) r = tc2_gather_gemm(lc, g, a, 0, packed, mkview(y, ldy, 0), stats);
+      if (r == 0) r = tc2_gather_gemm(lc, g, a, 0, packed, mkview(y, ldy, 0), stats, nullptr, tw);
       cudaStreamSynchronize(h->stream);
       cudaFree(abuf);
     } else if (r == 0) {
