@@ -239,8 +239,9 @@ int lat_dz(const LaunchCtx& lc, const float* dy, const float* w, int B, int KZ, 
 // ---- fused latent projections (kernels_lat.cu): fc (K <= 32) + 2-D batch norm + activation in one kernel per direction --
 bool lat_fused_supported(int B, int KZ);
 // y[B,N] = z.W ; stats = (sum, sumsq) per feature ; act(bn(y)) -> out (fp32 concat slot, may be NULL) and bf (may be NULL)
+// mom_scratch: 64 doubles of scratch (second moments of z, reduced once for batches > 512), may be NULL
 int lat_fwd_fused(const LaunchCtx& lc, View z, const float* w, const float* beta, int B, int KZ, int N, int act, float* y,
-                  double* stats, FeatView out, BfDst bf);
+                  double* stats, FeatView out, BfDst bf, double* mom_scratch = nullptr);
 // dw[KZ,N] += z^T dy ; dbeta = sum g ; dz[B, window] += dy.W^T  (dy never materialised)
 int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double* stats, const float* beta, View z,
                   const float* w, int B, int KZ, int N, int act, float* dw, float* dbeta, View dz);

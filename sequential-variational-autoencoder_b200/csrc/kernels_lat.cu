@@ -54,7 +54,7 @@ lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const fl
       float v = 0.f;
 #pragma unroll
       for (int k = 0; k < NM; ++k) v = fmaf(s_z[b * NM + k], wk[k], v);
-      y[(size_t)b * N + f] = v;
+      if (y != nullptr) y[(size_t)b * N + f] = v;
       s += (double)v;
       q += (double)v * (double)v;
     }
@@ -65,7 +65,7 @@ lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const fl
   s = 0.0; q = 0.0;
 #pragma unroll
   for (int i = 0; i < LAT_RY; ++i) { s += s_s[i][threadIdx.x]; q += s_q[i][threadIdx.x]; }   // same order in every row phase
-  if (threadIdx.y == 0) {
+  if (threadIdx.y == 0 && stats != nullptr) {
     stats[f] = s;            // the same (sum, sum of squares) the statistics-fused contraction epilogues leave
     stats[N + f] = q;
   }
@@ -90,6 +90,123 @@ lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const fl
     v = lat_act(fmaf(v, rstd, sh), act);
     if (out.p != nullptr) out.p[(size_t)b * ostride + ooff] = v;
     if (has_bf) {
+      const int64_t p = (int64_t)b * bppr + bpix;
+      const int n = (int)(p / HW);
+      const int hw = (int)(p - (int64_t)n * HW);
+      const int hh = hw / Wd;
+      bf.a.p[bf_index(bf.a, n, hh, hw - hh * Wd, bf.coff + bc)] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// Forward for narrow latent groups (K <= 8): y = z.W is a rank-K map of the batch, so its batch statistics follow from the
+// K x K second moments of z -  mean_y[f] = m.W[:,f],  var_y[f] = W[:,f]^T Cov(z) W[:,f]  - and no pass over the batch is needed
+// to normalise: every block first reduces the moments of z (B x K values, L2-resident), then the kernel is a pure map over
+// (row chunk, feature tile) with K FMAs per element.  Rows split freely over blockIdx.y (generation runs B = 4096).
+template <int NM>
+__global__ void __launch_bounds__(LAT_THREADS)
+lat_fwd_moment_kernel(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
+                      const float* __restrict__ beta, int B, int KZ, int N, int act, int rows_per_block,
+                      float* __restrict__ y, double* __restrict__ stats, FeatView out, BfDst bf,
+                      const double* __restrict__ mom_in, double* __restrict__ mom_out) {
+  constexpr int NP = NM * (NM + 1) / 2;
+  __shared__ double s_part[LAT_RY][NM + NP];
+  __shared__ double s_mom[NM + NP];           // sum z_k, then sum z_k z_k' (k <= k')
+  extern __shared__ float s_z[];              // [rows_per_block][NM] rows of this block
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  double acc[NM + NP];
+#pragma unroll
+  for (int i = 0; i < NM + NP; ++i) acc[i] = 0.0;
+  // mom_in: the moments were reduced once by a one-block launch of this kernel (mom_out != nullptr) - large batches
+  if (mom_in == nullptr)
+  for (int b = tid; b < B; b += LAT_THREADS) {
+    float zk[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) zk[k] = k < KZ ? __ldg(z + (size_t)b * z_ld + z_coff + k) : 0.f;
+    int q = NM;
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      acc[k] += (double)zk[k];
+#pragma unroll
+      for (int k2 = k; k2 < NM; ++k2) acc[q++] += (double)zk[k] * (double)zk[k2];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NM + NP; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_part[threadIdx.y][i] = v;
+  }
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(B, r0 + rows_per_block);
+  for (int i = tid; i < (r1 - r0) * NM; i += LAT_THREADS) {
+    const int b = i / NM, k = i - b * NM;
+    s_z[i] = k < KZ ? z[(size_t)(r0 + b) * z_ld + z_coff + k] : 0.f;
+  }
+  __syncthreads();
+  if (tid < NM + NP) {
+    double v = 0.0;
+    if (mom_in != nullptr) v = mom_in[tid];
+    else {
+#pragma unroll
+      for (int i = 0; i < LAT_RY; ++i) v += s_part[i][tid];
+    }
+    s_mom[tid] = v;
+    if (mom_out != nullptr) mom_out[tid] = v;
+  }
+  if (mom_out != nullptr) return;              // moments-only launch
+  __syncthreads();
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  if (f >= N) return;
+  float wk[NM];
+#pragma unroll
+  for (int k = 0; k < NM; ++k) wk[k] = k < KZ ? __ldg(w + (size_t)k * N + f) : 0.f;
+  // batch statistics of y[:, f] from the moments of z
+  double sy = 0.0, syy = 0.0;
+  {
+    int q = NM;
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      sy += s_mom[k] * (double)wk[k];
+#pragma unroll
+      for (int k2 = k; k2 < NM; ++k2) {
+        const double t = s_mom[q++] * (double)wk[k] * (double)wk[k2];
+        syy += k2 == k ? t : 2.0 * t;
+      }
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.y == 0 && stats != nullptr) { stats[f] = sy; stats[N + f] = syy; }
+  const double m = sy / (double)B;
+  double var = syy / (double)B - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)m;
+  const float rstd = (float)(1.0 / sqrt(var + (double)SVAE_BN_EPS));
+  const float sh = beta[f] - mean * rstd;
+  const int pix = f / out.inner, c = f - pix * out.inner;
+  const size_t ooff = (size_t)pix * out.ld + out.coff + c;
+  const size_t ostride = (size_t)out.ppr * out.ld;
+  const bool has_bf = bf.a.p != nullptr;
+  const int binner = bf.inner ? bf.inner : out.inner, bppr = bf.inner ? bf.ppr : out.ppr;
+  const int bpix = f / binner, bc = f - bpix * binner;
+  const int HW = has_bf ? bf.a.H * bf.a.W : 1, Wd = has_bf ? bf.a.W : 1;
+  // one image per row (ppr == H*W): the element's address is linear in the image index - no index math in the loop
+  const bool lin = has_bf && bppr == HW;
+  size_t bf_base = 0, bf_step = 0;
+  if (lin) {
+    const int hh = bpix / Wd;
+    bf_base = bf_index(bf.a, 0, hh, bpix - hh * Wd, bf.coff + bc);
+    bf_step = bf_index(bf.a, 1, hh, bpix - hh * Wd, bf.coff + bc) - bf_base;
+  }
+  for (int b = r0 + threadIdx.y; b < r1; b += LAT_RY) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < NM; ++k) v = fmaf(s_z[(b - r0) * NM + k], wk[k], v);
+    if (y != nullptr) y[(size_t)b * N + f] = v;
+    v = lat_act(fmaf(v, rstd, sh), act);
+    if (out.p != nullptr) out.p[(size_t)b * ostride + ooff] = v;
+    if (lin) {
+      bf.a.p[bf_base + (size_t)b * bf_step] = __float2bfloat16_rn(v);
+    } else if (has_bf) {
       const int64_t p = (int64_t)b * bppr + bpix;
       const int n = (int)(p / HW);
       const int hw = (int)(p - (int64_t)n * HW);
@@ -331,11 +448,30 @@ static int allow_smem(K kernel, size_t bytes) {   // opt in to > 48 KB of static
   }
 
 int lat_fwd_fused(const LaunchCtx& lc, View z, const float* w, const float* beta, int B, int KZ, int N, int act, float* y,
-                  double* stats, FeatView out, BfDst bf) {
-  if (!lat_fused_supported(B, KZ)) { svae_global_error() = "lat_fwd_fused: unsupported batch / latent width"; return -1; }
+                  double* stats, FeatView out, BfDst bf, double* mom_scratch) {
+  if (!(KZ >= 1 && KZ <= 8 && B >= 1) && !lat_fused_supported(B, KZ)) { svae_global_error() = "lat_fwd_fused: unsupported batch / latent width"; return -1; }
   Geom tg{}; tg.B = B; tg.Cin = KZ; tg.Cout = N;
   ProfScope ps(lc, KC_SKINNY, 4.0 * B * KZ * (double)N, (double)B * N * (4.0 + (out.p ? 4.0 : 0.0) + (bf.a.p ? 2.0 : 0.0)), &tg);
   const unsigned blocks = (unsigned)((N + 31) / 32);
+  if (KZ <= 8) {   // statistics from the moments of z: rows split over blockIdx.y, no pass over the batch
+    const int rpb = B <= 128 ? B : 128;
+    const dim3 grid(blocks, (unsigned)((B + rpb - 1) / rpb));
+    // large batches: the moments of z are reduced once by a one-block launch instead of by every block
+    const double* mom = (B > 512 && mom_scratch != nullptr) ? mom_scratch : nullptr;
+    if (KZ <= 4) {
+      if (mom) lat_fwd_moment_kernel<4><<<dim3(1, 1), dim3(32, LAT_RY), 0, lc.stream>>>(
+                   z.p, z.ld, z.coff, w, beta, B, KZ, N, act, 0, nullptr, nullptr, FeatView{}, BfDst{}, nullptr, mom_scratch);
+      lat_fwd_moment_kernel<4><<<grid, dim3(32, LAT_RY), (size_t)rpb * 4 * sizeof(float), lc.stream>>>(
+          z.p, z.ld, z.coff, w, beta, B, KZ, N, act, rpb, y, stats, out, bf, mom, nullptr);
+    } else {
+      if (mom) lat_fwd_moment_kernel<8><<<dim3(1, 1), dim3(32, LAT_RY), 0, lc.stream>>>(
+                   z.p, z.ld, z.coff, w, beta, B, KZ, N, act, 0, nullptr, nullptr, FeatView{}, BfDst{}, nullptr, mom_scratch);
+      lat_fwd_moment_kernel<8><<<grid, dim3(32, LAT_RY), (size_t)rpb * 8 * sizeof(float), lc.stream>>>(
+          z.p, z.ld, z.coff, w, beta, B, KZ, N, act, rpb, y, stats, out, bf, mom, nullptr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   LAT_DISPATCH(KZ, {
     const size_t smem = (size_t)B * NM * sizeof(float);
     if (allow_smem(lat_fwd_fused_kernel<NM>, smem) != 0) return -3;

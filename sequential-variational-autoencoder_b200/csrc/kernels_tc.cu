@@ -26,6 +26,7 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int MAX_STAGES = 4;
+constexpr int W2_STAGES_MAX = 6;   // weight ring of the TMA-fed kernel: streaming layers are bound by the bytes one CTA keeps in flight
 
 struct TcParams {
   const float* in; int in_ld, in_coff, cin_valid, in_vec;
@@ -755,7 +756,7 @@ struct Tc2Params {
 };
 
 struct SmemHeader2 {
-  unsigned long long a_full[A_STAGES_MAX], a_empty[A_STAGES_MAX], w_full[MAX_STAGES], w_empty[MAX_STAGES];
+  unsigned long long a_full[A_STAGES_MAX], a_empty[A_STAGES_MAX], w_full[W2_STAGES_MAX], w_empty[W2_STAGES_MAX];
   unsigned long long acc_full[2], acc_empty[2];
   unsigned tmem_base, pad;
   float s_sum[4][128], s_sq[4][128];
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
 
   if (tid == 0) {
     for (int s = 0; s < A_STAGES_MAX; ++s) { mbar_init(smem_u32(&hdr->a_full[s]), 1); mbar_init(smem_u32(&hdr->a_empty[s]), 1); }
-    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(smem_u32(&hdr->w_full[s]), 1); mbar_init(smem_u32(&hdr->w_empty[s]), 1); }
+    for (int s = 0; s < W2_STAGES_MAX; ++s) { mbar_init(smem_u32(&hdr->w_full[s]), 1); mbar_init(smem_u32(&hdr->w_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&hdr->acc_full[b]), 1); mbar_init(smem_u32(&hdr->acc_empty[b]), 128); }
     fence_barrier_init();
   }
@@ -1171,7 +1172,8 @@ bool build_params2(const Geom& g, Tc2Params& PP, int ntw = 128) {
     w_region = PP.w_bytes_ntile;        // region sized for a full tile; only w_need bytes are filled
     if (nt_max < 128) w_region = w_need;
   } else {
-    PP.w_stages = MAX_STAGES;
+    static const int ws_max = getenv("SVAE_W_STAGES") ? atoi(getenv("SVAE_W_STAGES")) : W2_STAGES_MAX;
+    PP.w_stages = ws_max < 2 ? 2 : (ws_max > W2_STAGES_MAX ? W2_STAGES_MAX : ws_max);
     while (PP.w_stages > 2 && hdr + (size_t)PP.w_stages * P.b_stage_max + 2 * (size_t)PP.a_bytes + 256 > 227 * 1024) --PP.w_stages;
     w_region = (size_t)PP.w_stages * P.b_stage_max;
   }

@@ -63,6 +63,9 @@ struct Block {
   BfAct in_bf{}; bool tc2_fwd = false, tc2_dgrad = false, tc2_wgrad = false;
   BfDst out_bf{};
   int tw_f = 128, tw_d = 128;    // tile width of the packed forward / input-gradient weights (tc2_pick_ntw at plan time)
+  // the fp32 copy of the activated output is not written when every reader takes the bf16 planar copy (TMA-fed consumer,
+  // and in training its TMA-fed weight gradient): 4 of the 10 bytes per element this block's batch-norm kernel moves
+  bool skip_f32 = false;
   // set by the input-gradient kernel that produced this block's dL/d(activated output) when it already turned it into
   // g = da * act' and reduced the two backward sums (BnBwdFuse): the block's backward then skips pass 1
   bool g_fused = false;
@@ -109,6 +112,7 @@ struct Step {
   Geom g_out, g_gate;
   Block outb, gateb;                      // the same two deconvs as contraction blocks (no batch-norm) for TC routing
   float *u, *xt;
+  double* lat_mom = nullptr;              // [L][64] scratch: second moments of z_t per latent group (lat_fwd_fused)
   BfAct xt_bf{};                          // bf16 copy of x_t for the next step's chain encoder
   int64_t p_begin, p_end;                 // parameter range (all-reduce bucket)
 };
@@ -467,7 +471,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       alias(s.decfc, r.decfc);
       for (size_t i = 0; i < s.ta.size(); ++i) alias(s.ta[i], r.ta[i]);
       for (size_t i = 0; i < s.tb.size(); ++i) alias(s.tb[i], r.tb[i]);
-      s.dcat = r.dcat; s.cc = r.cc; s.u = r.u; s.xt = r.xt;
+      s.dcat = r.dcat; s.cc = r.cc; s.u = r.u; s.xt = r.xt; s.lat_mom = r.lat_mom;
       s.mu_pre = r.mu_pre; s.sd_pre = r.sd_pre; s.mu = r.mu; s.sd = r.sd; s.z = r.z; s.eps = r.eps;
       continue;
     }
@@ -528,6 +532,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
     }
     s.u = act.get<float>((size_t)B * h->D * h->D * (C + 1));
     s.xt = act.get<float>((size_t)B * h->D * h->D * C);
+    s.lat_mom = act.get<double>((size_t)L * 64);
   }
   // ---- bf16 planar copies for the TMA-fed kernels: every tensor a tcgen05 conv reads gets one, in its consumer's layout
   const bool tc2 = h->use_tc2 && c.operand_dtype == SVAE_OPERAND_BF16;
@@ -690,6 +695,43 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
     h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * C);
     h->gx[1] = gr.get<float>((size_t)B * h->D * h->D * C);
   }
+  // ---- which blocks may skip the fp32 copy of their activated output (see Block::skip_f32) -----------------------------
+  {
+    const bool train = c.train_capacity != 0;
+    static const bool enabled = !(getenv("SVAE_SKIP_F32") && getenv("SVAE_SKIP_F32")[0] == '0');
+    auto bf_only = [&](const Block& consumer) {   // this consumer (and its weight gradient) never touches the fp32 tensor
+      return enabled && tc2 && consumer.tc2_fwd && consumer.in_bf.p != nullptr && (!train || consumer.tc2_wgrad);
+    };
+    for (int t = 0; t < T; ++t) {
+      Step& s = h->steps[t];
+      if ((t >= h->act_sets) && t >= 2) {   // aliased onto step 1: same decisions
+        const Step& r = h->steps[1];
+        for (size_t i = 0; i < s.inf.size(); ++i) s.inf[i].skip_f32 = r.inf[i].skip_f32;
+        for (size_t i = 0; i < s.enc.size(); ++i) s.enc[i].skip_f32 = r.enc[i].skip_f32;
+        for (size_t i = 0; i < s.lat.size(); ++i) s.lat[i].skip_f32 = r.lat[i].skip_f32;
+        s.decfc.skip_f32 = r.decfc.skip_f32;
+        for (size_t i = 0; i < s.ta.size(); ++i) { s.ta[i].skip_f32 = r.ta[i].skip_f32; s.tb[i].skip_f32 = r.tb[i].skip_f32; }
+        continue;
+      }
+      // recognition net: even blocks feed the next conv only; odd blocks also feed the heads (fp32)
+      for (int k = 0; k + 1 < (int)s.inf.size(); k += 2) s.inf[k].skip_f32 = bf_only(s.inf[k + 1]);
+      // chain encoder: even blocks feed the next conv only; odd blocks are the decoder's shortcuts, the last one feeds enc.fc
+      for (int k = 0; k + 1 < (int)s.enc.size(); k += 2) s.enc[k].skip_f32 = bf_only(s.enc[k + 1]);
+      // decoder: dec.fc -> ta[L-2]; ta[l], P_l -> tb[l]; tb[l] -> ta[l-1]; tb[0] -> the two output deconvs
+      s.decfc.skip_f32 = bf_only(s.ta[L - 2]);
+      for (int l = L - 2; l >= 0; --l) {
+        s.ta[l].skip_f32 = bf_only(s.tb[l]);
+        s.lat[l].skip_f32 = bf_only(s.tb[l]) && s.lat[l].out_bf.a.p != nullptr;
+        if (l > 0) s.tb[l].skip_f32 = bf_only(s.ta[l - 1]);
+      }
+      s.tb[0].skip_f32 = bf_only(s.outb) && (t == 0 || bf_only(s.gateb));
+      for (Block* b : {&s.decfc}) if (b->out_bf.a.p == nullptr) b->skip_f32 = false;
+      for (Block& b : s.inf) if (b.out_bf.a.p == nullptr) b.skip_f32 = false;
+      for (Block& b : s.enc) if (b.out_bf.a.p == nullptr) b.skip_f32 = false;
+      for (Block& b : s.ta) if (b.out_bf.a.p == nullptr) b.skip_f32 = false;
+      for (Block& b : s.tb) if (b.out_bf.a.p == nullptr) b.skip_f32 = false;
+    }
+  }
   // io staging (host-buffer entry points)
   h->in_x = act.get<float>((size_t)B * h->D * h->D * C);
   h->in_tgt = act.get<float>((size_t)B * h->D * h->D * C);
@@ -787,8 +829,10 @@ int block_fwd(svae_handle* h, Block& b, int B, View in) {
   H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
                     fc2d ? nullptr : b.stats, nullptr, b.tw_f));
   LaunchCtx lc = h->lc();
-  if (fc2d) H_TRY(bn2d_fwd(lc, b.y, h->pw(b.beta), B, b.feats, b.act, b.stats, b.out, b.out_bf));
-  else H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, b.out, b.out_bf));
+  FeatView out = b.out;
+  if (b.skip_f32) out.p = nullptr;   // only the bf16 planar copy is read downstream
+  if (fc2d) H_TRY(bn2d_fwd(lc, b.y, h->pw(b.beta), B, b.feats, b.act, b.stats, out, b.out_bf));
+  else H_TRY(bn_act_fwd(lc, b.y, b.stats, h->pw(b.beta), (int64_t)B * b.rpi, b.feats, b.act, b.res, out, b.out_bf));
   return 0;
 }
 
@@ -918,9 +962,14 @@ int latent_fwd(svae_handle* h, Step& s, int B, const float* z) {
   for (int i = 0; i < h->L; ++i) {
     Block& b = s.lat[i];
     View zv = mkview(const_cast<float*>(z), h->Z, h->zoff[i]);
-    if (lat_fused_supported(B, b.g.Cin)) {
+    if (b.g.Cin <= 8 || lat_fused_supported(B, b.g.Cin)) {
       LaunchCtx lc = h->lc();
-      H_TRY(lat_fwd_fused(lc, zv, h->pw(b.w), h->pw(b.beta), B, b.g.Cin, b.feats, b.act, b.y, b.stats, b.out, b.out_bf));
+      FeatView out = b.out;
+      if (b.skip_f32) out.p = nullptr;
+      // forward-only handles never run the backward: the pre-BN tensor and the statistics are not stored either
+      const bool keep = h->cfg.train_capacity != 0;
+      H_TRY(lat_fwd_fused(lc, zv, h->pw(b.w), h->pw(b.beta), B, b.g.Cin, b.feats, b.act, keep ? b.y : nullptr, keep ? b.stats : nullptr,
+                          out, b.out_bf, s.lat_mom ? s.lat_mom + (size_t)i * 64 : nullptr));
     } else {
       H_TRY(block_fwd(h, b, B, zv));
     }
