@@ -472,7 +472,12 @@ static int split_for(int rows_or_blocks, int sm_count, int max_split) {
 int heads_fwd(const LaunchCtx& lc, const float* flat, int B, int K, const HeadSet& hs, float* mu_pre, float* sd_pre, int Z) {
   int ntot = 0;
   for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
-  const int ks = split_for(B, lc.sm_count, (K + 2047) / 2048);
+  // K slices per image: enough blocks (~8 per SM) that the L2 latency of the two short load streams is hidden; every slice
+  // still spans >= 1024 inputs so that the per-slice reduction + atomics stay small
+  int ks = (8 * lc.sm_count + B - 1) / B;
+  const int ks_max = (K + 1023) / 1024;
+  if (ks > ks_max) ks = ks_max;
+  if (ks < 1) ks = 1;
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
   SK_DISPATCH(heads_nmax(hs), (heads_fwd_kernel<NM><<<dim3(B, ks), 256, 0, lc.stream>>>(flat, K, hs, mu_pre, sd_pre, Z)));
   CUDA_TRY(cudaGetLastError());

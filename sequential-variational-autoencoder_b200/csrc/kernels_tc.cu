@@ -1186,6 +1186,17 @@ bool build_params2(const Geom& g, Tc2Params& PP, int ntw = 128) {
   const int want = P.NC > 1 ? 3 : 2;   // keep the footprint modest: two CTAs per SM help the short layers
   if (PP.a_stages > want) PP.a_stages = want;
   if (PP.a_stages < 1) return false;
+  // Narrow layers (N <= 64) are paced by the per-CTA MMA issue latency (59 cycles per MMA alone, ~40 with two CTAs on the SM,
+  // scripts/mma_rate.cu): when dropping the halo prefetch depth lets two CTAs share an SM, do it - the second CTA covers the
+  // halo latency that the shallower ring exposes.
+  {
+    static const bool two = !(getenv("SVAE_CONV_2CTA") && getenv("SVAE_CONV_2CTA")[0] == '0');
+    const size_t cap = 113 * 1024;
+    if (two && nt_max <= 64 && PP.w_resident && hdr + w_region + 256 + (size_t)PP.a_stages * PP.a_bytes > cap &&
+        hdr + w_region + 256 + (size_t)PP.a_bytes <= cap) {
+      while (PP.a_stages > 1 && hdr + w_region + 256 + (size_t)PP.a_stages * PP.a_bytes > cap) --PP.a_stages;
+    }
+  }
   unsigned cols = (unsigned)(P.nacc * nt_max), t = 32;
   while (t < cols) t <<= 1;
   PP.acc_cols = t;
@@ -1648,7 +1659,8 @@ int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double 
   ProfScope ps(lc, KC_PACK, 0.0, 6.0 * total_elems);
   // blocks per entry: enough in total to fill the machine a few times over, whether the table holds every layer of the model
   // (one launch after a full Adam step) or one chain step's layers (bucketed update)
-  int bx = (8 * lc.sm_count + n - 1) / n;
+  // (entries differ 1000x in size: blocks beyond an entry's element count exit at once, the large entries need the threads)
+  int bx = (64 * lc.sm_count + n - 1) / n;
   if (bx < 32) bx = 32;
   if (bx > 256) bx = 256;
   tc_pack_batched_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, lc.stream>>>(reinterpret_cast<const TcPackEntry*>(dev_entries));
