@@ -104,6 +104,18 @@ int main() {
       if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       printf("LBO_B=%u N=%3d rot=1 : issue %.1f cyc/mma, complete %.1f cyc/mma\n", lbb, N, (double)out[0] / iters, (double)out[1] / iters);
     }
+  // MN-major operands (the weight-gradient layout): stride between the 8-channel planes (SBO of A / B)
+  for (unsigned pa : {2048u, 2064u, 3840u, 3856u})
+    for (unsigned pb : {2048u, 2064u})
+      for (int N : {32, 128})
+        for (int ctas = 1; ctas <= 2; ++ctas) {
+          Args a{N, iters, 1, 1, pa, pb, 1, out};
+          k<<<148 * ctas, 128, 96 * 1024, 0>>>(a);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+          printf("MN-major pitchA=%u pitchB=%u N=%3d ctas/SM=%d : issue %.1f cyc/mma, complete %.1f cyc/mma\n", pa, pb, N, ctas,
+                 (double)out[0] / iters, (double)out[1] / iters);
+        }
   if (getenv("MMA_RATE_SHORT")) return 0;
   for (int ctas = 1; ctas <= 2; ++ctas)
     for (int la = 0; la < 3; ++la)

@@ -776,7 +776,8 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
     const int ppb = threads / G;
     int64_t blocks = (rows + ppb - 1) / ppb;
     // enough blocks to fill the machine, few enough that the per-block reduction + atomics stay negligible
-    const int64_t cap = (int64_t)lc.sm_count * 2;
+    static const int red_per_sm = getenv("SVAE_RED_CAP") ? atoi(getenv("SVAE_RED_CAP")) : 2;
+    const int64_t cap = (int64_t)lc.sm_count * red_per_sm;
     if (blocks > cap) blocks = cap;
     const size_t smem = (3 * (size_t)feats + (size_t)threads * 17) * sizeof(float);
     CUDA_TRY(launch_k(lc, bn_bwd_reduce_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,

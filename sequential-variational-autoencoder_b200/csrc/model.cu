@@ -866,7 +866,12 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     }
     if (fr == 1) {
       H_TRY(bn_bwd_reduce(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, dy, b.S, dres, dres_acc));
-      H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta), dy_bf));
+      // the fp32 dy is only written for consumers that are not TMA-fed (they read the bf16 planar copy)
+      const bool need_f32 = !tc2w || (din != nullptr && !tc2d);
+      if (!need_f32 && dy_bf.a.p != nullptr && b.feats % 8 == 0 && b.feats <= 2048 && b.rpi > 1)
+        H_TRY(bn_bwd_apply_from(lc, mkview(dy, b.feats, 0), nullptr, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta), dy_bf));
+      else
+        H_TRY(bn_bwd_apply(lc, dy, b.y, b.stats, b.S, rows, b.feats, h->pg(b.beta), dy_bf));
     }
   }
   View dyv = mkview(dy, b.feats, 0);
