@@ -17,6 +17,9 @@ CONV_CASES = [
     (4, 4, 128, 128, 2), (100, 8, 64, 128, 2),
     # few pixel tiles, wide layers: the tcgen05 kernel splits the output channels over blockIdx.z (sub-tiles of 32 / 64)
     (100, 8, 128, 128, 2), (100, 8, 256, 128, 1), (100, 4, 384, 128, 2), (100, 8, 128, 384, 2),
+    # the layer shapes of __graft_entry__.smoke() (filter sizes 3/16/32/32/48, 32x32 images, batch 4)
+    (4, 32, 3, 16, 2), (4, 16, 16, 16, 1), (4, 16, 16, 32, 2), (4, 8, 32, 32, 1), (4, 4, 32, 32, 2), (4, 2, 48, 32, 2),
+    (4, 4, 64, 32, 1), (4, 8, 64, 32, 1), (4, 8, 32, 16, 2), (4, 16, 32, 16, 1), (4, 16, 16, 3, 2), (4, 16, 16, 1, 2),
 ]
 
 
