@@ -63,7 +63,10 @@ typedef struct svae_config {
   int32_t max_batch;                        /* largest batch any call will use                                   */
   int32_t train_capacity;                   /* 1: keep per-step activations for backward; 0: forward/generate only */
   int32_t operand_dtype;                    /* SVAE_OPERAND_*                                                    */
-  int32_t reserved[8];
+  int32_t share_theta_weights;              /* :213  homogeneous chain: one chain encoder and one decoder for all
+                                               steps t >= 1 (step 0 keeps its own decoder, :1683-1687,1757-1761)  */
+  int32_t share_phi_weights;                /* :214  one recognition net for all steps (:1573-1577)              */
+  int32_t reserved[6];
 } svae_config;
 
 /* Per-step ELBO terms of the last forward.  Replaces the scalars TF lets callers fetch: self.loss, self.final_loss

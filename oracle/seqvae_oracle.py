@@ -39,6 +39,18 @@ _NETNAMES = {
         "vlae_levels": 3, "vlae_latent_dims": [2, 2, 2], "image_sizes": [32, 16, 8, 4],
         "filter_sizes": [None, 64, 128, 192, 256], "mc_steps": 5,
     },
+    # homogeneous (weight-shared) chains and the other rows that only move knobs of the same path
+    "sequential_vae_celebA_homog": {"share_theta_weights": True, "share_phi_weights": True},          # :675-677
+    "sequential_vae_celebA_homog_fixed_length": {"share_theta_weights": True},                        # :709-710
+    "c_homog": {"share_theta_weights": True, "share_phi_weights": True, "mc_steps": 25},              # :730-733
+    "c_homog_v1": {"vlae_latent_dims": [12, 12, 12, 12], "filter_sizes": [None, 16, 32, 64, 128, 384],  # :316-321
+                   "share_theta_weights": True, "share_phi_weights": True},
+    "c_homog_one_step": {"vlae_latent_dims": [12, 12, 12, 12], "filter_sizes": [None, 16, 32, 64, 128, 384],  # :281-288
+                         "share_theta_weights": True, "share_phi_weights": True, "mc_steps": 1},
+    "s_homog_one_step": {"vlae_latent_dims": [12, 12, 12, 12], "share_theta_weights": True,           # :301-307
+                         "share_phi_weights": True, "mc_steps": 1},
+    "vlae_celebA": {"mc_steps": 1, "vlae_latent_dims": [16, 16, 16, 16]},                             # :704-707
+    "sequential_vae_lsun_final": {"vlae_latent_dims": [20, 30, 30, 30], "intermediate_reconstruction": False},  # :721-725
 }
 
 
@@ -57,6 +69,7 @@ def hyperparams(netname: str, data_dims: Sequence[int], data_range=(0.0, 1.0), *
         max_highway_ratio=1.0, min_highway_ratio=0.0,                                  # :240-241
         learning_rate=0.0002, learning_rate_decay=1.0, reg_coeff_rate=5000.0,          # :250-252
         clip_grads=True, clip_grad_value=10.0,                                         # :257-258
+        share_theta_weights=False, share_phi_weights=False,                            # :213-214
     )
     row = dict(_NETNAMES[netname])
     if "filter_sizes" in row:
@@ -382,16 +395,37 @@ def generator_ladder(hp, sc: Scope, enc, z, first_step: bool, declare_only=False
 # Parameter table (TF trainable_variables() creation order)
 # --------------------------------------------------------------------------------------------------------------
 
+def phi_scope(hp, t: int) -> str:
+    """sequential_vae.py:1573-1577: one scope per step, or "phi/inference_network" for every step when phi is shared
+    (tf.AUTO_REUSE; the default layer names restart on every scope entry, so the same variables are found again)."""
+    return "phi/inference_network" if hp.get("share_phi_weights") else "phi/inference_step_%d" % t
+
+
+def encoder_scope(hp, t: int) -> str:
+    """sequential_vae.py:1757-1761."""
+    return "theta/generative_encoder_network" if hp.get("share_theta_weights") else "theta/generative_encoder_step_%d" % t
+
+
+def generator_scope(hp, t: int) -> str:
+    """sequential_vae.py:1683-1687: shared only when the step has a chain input; step 0 keeps its own decoder."""
+    return "theta/generative_network" if hp.get("share_theta_weights") and t > 0 else "theta/generative_step_%d" % t
+
+
 def param_specs(hp) -> List[dict]:
     """All trainable variables in TF creation order: per step, phi/inference_step_t, then (t>=1)
     theta/generative_encoder_step_t, then theta/generative_step_t (construct_network, sequential_vae.py:934-975)."""
     specs: List[dict] = []
     for t in range(hp["mc_steps"]):
-        inference_ladder(hp, Scope("phi/inference_step_%d" % t, None, specs), None)
+        inference_ladder(hp, Scope(phi_scope(hp, t), None, specs), None)
         if t > 0:
-            compute_encodings(hp, Scope("theta/generative_encoder_step_%d" % t, None, specs), None)
-        generator_ladder(hp, Scope("theta/generative_step_%d" % t, None, specs), None, None, t == 0, declare_only=True)
-    return specs
+            compute_encodings(hp, Scope(encoder_scope(hp, t), None, specs), None)
+        generator_ladder(hp, Scope(generator_scope(hp, t), None, specs), None, None, t == 0, declare_only=True)
+    seen, uniq = set(), []
+    for sp in specs:            # a shared scope re-entered with tf.AUTO_REUSE finds its variables, it does not create new ones
+        if sp["name"] not in seen:
+            seen.add(sp["name"])
+            uniq.append(sp)
+    return uniq
 
 
 def init_params(hp, seed=0, dtype=torch.float64) -> "OrderedDict[str, torch.Tensor]":
@@ -429,10 +463,10 @@ def forward_chain(hp, P, x_in, x_target, eps, reg_coeff=1.0):
     loss = 0.0
     prev = None
     for t in range(T):
-        mu, sd = inference_ladder(hp, Scope("phi/inference_step_%d" % t, P, None), x_in)
+        mu, sd = inference_ladder(hp, Scope(phi_scope(hp, t), P, None), x_in)
         z = mu + sd * eps[t]                                                         # :1023
-        enc = compute_encodings(hp, Scope("theta/generative_encoder_step_%d" % t, P, None), prev) if t > 0 else None
-        xt, ratio = generator_ladder(hp, Scope("theta/generative_step_%d" % t, P, None), enc, z, t == 0)
+        enc = compute_encodings(hp, Scope(encoder_scope(hp, t), P, None), prev) if t > 0 else None
+        xt, ratio = generator_ladder(hp, Scope(generator_scope(hp, t), P, None), enc, z, t == 0)
         recon = ((xt - x_target) ** 2).mean(dim=(1, 2, 3)).mean()                    # :1146,1163
         kl = (-0.5 - torch.log(sd) + 0.5 * sd ** 2 / prior ** 2 + 0.5 * mu ** 2 / prior ** 2).mean(dim=1).mean()  # :1156-1164
         if hp["intermediate_reconstruction"] or t == T - 1:
@@ -455,8 +489,8 @@ def generate_chain(hp, P, z, batch_size):
     reference additionally prepends a uniform-noise x_0 that nothing depends on, :947-952)."""
     xs, prev = [], None
     for t in range(hp["mc_steps"]):
-        enc = compute_encodings(hp, Scope("theta/generative_encoder_step_%d" % t, P, None), prev) if t > 0 else None
-        xt, _ = generator_ladder(hp, Scope("theta/generative_step_%d" % t, P, None), enc, z[t], t == 0)
+        enc = compute_encodings(hp, Scope(encoder_scope(hp, t), P, None), prev) if t > 0 else None
+        xt, _ = generator_ladder(hp, Scope(generator_scope(hp, t), P, None), enc, z[t], t == 0)
         xs.append(xt)
         prev = xt
     return xs

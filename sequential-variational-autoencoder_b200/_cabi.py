@@ -28,7 +28,7 @@ class Config(C.Structure):
         ("min_highway", C.c_float), ("max_highway", C.c_float), ("range_lo", C.c_float), ("range_hi", C.c_float),
         ("clip_value", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
         ("max_batch", C.c_int32), ("train_capacity", C.c_int32), ("operand_dtype", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("share_theta_weights", C.c_int32), ("share_phi_weights", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

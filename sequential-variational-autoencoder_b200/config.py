@@ -2,8 +2,9 @@
 
 Mirrors the attribute block of ``SequentialVAE.__init__`` (reference sequential_vae.py:197-258) and the netname rows
 that are on the hot path: ``c_inhomog`` (:727), ``sequential_vae_celebA_inhomog`` (:671),
-``sequential_vae_lsun`` (:712-714), ``m_inhomog`` (:842-848).  The reference's other 61 netnames select ablations that
-are out of scope (weight sharing, InfoMax, chain noise, early stopping, flat / PixelCNN decoders)."""
+``sequential_vae_lsun`` (:712-714), ``m_inhomog`` (:842-848), plus the homogeneous (weight-shared) chains and the rows
+that only move knobs this path already has.  The reference's remaining netnames select ablations that
+are out of scope (InfoMax, chain noise, predicted stddev, early stopping, flat / PixelCNN decoders)."""
 import math
 
 NETNAMES = {
@@ -12,6 +13,18 @@ NETNAMES = {
     "sequential_vae_lsun": {"vlae_latent_dims": [20, 30, 30, 30]},
     "m_inhomog": {"vlae_levels": 3, "vlae_latent_dims": [2, 2, 2], "image_sizes": [32, 16, 8, 4],
                   "filter_sizes": [None, 64, 128, 192, 256], "mc_steps": 5},
+    # homogeneous (weight-shared) chains, sequential_vae.py:213-214, and rows that only move existing knobs
+    "sequential_vae_celebA_homog": {"share_theta_weights": True, "share_phi_weights": True},               # :675
+    "sequential_vae_celebA_homog_fixed_length": {"share_theta_weights": True},                             # :709
+    "c_homog": {"share_theta_weights": True, "share_phi_weights": True, "mc_steps": 25},                   # :730
+    "c_homog_v1": {"vlae_latent_dims": [12, 12, 12, 12], "filter_sizes": [None, 16, 32, 64, 128, 384],     # :316
+                   "share_theta_weights": True, "share_phi_weights": True},
+    "c_homog_one_step": {"vlae_latent_dims": [12, 12, 12, 12], "filter_sizes": [None, 16, 32, 64, 128, 384],   # :281
+                         "share_theta_weights": True, "share_phi_weights": True, "mc_steps": 1},
+    "s_homog_one_step": {"vlae_latent_dims": [12, 12, 12, 12], "share_theta_weights": True,                # :301
+                         "share_phi_weights": True, "mc_steps": 1},
+    "vlae_celebA": {"mc_steps": 1, "vlae_latent_dims": [16, 16, 16, 16]},                                  # :704
+    "sequential_vae_lsun_final": {"vlae_latent_dims": [20, 30, 30, 30], "intermediate_reconstruction": False},   # :721
 }
 
 
@@ -30,6 +43,7 @@ def hyperparams(name, data_dims, data_range, **overrides):
         latent_mean_clip=math.inf, latent_prior_stddev=1.0, max_highway_ratio=1.0, min_highway_ratio=0.0,
         learning_rate=0.0002, learning_rate_decay=1.0, reg_coeff_rate=5000.0, save_freq=2000,
         clip_grads=True, clip_grad_value=10.0,
+        share_theta_weights=False, share_phi_weights=False,
     )
     row = dict(NETNAMES[name])
     if "filter_sizes" in row:
@@ -73,4 +87,6 @@ def to_cabi_config(hp, max_batch, train=True, operand_dtype="fp32"):
     cfg.max_batch = int(max_batch)
     cfg.train_capacity = int(bool(train))
     cfg.operand_dtype = {"fp32": _cabi.OPERAND_FP32, "bf16": _cabi.OPERAND_BF16}[operand_dtype]
+    cfg.share_theta_weights = int(bool(hp.get("share_theta_weights", False)))
+    cfg.share_phi_weights = int(bool(hp.get("share_phi_weights", False)))
     return cfg

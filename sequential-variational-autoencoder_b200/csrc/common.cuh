@@ -309,6 +309,14 @@ int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, co
 // dyn != NULL: the step size is read from dyn->lr_t (lr_t ignored)
 int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, const SvaeDyn* dyn, float lr_t,
                 float beta1, float beta2, float eps, float clip, float grad_scale);
+// A run of tied gradient slices (homogeneous chains): `members` slices of `n` floats (multiple of 4) at element offsets off[]
+// of the gradient arena; tie_reduce leaves their element-wise sum (members added in ascending order) in every slice.
+struct TieRun {
+  int64_t n;
+  int members;
+  int64_t off[64];   // SVAE_MAX_STEPS (static_assert in model.cu)
+};
+int tie_reduce(const LaunchCtx& lc, float* grad_arena, const TieRun& run);
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base);
 int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n);  // dst += src
 

@@ -917,6 +917,27 @@ int adam_update(const LaunchCtx& lc, float* p, const float* g, float* m, float* 
   return 0;
 }
 
+// Homogeneous chains: sum of the per-step gradient slices of the shared variables, written back to every slice.  Pure HBM
+// streaming: (members reads + members writes) * 4 B per element, 16-byte accesses, grid sized to the SM count.
+__global__ void __launch_bounds__(256) tie_reduce_kernel(float* __restrict__ G, TieRun r) {
+  const int64_t n4 = r.n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = reinterpret_cast<const float4*>(G + r.off[0])[i];
+    for (int m = 1; m < r.members; ++m) {
+      const float4 v = reinterpret_cast<const float4*>(G + r.off[m])[i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    for (int m = 0; m < r.members; ++m) reinterpret_cast<float4*>(G + r.off[m])[i] = s;
+  }
+}
+
+int tie_reduce(const LaunchCtx& lc, float* G, const TieRun& run) {
+  ProfScope ps(lc, KC_MISC, (double)run.members * run.n, 8.0 * run.members * run.n);
+  tie_reduce_kernel<<<flat_blocks(run.n >> 2, lc.sm_count), 256, 0, lc.stream>>>(G, run);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base) {
   ProfScope ps(lc, KC_MISC, 60.0 * n, 4.0 * n);
   fill_normal_kernel<<<flat_blocks(n, lc.sm_count), 256, 0, lc.stream>>>(dst, n, seed, counter_base);

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,13 @@ struct Param {
   int shape[4];
   int64_t numel, offset;
   int step, flags;
+};
+
+static_assert(sizeof(TieRun::off) / sizeof(int64_t) == SVAE_MAX_STEPS, "TieRun holds one offset per chain step");
+
+struct PubParam {   // a variable as callers see it: one TF name, >= 1 per-step slices (see svae_handle::pub)
+  std::string name;
+  std::vector<int> members;   // indices into svae_handle::params, ascending chain step
 };
 
 // contraction + batch-norm + activation (conv2d_bn_lrelu / conv2d_t_bn[_relu] / fc_bn_lrelu, abstract_network.py:17-71)
@@ -169,6 +177,14 @@ struct svae_handle {
   // parameters
   std::vector<Param> params;
   int64_t arena_numel = 0;
+  // Homogeneous chains (share_theta_weights / share_phi_weights, sequential_vae.py:213-214): the engine keeps one parameter
+  // slice per chain step (`params`, above) and TIES the slices of a shared variable - they start equal (svae_param_set /
+  // svae_adam_set write every member), receive the same summed gradient (tie_reduce after the backward) and therefore the
+  // same deterministic element-wise Adam update, so they stay bit-identical.  `pub` is the variable table callers see:
+  // one entry per TF variable ("phi/inference_network/...", "theta/generative_network/..."), members = its step slices.
+  std::vector<PubParam> pub;
+  std::vector<TieRun> tie_runs;      // contiguous runs of tied slices (what tie_reduce sums)
+  bool tied = false;
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
   int64_t adam_t = 0;
   bool weights_dirty = true;
@@ -435,6 +451,58 @@ void build_params(svae_handle* h) {
     }
     s.p_end = h->arena_numel;
   }
+}
+
+// The caller-visible variable table (see svae_handle::pub).  Shared scopes follow the reference's scope names:
+// "phi/inference_network" (sequential_vae.py:1573-1577), "theta/generative_encoder_network" (:1757-1761) and
+// "theta/generative_network" for steps t >= 1 (:1683-1687; step 0 has no chain input and keeps "theta/generative_step_0").
+// Entries appear in order of first use, which is the order TF creates the variables in (construct_network, :934-975).
+void build_pub(svae_handle* h) {
+  const bool st = h->cfg.share_theta_weights != 0, sp = h->cfg.share_phi_weights != 0;
+  h->pub.clear();
+  h->tie_runs.clear();
+  std::map<std::string, int> index;
+  for (int i = 0; i < (int)h->params.size(); ++i) {
+    const Param& p = h->params[i];
+    std::string name = p.name;
+    auto rescoped = [&](const char* per_step, const char* shared) {
+      const std::string pre = std::string(per_step) + std::to_string(p.step) + "/";
+      if (name.compare(0, pre.size(), pre) == 0) { name = std::string(shared) + "/" + name.substr(pre.size()); return true; }
+      return false;
+    };
+    if (sp) rescoped("phi/inference_step_", "phi/inference_network");
+    if (st && !rescoped("theta/generative_encoder_step_", "theta/generative_encoder_network") && p.step >= 1)
+      rescoped("theta/generative_step_", "theta/generative_network");
+    auto it = index.find(name);
+    if (it == index.end()) {
+      index[name] = (int)h->pub.size();
+      h->pub.push_back(PubParam{name, {i}});
+    } else {
+      h->pub[it->second].members.push_back(i);
+    }
+  }
+  // contiguous runs of tied slices: consecutive variables whose members are laid out back to back in every step
+  for (const PubParam& q : h->pub) {
+    if (q.members.size() < 2) continue;
+    const Param& p0 = h->params[q.members[0]];
+    const int64_t padded = (p0.numel + 3) / 4 * 4;
+    bool extend = !h->tie_runs.empty() && h->tie_runs.back().members == (int)q.members.size();
+    if (extend) {
+      const TieRun& r = h->tie_runs.back();
+      for (size_t m = 0; m < q.members.size(); ++m)
+        if (r.off[m] + r.n != h->params[q.members[m]].offset) extend = false;
+    }
+    if (extend) {
+      h->tie_runs.back().n += padded;
+    } else {
+      TieRun r{};
+      r.n = padded;
+      r.members = (int)q.members.size();
+      for (size_t m = 0; m < q.members.size(); ++m) r.off[m] = h->params[q.members[m]].offset;
+      h->tie_runs.push_back(r);
+    }
+  }
+  h->tied = !h->tie_runs.empty();
 }
 
 // ---- activation arena ----------------------------------------------------------------------------------------------
@@ -1351,6 +1419,13 @@ int backward_impl(svae_handle* h) {
     H_TRY(link(h, h->upd_stream, h->stream));   // the next step reads the updated weights and operand copies
   }
   if (h->bucket_update) h->weights_dirty = false;
+  // homogeneous chain: every slice of a shared variable receives the gradient summed over the chain steps (and, when data
+  // parallel, over the ranks: the per-step buckets above were all-reduced first; both sums commute)
+  if (h->tied) {
+    h->cur = h->stream;
+    LaunchCtx lc = h->lc();
+    for (const TieRun& r : h->tie_runs) H_TRY(tie_reduce(lc, h->G, r));
+  }
   h->have_fwd = false;
   return 0;
 }
@@ -1546,9 +1621,10 @@ static int validate_cfg(const svae_config* cfg) {
   return 0;
 }
 
-static void fill_info(const Param& p, svae_param_info* o) {
+static void fill_info(const svae_handle* h, int i, svae_param_info* o) {
+  const Param& p = h->params[h->pub[i].members[0]];
   memset(o, 0, sizeof *o);
-  snprintf(o->name, SVAE_NAME_LEN, "%s", p.name.c_str());
+  snprintf(o->name, SVAE_NAME_LEN, "%s", h->pub[i].name.c_str());
   o->ndim = p.ndim;
   for (int k = 0; k < 4; ++k) o->shape[k] = p.shape[k];
   o->numel = p.numel; o->offset = p.offset; o->step = p.step; o->flags = p.flags;
@@ -1562,9 +1638,10 @@ int svae_param_table(const svae_config* cfg, svae_param_info* out, int capacity)
   h->cfg = *cfg;
   h->L = cfg->levels; h->T = cfg->mc_steps; h->D = cfg->height; h->C = cfg->channels;
   build_params(h);
-  const int n = (int)h->params.size();
+  build_pub(h);
+  const int n = (int)h->pub.size();
   if (out)
-    for (int i = 0; i < n && i < capacity; ++i) fill_info(h->params[i], &out[i]);
+    for (int i = 0; i < n && i < capacity; ++i) fill_info(h, i, &out[i]);
   delete h;
   return n;
 }
@@ -1640,6 +1717,10 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
   C_CUDA(cudaMallocHost((void**)&h->dyn_ring, sizeof(SvaeDyn) * 256));
   h->dyn_ev.assign(256, nullptr);
   build_params(h);
+  build_pub(h);
+  // tied slices only hold their final gradient after the whole backward: no per-chain-step update
+  if (h->tied) h->use_bucket_update = false;
+
   const size_t pbytes = (size_t)h->arena_numel * 4;
   C_CUDA(cudaMalloc(&h->P, pbytes));
   C_CUDA(cudaMemset(h->P, 0, pbytes));
@@ -1715,19 +1796,29 @@ int svae_sync(svae_handle* h) {
   return SVAE_OK;
 }
 
-int svae_param_count(const svae_handle* h) { return h ? (int)h->params.size() : SVAE_EINVAL; }
+int svae_param_count(const svae_handle* h) { return h ? (int)h->pub.size() : SVAE_EINVAL; }
 int svae_param_info_get(const svae_handle* h, int i, svae_param_info* o) {
-  if (!h || !o || i < 0 || i >= (int)h->params.size()) return SVAE_EINVAL;
-  fill_info(h->params[i], o);
+  if (!h || !o || i < 0 || i >= (int)h->pub.size()) return SVAE_EINVAL;
+  fill_info(h, i, o);
   return SVAE_OK;
 }
+// `i` indexes the caller-visible table (svae_handle::pub).  Uploads go to every tied slice; reads take the first one (the
+// slices of a shared variable are bit-identical, and after svae_backward each holds the gradient summed over the chain).
 static int param_copy(svae_handle* h, float* arena, int i, float* host, bool to_dev) {
-  if (!h || !host || i < 0 || i >= (int)h->params.size() || !arena) return fail(h, SVAE_EINVAL, "bad parameter index or arena");
+  if (!h || !host || i < 0 || i >= (int)h->pub.size() || !arena) return fail(h, SVAE_EINVAL, "bad parameter index or arena");
   H_CUDA(cudaSetDevice(h->device));
-  const Param& p = h->params[i];
   H_CUDA(cudaStreamSynchronize(h->stream));
-  if (to_dev) H_CUDA(cudaMemcpy(arena + p.offset, host, p.numel * 4, cudaMemcpyHostToDevice));
-  else H_CUDA(cudaMemcpy(host, arena + p.offset, p.numel * 4, cudaMemcpyDeviceToHost));
+  if (h->upd_stream) H_CUDA(cudaStreamSynchronize(h->upd_stream));
+  const PubParam& q = h->pub[i];
+  if (to_dev) {
+    for (int m : q.members) {
+      const Param& p = h->params[m];
+      H_CUDA(cudaMemcpy(arena + p.offset, host, p.numel * 4, cudaMemcpyHostToDevice));
+    }
+  } else {
+    const Param& p = h->params[q.members[0]];
+    H_CUDA(cudaMemcpy(host, arena + p.offset, p.numel * 4, cudaMemcpyDeviceToHost));
+  }
   return SVAE_OK;
 }
 int svae_param_set(svae_handle* h, int i, const float* src) {

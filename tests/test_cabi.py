@@ -41,7 +41,12 @@ def test_struct_layouts_match_header():
 
 @pytest.mark.parametrize("name,dims,rng", [("c_inhomog", [64, 64, 3], (-1, 1)), ("m_inhomog", [32, 32, 1], (0, 1)),
                                            ("sequential_vae_lsun", [64, 64, 3], (-1, 1)),
-                                           ("sequential_vae_celebA_inhomog", [64, 64, 3], (-1, 1))])
+                                           ("sequential_vae_celebA_inhomog", [64, 64, 3], (-1, 1)),
+                                           ("sequential_vae_celebA_homog", [64, 64, 3], (-1, 1)),
+                                           ("sequential_vae_celebA_homog_fixed_length", [64, 64, 3], (-1, 1)),
+                                           ("c_homog", [64, 64, 3], (-1, 1)), ("c_homog_v1", [32, 32, 3], (0, 1)),
+                                           ("c_homog_one_step", [32, 32, 3], (0, 1)), ("vlae_celebA", [64, 64, 3], (-1, 1)),
+                                           ("sequential_vae_lsun_final", [64, 64, 3], (-1, 1))])
 def test_param_table_matches_oracle(name, dims, rng):
     L = _cabi.lib()
     cfg = to_cabi_config(S.hyperparams(name, dims, rng), 100)
@@ -61,7 +66,11 @@ def test_param_table_matches_oracle(name, dims, rng):
         assert bool(a.flags & _cabi.PF_THETA) == s["name"].startswith("theta/")
         assert a.offset >= off and a.offset % 4 == 0
         off = a.offset + a.numel
-        assert a.step == int(re.search(r"step_(\d+)", s["name"]).group(1))
+        m = re.search(r"step_(\d+)", s["name"])
+        if m:
+            assert a.step == int(m.group(1))
+        else:       # shared scope (homogeneous chain): owned by the first step that uses it
+            assert a.step == (0 if s["name"].startswith("phi/inference_network") else 1)
 
 
 def test_invalid_configs_are_rejected():
@@ -85,6 +94,26 @@ def test_unknown_netname_and_bad_image_sizes():
         S.hyperparams("m_inhomog", [64, 64, 1], (0, 1))             # image_sizes [32,16,8,4] vs 64x64 input (:1617-1627)
 
 
+def test_shared_scopes_hold_one_copy():
+    """sequential_vae.py:1573-1577,1683-1687,1757-1761: a homogeneous chain has ONE recognition net, ONE chain encoder and
+    ONE decoder for steps >= 1 (+ step 0's own decoder), whatever the chain length."""
+    names = lambda hp: [s["name"] for s in O.param_specs(hp)]
+    a = names(O.hyperparams("sequential_vae_celebA_homog", [64, 64, 3], (-1, 1)))
+    b = names(O.hyperparams("c_homog", [64, 64, 3], (-1, 1)))                      # same nets, 25 steps
+    assert a == b and len(set(a)) == len(a)
+    scopes = []
+    for n in a:
+        sc = "/".join(n.split("/")[:2])
+        if sc not in scopes:
+            scopes.append(sc)
+    assert scopes == ["phi/inference_network", "theta/generative_step_0", "theta/generative_encoder_network",
+                      "theta/generative_network"]
+    inh = O.param_specs(O.hyperparams("c_inhomog", [64, 64, 3], (-1, 1)))
+    per_step = [s for s in inh if "_step_1/" in s["name"]]
+    step0_dec = [s for s in inh if s["name"].startswith("theta/generative_step_0/")]
+    assert len(a) == len(per_step) + len(step0_dec)
+
+
 def test_netname_rows():
     hp = S.hyperparams("m_inhomog", [32, 32, 1], (0, 1))
     assert (hp["vlae_levels"], hp["mc_steps"], hp["latent_dim"]) == (3, 5, 6)
@@ -93,8 +122,14 @@ def test_netname_rows():
     assert hp["latent_dim"] == 110 and hp["mc_steps"] == 8
     hp = S.hyperparams("c_inhomog", [64, 64, 3], (-1, 1))
     assert hp["filter_sizes"] == [3, 32, 64, 128, 384, 512] and hp["learning_rate"] == 2e-4
-    for k, v in O.hyperparams("c_inhomog", [64, 64, 3], (-1, 1)).items():       # product table == oracle table
-        assert hp[k] == v, k
+    for name in S.NETNAMES:                                                      # product table == oracle table
+        hp = S.hyperparams(name, [32, 32, 3] if name.startswith("m_") is False else [32, 32, 1], (-1, 1))
+        for k, v in O.hyperparams(name, hp["data_dims"], (-1, 1)).items():
+            assert hp[k] == v, (name, k)
+    assert set(S.NETNAMES) == set(O._NETNAMES)
+    hp = S.hyperparams("c_homog", [64, 64, 3], (-1, 1))
+    assert hp["mc_steps"] == 25 and hp["share_theta_weights"] and hp["share_phi_weights"]
+    assert not S.hyperparams("sequential_vae_celebA_homog_fixed_length", [64, 64, 3], (-1, 1))["share_phi_weights"]
 
 
 def test_no_gpu_means_loud_failure():
