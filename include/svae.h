@@ -117,6 +117,13 @@ int svae_param_count(const svae_handle* h);
  * negative SVAE_E* code) and fills up to `capacity` entries of `out` (may be NULL). */
 int svae_param_table(const svae_config* cfg, svae_param_info* out, int capacity);
 int svae_param_info_get(const svae_handle* h, int index, svae_param_info* out);
+/* Homogeneous chains (share_theta_weights / share_phi_weights): a shared variable appears ONCE in the table, under the
+ * reference's shared scope name ("phi/inference_network/...", "theta/generative_encoder_network/...",
+ * "theta/generative_network/..."; sequential_vae.py:1573-1577,1683-1687,1757-1761).  Inside the arenas it is kept as one
+ * slice per chain step that uses it; the slices are tied (equal values, equal Adam slots, each receives the gradient
+ * summed over the chain).  svae_param_slices returns the number of slices of variable `index` and writes up to `capacity`
+ * of their arena element offsets (the first equals svae_param_info.offset); 1 for a variable that is not shared. */
+int svae_param_slices(const svae_handle* h, int index, int64_t* offsets_out, int capacity);
 int svae_param_set(svae_handle* h, int index, const float* host_src);   /* reference layout (HWIO / [kh,kw,out,in] / [in,out]) */
 int svae_param_get(svae_handle* h, int index, float* host_dst);
 int svae_grad_get(svae_handle* h, int index, float* host_dst);          /* gradient of the last svae_backward */
@@ -127,6 +134,9 @@ int svae_adam_set_step_count(svae_handle* h, int64_t t);
 void* svae_param_arena(svae_handle* h); /* device base pointers of the flat fp32 arenas (offsets from param_info) */
 void* svae_grad_arena(svae_handle* h);
 int64_t svae_arena_numel(const svae_handle* h);
+/* Copy `n` floats starting at element `offset` of arena `which` (0 parameters, 1 gradients, 2 Adam m, 3 Adam v) to host
+ * memory; synchronises.  With svae_param_slices this reads an individual slice of a shared variable. */
+int svae_arena_read(svae_handle* h, int which, int64_t offset, int64_t n, float* host_dst);
 
 /* ---- training-mode chain ----------------------------------------------------------------------------------------
  * svae_forward replaces sess.run(self.training_mles / training_samples / loss) (sequential_vae.py:1381-1391,
@@ -153,6 +163,27 @@ int svae_train_step(svae_handle* h, const float* x_in_dev, const float* x_tgt_de
 int svae_train_step_host(svae_handle* h, const float* x_in_host, const float* x_tgt_host, int batch,
                          const float* eps_host, uint64_t seed, float learning_rate, float reg_coeff,
                          svae_losses* losses_out);
+/* ---- denoising corruption (the host step in front of train/test) -------------------------------------------------------
+ * Replaces NoisyTrainer.apply_noise (trainer.py:56-78; constants pepper_prob = salt_prob = gaussian_noise_scale = 0.1,
+ * trainer.py:16-18):  out = clip(x * Bernoulli(1 - pepper_prob) + Bernoulli(salt_prob) + N(0, gaussian_scale), lo, hi)
+ * element-wise over `n` floats, drawn on the device with counter-based Philox4x32-10 keyed by `seed` (the reference uses
+ * the unseeded numpy global RNG on the host).  In place (out_dev == x_dev) is allowed.  draws_out_dev: optional [3,n]
+ * buffer receiving the three random fields (keep mask, salt mask, Gaussian term) so that a checker can replay
+ * trainer.py:69-78 on the same draws. */
+int svae_apply_noise(svae_handle* h, const float* x_dev, float* out_dev, int64_t n, float pepper_prob, float salt_prob,
+                     float gaussian_scale, float clip_lo, float clip_hi, uint64_t seed, float* draws_out_dev);
+/* Same through host buffers (upload, corrupt, download; synchronises). draws_out_host: optional [3,n]. */
+int svae_apply_noise_host(svae_handle* h, const float* x_host, float* out_host, int64_t n, float pepper_prob,
+                          float salt_prob, float gaussian_scale, float clip_lo, float clip_hi, uint64_t seed,
+                          float* draws_out_host);
+/* One denoising training iteration, trainer.py:100-104 with --denoise_train: the clean batch is uploaded ONCE and is the
+ * target; the network input is its corruption, produced on the device (half the host->device bytes of the reference's
+ * feed, no host RNG).  Clips to the configured range_lo/range_hi (dataset.range, trainer.py:78).  x_noisy_out_host: optional
+ * [B,H,W,C] copy of the corrupted input (what plot_reconstruction shows). */
+int svae_train_step_host_denoise(svae_handle* h, const float* x_clean_host, int batch, const float* eps_host,
+                                 uint64_t seed, float learning_rate, float reg_coeff, float pepper_prob, float salt_prob,
+                                 float gaussian_scale, uint64_t noise_seed, float* x_noisy_out_host,
+                                 svae_losses* losses_out);
 /* SequentialVAE.test / training_mc_samples through host buffers (sequential_vae.py:1381-1391,1434-1455):
  * x_steps_out_host [T,B,H,W,C] (may be NULL), last_out_host [B,H,W,C] (may be NULL). */
 int svae_forward_host(svae_handle* h, const float* x_in_host, const float* x_tgt_host, int batch,

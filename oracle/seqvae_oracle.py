@@ -567,3 +567,19 @@ class OracleModel:
         z = torch.as_tensor(z, dtype=self.dtype)
         with torch.no_grad():
             return generate_chain(self.hp, self.P, z, z.shape[1])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Host step in front of the path: denoising corruption (trainer.py:56-78)
+# --------------------------------------------------------------------------------------------------------------
+
+def apply_noise(original, keep, salt, gauss, data_range):
+    """NoisyTrainer.apply_noise (trainer.py:56-78) with the three random fields passed in instead of drawn from numpy's
+    unseeded global RNG: keep ~ binomial(1, 1 - pepper_prob) (:69), salt ~ binomial(1, salt_prob) (:70),
+    gauss ~ normal(scale=gaussian_noise_scale) (:73); the result is clipped to dataset.range (:76)."""
+    noisy = np.multiply(original, keep) + salt
+    noisy = noisy + gauss
+    return np.clip(noisy, a_min=data_range[0], a_max=data_range[1])
+
+
+NOISE_DEFAULTS = dict(pepper_prob=0.1, salt_prob=0.1, gaussian_noise_scale=0.1)   # trainer.py:16-18

@@ -7,6 +7,7 @@ without the built library or without a CUDA device raises.
 from .config import hyperparams, NETNAMES  # noqa: F401
 from .dataset import Dataset, SyntheticDataset  # noqa: F401
 from .sequential_vae import SequentialVAE  # noqa: F401
+from .trainer import NoisyTrainer  # noqa: F401
 from . import _cabi  # noqa: F401
 
-__all__ = ["SequentialVAE", "SyntheticDataset", "Dataset", "hyperparams", "NETNAMES"]
+__all__ = ["SequentialVAE", "NoisyTrainer", "SyntheticDataset", "Dataset", "hyperparams", "NETNAMES"]

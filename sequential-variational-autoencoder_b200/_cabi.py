@@ -61,6 +61,7 @@ PROTOTYPES = {
     "svae_param_count": (C.c_int, [_P]),
     "svae_param_table": (C.c_int, [C.POINTER(Config), C.POINTER(ParamInfo), C.c_int]),
     "svae_param_info_get": (C.c_int, [_P, C.c_int, C.POINTER(ParamInfo)]),
+    "svae_param_slices": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "svae_param_set": (C.c_int, [_P, C.c_int, _P]),
     "svae_param_get": (C.c_int, [_P, C.c_int, _P]),
     "svae_grad_get": (C.c_int, [_P, C.c_int, _P]),
@@ -71,11 +72,18 @@ PROTOTYPES = {
     "svae_param_arena": (_P, [_P]),
     "svae_grad_arena": (_P, [_P]),
     "svae_arena_numel": (C.c_int64, [_P]),
+    "svae_arena_read": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P]),
     "svae_forward": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_uint64, C.c_float, _P, _P, _P]),
     "svae_backward": (C.c_int, [_P]),
     "svae_adam_step": (C.c_int, [_P, C.c_float]),
     "svae_train_step": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_uint64, C.c_float, C.c_float]),
     "svae_train_step_host": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_uint64, C.c_float, C.c_float, C.POINTER(Losses)]),
+    "svae_apply_noise": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_uint64, _P]),
+    "svae_apply_noise_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_uint64, _P]),
+    "svae_train_step_host_denoise": (C.c_int, [_P, _P, C.c_int, _P, C.c_uint64, C.c_float, C.c_float, C.c_float,
+                                               C.c_float, C.c_float, C.c_uint64, _P, C.POINTER(Losses)]),
     "svae_forward_host": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_uint64, C.c_float, _P, _P, _P, _P, C.POINTER(Losses)]),
     "svae_read_losses": (C.c_int, [_P, C.POINTER(Losses)]),
     "svae_generate": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),

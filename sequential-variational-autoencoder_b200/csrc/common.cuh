@@ -317,6 +317,8 @@ struct TieRun {
   int64_t off[64];   // SVAE_MAX_STEPS (static_assert in model.cu)
 };
 int tie_reduce(const LaunchCtx& lc, float* grad_arena, const TieRun& run);
+int apply_noise(const LaunchCtx& lc, const float* x, float* out, int64_t n, float pepper_prob, float salt_prob, float scale,
+                float lo, float hi, uint64_t seed, float* draws /* [3,n] keep, salt, gaussian; may be nullptr */);
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base);
 int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n);  // dst += src
 

@@ -630,6 +630,62 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t counter) 
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// ---- NoisyTrainer.apply_noise on the device (reference trainer.py:56-78) ---------------------------------------------------
+// noisy = clip(x * Bernoulli(1 - pepper) + Bernoulli(salt) + N(0, scale), lo, hi).  One Philox4x32-10 block serves TWO
+// elements: words 0,1 -> one Box-Muller pair (cos and sin branch), words 2,3 -> four 16-bit uniforms for the Bernoulli draws
+// (probabilities quantised to 1/65536).  8 B of HBM traffic per element against ~80 integer operations: this kernel is bound
+// by the integer pipe (Philox), not by HBM - at the path's batch sizes (1.2 M elements) it is a few microseconds.
+__device__ __forceinline__ void noise_pair(uint64_t seed, uint64_t pair, uint32_t keep_thr, uint32_t salt_thr, float scale,
+                                           float (&keep)[2], float (&salt)[2], float (&gauss)[2]) {
+  uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), 0x6e015e00u, 1u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((float)c[0] + 1.0f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)c[1] + 1.0f) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.f * logf(u1)) * scale;
+  float sn, cs;
+  sincospif(2.f * u2, &sn, &cs);
+  gauss[0] = __fmul_rn(r, cs); gauss[1] = __fmul_rn(r, sn);   // rounded products: never contracted into the add below
+  keep[0] = (c[2] & 0xffffu) < keep_thr ? 1.f : 0.f;
+  keep[1] = (c[2] >> 16) < keep_thr ? 1.f : 0.f;
+  salt[0] = (c[3] & 0xffffu) < salt_thr ? 1.f : 0.f;
+  salt[1] = (c[3] >> 16) < salt_thr ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+apply_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, uint32_t keep_thr, uint32_t salt_thr,
+                   float scale, float lo, float hi, uint64_t seed, float* __restrict__ draws) {
+  const int64_t pairs = (n + 1) >> 1;
+  const bool vec = ((((uintptr_t)x) | ((uintptr_t)out)) & 7) == 0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+    float keep[2], salt[2], gauss[2];
+    noise_pair(seed, (uint64_t)p, keep_thr, salt_thr, scale, keep, salt, gauss);
+    const int64_t i = 2 * p;
+    const bool two = i + 1 < n;
+    float v[2];
+    if (vec && two) { const float2 t = *reinterpret_cast<const float2*>(x + i); v[0] = t.x; v[1] = t.y; }
+    else { v[0] = x[i]; v[1] = two ? x[i + 1] : 0.f; }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      // trainer.py:69-76: original * binomial(1, 1 - pepper) + binomial(1, salt), += normal(scale), clip to dataset.range
+      float y = v[k] * keep[k] + salt[k];
+      y += gauss[k];
+      v[k] = fminf(fmaxf(y, lo), hi);
+    }
+    if (vec && two) *reinterpret_cast<float2*>(out + i) = make_float2(v[0], v[1]);
+    else { out[i] = v[0]; if (two) out[i + 1] = v[1]; }
+    if (draws != nullptr) {
+      draws[i] = keep[0]; draws[n + i] = salt[0]; draws[2 * n + i] = gauss[0];
+      if (two) { draws[i + 1] = keep[1]; draws[n + i + 1] = salt[1]; draws[2 * n + i + 1] = gauss[1]; }
+    }
+  }
+}
+
 __global__ void fill_normal_kernel(float* __restrict__ dst, int64_t n, uint64_t seed, uint64_t base) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = philox_normal(seed, base + (uint64_t)i);
@@ -934,6 +990,16 @@ __global__ void __launch_bounds__(256) tie_reduce_kernel(float* __restrict__ G, 
 int tie_reduce(const LaunchCtx& lc, float* G, const TieRun& run) {
   ProfScope ps(lc, KC_MISC, (double)run.members * run.n, 8.0 * run.members * run.n);
   tie_reduce_kernel<<<flat_blocks(run.n >> 2, lc.sm_count), 256, 0, lc.stream>>>(G, run);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int apply_noise(const LaunchCtx& lc, const float* x, float* out, int64_t n, float pepper_prob, float salt_prob, float scale,
+                float lo, float hi, uint64_t seed, float* draws) {
+  auto thr = [](float p) { p = fminf(fmaxf(p, 0.f), 1.f); return (uint32_t)lrintf(p * 65536.f); };
+  ProfScope ps(lc, KC_MISC, 90.0 * n, 8.0 * n);
+  apply_noise_kernel<<<flat_blocks((n + 1) >> 1, lc.sm_count), 256, 0, lc.stream>>>(x, out, n, thr(1.f - pepper_prob), thr(salt_prob),
+                                                                                  scale, lo, hi, seed, draws);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

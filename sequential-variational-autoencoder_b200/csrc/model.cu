@@ -1802,6 +1802,12 @@ int svae_param_info_get(const svae_handle* h, int i, svae_param_info* o) {
   fill_info(h, i, o);
   return SVAE_OK;
 }
+int svae_param_slices(const svae_handle* h, int i, int64_t* offsets_out, int capacity) {
+  if (!h || i < 0 || i >= (int)h->pub.size()) return SVAE_EINVAL;
+  const PubParam& q = h->pub[i];
+  for (int m = 0; m < (int)q.members.size() && m < capacity && offsets_out; ++m) offsets_out[m] = h->params[q.members[m]].offset;
+  return (int)q.members.size();
+}
 // `i` indexes the caller-visible table (svae_handle::pub).  Uploads go to every tied slice; reads take the first one (the
 // slices of a shared variable are bit-identical, and after svae_backward each holds the gradient summed over the chain).
 static int param_copy(svae_handle* h, float* arena, int i, float* host, bool to_dev) {
@@ -1841,6 +1847,16 @@ int svae_adam_set_step_count(svae_handle* h, int64_t t) { if (!h) return SVAE_EI
 void* svae_param_arena(svae_handle* h) { return h ? h->P : nullptr; }
 void* svae_grad_arena(svae_handle* h) { return h ? h->G : nullptr; }
 int64_t svae_arena_numel(const svae_handle* h) { return h ? h->arena_numel : 0; }
+int svae_arena_read(svae_handle* h, int which, int64_t offset, int64_t n, float* host_dst) {
+  if (!h || !host_dst || which < 0 || which > 3 || offset < 0 || n < 0 || offset + n > h->arena_numel)
+    return fail(h, SVAE_EINVAL, "svae_arena_read: bad arena or range");
+  float* arenas[4] = {h->P, h->G, h->M, h->V};
+  if (!arenas[which]) return fail(h, SVAE_ESTATE, "svae_arena_read: arena not allocated (handle created without train_capacity)");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  H_CUDA(cudaMemcpy(host_dst, arenas[which] + offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return SVAE_OK;
+}
 
 int svae_forward(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float reg,
                  float* mu_out, float* sd_out, float* xs_out) {
@@ -1969,6 +1985,59 @@ int svae_train_step_host(svae_handle* h, const float* x, const float* tgt, int B
     deps = h->in_eps;
   }
   H_TRY(svae_train_step(h, h->in_x, dtgt, B, deps, seed, lr, reg));
+  if (losses) H_TRY(read_losses_impl(h, losses)); else H_CUDA(cudaStreamSynchronize(h->stream));
+  return SVAE_OK;
+}
+int svae_apply_noise(svae_handle* h, const float* x, float* out, int64_t n, float pepper, float salt, float scale, float lo,
+                     float hi, uint64_t seed, float* draws) {
+  if (!h || !x || !out || n < 0) return fail(h, SVAE_EINVAL, "null argument");
+  if (!(pepper >= 0.f && pepper <= 1.f && salt >= 0.f && salt <= 1.f && scale >= 0.f && lo <= hi))
+    return fail(h, SVAE_EINVAL, "svae_apply_noise: probabilities must be in [0,1], scale >= 0, clip_lo <= clip_hi");
+  if (n == 0) return SVAE_OK;
+  H_CUDA(cudaSetDevice(h->device));
+  h->cur = h->stream;
+  h->pdl_prev = 0;
+  LaunchCtx lc = h->lc();
+  lc.pdl_state = nullptr;
+  return apply_noise(lc, x, out, n, pepper, salt, scale, lo, hi, seed, draws);
+}
+int svae_apply_noise_host(svae_handle* h, const float* x, float* out, int64_t n, float pepper, float salt, float scale,
+                          float lo, float hi, uint64_t seed, float* draws) {
+  if (!h || !x || !out || n < 0) return fail(h, SVAE_EINVAL, "null argument");
+  if (n == 0) return SVAE_OK;
+  H_CUDA(cudaSetDevice(h->device));
+  float* buf = nullptr;
+  H_CUDA(cudaMallocAsync((void**)&buf, (size_t)n * 4 * (draws ? 4 : 1), h->stream));
+  int r = SVAE_OK;
+  cudaError_t e = cudaMemcpyAsync(buf, x, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    r = svae_apply_noise(h, buf, buf, n, pepper, salt, scale, lo, hi, seed, draws ? buf + n : nullptr);
+    if (r == 0) e = cudaMemcpyAsync(out, buf, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (r == 0 && e == cudaSuccess && draws) e = cudaMemcpyAsync(draws, buf + n, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream);
+  }
+  cudaFreeAsync(buf, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (r != 0) return r;
+  H_CUDA(e);
+  return SVAE_OK;
+}
+int svae_train_step_host_denoise(svae_handle* h, const float* x, int B, const float* eps, uint64_t seed, float lr, float reg,
+                                 float pepper, float salt, float scale, uint64_t noise_seed, float* noisy_out,
+                                 svae_losses* losses) {
+  if (!h || !x) return fail(h, SVAE_EINVAL, "null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t img = (size_t)B * h->D * h->D * h->C, cap = (size_t)h->cfg.max_batch * h->D * h->D * h->C;
+  H_TRY(stage_in(h, h->in_tgt, &h->pin_tgt, x, img, cap));          // the clean batch: target of every step's ELBO
+  H_TRY(svae_apply_noise(h, h->in_tgt, h->in_x, (int64_t)img, pepper, salt, scale, h->cfg.range_lo, h->cfg.range_hi,
+                         noise_seed, nullptr));                      // its corruption: the network input
+  const float* deps = nullptr;
+  if (eps) {
+    H_TRY(stage_in(h, h->in_eps, &h->pin_eps, eps, (size_t)h->T * B * h->Z, (size_t)h->T * h->cfg.max_batch * h->Z));
+    deps = h->in_eps;
+  }
+  if (noisy_out) H_CUDA(cudaMemcpyAsync(noisy_out, h->in_x, img * 4, cudaMemcpyDeviceToHost, h->stream));
+  H_TRY(svae_train_step(h, h->in_x, h->in_tgt, B, deps, seed, lr, reg));
   if (losses) H_TRY(read_losses_impl(h, losses)); else H_CUDA(cudaStreamSynchronize(h->stream));
   return SVAE_OK;
 }

@@ -59,6 +59,8 @@ class SequentialVAE:
         self.learning_rate = hp["learning_rate"]
         self.learning_rate_decay = hp["learning_rate_decay"]
         self.reg_coeff_rate = hp["reg_coeff_rate"]
+        self.share_theta_weights = bool(hp["share_theta_weights"])        # sequential_vae.py:213-214
+        self.share_phi_weights = bool(hp["share_phi_weights"])
         self.save_freq = hp["save_freq"]
         self.operand_dtype = operand_dtype
         self.device = device
@@ -111,6 +113,25 @@ class SequentialVAE:
     def param_table(self):
         """[{name, shape, flags, step, ...}] in tf.trainable_variables() order."""
         return self._params
+
+    def param_slices(self, name):
+        """Arena element offsets of the per-chain-step slices of variable ``name`` (one for an unshared variable; one per
+        step that uses it for a shared variable of a homogeneous chain, sequential_vae.py:213-214)."""
+        idx = {p["name"]: p["index"] for p in self._params}[name]
+        offs = (C.c_int64 * 64)()
+        n = self._L.svae_param_slices(self._h, idx, offs, 64)
+        if n < 0:
+            self._chk(n)
+        return [int(offs[i]) for i in range(n)]
+
+    def read_arena(self, which="param"):
+        """The whole flat fp32 arena ("param", "grad", "adam_m", "adam_v") as a numpy array (offsets: ``param_table`` /
+        ``param_slices``)."""
+        n = int(self._L.svae_arena_numel(self._h))
+        buf = np.empty(n, np.float32)
+        self._chk(self._L.svae_arena_read(self._h, {"param": 0, "grad": 1, "adam_m": 2, "adam_v": 3}[which], 0, n,
+                                          buf.ctypes.data_as(C.c_void_p)))
+        return buf
 
     def init_network(self, seed=0, restore=True):
         """abstract_network.py:139-152: restore the checkpoint if one exists, else reference initialisers
@@ -267,6 +288,56 @@ class SequentialVAE:
         if self.iteration % self.save_freq == 0:                                     # :1368-1369
             self.save_network()
         return self.last_losses["final_loss"] / self.data_dims[0] / self.data_dims[1]   # :1375
+
+    # --- denoising corruption on the device (NoisyTrainer.apply_noise, trainer.py:56-78; constants trainer.py:16-18)
+    def apply_noise(self, original, pepper_prob=0.1, salt_prob=0.1, gaussian_noise_scale=0.1, seed=0, return_draws=False):
+        """clip(original * Bernoulli(1 - pepper) + Bernoulli(salt) + N(0, scale), *dataset.range) with device-side Philox
+        draws keyed by ``seed``.  numpy in -> numpy out; a torch CUDA tensor is corrupted into a new CUDA tensor without
+        leaving the device.  return_draws: also return the [3, ...] keep / salt / Gaussian fields that were used."""
+        lo, hi = float(self.hp["range"][0]), float(self.hp["range"][1])
+        args = (float(pepper_prob), float(salt_prob), float(gaussian_noise_scale), lo, hi, int(seed))
+        if _is_cuda_tensor(original):
+            import torch
+
+            x = original.contiguous().float()
+            out = torch.empty_like(x)
+            draws = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=x.device) if return_draws else None
+            torch.cuda.current_stream(x.device).synchronize()      # libsvae runs on its own stream
+            self._chk(self._L.svae_apply_noise(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), x.numel(),
+                                               *args, C.c_void_p(draws.data_ptr()) if draws is not None else None))
+            self.sync()
+            return (out, draws) if return_draws else out
+        x = _f32(original)
+        out = np.empty_like(x)
+        draws = np.empty((3,) + x.shape, np.float32) if return_draws else None
+        self._chk(self._L.svae_apply_noise_host(self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                x.size, *args,
+                                                draws.ctypes.data_as(C.c_void_p) if draws is not None else None))
+        return (out, draws) if return_draws else out
+
+    def train_denoise(self, batch_target, pepper_prob=0.1, salt_prob=0.1, gaussian_noise_scale=0.1, eps=None, seed=None,
+                      noise_seed=None, return_input=False):
+        """trainer.py:100-104 with --denoise_train as ONE call: ``train(apply_noise(batch), batch)`` where the corruption
+        happens on the device - the clean batch is uploaded once (half the reference's host->device bytes, no host RNG)."""
+        self.iteration += 1
+        self.learning_rate *= self.learning_rate_decay
+        reg = 1 - math.exp(-self.iteration / self.reg_coeff_rate)                    # :1357
+        seed = int(self.iteration if seed is None else seed)
+        noise_seed = int(self.iteration if noise_seed is None else noise_seed)
+        x = _f32(batch_target)
+        B = self._check_batch(x)
+        e = None if eps is None else _f32(eps)
+        noisy = np.empty_like(x) if return_input else None
+        ls = _cabi.Losses()
+        self._chk(self._L.svae_train_step_host_denoise(
+            self._h, x.ctypes.data_as(C.c_void_p), B, e.ctypes.data_as(C.c_void_p) if e is not None else None, seed,
+            float(self.learning_rate), float(reg), float(pepper_prob), float(salt_prob), float(gaussian_noise_scale),
+            noise_seed, noisy.ctypes.data_as(C.c_void_p) if noisy is not None else None, C.byref(ls)))
+        self.last_losses = self._losses(ls)
+        if self.iteration % self.save_freq == 0:
+            self.save_network()
+        r = self.last_losses["final_loss"] / self.data_dims[0] / self.data_dims[1]
+        return (r, noisy) if return_input else r
 
     def train_async(self, x_dev, tgt_dev, eps_dev=None, seed=None):
         """Device-resident, non-blocking variant of ``train`` for benchmarking: no loss read-back, no sync."""

@@ -1,0 +1,111 @@
+"""GPU parity of the host step in front of the path: the denoising corruption NoisyTrainer.apply_noise (reference
+trainer.py:56-78, constants :16-18) on the device, the one-call denoising train step, and the NoisyTrainer loop mirror.
+
+The reference draws from numpy's unseeded global RNG, so there is nothing to match draw for draw: the arithmetic is checked
+EXACTLY (bit for bit, fp32) against the oracle's restatement of trainer.py:69-78 replayed on the very draws the kernel used
+(svae_apply_noise exports them), and the draws are checked against their distributions."""
+import argparse
+import logging
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import seqvae_b200 as S
+from oracle import seqvae_oracle as O
+from gpu_util import TINY, op_handle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(100, 64, 64, 3), (7, 5, 3), (1,), (2, 1)])
+@pytest.mark.parametrize("via", ["host", "device"])
+def test_apply_noise_matches_oracle_on_the_same_draws(shape, via):
+    model, _, _ = op_handle()                      # range [-1, 1]
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, size=shape).astype(np.float32)
+    if via == "host":
+        out, draws = model.apply_noise(x, 0.1, 0.1, 0.1, seed=11, return_draws=True)
+    else:
+        # an odd element offset makes the buffer only 4-byte aligned: the scalar path of the kernel
+        xd = torch.cat([torch.zeros(1), torch.as_tensor(x).flatten()]).cuda()[1:].view(shape)
+        assert xd.data_ptr() % 8 == 4 and xd.is_contiguous()
+        o, d = model.apply_noise(xd, 0.1, 0.1, 0.1, seed=11, return_draws=True)
+        out, draws = o.cpu().numpy(), d.cpu().numpy()
+    keep, salt, gauss = draws
+    assert set(np.unique(keep)) <= {0.0, 1.0} and set(np.unique(salt)) <= {0.0, 1.0}
+    ref = O.apply_noise(x, keep, salt, gauss, (-1.0, 1.0)).astype(np.float32)
+    assert np.array_equal(out, ref)
+    assert out.min() >= -1.0 and out.max() <= 1.0
+    # same seed -> same draws whatever the route; another seed -> other draws
+    again = model.apply_noise(x, 0.1, 0.1, 0.1, seed=11)
+    assert np.array_equal(again, out)
+    if x.size > 100:
+        assert not np.array_equal(model.apply_noise(x, 0.1, 0.1, 0.1, seed=12), out)
+
+
+def test_apply_noise_draw_statistics():
+    model, _, _ = op_handle()
+    n = 1 << 22
+    x = np.zeros(n, np.float32)
+    _, (keep, salt, gauss) = model.apply_noise(x, 0.1, 0.25, 0.5, seed=3, return_draws=True)
+    s = 4.5 / math.sqrt(n)                                                   # 4.5 sigma of a mean of n draws
+    assert abs(keep.mean() - 0.9) < s * math.sqrt(0.09) + 1e-5                # probabilities are quantised to 1/65536
+    assert abs(salt.mean() - 0.25) < s * math.sqrt(0.1875) + 1e-5
+    assert abs(gauss.mean()) < s * 0.5 and abs(gauss.std() - 0.5) < 2e-3
+    g = gauss / 0.5
+    assert abs((g ** 3).mean()) < 0.01 and abs((g ** 4).mean() - 3.0) < 0.03   # skewness 0, kurtosis 3
+    assert abs(np.mean(np.abs(g) < 1.0) - 0.682689) < 2e-3
+    # independence: the three fields and neighbouring elements (two elements share one Philox block) are uncorrelated
+    for a, b in ((keep, salt), (keep, gauss), (salt, gauss), (gauss[0::2], gauss[1::2]), (keep[0::2], keep[1::2])):
+        assert abs(np.corrcoef(a, b)[0, 1]) < 4.5 / math.sqrt(min(a.size, b.size))
+    # degenerate settings: identity, and all-salt saturating at the upper clip
+    xr = np.random.default_rng(1).uniform(-1, 1, 1000).astype(np.float32)
+    assert np.array_equal(model.apply_noise(xr, 0.0, 0.0, 0.0, seed=1), xr)
+    assert np.array_equal(model.apply_noise(xr, 1.0, 1.0, 0.0, seed=1), np.ones_like(xr))
+    with pytest.raises(S._cabi.SvaeError):
+        model.apply_noise(xr, 1.5, 0.1, 0.1)
+
+
+def test_train_denoise_equals_train_on_the_corrupted_batch():
+    """svae_train_step_host_denoise == apply_noise followed by train(noisy, clean) (trainer.py:100-104)."""
+    B = 6
+    ds = S.SyntheticDataset("x", B, data_dims=[16, 16, 3], data_range=[-1.0, 1.0])
+    a = S.SequentialVAE(ds, B, "c_inhomog", restore=False, **TINY)
+    b = S.SequentialVAE(ds, B, "c_inhomog", restore=False, **TINY)
+    b.set_params(a.get_params())
+    rng = np.random.default_rng(0)
+    for it in range(3):                                          # eager step, then the captured graph
+        x = ds.next_batch(B)
+        eps = rng.normal(size=(a.mc_steps, B, a.latent_dim)).astype(np.float32)
+        ra, noisy = a.train_denoise(x, eps=eps, noise_seed=100 + it, return_input=True)
+        assert np.array_equal(noisy, b.apply_noise(x, seed=100 + it))
+        assert not np.array_equal(noisy, x)
+        rb = b.train(noisy, x, eps)
+        assert math.isclose(ra, rb, rel_tol=1e-4), (it, ra, rb)
+        assert math.isclose(a.last_losses["loss"], b.last_losses["loss"], rel_tol=1e-4)
+    pa, pb = a.get_params(live_only=True), b.get_params(live_only=True)
+    for k in pa:
+        np.testing.assert_allclose(pa[k], pb[k], rtol=0, atol=2e-5, err_msg=k)
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("denoise", [True, False])
+def test_noisy_trainer_loop(denoise):
+    """NoisyTrainer(network, dataset, args, logger, base_dir).train() as main.py drives it (main.py:87-89)."""
+    B = 8
+    ds = S.SyntheticDataset("x", B, data_dims=[16, 16, 3], data_range=[-1.0, 1.0])
+    net = S.SequentialVAE(ds, B, "c_inhomog", restore=False, **TINY)
+    args = argparse.Namespace(batch_size=B, denoise_train=denoise, vis_frequency=4, plot_reconstruction=False, use_gui=False)
+    tr = S.NoisyTrainer(net, ds, args, logging.getLogger("test"), "unused")
+    if not denoise:
+        with pytest.raises(Exception):
+            tr.apply_noise(ds.next_batch(B))                      # trainer.py:66-67
+    before = tr.test(0, num_iters=2)
+    loss = tr.train(max_iters=8)
+    assert net.iteration == 8 and np.isfinite(loss) and np.isfinite(before)
+    # per-pixel error of an untrained net on U[-1,1] data: sum over C of squared error, O(1)
+    assert 0.05 < before < 10.0
+    net.close()

@@ -1,6 +1,8 @@
 """CPU tests of the oracle itself: TF-semantics pinning against an independent naive numpy restatement, finite
 differences, parameter counts derived from the reference graph, golden fixtures (so that the oracle cannot drift)."""
 import math
+import re
+from collections import OrderedDict
 import os
 
 import numpy as np
@@ -200,3 +202,66 @@ def test_train_wrapper_schedules():
     reg = 1 - math.exp(-1 / 5000.0)
     total = sum(16 * float(a) + reg * float(b) for a, b in zip(fw["recon"], fw["kl"]))
     assert math.isclose(float(fw["loss"]), total, rel_tol=1e-12)
+
+
+def test_shared_scopes_gradient_is_the_sum_over_steps():
+    """Homogeneous chain (share_theta_weights / share_phi_weights, sequential_vae.py:213-214): evaluating the SAME values
+    through per-step scopes gives the same forward, and the gradient of a shared variable is the sum of the per-step
+    gradients - what TF's tf.AUTO_REUSE variable sharing computes and what libsvae's tied slices + tie_reduce restate."""
+    over = dict(filter_sizes=[3, 8, 16, 16, 24, 24], vlae_latent_dims=[2, 3, 2, 2], mc_steps=3)
+    hp_h = O.hyperparams("sequential_vae_celebA_homog", [16, 16, 3], (-1.0, 1.0), **over)
+    hp_i = O.hyperparams("c_inhomog", [16, 16, 3], (-1.0, 1.0), **over)
+    assert hp_h["share_theta_weights"] and hp_h["share_phi_weights"] and not hp_i["share_theta_weights"]
+    P_h = O.init_params(hp_h, 3)
+    g = torch.Generator().manual_seed(5)
+    for k in P_h:
+        if k.endswith("/beta") or k.endswith("/biases"):
+            P_h[k] = 0.1 * torch.randn(P_h[k].shape, generator=g, dtype=torch.float64)
+
+    def shared_name(k):
+        m = re.match(r"(phi/inference|theta/generative_encoder|theta/generative)_step_(\d+)/(.*)", k)
+        scope, t, rest = m.group(1), int(m.group(2)), m.group(3)
+        if scope == "theta/generative" and t == 0:
+            return k
+        return scope + "_network/" + rest
+
+    P_i = OrderedDict((s["name"], P_h[shared_name(s["name"])].clone()) for s in O.param_specs(hp_i))
+    x = torch.rand(4, 16, 16, 3, generator=g, dtype=torch.float64) * 2 - 1
+    eps = torch.randn(3, 4, hp_h["latent_dim"], generator=g, dtype=torch.float64)
+    fw_h, g_h = O.loss_and_grads(hp_h, P_h, x, x, eps, 0.7)
+    fw_i, g_i = O.loss_and_grads(hp_i, P_i, x, x, eps, 0.7)
+    assert abs(float(fw_h["loss"]) - float(fw_i["loss"])) < 1e-12
+    for t in range(3):
+        assert torch.equal(fw_h["x"][t], fw_i["x"][t])
+    summed = {}
+    for k, v in g_i.items():
+        if v is not None:
+            summed[shared_name(k)] = summed.get(shared_name(k), 0) + v
+    n_shared = 0
+    for k, v in g_h.items():
+        if v is None:
+            assert k not in summed
+            continue
+        assert torch.allclose(v, summed[k], rtol=1e-10, atol=1e-14), k
+        n_shared += k.startswith(("phi/inference_network", "theta/generative_network", "theta/generative_encoder_network"))
+    assert n_shared > 40
+    # the recognition net is one function of x for every step: identical mu_t, sigma_t along the chain
+    assert torch.equal(fw_h["mu"][0], fw_h["mu"][2]) and torch.equal(fw_h["sigma"][0], fw_h["sigma"][1])
+
+
+def test_apply_noise_restatement():
+    """oracle.apply_noise restates trainer.py:69-78 given the three random fields."""
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, size=(4, 8, 8, 3))
+    keep = rng.binomial(1, 0.9, size=x.shape)
+    salt = rng.binomial(1, 0.1, size=x.shape)
+    gauss = rng.normal(scale=0.1, size=x.shape)
+    out = O.apply_noise(x, keep, salt, gauss, (-1.0, 1.0))
+    assert out.min() >= -1 and out.max() <= 1
+    i = (keep == 1) & (salt == 0)
+    np.testing.assert_allclose(out[i], np.clip(x[i] + gauss[i], -1, 1))
+    i = (keep == 0) & (salt == 1)
+    np.testing.assert_allclose(out[i], np.clip(1 + gauss[i], -1, 1))
+    i = (keep == 0) & (salt == 0)
+    np.testing.assert_allclose(out[i], gauss[i])
+    assert O.NOISE_DEFAULTS == dict(pepper_prob=0.1, salt_prob=0.1, gaussian_noise_scale=0.1)
