@@ -30,6 +30,9 @@ WORKLOADS = {
     "mnist32_b100": ("m_inhomog", "mnist", 100, {}),
     "cifar32_b100": ("c_inhomog", "cifar", 100, {}),
     "lsun64_b256_t16": ("sequential_vae_lsun", "lsun", 256, {"mc_steps": 16}),
+    # homogeneous (weight-shared) chains, SURVEY 8 f1: the same per-image work as celeba64_b100 at T=8
+    "celeba64_b100_homog": ("sequential_vae_celebA_homog", "celebA", 100, {}),
+    "celeba64_b100_homog_t25": ("c_homog", "celebA", 100, {}),
 }
 # Algorithmic work per image (DESIGN.md "Roofline arithmetic")
 ALGO = {
@@ -37,6 +40,8 @@ ALGO = {
     "mnist32_b100": dict(train_flops=4.9002e9, train_bytes=16.46e6),
     "cifar32_b100": dict(train_flops=3.2517e9, train_bytes=22.56e6),
     "lsun64_b256_t16": dict(train_flops=26.8676e9, train_bytes=101.42e6),
+    # 5 x 3.294 M activation elements x 2 B + 40 B x 14.87 M live (shared) parameters / 100
+    "celeba64_b100_homog": dict(train_flops=13.0065e9, train_bytes=38.89e6),
 }
 METRIC = "train img/s (fwd+bwd+ELBO) CelebA-64 SeqVAE @1/2/4/8 B200; sample img/s"
 

@@ -15,6 +15,14 @@ from gpu_util import TINY, make_inputs, make_pair, oracle_mode, rel_err
 from test_gpu_chain import _check_forward, _check_grads, _oracle_pair
 
 pytestmark = pytest.mark.gpu
+# bf16 family: the kernels are compared with the oracle evaluating the SAME graph with the same operands rounded to bf16.  An
+# activation that sits on a bf16 rounding boundary can round the other way in the kernel (fp32 accumulation order) than in the
+# emulation (fp64 accumulation): that element then differs by one bf16 ulp, 2^-8 relative, and so does what it feeds.  The
+# forward bound for the bf16 family is therefore one bf16 ulp of an O(1) activation at step 0, growing 3.5x per chain step (the
+# amplification of any perturbation by this chain at random init, measured on the CPU oracle: tests/test_gpu_chain.py
+# header); the fp32 family keeps a flat 1e-3.
+FWD_TOL = {"fp32": 1e-3, "bf16": 2.0 ** -8}
+FWD_GROWTH = {"fp32": 1.0, "bf16": 3.5}
 SHARED_SCOPES = ("phi/inference_network/", "theta/generative_encoder_network/", "theta/generative_network/")
 
 
@@ -54,7 +62,7 @@ def test_homog_forward_and_gradients_match_oracle(netname, dims, rng, B, over, o
     with oracle_mode(operand):
         fw, grads, fw32, g32 = _oracle_pair(hp, P, x, tgt, eps, 0.6)
     out = model.forward(x.numpy(), tgt.numpy(), eps.numpy(), 0.6)
-    _check_forward(out, fw, operand, fw32)
+    _check_forward(out, fw, operand, fw32, tol=FWD_TOL[operand], growth=FWD_GROWTH[operand])
     model.backward()
     _check_grads(model, grads, hp, operand, g32)
     # every slice of a shared variable holds the summed gradient

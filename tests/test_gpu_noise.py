@@ -86,8 +86,15 @@ def test_train_denoise_equals_train_on_the_corrupted_batch():
         assert math.isclose(ra, rb, rel_tol=1e-4), (it, ra, rb)
         assert math.isclose(a.last_losses["loss"], b.last_losses["loss"], rel_tol=1e-4)
     pa, pb = a.get_params(live_only=True), b.get_params(live_only=True)
+    # Adam's first steps move every weight by ~lr * sign(gradient): an element whose gradient is rounding noise may step the
+    # other way in one of the two runs (atomics order), so a handful of elements may differ by up to 2 * steps * lr
+    n = bad = 0
     for k in pa:
-        np.testing.assert_allclose(pa[k], pb[k], rtol=0, atol=2e-5, err_msg=k)
+        d = np.abs(pa[k].astype(np.float64) - pb[k])
+        assert d.max() <= 2 * 3 * 2e-4 * 1.01, k
+        n += d.size
+        bad += int((d > 2e-5).sum())
+    assert bad <= 1e-3 * n, (bad, n)
     a.close()
     b.close()
 
