@@ -1591,7 +1591,15 @@ int ensure_io_steps(svae_handle* h, size_t elems) {
 }
 
 int stage_in(svae_handle* h, float* dev, float** pin, const float* host, size_t elems, size_t cap_elems) {
-  // host -> pinned staging -> device (pinned staging keeps the copy asynchronous for pageable callers)
+  // Caller's buffer already page-locked (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor viewed as numpy): the
+  // DMA engine reads it directly.  Pageable memory goes through the handle's pinned staging buffer, which keeps the copy
+  // asynchronous but costs one host memcpy (~1 ms for the 9.8 MB of a CelebA B=100 input + target).
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+    H_CUDA(cudaMemcpyAsync(dev, host, elems * 4, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  }
+  cudaGetLastError();
   if (*pin == nullptr) H_CUDA(cudaMallocHost((void**)pin, cap_elems * 4));
   memcpy(*pin, host, elems * 4);
   H_CUDA(cudaMemcpyAsync(dev, *pin, elems * 4, cudaMemcpyHostToDevice, h->stream));

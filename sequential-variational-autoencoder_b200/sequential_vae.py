@@ -20,6 +20,7 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _cabi
+from .checkpoint import adam_t_from_beta1_power, beta_powers, tf_checkpoint_layout
 from .config import hyperparams, to_cabi_config
 
 
@@ -197,23 +198,45 @@ class SequentialVAE:
 
     # ------------------------------------------------------------------------------------------------ checkpoint
     def save_network(self):
-        """abstract_network.py:124-135 (tf.train.Saver) -> one .npz keyed by the TF variable names, with the Adam slots
-        ``<var>/Adam``, ``<var>/Adam_1`` and the step / iteration counters (the reference forgets the latter two)."""
+        """abstract_network.py:124-135 (tf.train.Saver) -> one .npz holding exactly the variable set the TF Saver writes
+        (``checkpoint.tf_checkpoint_layout``: trainable variables, batch-norm moving statistics, Adam slots, beta powers)
+        plus the host-side schedule state the reference forgets (``__iteration``, ``__learning_rate``, ``__adam_t``).  An
+        existing file is moved to ``<models>/old`` first, like the reference."""
         os.makedirs(self.base_dir, exist_ok=True)
         path = os.path.join(self.base_dir, self.name + ".npz")
         if os.path.exists(path):
             old = os.path.join(os.path.dirname(self.base_dir) or ".", "old")
             os.makedirs(old, exist_ok=True)
-            os.replace(path, os.path.join(old, os.path.basename(path)))
-        blob = dict(self.get_params())
-        if self._cfg.train_capacity:
+            os.replace(path, os.path.join(old, self.name + "_v" + str(self.version) + ".npz"))
+        train = bool(self._cfg.train_capacity)
+        values = self.get_params()
+        slots = {}
+        if train:
             for p in self._params:
                 m = np.empty(p["shape"], np.float32)
                 v = np.empty(p["shape"], np.float32)
                 self._chk(self._L.svae_adam_get(self._h, p["index"], m.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
-                blob[p["name"] + "/Adam"] = m
-                blob[p["name"] + "/Adam_1"] = v
-            blob["__adam_t"] = np.int64(self._L.svae_adam_step_count(self._h))
+                slots[p["name"]] = (m, v)
+        adam_t = int(self._L.svae_adam_step_count(self._h)) if train else 0
+        b1p, b2p = beta_powers(adam_t, self._cfg.adam_beta1, self._cfg.adam_beta2)
+        blob = {}
+        for name, shape, kind, src in tf_checkpoint_layout(self._params, train):
+            if kind == "param":
+                blob[name] = values[src]
+            elif kind == "bn_moving_mean":
+                blob[name] = np.zeros(shape, np.float32)          # never updated by the reference (SURVEY Q1)
+            elif kind == "bn_moving_variance":
+                blob[name] = np.ones(shape, np.float32)
+            elif kind == "adam_m":
+                blob[name] = slots[src][0]
+            elif kind == "adam_v":
+                blob[name] = slots[src][1]
+            elif kind == "beta1_power":
+                blob[name] = np.float32(b1p)
+            elif kind == "beta2_power":
+                blob[name] = np.float32(b2p)
+        if train:
+            blob["__adam_t"] = np.int64(adam_t)
         blob["__iteration"] = np.int64(self.iteration)
         blob["__learning_rate"] = np.float64(self.learning_rate)
         np.savez(path, **blob)
@@ -221,14 +244,29 @@ class SequentialVAE:
         return path
 
     def load_network(self, path):
+        """Restore from ``save_network``'s file (or any .npz keyed by the TF variable names, e.g. a converted TF checkpoint):
+        every trainable variable must be present (tf.train.Saver.restore fails on a missing key too); Adam slots, beta
+        powers and the schedule keys are optional."""
         blob = np.load(path)
+        missing = [p["name"] for p in self._params if p["name"] not in blob.files]
+        if missing:
+            raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (path, len(missing), missing[0]))
         self.set_params({p["name"]: blob[p["name"]] for p in self._params})
-        if self._cfg.train_capacity and "__adam_t" in blob:
+        if self._cfg.train_capacity:
+            have_slots = False
             for p in self._params:
-                m, v = _f32(blob[p["name"] + "/Adam"]), _f32(blob[p["name"] + "/Adam_1"])
+                if p["name"] + "/Adam" in blob.files:
+                    m, v = _f32(blob[p["name"] + "/Adam"]), _f32(blob[p["name"] + "/Adam_1"])
+                    have_slots = True
+                else:                                       # dead-branch variables have no slots in a TF checkpoint
+                    m = v = np.zeros(p["shape"], np.float32)
                 self._chk(self._L.svae_adam_set(self._h, p["index"], m.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
-            self._chk(self._L.svae_adam_set_step_count(self._h, int(blob["__adam_t"])))
-        if "__iteration" in blob:
+            if "__adam_t" in blob.files:
+                self._chk(self._L.svae_adam_set_step_count(self._h, int(blob["__adam_t"])))
+            elif have_slots and "beta1_power" in blob.files:
+                self._chk(self._L.svae_adam_set_step_count(
+                    self._h, adam_t_from_beta1_power(blob["beta1_power"], self._cfg.adam_beta1)))
+        if "__iteration" in blob.files:
             self.iteration = int(blob["__iteration"])
             self.learning_rate = float(blob["__learning_rate"])
 

@@ -41,12 +41,16 @@ def main():
     faulthandler.dump_traceback_later(150, exit=True)   # a hung collective must become a failed test, not a stuck box
     backend = sys.argv[1]
     out_path = sys.argv[2]
+    # optional third argument: netname (a homogeneous chain exercises the tied slices under the all-reduce)
+    net = sys.argv[3] if len(sys.argv) > 3 else "c_inhomog"
+    if net != "c_inhomog":
+        OVER["mc_steps"] = 3
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if backend == "nccl":
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group(backend)
-    hp = O.hyperparams("c_inhomog", DIMS, RNG, **OVER)
+    hp = O.hyperparams(net, DIMS, RNG, **OVER)
     P = O.init_params(hp, 0)
     x, eps = inputs(hp)
     lo, hi = shard_batch(GB, rank, world)
@@ -90,7 +94,7 @@ def main():
     else:
         dev = int(os.environ["LOCAL_RANK"])
         ds = S.SyntheticDataset("x", hi - lo, data_dims=DIMS, data_range=list(RNG))
-        model = S.SequentialVAE(ds, hi - lo, "c_inhomog", device=dev, restore=False, **OVER)
+        model = S.SequentialVAE(ds, hi - lo, net, device=dev, restore=False, **OVER)
         model.set_params({k: v.numpy() for k, v in P.items()})
         attach_communicator(model, dist, rank, world)
         model.iteration = 4999          # reg_coeff = 1 - exp(-1) on the step below
@@ -108,7 +112,7 @@ def main():
             for r in range(world):
                 a, b = shard_batch(GB, r, world)
                 dsr = S.SyntheticDataset("x", b - a, data_dims=DIMS, data_range=list(RNG))
-                m2 = S.SequentialVAE(dsr, b - a, "c_inhomog", device=dev, restore=False, **OVER)
+                m2 = S.SequentialVAE(dsr, b - a, net, device=dev, restore=False, **OVER)
                 m2.set_params({k: v.numpy() for k, v in P.items()})
                 m2.forward(x[a:b].numpy(), None, eps[:, a:b].numpy(), reg)
                 m2.backward()
@@ -137,6 +141,19 @@ def main():
         dist.all_reduce(same2, op=dist.ReduceOp.MIN)
         if rank == 0:
             result["all_same_after_graph_steps"] = bool(same2.item())
+        # homogeneous chain: the per-step slices of every shared variable must still be bit-identical on every rank
+        arena = model.read_arena("param")
+        tied = 1
+        for p in model.param_table:
+            offs = model.param_slices(p["name"])
+            for o in offs[1:]:
+                if not np.array_equal(arena[offs[0]:offs[0] + p["numel"]], arena[o:o + p["numel"]]):
+                    tied = 0
+        tied = torch.tensor([tied], device="cuda")
+        dist.all_reduce(tied, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            result["slices_tied"] = bool(tied.item())
+            result["shared_variables"] = sum(1 for p in model.param_table if len(model.param_slices(p["name"])) > 1)
         model.close()
     if rank == 0:
         with open(out_path, "w") as f:

@@ -161,3 +161,36 @@ def test_synthetic_dataset_shapes():
     assert b.shape == (3, 64, 64, 3) and -1 <= b.min() and b.max() <= 1
     ds.reset()
     np.testing.assert_array_equal(ds.next_test_batch(3), b)
+
+
+def test_checkpoint_layout_is_the_tf_saver_variable_set():
+    """abstract_network.py:124-152: tf.train.Saver() writes every global variable - trainables, BN moving statistics,
+    Adam slots of the variables that receive a gradient (not the dead branch), beta powers."""
+    from seqvae_b200.checkpoint import adam_t_from_beta1_power, beta_powers, tf_checkpoint_layout
+
+    L = _cabi.lib()
+    for name, shared in (("c_inhomog", False), ("sequential_vae_celebA_homog", True)):
+        cfg = to_cabi_config(S.hyperparams(name, [64, 64, 3], (-1, 1)), 100)
+        n = L.svae_param_table(C.byref(cfg), None, 0)
+        arr = (_cabi.ParamInfo * n)()
+        L.svae_param_table(C.byref(cfg), arr, n)
+        table = [dict(name=a.name.decode(), shape=tuple(a.shape[:a.ndim]), flags=a.flags) for a in arr]
+        lay = tf_checkpoint_layout(table, train=True)
+        names = [e[0] for e in lay]
+        assert len(set(names)) == len(names)
+        kinds = {}
+        for e in lay:
+            kinds[e[2]] = kinds.get(e[2], 0) + 1
+        n_bn = sum(1 for t in table if t["name"].endswith("/beta"))
+        n_dead = sum(1 for t in table if t["flags"] & _cabi.PF_DEAD)
+        assert kinds["param"] == n and kinds["bn_moving_mean"] == kinds["bn_moving_variance"] == n_bn
+        assert kinds["adam_m"] == kinds["adam_v"] == n - n_dead and kinds["beta1_power"] == kinds["beta2_power"] == 1
+        if not shared:
+            assert n == 782 and n_dead == 6 * 8        # SURVEY 8c: 782 trainable tensors; 6 dead-branch variables per step
+            assert "phi/inference_step_3/BatchNorm_2/moving_variance" in names
+            assert "theta/generative_step_7/Conv2d_transpose_7/weights/Adam_1" in names
+        else:
+            assert "theta/generative_network/BatchNorm/moving_mean" in names and not any("_step_1/" in x for x in names)
+        assert len(tf_checkpoint_layout(table, train=False)) == n + 2 * n_bn
+    for t in (0, 1, 7, 250):
+        assert adam_t_from_beta1_power(beta_powers(t)[0]) == t

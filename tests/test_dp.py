@@ -11,10 +11,10 @@ from seqvae_b200.dist import average_gradients_reference, shard_batch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _launch(backend, nproc, tmp_path, port):
-    out = str(tmp_path / ("dp_%s.json" % backend))
+def _launch(backend, nproc, tmp_path, port, net="c_inhomog"):
+    out = str(tmp_path / ("dp_%s_%s.json" % (backend, net)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dp_worker.py"), backend, out]
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dp_worker.py"), backend, out, net]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
@@ -57,3 +57,24 @@ def test_dp_nccl_world2(tmp_path):
     assert res["all_same"]
     assert res["all_same_after_graph_steps"], res
     assert res["err"] < 2e-2, res       # Adam's first step normalises gradient noise to ~lr: compare updates loosely
+
+
+def test_dp_semantics_gloo_world2_homogeneous(tmp_path):
+    """The same protocol on a weight-shared chain: the gradient of a shared variable is the mean over ranks of the sum over
+    chain steps."""
+    res = _launch("gloo", 2, tmp_path, 29543, net="sequential_vae_celebA_homog")
+    assert res["all_same"] and res["same"]
+    assert res["err"] < 1e-12
+
+
+@pytest.mark.gpu
+def test_dp_nccl_world2_homogeneous(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _launch("nccl", 2, tmp_path, 29544, net="sequential_vae_celebA_homog")
+    assert res["all_same"]
+    assert res["all_same_after_graph_steps"], res
+    assert res["slices_tied"] and res["shared_variables"] > 40, res
+    assert res["err"] < 2e-2, res

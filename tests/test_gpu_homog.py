@@ -167,7 +167,10 @@ def test_homog_checkpoint_round_trip(tmp_path):
     path = a.save_network()
     blob = np.load(path)
     names = [p["name"] for p in a.param_table]
-    assert all(n in blob.files and n + "/Adam" in blob.files and n + "/Adam_1" in blob.files for n in names)
+    live = [p["name"] for p in a.param_table if not p["flags"] & S._cabi.PF_DEAD]
+    assert all(n in blob.files for n in names)
+    assert all(n + "/Adam" in blob.files and n + "/Adam_1" in blob.files for n in live)
+    assert "theta/generative_network/BatchNorm/moving_mean" in blob.files and "beta1_power" in blob.files
     assert not any("_step_1/" in n or "_step_2/" in n for n in blob.files)
     b = S.SequentialVAE(ds, B, "sequential_vae_celebA_homog", base_dir=str(tmp_path / "m"), restore=True, **over)
     assert b.iteration == 2
@@ -202,3 +205,46 @@ def test_c_homog_full_chain_length_properties():
     assert all(np.isfinite(v).all() for v in after.values())
     assert _slices_identical(model, _arena(model)) > 40
     model.close()
+
+
+def test_checkpoint_resume_equals_uninterrupted_training(tmp_path):
+    """Inhomogeneous chain: train 2 steps, save, restore into a fresh handle, train 1 more == 3 uninterrupted steps (weights,
+    both Adam slots, step count, schedules); the file holds the TF Saver's variable set (checkpoint.tf_checkpoint_layout)."""
+    from seqvae_b200.checkpoint import tf_checkpoint_layout
+
+    B = 4
+    ds = S.SyntheticDataset("x", B, data_dims=[16, 16, 3], data_range=[-1.0, 1.0])
+    rng = np.random.default_rng(0)
+    xs = [ds.next_batch(B) for _ in range(3)]
+    es = [rng.normal(size=(2, B, 9)).astype(np.float32) for _ in range(3)]
+    a = S.SequentialVAE(ds, B, "c_inhomog", base_dir=str(tmp_path / "a"), restore=False, **TINY)
+    c = S.SequentialVAE(ds, B, "c_inhomog", base_dir=str(tmp_path / "c"), restore=False, **TINY)
+    c.set_params(a.get_params())
+    for i in range(2):
+        a.train(xs[i], xs[i], es[i])
+    path = a.save_network()
+    blob = np.load(path)
+    want = [e[0] for e in tf_checkpoint_layout(a.param_table, True)]
+    assert sorted(want + ["__adam_t", "__iteration", "__learning_rate"]) == sorted(blob.files)
+    assert abs(float(blob["beta1_power"]) - 0.9 ** 3) < 1e-6 and not blob["phi/inference_step_0/BatchNorm/moving_mean"].any()
+    b = S.SequentialVAE(ds, B, "c_inhomog", base_dir=str(tmp_path / "a"), restore=True, **TINY)
+    assert b.iteration == 2
+    for w in ("param", "adam_m", "adam_v"):
+        assert np.array_equal(a.read_arena(w), b.read_arena(w)), w
+    rb = b.train(xs[2], xs[2], es[2])
+    for i in range(3):
+        rc = c.train(xs[i], xs[i], es[i])
+    assert math.isclose(rb, rc, rel_tol=1e-4)
+    pb, pc = b.get_params(live_only=True), c.get_params(live_only=True)
+    n = bad = 0
+    for k in pb:
+        d = np.abs(pb[k].astype(np.float64) - pc[k])
+        assert d.max() <= 2 * 3 * 2e-4 * 1.01, k
+        n += d.size
+        bad += int((d > 2e-5).sum())
+    assert bad <= 1e-3 * n, (bad, n)
+    # a second save moves the first file to <models>/old like the reference (abstract_network.py:131-133)
+    a.save_network()
+    assert (tmp_path / "old" / "c_inhomog_v0.npz").exists()
+    for m in (a, b, c):
+        m.close()
