@@ -50,7 +50,7 @@ def _slices_identical(model, arena):
 @pytest.mark.parametrize("operand", ["fp32", "bf16"])
 @pytest.mark.parametrize("netname,dims,rng,B,over", [
     ("sequential_vae_celebA_homog", [16, 16, 3], (-1.0, 1.0), 5, dict(TINY, mc_steps=3)),
-    ("sequential_vae_celebA_homog_fixed_length", [16, 16, 3], (-1.0, 1.0), 6, dict(TINY, mc_steps=3)),   # theta only
+    ("sequential_vae_celebA_homog_fixed_length", [16, 16, 3], (-1.0, 1.0), 8, dict(TINY, mc_steps=3)),   # theta only
     ("c_homog_v1", [32, 32, 3], (0.0, 1.0), 8, dict(mc_steps=3)),                 # narrow filters [3,16,32,64,128,384], Z=48
     ("sequential_vae_celebA_homog", [64, 64, 3], (-1.0, 1.0), 6, dict(mc_steps=3)),   # benchmarked architecture, shared
 ])
