@@ -1,7 +1,7 @@
 # Round-end evidence run on one B200: parity tests, the default bench line, the ncu launch list of one graph-replayed step and
 # one `ncu --set full` capture of the dominant kernel.  Outputs land in gpurun_out/ (copied into profiles/ by hand).
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_final.log
+OMP_NUM_THREADS=4 python -m pytest tests -m gpu -x -q -n 4 > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_final.log
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-generation > gpurun_out/plain_final.log 2>&1 &&
