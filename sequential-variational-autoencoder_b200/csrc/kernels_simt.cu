@@ -347,6 +347,233 @@ heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __re
   }
 }
 
+// ---- tiled head kernels (v2) ------------------------------------------------------------------------------------------
+// The kernels above walk ONE batch row per block (GEMV): every block re-reads the whole weight slice, with one load per
+// FMA.  That is fine for the 2-3 wide latent groups of the MNIST / CelebA nets but not for the LSUN net (groups of 20-30,
+// up to 120 columns per feature map, B = 256): measured 286 / 259 / 142 us per launch against ~7 us of HBM time.  The v2
+// kernels treat the heads of one feature map as what they are - a [B, K] x [K, ntot] GEMM with a huge K - and tile it:
+// all columns of all heads side by side (dense, column c = sum of the widths before head h + i), operands staged through
+// shared memory (forward) or held in registers (input / weight gradients), >= 4 FMAs per shared-memory load.
+constexpr int HV_BM = 64;    // batch rows per tile
+constexpr int HV_KC = 32;    // K chunk staged per iteration (forward)
+
+struct HeadCols {            // dense column map of a HeadSet, built per block in shared memory
+  int head[128], idx[128];
+};
+
+__device__ __forceinline__ int heads_ntot(const HeadSet& hs) {
+  int t = 0;
+  for (int h = 0; h < hs.nheads; ++h) t += hs.n[h];
+  return t;
+}
+
+// forward: grid (row tiles, K slices); thread (tx, ty) owns rows ty*4..+4 and columns tx*TN..+TN of the tile
+template <int NT>
+__global__ void __launch_bounds__(256)
+heads_fwd_tiled_kernel(const float* __restrict__ flat, int B, int K, int kslice, HeadSet hs, float* __restrict__ mu_pre,
+                       float* __restrict__ sd_pre, int Z) {
+  constexpr int TN = NT / 16;
+  __shared__ __align__(16) float s_a[HV_KC][HV_BM + 4];
+  __shared__ __align__(16) float s_w[HV_KC][NT];
+  __shared__ int s_dst[NT];        // destination offset inside a [Z] row, bit 30 set: sd_pre
+  __shared__ float s_bias[NT];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * HV_BM;
+  const int k0 = blockIdx.y * kslice, k1 = min(K, k0 + kslice);
+  const int ntot = heads_ntot(hs);
+  for (int c = tid; c < NT; c += 256) {
+    int h = 0, base = 0;
+    while (h < hs.nheads && c >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+    if (h < hs.nheads) {
+      s_dst[c] = (hs.col[h] + (c - base)) | (hs.is_sd[h] ? (1 << 30) : 0);
+      s_bias[c] = hs.b[h][c - base];
+    } else {
+      s_dst[c] = -1;
+      s_bias[c] = 0.f;
+    }
+  }
+  for (int i = tid; i < HV_KC * NT; i += 256) (&s_w[0][0])[i] = 0.f;   // pad columns stay zero
+  float acc[4][TN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  __syncthreads();
+  for (int kc = k0; kc < k1; kc += HV_KC) {
+    const int kn = min(HV_KC, k1 - kc);
+    // activations: 32 consecutive k of one row per warp (128-byte segments), transposed into [k][row]
+    {
+      const int kk = tid & 31;
+#pragma unroll
+      for (int r = tid >> 5; r < HV_BM; r += 8) {
+        const int b = row0 + r;
+        s_a[kk][r] = (b < B && kk < kn) ? __ldg(flat + (size_t)b * K + kc + kk) : 0.f;
+      }
+    }
+    // weights: the chunk of head h is kn*n contiguous floats
+    {
+      int cbase = 0;
+      for (int h = 0; h < hs.nheads; ++h) {
+        const int n = hs.n[h];
+        const float* __restrict__ src = hs.w[h] + (size_t)kc * n;
+        for (int i = tid; i < HV_KC * n; i += 256) {
+          const int kk = i / n, c = i - kk * n;
+          s_w[kk][cbase + c] = kk < kn ? __ldg(src + i) : 0.f;
+        }
+        cbase += n;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < HV_KC; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&s_a[kk][ty * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float w[TN];
+      if constexpr (TN % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&s_w[kk][tx * TN + j]);
+          w[j] = w4.x; w[j + 1] = w4.y; w[j + 2] = w4.z; w[j + 3] = w4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) w[j] = s_w[kk][tx * TN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = row0 + ty * 4 + i;
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int c = tx * TN + j;
+      if (c >= ntot) continue;
+      const int d = s_dst[c];
+      float* dst = ((d >> 30) & 1 ? sd_pre : mu_pre) + (size_t)b * Z + (d & 0x3fffffff);
+      atomicAdd(dst, acc[i][j] + (blockIdx.y == 0 ? s_bias[c] : 0.f));
+    }
+  }
+}
+
+// input gradient: d_flat[b, k] = sum_c d[b, c] * W[k, c]  (overwrite).  Thread = one k with its NT weights in registers;
+// the d rows of the tile sit in shared memory and are read as broadcast float4 (4 FMAs per shared load).
+template <int NT>
+__global__ void __launch_bounds__(256)
+heads_dgrad_tiled_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int B, int Z, int K,
+                         float* __restrict__ d_flat) {
+  __shared__ __align__(16) float s_d[HV_BM][NT];
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.y * HV_BM;
+  const int rows = min(HV_BM, B - row0);
+  for (int i = tid; i < HV_BM * NT; i += 256) {
+    const int r = i / NT, c = i - r * NT;
+    int h = 0, base = 0;
+    while (h < hs.nheads && c >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+    float v = 0.f;
+    if (h < hs.nheads && r < rows) v = (hs.is_sd[h] ? dsd : dmu)[(size_t)(row0 + r) * Z + hs.col[h] + (c - base)];
+    s_d[r][c] = v;
+  }
+  const int k = blockIdx.x * 256 + tid;
+  float w[NT];
+#pragma unroll
+  for (int c = 0; c < NT; ++c) w[c] = 0.f;
+  if (k < K) {
+    int base = 0;
+    for (int h = 0; h < hs.nheads; ++h) {
+      const int n = hs.n[h];
+      const float* __restrict__ wr = hs.w[h] + (size_t)k * n;
+#pragma unroll
+      for (int c = 0; c < NT; ++c) {
+        const int i = c - base;
+        if (i >= 0 && i < n) w[c] = __ldg(wr + i);
+      }
+      base += n;
+    }
+  }
+  __syncthreads();
+  if (k >= K) return;
+  for (int r = 0; r < rows; ++r) {
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < NT; c += 4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&s_d[r][c]);
+      v = fmaf(d4.x, w[c], v); v = fmaf(d4.y, w[c + 1], v); v = fmaf(d4.z, w[c + 2], v); v = fmaf(d4.w, w[c + 3], v);
+    }
+    d_flat[(size_t)(row0 + r) * K + k] = v;
+  }
+}
+
+// weight gradient: gw[k, c] += sum_{b in slice} flat[b, k] * d[b, c]; thread = one k with NT accumulators in registers, the d
+// rows of the slice in shared memory (broadcast float4).  gb[c] = sum_b d[b, c] from block (0, 0).
+template <int NT>
+__global__ void __launch_bounds__(256)
+heads_wgrad_tiled_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu,
+                         const float* __restrict__ dsd, int B, int Z, int K, int bper) {
+  __shared__ __align__(16) float s_d[HV_BM][NT];
+  const int tid = threadIdx.x;
+  const int k = blockIdx.x * 256 + tid;
+  const int r0 = blockIdx.y * bper, r1 = min(B, r0 + bper);
+  float acc[NT];
+#pragma unroll
+  for (int c = 0; c < NT; ++c) acc[c] = 0.f;
+  for (int rb = r0; rb < r1; rb += HV_BM) {
+    const int rows = min(HV_BM, r1 - rb);
+    __syncthreads();
+    for (int i = tid; i < HV_BM * NT; i += 256) {
+      const int r = i / NT, c = i - r * NT;
+      int h = 0, base = 0;
+      while (h < hs.nheads && c >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+      float v = 0.f;
+      if (h < hs.nheads && r < rows) v = (hs.is_sd[h] ? dsd : dmu)[(size_t)(rb + r) * Z + hs.col[h] + (c - base)];
+      s_d[r][c] = v;
+    }
+    __syncthreads();
+    if (k < K) {
+#pragma unroll 2
+      for (int r = 0; r < rows; ++r) {
+        const float a = __ldg(flat + (size_t)(rb + r) * K + k);
+#pragma unroll
+        for (int c = 0; c < NT; c += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(&s_d[r][c]);
+          acc[c] = fmaf(a, d4.x, acc[c]); acc[c + 1] = fmaf(a, d4.y, acc[c + 1]);
+          acc[c + 2] = fmaf(a, d4.z, acc[c + 2]); acc[c + 3] = fmaf(a, d4.w, acc[c + 3]);
+        }
+      }
+    }
+  }
+  if (k < K) {
+    int base = 0;
+    for (int h = 0; h < hs.nheads; ++h) {
+      const int n = hs.n[h];
+      float* __restrict__ g = hs.gw[h] + (size_t)k * n;
+#pragma unroll
+      for (int c = 0; c < NT; ++c) {
+        const int i = c - base;
+        if (i >= 0 && i < n) {
+          if (gridDim.y == 1) g[i] += acc[c]; else atomicAdd(g + i, acc[c]);
+        }
+      }
+      base += n;
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int h = 0; h < hs.nheads; ++h) {
+      if (tid < hs.n[h]) {
+        const float* __restrict__ d = (hs.is_sd[h] ? dsd : dmu) + hs.col[h];
+        float sum = 0.f;
+        for (int b = 0; b < B; ++b) sum += d[(size_t)b * Z + tid];
+        hs.gb[h][tid] = sum;
+      }
+    }
+  }
+}
+
 // Latent projections (split_latent, sequential_vae.py:1801-1806): [B, kz<=32] x [kz, N] with N up to 32768.
 // dW[k, f] += sum_{b in slice} z[b, k] * dy[b, f]      (grid: f tiles x batch slices, grads pre-zeroed)
 template <int NM>
@@ -462,6 +689,23 @@ static int heads_nmax(const HeadSet& hs) {
     default: { constexpr int NM = 32; CALL; } break;     \
   }
 
+// Tiled head kernels (v2) for feature maps whose heads are more than HV_MIN_NTOT columns wide in total (SVAE_HEADS_TILED=0/1
+// forces the choice).  NT = padded column count of the launch.
+static bool heads_use_tiled(int ntot) {
+  static const int mode = [] { const char* e = getenv("SVAE_HEADS_TILED"); return e ? atoi(e) : -1; }();
+  if (ntot > 128) return false;
+  if (mode >= 0) return mode != 0;
+  return ntot > 16;
+}
+#define HV_DISPATCH(NTOTV, CALL)                                   \
+  do {                                                             \
+    const int _n = (NTOTV);                                        \
+    if (_n <= 16) { constexpr int NT = 16; CALL; }                 \
+    else if (_n <= 32) { constexpr int NT = 32; CALL; }            \
+    else if (_n <= 64) { constexpr int NT = 64; CALL; }            \
+    else { constexpr int NT = 128; CALL; }                         \
+  } while (0)
+
 static int split_for(int rows_or_blocks, int sm_count, int max_split) {
   int s = (2 * sm_count + rows_or_blocks - 1) / rows_or_blocks;
   if (s < 1) s = 1;
@@ -479,6 +723,20 @@ int heads_fwd(const LaunchCtx& lc, const float* flat, int B, int K, const HeadSe
   if (ks > ks_max) ks = ks_max;
   if (ks < 1) ks = 1;
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
+  if (heads_use_tiled(ntot)) {
+    // row tiles x K slices: ~2 blocks per SM, every slice a multiple of the staged chunk and >= 256 inputs
+    const int rt = (B + HV_BM - 1) / HV_BM;
+    int kslices = (2 * lc.sm_count + rt - 1) / rt;
+    const int ks_cap = (K + 255) / 256;
+    if (kslices > ks_cap) kslices = ks_cap;
+    if (kslices < 1) kslices = 1;
+    const int kslice = ((K + kslices - 1) / kslices + HV_KC - 1) / HV_KC * HV_KC;
+    kslices = (K + kslice - 1) / kslice;
+    HV_DISPATCH(ntot, (heads_fwd_tiled_kernel<NT><<<dim3(rt, kslices), 256, 0, lc.stream>>>(flat, B, K, kslice, hs, mu_pre,
+                                                                                            sd_pre, Z)));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   SK_DISPATCH(heads_nmax(hs), (heads_fwd_kernel<NM><<<dim3(B, ks), 256, 0, lc.stream>>>(flat, K, hs, mu_pre, sd_pre, Z)));
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -489,6 +747,12 @@ int heads_dgrad(const LaunchCtx& lc, const HeadSet& hs, const float* dmu, const 
   int ntot = 0;
   for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
+  if (heads_use_tiled(ntot)) {
+    HV_DISPATCH(ntot, (heads_dgrad_tiled_kernel<NT><<<dim3((K + 255) / 256, (B + HV_BM - 1) / HV_BM), 256, 0, lc.stream>>>(
+                          hs, dmu, dsd, B, Z, K, d_flat)));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   heads_dgrad_kernel<<<dim3((K + 255) / 256, B), 256, 0, lc.stream>>>(hs, dmu, dsd, Z, K, d_flat);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -501,6 +765,18 @@ int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const
   const int kb = (K + 255) / 256;
   const int bs = split_for(kb, lc.sm_count, (B + 7) / 8);
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
+  if (heads_use_tiled(ntot)) {
+    // batch slices only as far as needed to fill the machine (each slice costs K * ntot atomics)
+    int slices = (2 * lc.sm_count + kb - 1) / kb;
+    const int cap = (B + 31) / 32;
+    if (slices > cap) slices = cap;
+    if (slices < 1) slices = 1;
+    const int bper = (B + slices - 1) / slices;
+    slices = (B + bper - 1) / bper;
+    HV_DISPATCH(ntot, (heads_wgrad_tiled_kernel<NT><<<dim3(kb, slices), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K, bper)));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   SK_DISPATCH(heads_nmax(hs), (heads_wgrad_kernel<NM><<<dim3(kb, bs), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K)));
   CUDA_TRY(cudaGetLastError());
   return 0;
