@@ -399,31 +399,47 @@ heads_fwd_tiled_kernel(const float* __restrict__ flat, int B, int K, int kslice,
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   __syncthreads();
-  for (int kc = k0; kc < k1; kc += HV_KC) {
+  // Software pipeline: the next chunk's global loads are issued into registers before the current chunk is multiplied, so
+  // the L2 / HBM latency of a chunk overlaps the FMAs of the previous one instead of adding to them.
+  constexpr int WREG = (HV_KC * NT + 255) / 256;     // weight elements per thread and chunk (dense columns: <= this)
+  float ra[HV_BM / 8], rw[WREG];
+  const int akk = tid & 31, ar0 = tid >> 5;
+  auto fetch = [&](int kc) {
     const int kn = min(HV_KC, k1 - kc);
-    // activations: 32 consecutive k of one row per warp (128-byte segments), transposed into [k][row]
-    {
-      const int kk = tid & 31;
 #pragma unroll
-      for (int r = tid >> 5; r < HV_BM; r += 8) {
-        const int b = row0 + r;
-        s_a[kk][r] = (b < B && kk < kn) ? __ldg(flat + (size_t)b * K + kc + kk) : 0.f;
-      }
+    for (int j = 0; j < HV_BM / 8; ++j) {
+      const int b = row0 + ar0 + 8 * j;
+      ra[j] = (b < B && akk < kn) ? __ldg(flat + (size_t)b * K + kc + akk) : 0.f;
     }
-    // weights: the chunk of head h is kn*n contiguous floats
-    {
-      int cbase = 0;
-      for (int h = 0; h < hs.nheads; ++h) {
-        const int n = hs.n[h];
-        const float* __restrict__ src = hs.w[h] + (size_t)kc * n;
-        for (int i = tid; i < HV_KC * n; i += 256) {
-          const int kk = i / n, c = i - kk * n;
-          s_w[kk][cbase + c] = kk < kn ? __ldg(src + i) : 0.f;
-        }
-        cbase += n;
+#pragma unroll
+    for (int j = 0; j < WREG; ++j) {
+      // element e of the dense [HV_KC][ntot] chunk: row kk, dense column c -> head h, local column
+      const int e = tid + 256 * j;
+      const int kk = e / ntot, c = e - kk * ntot;
+      float v = 0.f;
+      if (kk < kn) {
+        int h = 0, base = 0;
+        while (c >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+        v = __ldg(hs.w[h] + (size_t)(kc + kk) * hs.n[h] + (c - base));
       }
+      rw[j] = v;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int j = 0; j < HV_BM / 8; ++j) s_a[akk][ar0 + 8 * j] = ra[j];
+#pragma unroll
+    for (int j = 0; j < WREG; ++j) {
+      const int e = tid + 256 * j;
+      const int kk = e / ntot, c = e - kk * ntot;
+      if (kk < HV_KC) s_w[kk][c] = rw[j];
+    }
+  };
+  if (k0 < k1) fetch(k0);
+  for (int kc = k0; kc < k1; kc += HV_KC) {
+    stash();
     __syncthreads();
+    if (kc + HV_KC < k1) fetch(kc + HV_KC);
 #pragma unroll 8
     for (int kk = 0; kk < HV_KC; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&s_a[kk][ty * 4]);
@@ -509,40 +525,57 @@ heads_dgrad_tiled_kernel(HeadSet hs, const float* __restrict__ dmu, const float*
   }
 }
 
-// weight gradient: gw[k, c] += sum_{b in slice} flat[b, k] * d[b, c]; thread = one k with NT accumulators in registers, the d
-// rows of the slice in shared memory (broadcast float4).  gb[c] = sum_b d[b, c] from block (0, 0).
-template <int NT>
-__global__ void __launch_bounds__(256)
+// weight gradient: gw[k, c] = sum_b flat[b, k] * d[b, c].  Thread = one k with CT accumulators in registers for the CT dense
+// columns of its column group (blockIdx.y); the d rows sit in shared memory (broadcast float4).  Every (k, c) has exactly one
+// owner, so there are no atomics (the GEMV kernel splits the batch and pays K * ntot atomics per slice - 6-8 M per launch
+// for the LSUN heads); machine filling comes from 128-thread blocks and the column groups instead.
+// gb[c] = sum_b d[b, c] from the blocks of row blockIdx.x == 0.
+template <int CT>
+__global__ void __launch_bounds__(128)
 heads_wgrad_tiled_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu,
-                         const float* __restrict__ dsd, int B, int Z, int K, int bper) {
-  __shared__ __align__(16) float s_d[HV_BM][NT];
+                         const float* __restrict__ dsd, int B, int Z, int K) {
+  __shared__ __align__(16) float s_d[HV_BM][CT];
+  __shared__ int s_src[CT];      // source offset inside a [Z] row, bit 30: dsd, -1: pad column
   const int tid = threadIdx.x;
-  const int k = blockIdx.x * 256 + tid;
-  const int r0 = blockIdx.y * bper, r1 = min(B, r0 + bper);
-  float acc[NT];
+  const int k = blockIdx.x * 128 + tid;
+  const int c0 = blockIdx.y * CT;
+  const int ntot = heads_ntot(hs);
+  for (int c = tid; c < CT; c += 128) {
+    const int cc = c0 + c;
+    int h = 0, base = 0;
+    while (h < hs.nheads && cc >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+    s_src[c] = (h < hs.nheads && cc < ntot) ? ((hs.col[h] + (cc - base)) | (hs.is_sd[h] ? (1 << 30) : 0)) : -1;
+  }
+  float acc[CT];
 #pragma unroll
-  for (int c = 0; c < NT; ++c) acc[c] = 0.f;
-  for (int rb = r0; rb < r1; rb += HV_BM) {
-    const int rows = min(HV_BM, r1 - rb);
+  for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+  for (int rb = 0; rb < B; rb += HV_BM) {
+    const int rows = min(HV_BM, B - rb);
     __syncthreads();
-    for (int i = tid; i < HV_BM * NT; i += 256) {
-      const int r = i / NT, c = i - r * NT;
-      int h = 0, base = 0;
-      while (h < hs.nheads && c >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+    for (int i = tid; i < HV_BM * CT; i += 128) {
+      const int r = i / CT, c = i - r * CT;
+      const int src = s_src[c];
       float v = 0.f;
-      if (h < hs.nheads && r < rows) v = (hs.is_sd[h] ? dsd : dmu)[(size_t)(rb + r) * Z + hs.col[h] + (c - base)];
+      if (src >= 0 && r < rows) v = ((src >> 30) & 1 ? dsd : dmu)[(size_t)(rb + r) * Z + (src & 0x3fffffff)];
       s_d[r][c] = v;
     }
     __syncthreads();
     if (k < K) {
-#pragma unroll 2
-      for (int r = 0; r < rows; ++r) {
-        const float a = __ldg(flat + (size_t)(rb + r) * K + k);
+      const float* __restrict__ ap = flat + (size_t)rb * K + k;
+      for (int r = 0; r < rows; r += 4) {
+        float a[4];
 #pragma unroll
-        for (int c = 0; c < NT; c += 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(&s_d[r][c]);
-          acc[c] = fmaf(a, d4.x, acc[c]); acc[c + 1] = fmaf(a, d4.y, acc[c + 1]);
-          acc[c + 2] = fmaf(a, d4.z, acc[c + 2]); acc[c + 3] = fmaf(a, d4.w, acc[c + 3]);
+        for (int u = 0; u < 4; ++u) a[u] = r + u < rows ? __ldg(ap + (size_t)(r + u) * K) : 0.f;   // 4 loads in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r + u < rows) {
+#pragma unroll
+            for (int c = 0; c < CT; c += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(&s_d[r + u][c]);
+              acc[c] = fmaf(a[u], d4.x, acc[c]); acc[c + 1] = fmaf(a[u], d4.y, acc[c + 1]);
+              acc[c + 2] = fmaf(a[u], d4.z, acc[c + 2]); acc[c + 3] = fmaf(a[u], d4.w, acc[c + 3]);
+            }
+          }
         }
       }
     }
@@ -553,23 +586,23 @@ heads_wgrad_tiled_kernel(const float* __restrict__ flat, HeadSet hs, const float
       const int n = hs.n[h];
       float* __restrict__ g = hs.gw[h] + (size_t)k * n;
 #pragma unroll
-      for (int c = 0; c < NT; ++c) {
-        const int i = c - base;
-        if (i >= 0 && i < n) {
-          if (gridDim.y == 1) g[i] += acc[c]; else atomicAdd(g + i, acc[c]);
-        }
+      for (int c = 0; c < CT; ++c) {
+        const int i = c0 + c - base;
+        if (i >= 0 && i < n) g[i] += acc[c];      // pre-zeroed, single owner
       }
       base += n;
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
-    for (int h = 0; h < hs.nheads; ++h) {
-      if (tid < hs.n[h]) {
-        const float* __restrict__ d = (hs.is_sd[h] ? dsd : dmu) + hs.col[h];
-        float sum = 0.f;
-        for (int b = 0; b < B; ++b) sum += d[(size_t)b * Z + tid];
-        hs.gb[h][tid] = sum;
-      }
+  if (blockIdx.x == 0 && tid < CT) {
+    const int src = s_src[tid];
+    if (src >= 0) {
+      const float* __restrict__ d = ((src >> 30) & 1 ? dsd : dmu) + (src & 0x3fffffff);
+      float sum = 0.f;
+      for (int b = 0; b < B; ++b) sum += d[(size_t)b * Z];
+      const int cc = c0 + tid;
+      int h = 0, base = 0;
+      while (cc >= base + hs.n[h]) { base += hs.n[h]; ++h; }
+      hs.gb[h][cc - base] = sum;
     }
   }
 }
@@ -766,14 +799,13 @@ int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const
   const int bs = split_for(kb, lc.sm_count, (B + 7) / 8);
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
   if (heads_use_tiled(ntot)) {
-    // batch slices only as far as needed to fill the machine (each slice costs K * ntot atomics)
-    int slices = (2 * lc.sm_count + kb - 1) / kb;
-    const int cap = (B + 31) / 32;
-    if (slices > cap) slices = cap;
-    if (slices < 1) slices = 1;
-    const int bper = (B + slices - 1) / slices;
-    slices = (B + bper - 1) / bper;
-    HV_DISPATCH(ntot, (heads_wgrad_tiled_kernel<NT><<<dim3(kb, slices), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K, bper)));
+    // 128 k per block x column groups of 16 or 32: narrower groups when the k blocks alone do not fill the machine
+    const int kb128 = (K + 127) / 128;
+    if (kb128 * ((ntot + 31) / 32) >= 2 * lc.sm_count) {
+      heads_wgrad_tiled_kernel<32><<<dim3(kb128, (ntot + 31) / 32), 128, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K);
+    } else {
+      heads_wgrad_tiled_kernel<16><<<dim3(kb128, (ntot + 15) / 16), 128, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
   }

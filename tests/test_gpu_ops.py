@@ -54,7 +54,7 @@ def test_conv2d_forward_and_stats(B, H, Ci, Co, stride, operand):
         ref = O.conv2d_same(x, w, stride)
     y = torch.empty(B, H // stride, H // stride, Co, device="cuda")
     stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
+    torch.cuda.synchronize()                    # the fill runs on torch's stream, libsvae on its own
     dx_, dw_ = dev(x), dev(w)          # keep the uploads alive: a temporary's block would be reused by the next upload
     rc = L.svae_op_conv2d(h, ptr(dx_), ptr(dw_), ptr(y), ptr(stats), B, H, H, Ci, Co, stride, operand)
     _maybe_skip_tc(rc, L, h)
@@ -228,6 +228,7 @@ def test_adam_matches_tf_formulation():
     g = (rs.randn(n) * 8).astype(np.float32)    # some elements beyond the +-10 clip
     dp, dg = dev(p), dev(g)
     dm, dv = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    torch.cuda.synchronize()                    # the fills run on torch's stream, libsvae on its own
     rp, rm, rv = p.astype(np.float64), np.zeros(n), np.zeros(n)
     for t in (1, 2, 3):
         assert L.svae_op_adam(h, ptr(dp), ptr(dg), ptr(dm), ptr(dv), n, 2e-4, t, 0.9, 0.999, 1e-8, 10.0, 1.0) == 0
