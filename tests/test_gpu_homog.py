@@ -248,3 +248,33 @@ def test_checkpoint_resume_equals_uninterrupted_training(tmp_path):
     assert (tmp_path / "old" / "c_inhomog_v0.npz").exists()
     for m in (a, b, c):
         m.close()
+
+
+@pytest.mark.parametrize("netname,dims,rng,B,over", [
+    ("vlae_celebA", [16, 16, 3], (-1.0, 1.0), 6, dict(filter_sizes=TINY["filter_sizes"])),        # :704-707: mc_steps 1, Z = 64
+    ("c_homog_one_step", [32, 32, 3], (0.0, 1.0), 8, {}),                                          # :281-288: shared scopes, one step
+])
+def test_single_step_netnames(netname, dims, rng, B, over):
+    """mc_steps = 1 (a plain VLAE): no chain encoder, no gate, nothing to tie - forward, gradients, one Adam step, generation."""
+    model, hp, P = make_pair(netname, dims, rng, B, "fp32", **over)
+    assert model.mc_steps == 1 and [p["name"] for p in model.param_table] == [s["name"] for s in O.param_specs(hp)]
+    assert all(len(model.param_slices(p["name"])) == 1 for p in model.param_table)
+    x, eps = make_inputs(hp, B)
+    fw, grads, fw32, g32 = _oracle_pair(hp, P, x, x, eps, 0.7)
+    out = model.forward(x.numpy(), None, eps.numpy(), 0.7)
+    _check_forward(out, fw, "fp32", fw32)
+    model.backward()
+    _check_grads(model, grads, hp, "fp32", g32)
+    r = model.train(x.numpy().astype(np.float32), x.numpy().astype(np.float32), eps.numpy())
+    assert np.isfinite(r)
+    r2 = model.train(x.numpy().astype(np.float32), x.numpy().astype(np.float32), eps.numpy())       # graph replay
+    assert np.isfinite(r2) and r2 != r
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, B, hp["latent_dim"], generator=g, dtype=torch.float64).float().double()
+    P2 = {k: torch.tensor(v, dtype=torch.float64) for k, v in model.get_params().items()}
+    with torch.no_grad():
+        ref = O.generate_chain(hp, P2, z, B)
+    gen = model.generate_mc_samples(None, B, z=z.numpy())
+    assert len(gen) == 2
+    np.testing.assert_allclose(gen[1], ref[0].numpy(), rtol=1e-3, atol=1e-3)
+    model.close()
