@@ -194,3 +194,55 @@ def test_checkpoint_layout_is_the_tf_saver_variable_set():
         assert len(tf_checkpoint_layout(table, train=False)) == n + 2 * n_bn
     for t in (0, 1, 7, 250):
         assert adam_t_from_beta1_power(beta_powers(t)[0]) == t
+
+
+def test_noisy_trainer_host_logic_with_a_fake_network():
+    """NoisyTrainer (trainer.py:82-141) is host logic only: which network calls it makes, when it tests / visualises / logs,
+    what error it reports - checked here without a GPU against a recording stand-in for SequentialVAE."""
+    import argparse
+    import logging
+
+    class FakeNet:
+        def __init__(self):
+            self.calls = []
+
+        def train(self, x, tgt):
+            self.calls.append(("train", x is tgt))
+            return 0.5
+
+        def train_denoise(self, tgt, pepper, salt, scale):
+            self.calls.append(("train_denoise", (pepper, salt, scale)))
+            return 0.25
+
+        def apply_noise(self, x, pepper, salt, scale, seed=0):
+            self.calls.append(("apply_noise", seed))
+            return x + 1.0
+
+        def test(self, x):
+            self.calls.append(("test", float(x.mean())))
+            return x                                   # reconstruction == (noisy) input
+
+        def visualize(self, epoch):
+            self.calls.append(("visualize", epoch))
+
+    ds = S.SyntheticDataset("x", 4, data_dims=[8, 8, 3], data_range=[0.0, 1.0])
+    for denoise in (False, True):
+        net = FakeNet()
+        args = argparse.Namespace(batch_size=4, denoise_train=denoise, vis_frequency=3, plot_reconstruction=False)
+        tr = S.NoisyTrainer(net, ds, args, logging.getLogger("t"), "unused")
+        loss = tr.train(max_iters=7)
+        kinds = [c[0] for c in net.calls]
+        assert kinds.count("visualize") == 3 and [c[1] for c in net.calls if c[0] == "visualize"] == [0, 1, 2]   # iterations 0, 3, 6
+        assert kinds.count("test") == 3 * S.NoisyTrainer.test_num_iters
+        if denoise:
+            assert loss == 0.25 and kinds.count("train_denoise") == 7 and kinds.count("train") == 0
+            assert ("train_denoise", (0.1, 0.1, 0.1)) in net.calls                     # trainer.py:16-18
+            seeds = [c[1] for c in net.calls if c[0] == "apply_noise"]
+            assert len(seeds) == 15 and len(set(seeds)) == 15                          # a fresh Philox key per corrupted test batch
+            # reconstruction = input + 1 everywhere -> error per pixel = sum over C of 1 = 3 (trainer.py:131)
+            assert abs(tr.test(0, num_iters=2) - 3.0) < 1e-5
+        else:
+            assert loss == 0.5 and kinds.count("train") == 7 and all(c[1] for c in net.calls if c[0] == "train")
+            assert tr.test(0, num_iters=1) == 0.0
+            with pytest.raises(Exception, match="denoise_train==False"):
+                tr.apply_noise(ds.next_batch(4))                                       # trainer.py:66-67
