@@ -117,7 +117,7 @@ def _check_grads(model, grads, hp, operand, g32=None):
 
 
 @pytest.mark.parametrize("operand", ["fp32", "bf16"])
-@pytest.mark.parametrize("case", ["tiny_c", "tiny_m"])
+@pytest.mark.parametrize("case", ["tiny_c", "tiny_m", "tiny_h"])
 def test_golden_fixture(case, operand):
     import importlib.util
 

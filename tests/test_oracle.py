@@ -159,7 +159,7 @@ def test_gradient_flows_through_the_chain():
     assert float(grads["theta/generative_step_0/Conv2d_transpose/weights"].abs().max()) > 0
 
 
-@pytest.mark.parametrize("case", ["tiny_c", "tiny_m"])
+@pytest.mark.parametrize("case", ["tiny_c", "tiny_m", "tiny_h"])
 def test_oracle_reproduces_golden(case):
     import importlib.util
 
