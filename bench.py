@@ -106,9 +106,11 @@ class ClockSampler:
                     power_w_max=max(power))
 
 
-def cpu_oracle_arm(workload, steps, warmup, threads=None):
+def cpu_oracle_arm(workload, steps, warmup, threads=None, budget_s=None):
     """The reference's CPU path: fp32 PyTorch-CPU restatement of the reference graph (TF 1.x is not installable,
-    SURVEY Q14), one full train step = forward over all T steps + autograd backward + clip + TF-Adam."""
+    SURVEY Q14), one full train step = forward over all T steps + autograd backward + clip + TF-Adam.  budget_s: stop
+    timing new steps once this much wall time has been spent (at least one timed step always runs); the number of steps
+    actually timed is returned."""
     import numpy as np
     import torch
 
@@ -124,34 +126,44 @@ def cpu_oracle_arm(workload, steps, warmup, threads=None):
     g = torch.Generator().manual_seed(1234)
     x = torch.rand([B] + dims, generator=g) * (rng[1] - rng[0]) + rng[0]
     times = []
+    t_begin = time.perf_counter()
+    warm_done = 0
     for i in range(warmup + steps):
         eps = torch.randn(hp["mc_steps"], B, hp["latent_dim"], generator=g)
         t0 = time.perf_counter()
         om.train(x, x, eps)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    times.sort()
-    med = times[len(times) // 2]
-    return dict(value=B / med, ms_per_step=med * 1e3, cores=cores, B=B,
-                sample="%d full train steps (B=%d, T=%d, fp32) after %d warm-up" % (steps, B, hp["mc_steps"], warmup))
+        else:
+            warm_done += 1
+        if budget_s is not None and times and time.perf_counter() - t_begin > budget_s:
+            break
+    total = sum(times)
+    mean = total / len(times)
+    return dict(value=B / mean, ms_per_step=mean * 1e3, cores=cores, B=B, steps=len(times), warmup=warm_done,
+                mc_steps=hp["mc_steps"], latent_dim=hp["latent_dim"], image=list(dims),
+                sample="%d full train steps (B=%d, T=%d, fp32, forward + autograd backward + clip + TF-Adam) after %d warm-up"
+                       % (len(times), B, hp["mc_steps"], warm_done))
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, on this box's host cores.  The reference
-    itself needs TensorFlow 1.x (tf.contrib) which cannot be installed for Python 3.12, so this is the oracle PORT."""
+    itself needs TensorFlow 1.x (tf.contrib) which cannot be installed for Python 3.12, so this is the oracle PORT.
+    Honours --steps / --warmup (a wall-time budget of --ref-budget seconds only cuts the run short on a very slow host);
+    under torchrun (N > 1) rank 0 alone runs ONE CPU process on its host cores - the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1
-    r = cpu_oracle_arm(args.workload, steps, warm)
+    r = cpu_oracle_arm(args.workload, args.steps, args.warmup, budget_s=args.ref_budget)
     netname, shape, B, over = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "img/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "netname": netname, "batch_per_gpu": B, "mc_steps": over.get("mc_steps"),
-                   "note": "CPU oracle port of the reference graph (TensorFlow 1.x not installable); rank 0 only"},
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "netname": netname, "image": r["image"], "batch_per_gpu": B,
+                   "global_batch": B, "mc_steps": r["mc_steps"], "latent_dim": r["latent_dim"],
+                   "note": "CPU oracle port of the reference graph (TensorFlow 1.x not installable); ONE CPU process on rank "
+                           "0's host cores whatever --gpus is: at N > 1 compare it with the per-GPU rate, not the aggregate"},
         "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -175,6 +187,7 @@ def main():
     ap.add_argument("--no-generation", action="store_true")
     ap.add_argument("--gen-batch", type=int, default=4096)
     ap.add_argument("--profile-json", default=None, help="also write the per-kernel-class table to this file")
+    ap.add_argument("--ref-budget", type=float, default=300.0, help="--impl reference: wall-time cap in seconds")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -266,24 +279,46 @@ def main():
 
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------------------------
     e2e_steps = max(3, min(args.steps, 10))
-    # the step's inputs live in page-locked host memory (numpy views of torch pinned tensors): libsvae DMAs from them directly
-    x_host = torch.from_numpy(x_host).pin_memory().numpy()
-    tgt_host = torch.from_numpy(tgt_host).pin_memory().numpy()
-    for _ in range(2):
-        model.train(x_host, tgt_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        model.train(x_host, tgt_host)             # numpy in, float out: H2D of x and target, D2H of the losses, sync
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+
+    def time_e2e(xh, th):
+        for _ in range(2):
+            model.train(xh, th)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            model.train(xh, th)                   # numpy in, float out: H2D of x and target, D2H of the losses, sync
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # (a) ordinary pageable numpy arrays - what trainer.py:100-104 passes (dataset.next_batch output): the library stages
+    #     them through its pinned buffer; (b) page-locked arrays (numpy views of torch pinned tensors): DMA straight from them
+    e2e_pageable_ms = time_e2e(x_host, tgt_host)
+    x_pin = torch.from_numpy(x_host).pin_memory().numpy()
+    tgt_pin = torch.from_numpy(tgt_host).pin_memory().numpy()
+    e2e_ms = time_e2e(x_pin, tgt_pin)
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "img/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(2 * x_host.nbytes), "d2h_bytes_per_step": int(4 * (2 + 2 * 64)),
-           "host_buffers": "pinned (page-locked) numpy arrays, copied host->device inside every timed call"}
+           "host_buffers": "pinned (page-locked) numpy arrays, copied host->device inside every timed call",
+           "pageable": {"value": world * B / (e2e_pageable_ms * 1e-3), "ms_per_step": e2e_pageable_ms,
+                        "host_buffers": "ordinary pageable numpy arrays (what trainer.py:100-104 passes), staged through "
+                                        "the library's pinned buffer inside every timed call"}}
+
+    # ---- data-parallel consistency: after all those updates every rank must hold bit-identical parameters ---------------
+    dp_check = None
+    if dist is not None:
+        import zlib
+
+        arena = model.read_arena("param")
+        mine = (int(zlib.crc32(arena.tobytes())), float(arena.astype(np.float64).sum()))
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+        dp_check = {"ranks": world, "param_crc32": [v[0] for v in allv], "ranks_agree": len({v[0] for v in allv}) == 1,
+                    "train_steps_before_check": int(model.iteration), "param_sum": allv[0][1]}
+        del arena
 
     # ---- roofline of the dominant kernel class (live CUDA-event durations from the timed region) -------------------------
     peaks = measured_peaks()
@@ -316,6 +351,12 @@ def main():
                 roof["traffic_source"] = ent.get("source")
         except (OSError, ValueError):
             pass
+    parity = None
+    try:      # measured by tests/test_gpu_fullsize.py::test_full_size_oracle_parity on a B200 (committed copy under profiles/)
+        parity = json.load(open(os.path.join(ROOT, "profiles", "parity_fullsize.json")))
+        parity["source"] = "profiles/parity_fullsize.json (tests/test_gpu_fullsize.py::test_full_size_oracle_parity, B200)"
+    except (OSError, ValueError):
+        pass
     algo = ALGO.get(args.workload, {})
     path_roof = None
     if algo:
@@ -384,6 +425,7 @@ def main():
                                     "right after the timed region" % prof_steps},
             "roofline": roof, "path_roofline": path_roof, "kernels": table, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "generation": generation,
+            "parity": parity if args.workload == "celeba64_b100" else None, "dp_consistency": dp_check,
         }
         print(json.dumps(line), flush=True)
         if args.profile_json:

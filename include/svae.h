@@ -250,6 +250,21 @@ int svae_op_fc_backward(svae_handle* h, const float* x, const float* w, const fl
  * (it then runs on the fp32 SIMT kernels).  transposed: 0 conv, 1 transposed conv, 2 fully connected (Ci -> Co, H = W = 1);
  * direction: 0 forward, 1 input gradient, 2 weight gradient. */
 int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int stride, int direction);
+/* 1 when the SVAE_OPERAND_BF16 family runs this contraction at batch B on the TMA-fed PRODUCTION kernels of the chain
+ * (tc2_conv_kernel for direction 0 / 1, tc2_wgrad_kernel for direction 2): the layer-level entry points above then exercise
+ * exactly the kernels a train step launches.  0: SIMT-staged tcgen05 variant or fp32 kernels. */
+int svae_op_tc2_supported(int transposed, int B, int H, int W, int Ci, int Co, int stride, int direction);
+/* Parity probe (tests only; TF lets callers fetch any tensor of the graph, sequential_vae.py:919-923): one tensor of one
+ * block of the LAST svae_forward / svae_backward as a dense fp32 host array, exactly as the kernels consumed or produced it
+ * (a tensor kept only as a bf16 copy is returned with its bf16 values).
+ *   net:   0 recognition conv block (index 0..2(L-1)-1), 1 chain-encoder conv block (0..2(L-1)), 2 chain-encoder fc block,
+ *          3 latent projection (0..L-1), 4 decoder fc block, 5 stride-2 deconv of level `index`, 6 stride-1 deconv of level
+ *          `index`, 7 output deconv, 8 highway-gate deconv
+ *   which: 0 contraction input, 1 pre-batch-norm contraction output, 2 activated output, 3 dL/d(activated output),
+ *          4 dL/d(pre-batch-norm output), 5 tensor added before the activation (ladder shortcut)
+ * dims_out receives [B,H,W,C] of the tensor; host_dst == NULL only queries the dims.  Synchronises. */
+int svae_debug_block_tensor(svae_handle* h, int step, int net, int index, int which, float* host_dst, int64_t capacity,
+                            int32_t dims_out[4]);
 /* Development aid: when non-NULL, the tcgen05 conv kernel writes per-CTA phase timestamps ([cta][8] uint64 ns) here. */
 int svae_debug_set_buffer(void* dev_buffer);
 /* batch_norm (training mode, no gamma, eps 1e-3) + activation (0 none, 1 lrelu(0.1), 2 relu), rows x channels */

@@ -71,13 +71,14 @@ def hyperparams(netname: str, data_dims: Sequence[int], data_range=(0.0, 1.0), *
         clip_grads=True, clip_grad_value=10.0,                                         # :257-258
         share_theta_weights=False, share_phi_weights=False,                            # :213-214
     )
-    row = dict(_NETNAMES[netname])
+    hp["regularized_steps"] = list(range(hp["mc_steps"]))     # :224 - runs BEFORE the netname rows, i.e. with mc_steps == 8:
+    row = dict(_NETNAMES[netname])                             # a row that lengthens the chain (c_homog, :733) keeps KL on steps 0..7
     if "filter_sizes" in row:
         row["filter_sizes"] = [C if f is None else f for f in row["filter_sizes"]]
     hp.update(row)
     hp.update(overrides)
     hp["latent_dim"] = int(np.sum(hp["vlae_latent_dims"]))                             # :220
-    hp["regularized_steps"] = list(range(hp["mc_steps"]))                              # :224
+    hp["regularized_steps"] = [int(t) for t in hp["regularized_steps"] if 0 <= int(t) < hp["mc_steps"]]   # `step in ...`, :1154
     L = hp["vlae_levels"]
     assert len(hp["image_sizes"]) == L + 1 and len(hp["filter_sizes"]) == L + 2 and len(hp["vlae_latent_dims"]) == L
     return hp

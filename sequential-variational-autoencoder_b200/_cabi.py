@@ -103,6 +103,8 @@ PROTOTYPES = {
     "svae_op_fc": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 4),
     "svae_op_fc_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 4),
     "svae_op_tc_supported": (C.c_int, [C.c_int] * 7),
+    "svae_op_tc2_supported": (C.c_int, [C.c_int] * 8),
+    "svae_debug_block_tensor": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int64, C.POINTER(C.c_int32)]),
     "svae_debug_set_buffer": (C.c_int, [_P]),
     "svae_op_bn_act": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int]),
     "svae_op_bn_act_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int]),

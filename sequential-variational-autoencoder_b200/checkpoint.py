@@ -44,7 +44,17 @@ def beta_powers(adam_t, beta1=0.9, beta2=0.999):
     return beta1 ** (adam_t + 1), beta2 ** (adam_t + 1)
 
 
-def adam_t_from_beta1_power(beta1_power, beta1=0.9):
-    """Inverse of ``beta_powers`` (exact for any step count a float64 power can resolve, ~600 steps for beta1 = 0.9; the
-    ``__adam_t`` key is authoritative when present)."""
-    return max(0, int(round(math.log(float(beta1_power)) / math.log(beta1))) - 1)
+def adam_t_from_beta_powers(beta1_power, beta2_power, beta1=0.9, beta2=0.999):
+    """Inverse of ``beta_powers`` for a checkpoint written by TensorFlow (no ``__adam_t`` key).  The fp32 ``beta1_power``
+    = 0.9^(t+1) underflows to 0 after ~1000 updates, i.e. for any real checkpoint; ``beta2_power`` = 0.999^(t+1) resolves the
+    step count up to ~88 000 updates in fp32 and is used whenever it is positive.  Beyond that both bias corrections equal 1
+    to fp32 precision, so any large count gives the same update: 10^6 is returned."""
+    for power, beta in ((beta2_power, beta2), (beta1_power, beta1)):
+        if power is None:
+            continue
+        p = float(power)
+        if p > 0.0 and p < 1.0:
+            return max(0, int(round(math.log(p) / math.log(beta))) - 1)
+        if p >= 1.0:
+            return 0
+    return 1000000

@@ -45,13 +45,16 @@ def hyperparams(name, data_dims, data_range, **overrides):
         clip_grads=True, clip_grad_value=10.0,
         share_theta_weights=False, share_phi_weights=False,
     )
+    # sequential_vae.py:224 evaluates range(self.mc_steps) while mc_steps still holds its default 8, BEFORE the netname rows
+    # run: a row that lengthens the chain (c_homog: 25 steps, :733) keeps the KL term on steps 0..7 only
+    hp["regularized_steps"] = list(range(hp["mc_steps"]))
     row = dict(NETNAMES[name])
     if "filter_sizes" in row:
         row["filter_sizes"] = [C if f is None else f for f in row["filter_sizes"]]
     hp.update(row)
     hp.update(overrides)
     hp["latent_dim"] = int(sum(hp["vlae_latent_dims"]))
-    hp.setdefault("regularized_steps", list(range(hp["mc_steps"])))
+    hp["regularized_steps"] = [int(t) for t in hp["regularized_steps"] if 0 <= int(t) < hp["mc_steps"]]
     L = hp["vlae_levels"]
     if "image_sizes" not in row and "image_sizes" not in overrides:
         hp["image_sizes"] = [D >> i for i in range(L + 1)]

@@ -321,6 +321,9 @@ int apply_noise(const LaunchCtx& lc, const float* x, float* out, int64_t n, floa
                 float lo, float hi, uint64_t seed, float* draws /* [3,n] keep, salt, gaussian; may be nullptr */);
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base);
 int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n);  // dst += src
+// debug probes (parity tests only): dense fp32 copies of a bf16 planar copy / of a feature view
+int probe_bf_unpack(const LaunchCtx& lc, const BfAct& a, int coff, int C, int B, float* dst);   // -> [B,H,W,C]
+int probe_fv_gather(const LaunchCtx& lc, const FeatView& v, int64_t rows, int feats, float* dst);   // -> [rows,feats]
 
 // ---- tcgen05 contractions (kernels_tc.cu) ----------------------------------------------------------------------
 struct TcPlan;  // opaque per-layer packed-weight + schedule state

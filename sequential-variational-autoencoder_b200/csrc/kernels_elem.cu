@@ -1017,3 +1017,36 @@ int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n) {
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+// ---- debug probes (svae_debug_block_tensor): dense fp32 copies of tensors the step keeps in its own layouts ------------
+// Test infrastructure of the parity suite (local replay of every block of the real chain against the oracle layer); never
+// launched by a train / forward / generate call.
+__global__ void probe_bf_unpack_kernel(BfAct a, int coff, int C, int B, float* __restrict__ dst) {
+  const int64_t n = (int64_t)B * a.H * a.W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t p = i / C;
+    const int w = (int)(p % a.W); p /= a.W;
+    const int hh = (int)(p % a.H);
+    const int img = (int)(p / a.H);
+    dst[i] = __bfloat162float(a.p[bf_index(a, img, hh, w, coff + c)]);
+  }
+}
+__global__ void probe_fv_gather_kernel(FeatView v, int64_t rows, int feats, float* __restrict__ dst) {
+  const int64_t n = rows * feats;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / feats;
+    dst[i] = v.p[fv_addr(v, r, (int)(i - r * feats))];
+  }
+}
+
+int probe_bf_unpack(const LaunchCtx& lc, const BfAct& a, int coff, int C, int B, float* dst) {
+  probe_bf_unpack_kernel<<<flat_blocks((int64_t)B * a.H * a.W * C, lc.sm_count), 256, 0, lc.stream>>>(a, coff, C, B, dst);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int probe_fv_gather(const LaunchCtx& lc, const FeatView& v, int64_t rows, int feats, float* dst) {
+  probe_fv_gather_kernel<<<flat_blocks(rows * feats, lc.sm_count), 256, 0, lc.stream>>>(v, rows, feats, dst);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -77,6 +77,10 @@ struct Block {
   // set by the input-gradient kernel that produced this block's dL/d(activated output) when it already turned it into
   // g = da * act' and reduced the two backward sums (BnBwdFuse): the block's backward then skips pass 1
   bool g_fused = false;
+  // what the last forward / backward of this block read (svae_debug_block_tensor: local-replay parity tests)
+  View dbg_in{}; FeatView dbg_da{}; int dbg_gs = -1;
+  bool in_f32_valid = true;    // plan: the fp32 tensor this block reads is materialised (its producer does not skip_f32)
+  bool dbg_dy_f32 = false;     // last backward: the fp32 dL/dy was written (some consumer is not TMA-fed)
 };
 
 // Gradient scratch of ONE chain step's backward.  Two sets (step parity) let the side streams (weight gradients,
@@ -799,6 +803,18 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       for (Block& b : s.ta) if (b.out_bf.a.p == nullptr) b.skip_f32 = false;
       for (Block& b : s.tb) if (b.out_bf.a.p == nullptr) b.skip_f32 = false;
     }
+    // consumers of a skipped fp32 tensor (debug probe: which representation of its input a block can be shown)
+    for (int t = 0; t < T; ++t) {
+      Step& s = h->steps[t];
+      for (int k = 0; k + 1 < (int)s.inf.size(); ++k) s.inf[k + 1].in_f32_valid = !s.inf[k].skip_f32;
+      for (int k = 0; k + 1 < (int)s.enc.size(); ++k) s.enc[k + 1].in_f32_valid = !s.enc[k].skip_f32;
+      s.ta[L - 2].in_f32_valid = !s.decfc.skip_f32;
+      for (int l = L - 2; l >= 0; --l) {
+        s.tb[l].in_f32_valid = !s.ta[l].skip_f32 && !s.lat[l].skip_f32;
+        if (l > 0) s.ta[l - 1].in_f32_valid = !s.tb[l].skip_f32;
+      }
+      s.outb.in_f32_valid = s.gateb.in_f32_valid = !s.tb[0].skip_f32;
+    }
   }
   // io staging (host-buffer entry points)
   h->in_x = act.get<float>((size_t)B * h->D * h->D * C);
@@ -894,6 +910,7 @@ bool is_fc2d(const Block& b, int B) { return b.g.KH == 1 && b.rpi == 1 && b.res.
 
 int block_fwd(svae_handle* h, Block& b, int B, View in) {
   const bool fc2d = is_fc2d(b, B);
+  b.dbg_in = in;
   H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
                     fc2d ? nullptr : b.stats, nullptr, b.tw_f));
   LaunchCtx lc = h->lc();
@@ -910,11 +927,13 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
               int din_acc, cudaStream_t wst, Block* up = nullptr, float* up_dres = nullptr, int up_dres_acc = 0) {
   LaunchCtx lc = h->lc();
   const int64_t rows = (int64_t)B * b.rpi;
+  b.dbg_da = da; b.dbg_gs = (int)(&gs - h->gs);
   float* dy = gs.dy[b.dy_slot];
   const bool have_bf = gs.dy_bf[b.dy_slot].p != nullptr;
   const bool tc2d = b.tc2_dgrad && din != nullptr && have_bf;
   const bool tc2w = b.tc2_wgrad && have_bf && b.in_bf.p != nullptr;
   const BfDst dy_bf = (tc2d || tc2w) ? BfDst{gs.dy_bf[b.dy_slot], 0, 0, 0} : BfDst{};
+  b.dbg_dy_f32 = !tc2w || (din != nullptr && !tc2d) || dy_bf.a.p == nullptr;
   if (b.g_fused) {
     // pass 1 ran inside the kernel that produced da (it holds g now); the fp32 dy is only written for consumers that are
     // not TMA-fed
@@ -974,6 +993,7 @@ int skinny_block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, 
   // latent projection (K <= 32 inputs): dW via thread-per-feature, dz via row-wise dot with the [K,N] weights
   if (h->ablate & 2) return 0;
   LaunchCtx lc = h->lc();
+  b.dbg_da = da; b.dbg_gs = (int)(&gs - h->gs);
   if (lat_fused_supported(B, K))
     return lat_bwd_fused(lc, da, b.y, b.stats, h->pw(b.beta), zin, h->pw(b.w), B, K, b.feats, b.act, h->pg(b.w), h->pg(b.beta),
                          dz_out);
@@ -1108,6 +1128,17 @@ int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float*
   return 0;
 }
 
+// Philox key of the in-kernel eps.  Data-parallel replicas must draw INDEPENDENT noise for their shards (the effective batch
+// of noise samples is N*B, not B): the rank is folded into the key (splitmix64 of the rank, so that neighbouring ranks get
+// unrelated keys); rank 0 / single GPU keeps the caller's seed unchanged.
+uint64_t rank_seed(const svae_handle* h, uint64_t seed) {
+  if (h->rank == 0) return seed;
+  uint64_t z = (uint64_t)h->rank * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return seed ^ (z ^ (z >> 31));
+}
+
 float step_coef(const svae_handle* h, int t) { return t == 0 ? h->cfg.first_step_loss_coeff : 1.f; }
 bool step_has_recon(const svae_handle* h, int t) { return h->cfg.intermediate_reconstruction || t == h->T - 1; }
 bool step_has_kl(const svae_handle* h, int t) { return (h->cfg.regularized_mask >> t) & 1ull; }
@@ -1118,7 +1149,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
   h->cur = h->stream;
   h->ev_used = 0;
   tl_mark(h, h->stream, "main: step start", -1);
-  h->dyn_host.reg = reg; h->dyn_host.seed = seed; h->dyn_host.iteration = h->iteration;
+  h->dyn_host.reg = reg; h->dyn_host.seed = rank_seed(h, seed); h->dyn_host.iteration = h->iteration;
   H_TRY(dyn_push(h));
   H_TRY(repack_if_dirty(h));
   H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
@@ -1186,6 +1217,7 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   LaunchCtx lc = h->lc();
   const int has_gate = s.t > 0 ? 1 : 0;
   const int ldu = C + has_gate;
+  s.outb.dbg_gs = s.gateb.dbg_gs = (int)(&gs - h->gs);
   const float coef = step_has_recon(h, s.t)
                          ? 16.f * step_coef(h, s.t) * 2.f / ((float)B * h->D * h->D * C) : 0.f;   // :1146,1163,1168
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
@@ -1897,7 +1929,7 @@ static int train_step_graph(svae_handle* h, const float* x, const float* tgt, in
   h->adam_t += 1;
   const double b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
   h->dyn_host.lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, (double)h->adam_t)) / (1.0 - pow(b1, (double)h->adam_t)));
-  h->dyn_host.reg = reg; h->dyn_host.seed = seed; h->dyn_host.iteration = h->iteration;
+  h->dyn_host.reg = reg; h->dyn_host.seed = rank_seed(h, seed); h->dyn_host.iteration = h->iteration;
   H_TRY(dyn_push(h));
   if (ge == nullptr) {
     if (h->graphs.size() >= 8) {   // callers that rotate many buffers: drop the oldest
@@ -2242,6 +2274,35 @@ static int op_contract(svae_handle* h, Geom g, int B, const float* x, int ldx, c
   return 0;
 }
 
+
+// Weight gradient of the layer-level entry points: the SVAE_OPERAND_BF16 family takes the PRODUCTION kernel (tc2_wgrad, both
+// operands staged as bf16 planar copies exactly as the chain's producers write them) whenever the plan would; the
+// SIMT-staged tc_wgrad otherwise.  g: conv-gather geometry (X = conv input side, dY = conv output side), B set.
+static int op_wgrad(svae_handle* h, const Geom& g, const float* xrole, const float* yrole, float* dw, int operand, const Geom& fwd) {
+  LaunchCtx lc = h->lc();
+  H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * g.Cin * g.Cout, h->stream));
+  View xv = mkview(const_cast<float*>(xrole), g.Cin, 0), yv = mkview(const_cast<float*>(yrole), g.Cout, 0);
+  if (operand != SVAE_OPERAND_BF16 || !tc_wgrad_supported(fwd)) { H_TRY(simt_wgrad(lc, g, xv, yv, dw)); return 0; }
+  const char* e2 = getenv("SVAE_TC2");
+  if (!(e2 && e2[0] == '0') && tc2_wgrad_supported(g)) {
+    BfAct ax = bf_act_describe(tc2_input_kind(g), g.B, g.Hin, g.Win, g.Cin);
+    BfAct ay = bf_act_describe(g.stride == 1 ? 0 : 1, g.B, g.Hout, g.Wout, g.Cout);
+    void *bx = nullptr, *by = nullptr;
+    H_CUDA(cudaMalloc(&bx, bf_act_bytes(ax)));
+    if (cudaMalloc(&by, bf_act_bytes(ay)) != cudaSuccess) { cudaFree(bx); return fail(h, SVAE_ENOMEM, "op_wgrad: staging buffer"); }
+    ax.p = reinterpret_cast<__nv_bfloat16*>(bx); ay.p = reinterpret_cast<__nv_bfloat16*>(by);
+    int r = bf_act_fill(lc, ax, xv, g.Cin);
+    if (r == 0) r = bf_act_fill(lc, ay, yv, g.Cout);
+    if (r == 0) r = tc2_wgrad(lc, g, ax, ay, dw);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(bx); cudaFree(by);
+    if (r != 0) { h->err = g_err; return r; }
+    return 0;
+  }
+  H_TRY(tc_wgrad(lc, g, xv, yv, dw));
+  return 0;
+}
+
 int svae_op_conv2d(svae_handle* h, const float* x, const float* w, float* y, double* stats, int B, int H, int W, int Ci,
                    int Co, int stride, int operand) {
   if (!h) return SVAE_EINVAL;
@@ -2263,13 +2324,8 @@ int svae_op_conv2d_backward(svae_handle* h, const float* x, const float* w, cons
   Geom f = conv_geom(H, W, Ci, Co, stride);
   if (dx) { int r = op_contract(h, dgrad_geom(f), B, dy, Co, w, dx, Ci, nullptr, operand); if (r) return r; }
   if (dw) {
-    LaunchCtx lc = h->lc();
-    H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * Ci * Co, h->stream));
     Geom g = f; g.B = B;
-    if (operand == SVAE_OPERAND_BF16 && tc_wgrad_supported(f))
-      H_TRY(tc_wgrad(lc, g, mkview(const_cast<float*>(x), Ci, 0), mkview(const_cast<float*>(dy), Co, 0), dw));
-    else
-      H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(x), Ci, 0), mkview(const_cast<float*>(dy), Co, 0), dw));
+    H_TRY(op_wgrad(h, g, x, dy, dw, operand, f));
   }
   return 0;
 }
@@ -2280,13 +2336,8 @@ int svae_op_conv2d_transpose_backward(svae_handle* h, const float* x, const floa
   Geom f = deconv_geom(H, W, Ci, Co, stride);
   if (dx) { int r = op_contract(h, dgrad_geom(f), B, dy, Co, w, dx, Ci, nullptr, operand); if (r) return r; }
   if (dw) {
-    LaunchCtx lc = h->lc();
-    H_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * Ci * Co, h->stream));
-    Geom g = dgrad_geom(f); g.B = B; g.mode = 0;
-    if (operand == SVAE_OPERAND_BF16 && tc_wgrad_supported(f))
-      H_TRY(tc_wgrad(lc, g, mkview(const_cast<float*>(dy), Co, 0), mkview(const_cast<float*>(x), Ci, 0), dw));
-    else
-      H_TRY(simt_wgrad(lc, g, mkview(const_cast<float*>(dy), Co, 0), mkview(const_cast<float*>(x), Ci, 0), dw));
+    Geom g = dgrad_geom(f); g.B = B; g.mode = 0;   // conv geometry from the deconv's output grid (X role: dy) to its input grid
+    H_TRY(op_wgrad(h, g, dy, x, dw, operand, f));
   }
   return 0;
 }
@@ -2317,6 +2368,109 @@ int svae_op_fc_backward(svae_handle* h, const float* x, const float* w, const fl
   }
   return 0;
 }
+
+/* Debug probe (parity tests): one tensor of one block of the LAST forward / backward as a dense fp32 host array, exactly
+ * as the kernels consumed or produced it (a tensor that only exists as a bf16 planar copy is returned with its bf16 values). */
+int svae_debug_block_tensor(svae_handle* h, int t, int net, int index, int which, float* host_dst, int64_t capacity,
+                            int32_t dims_out[4]) {
+  if (!h || t < 0 || t >= h->T || !dims_out) return fail(h, SVAE_EINVAL, "svae_debug_block_tensor: bad argument");
+  H_CUDA(cudaSetDevice(h->device));
+  Step& s = h->steps[t];
+  const int B = h->last_B, L = h->L, C = h->C;
+  if (B <= 0) return fail(h, SVAE_ESTATE, "svae_debug_block_tensor: no forward has run");
+  Block* b = nullptr;
+  switch (net) {
+    case 0: if (index >= 0 && index < (int)s.inf.size()) b = &s.inf[index]; break;
+    case 1: if (index >= 0 && index < (int)s.enc.size()) b = &s.enc[index]; break;
+    case 2: if (t > 0) b = &s.encfc; break;
+    case 3: if (index >= 0 && index < (int)s.lat.size()) b = &s.lat[index]; break;
+    case 4: b = &s.decfc; break;
+    case 5: if (index >= 0 && index < (int)s.ta.size()) b = &s.ta[index]; break;
+    case 6: if (index >= 0 && index < (int)s.tb.size()) b = &s.tb[index]; break;
+    case 7: b = &s.outb; break;
+    case 8: if (t > 0) b = &s.gateb; break;
+    default: break;
+  }
+  if (b == nullptr) return fail(h, SVAE_EINVAL, "svae_debug_block_tensor: no such block");
+  const bool head = net == 7 || net == 8;
+  const Geom& g = b->g;
+  const int64_t rows = head ? (int64_t)B * g.Hout * g.Wout : (int64_t)B * b->rpi;
+  const int feats = head ? g.Cout : b->feats;
+  h->cur = h->stream;
+  LaunchCtx lc = h->lc();
+  lc.pdl_state = nullptr;
+  h->pdl_prev = 0;
+  // every stream that may still be writing the tensors
+  H_TRY(svae_sync(h));
+  if (h->upd_stream) H_CUDA(cudaStreamSynchronize(h->upd_stream));
+  int64_t n = 0;
+  int d[4] = {0, 0, 0, 0};
+  enum { SRC_NONE, SRC_BF, SRC_FV } kind = SRC_NONE;
+  BfAct bf{}; int bf_coff = 0, bf_C = 0; FeatView fv{}; int64_t fv_rows = 0; int fv_feats = 0;
+  const bool bwd = which == 3 || which == 4;
+  if (bwd && (!h->cfg.train_capacity || b->dbg_gs < 0)) return fail(h, SVAE_ESTATE, "svae_debug_block_tensor: no backward has run for this block");
+  GradSet* gs = bwd ? &h->gs[b->dbg_gs] : nullptr;
+  const int ldu = C + (t > 0 ? 1 : 0);
+  switch (which) {
+    case 0:   // IN: the contraction's input
+      if (b->tc2_fwd && b->in_bf.p != nullptr && !b->in_f32_valid) { kind = SRC_BF; bf = b->in_bf; bf_coff = 0; bf_C = g.Cin; d[0] = B; d[1] = g.Hin; d[2] = g.Win; d[3] = g.Cin; }
+      else if (head) { kind = SRC_FV; fv = FeatView{s.tb[0].out.p, s.tb[0].feats, 0, s.tb[0].feats, 1}; fv_rows = (int64_t)B * g.Hin * g.Win; fv_feats = g.Cin; d[0] = B; d[1] = g.Hin; d[2] = g.Win; d[3] = g.Cin; }
+      else if (b->dbg_in.p != nullptr) { kind = SRC_FV; fv = FeatView{b->dbg_in.p, b->dbg_in.ld, b->dbg_in.coff, g.Cin, 1}; fv_rows = (int64_t)B * g.Hin * g.Win; fv_feats = g.Cin; d[0] = B; d[1] = g.Hin; d[2] = g.Win; d[3] = g.Cin; }
+      break;
+    case 1:   // Y: pre-BN contraction output (heads: pre-sigmoid, without the bias)
+      if (head) { kind = SRC_FV; fv = FeatView{s.u, ldu, net == 8 ? C : 0, feats, 1}; }
+      else if (b->y != nullptr) { kind = SRC_FV; fv = FeatView{b->y, feats, 0, feats, 1}; }
+      fv_rows = rows; fv_feats = feats; d[0] = B; d[1] = g.Hout; d[2] = g.Wout; d[3] = g.Cout;
+      break;
+    case 2:   // OUT: activated output
+      if (head) break;
+      if (b->out.p != nullptr && !b->skip_f32) { kind = SRC_FV; fv = b->out; fv_rows = rows; fv_feats = feats; }
+      else if (b->out_bf.a.p != nullptr) {
+        kind = SRC_BF; bf = b->out_bf.a; bf_coff = b->out_bf.coff;
+        bf_C = b->out_bf.inner ? b->out_bf.inner : b->out.inner;
+      }
+      d[0] = B; d[1] = g.Hout; d[2] = g.Wout; d[3] = g.Cout;
+      if (kind == SRC_BF) { d[1] = bf.H; d[2] = bf.W; d[3] = bf_C; }
+      break;
+    case 3:   // DA: dL/d(activated output) as the block's backward read it
+      if (head || b->dbg_da.p == nullptr) break;
+      kind = SRC_FV; fv = b->dbg_da; fv_rows = rows; fv_feats = feats; d[0] = B; d[1] = g.Hout; d[2] = g.Wout; d[3] = g.Cout;
+      break;
+    case 4: { // DY: dL/d(pre-BN output) as the input / weight gradient kernels read it
+      d[0] = B; d[1] = g.Hout; d[2] = g.Wout; d[3] = g.Cout;
+      if (head) {
+        kind = SRC_FV; fv = FeatView{gs->d_u, ldu, net == 8 ? C : 0, feats, 1}; fv_rows = rows; fv_feats = feats;   // always written in fp32
+        break;
+      }
+      if (b->dy_slot < 0) break;
+      const bool have_bf = gs->dy_bf[b->dy_slot].p != nullptr && (b->tc2_dgrad || b->tc2_wgrad) && !b->dbg_dy_f32;
+      if (have_bf) { kind = SRC_BF; bf = gs->dy_bf[b->dy_slot]; bf_coff = 0; bf_C = g.Cout; }
+      else if (gs->dy[b->dy_slot] != nullptr && !(net == 3 && lat_fused_supported(B, g.Cin))) {
+        kind = SRC_FV; fv = FeatView{gs->dy[b->dy_slot], feats, 0, feats, 1}; fv_rows = rows; fv_feats = feats;
+      }
+      break;
+    }
+    case 5:   // RES: tensor added before the activation
+      if (!head && b->res.p != nullptr) { kind = SRC_FV; fv = b->res; fv_rows = rows; fv_feats = feats; d[0] = B; d[1] = g.Hout; d[2] = g.Wout; d[3] = g.Cout; }
+      break;
+    default: break;
+  }
+  if (kind == SRC_NONE) return fail(h, SVAE_EINVAL, "svae_debug_block_tensor: this tensor is not materialised for this block");
+  n = kind == SRC_BF ? (int64_t)B * bf.H * bf.W * bf_C : fv_rows * fv_feats;
+  for (int i = 0; i < 4; ++i) dims_out[i] = d[i];
+  if (host_dst == nullptr) return SVAE_OK;                       // size query
+  if (capacity < n) return fail(h, SVAE_EINVAL, "svae_debug_block_tensor: destination too small");
+  float* tmp = nullptr;
+  H_CUDA(cudaMalloc(&tmp, (size_t)n * 4));
+  int r = kind == SRC_BF ? probe_bf_unpack(lc, bf, bf_coff, bf_C, B, tmp) : probe_fv_gather(lc, fv, fv_rows, fv_feats, tmp);
+  cudaError_t e = cudaSuccess;
+  if (r == 0) e = cudaMemcpyAsync(host_dst, tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (r != 0) { h->err = g_err; return r; }
+  H_CUDA(e);
+  return SVAE_OK;
+}
 extern void* g_tc_debug_buffer;
 int svae_debug_set_buffer(void* dev_buffer) { g_tc_debug_buffer = dev_buffer; return 0; }
 
@@ -2326,6 +2480,20 @@ int svae_op_tc_supported(int transposed, int H, int W, int Ci, int Co, int strid
   if (direction == 0) return tc_supported(f) ? 1 : 0;
   if (direction == 1) { Geom d = dgrad_geom(f); d.B = 1; return tc_supported(d) ? 1 : 0; }
   return tc_wgrad_supported(f) ? 1 : 0;
+}
+/* 1 when the SVAE_OPERAND_BF16 family runs this contraction on the TMA-fed production kernels (tc2_conv_kernel for direction
+ * 0 / 1, tc2_wgrad_kernel for direction 2) at batch B, i.e. when the layer-level entry points exercise exactly the kernels of
+ * the chain; 0 when it takes the SIMT-staged tcgen05 variant or the fp32 kernels. */
+int svae_op_tc2_supported(int transposed, int B, int H, int W, int Ci, int Co, int stride, int direction) {
+  if (transposed == 2) return 0;
+  { const char* e2 = getenv("SVAE_TC2"); if (e2 && e2[0] == '0') return 0; }
+  Geom f = transposed ? deconv_geom(H, W, Ci, Co, stride) : conv_geom(H, W, Ci, Co, stride);
+  f.B = B;
+  if (direction == 0) return tc_supported(f) && tc2_supported(f) ? 1 : 0;
+  if (direction == 1) { Geom d = dgrad_geom(f); d.B = B; return tc_supported(d) && tc2_supported(d) ? 1 : 0; }
+  Geom g = f;
+  if (transposed) { g = dgrad_geom(f); g.mode = 0; g.B = B; }
+  return tc_wgrad_supported(f) && tc2_wgrad_supported(g) ? 1 : 0;
 }
 int svae_op_bn_act(svae_handle* h, const float* y, const float* beta, float* out, int64_t rows, int C, int act) {
   if (!h) return SVAE_EINVAL;

@@ -20,7 +20,7 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _cabi
-from .checkpoint import adam_t_from_beta1_power, beta_powers, tf_checkpoint_layout
+from .checkpoint import adam_t_from_beta_powers, beta_powers, tf_checkpoint_layout
 from .config import hyperparams, to_cabi_config
 
 
@@ -34,7 +34,7 @@ def _f32(a):
 
 class SequentialVAE:
     def __init__(self, dataset, batch_size, name, logger=None, version=0, base_dir=None, num_gpus=1, *, device=0,
-                 operand_dtype="fp32", train=True, max_batch=None, seed=0, restore=True, **overrides):
+                 operand_dtype=None, train=True, max_batch=None, seed=0, restore=True, **overrides):
         # --- attribute block (sequential_vae.py:195-258, abstract_network.py:85-107)
         self.dataset = dataset
         self.batch_size = batch_size
@@ -63,6 +63,13 @@ class SequentialVAE:
         self.share_theta_weights = bool(hp["share_theta_weights"])        # sequential_vae.py:213-214
         self.share_phi_weights = bool(hp["share_phi_weights"])
         self.save_freq = hp["save_freq"]
+        # A main.py-style caller (SequentialVAE(dataset, batch_size=..., name=...)) gets the production kernel family: bf16
+        # operands on the tcgen05 tensor cores with fp32 accumulation.  operand_dtype="fp32" (or SVAE_OPERAND=fp32) selects the
+        # strict-parity fp32 SIMT family.
+        if operand_dtype is None:
+            operand_dtype = os.environ.get("SVAE_OPERAND", "bf16")
+        if operand_dtype not in ("fp32", "bf16"):
+            raise ValueError("operand_dtype must be 'fp32' or 'bf16', got %r" % (operand_dtype,))
         self.operand_dtype = operand_dtype
         self.device = device
         self.max_batch = int(max_batch if max_batch is not None else batch_size)
@@ -143,7 +150,10 @@ class SequentialVAE:
                 self.load_network(ckpt)
                 self.LOG.info("Restored network from %s" % ckpt)
                 return
-            except Exception as e:  # abstract_network.py:146-150: warn and re-initialise
+            except (OSError, KeyError, ValueError, EOFError) as e:
+                # abstract_network.py:146-150: an unreadable / incompatible checkpoint -> warn and re-initialise.  Anything
+                # else (a library error half-way through the upload, ...) propagates: silently training from scratch on top
+                # of a partially restored handle would discard the checkpoint without telling anyone.
                 self.LOG.warning("Could not restore %s (%s); re-initialising" % (ckpt, e))
         rng = np.random.default_rng(seed)
         for p in self._params:
@@ -204,10 +214,6 @@ class SequentialVAE:
         existing file is moved to ``<models>/old`` first, like the reference."""
         os.makedirs(self.base_dir, exist_ok=True)
         path = os.path.join(self.base_dir, self.name + ".npz")
-        if os.path.exists(path):
-            old = os.path.join(os.path.dirname(self.base_dir) or ".", "old")
-            os.makedirs(old, exist_ok=True)
-            os.replace(path, os.path.join(old, self.name + "_v" + str(self.version) + ".npz"))
         train = bool(self._cfg.train_capacity)
         values = self.get_params()
         slots = {}
@@ -239,7 +245,14 @@ class SequentialVAE:
             blob["__adam_t"] = np.int64(adam_t)
         blob["__iteration"] = np.int64(self.iteration)
         blob["__learning_rate"] = np.float64(self.learning_rate)
-        np.savez(path, **blob)
+        # write next to the target, then swap: a crash mid-save leaves the previous checkpoint in place
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, **blob)
+        if os.path.exists(path):
+            old = os.path.join(os.path.dirname(self.base_dir) or ".", "old")
+            os.makedirs(old, exist_ok=True)
+            os.replace(path, os.path.join(old, self.name + "_v" + str(self.version) + ".npz"))
+        os.replace(tmp, path)
         self.LOG.info("Saved network to %s" % path)
         return path
 
@@ -263,9 +276,11 @@ class SequentialVAE:
                 self._chk(self._L.svae_adam_set(self._h, p["index"], m.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
             if "__adam_t" in blob.files:
                 self._chk(self._L.svae_adam_set_step_count(self._h, int(blob["__adam_t"])))
-            elif have_slots and "beta1_power" in blob.files:
-                self._chk(self._L.svae_adam_set_step_count(
-                    self._h, adam_t_from_beta1_power(blob["beta1_power"], self._cfg.adam_beta1)))
+            elif have_slots and ("beta2_power" in blob.files or "beta1_power" in blob.files):
+                self._chk(self._L.svae_adam_set_step_count(self._h, adam_t_from_beta_powers(
+                    blob["beta1_power"] if "beta1_power" in blob.files else None,
+                    blob["beta2_power"] if "beta2_power" in blob.files else None,
+                    self._cfg.adam_beta1, self._cfg.adam_beta2)))
         if "__iteration" in blob.files:
             self.iteration = int(blob["__iteration"])
             self.learning_rate = float(blob["__learning_rate"])
@@ -296,6 +311,34 @@ class SequentialVAE:
             raise ValueError("batch %d exceeds max_batch %d" % (shp[0], self.max_batch))
         return shp[0]
 
+    def _device_args(self, x, tgt, eps):
+        """Device-pointer path: libsvae reads raw ``data_ptr()`` values, so the tensors must be what the C ABI documents
+        (dense float32 on this handle's device, target shaped like the input, eps [T,B,Z]) and the work that PRODUCED them
+        must be ordered before the library's stream: when the handle runs on its own stream (no ``use_torch_stream``, or a
+        different torch stream is current) the producing stream is drained first.  Converted copies are kept alive until
+        the next call - the library's stream may still be reading them when this method returns."""
+        import torch
+
+        B = self._check_batch(x)
+        if not _is_cuda_tensor(tgt) or tuple(tgt.shape) != tuple(x.shape):
+            raise ValueError("batch_target must be a CUDA tensor shaped like input_batch, got %s" % (tuple(getattr(tgt, "shape", ())),))
+        if eps is not None and (not _is_cuda_tensor(eps) or tuple(eps.shape) != (self.mc_steps, B, self.latent_dim)):
+            raise ValueError("eps must be a CUDA tensor of shape [T,B,Z] = %s" % ((self.mc_steps, B, self.latent_dim),))
+        dev = torch.device("cuda", self.device)
+        for t in (x, tgt) + (() if eps is None else (eps,)):
+            if t.device != dev:
+                raise ValueError("tensor lives on %s, the handle on %s" % (t.device, dev))
+        conv = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+        same = tgt is x
+        x = conv(x)
+        tgt = x if same else conv(tgt)
+        eps = None if eps is None else conv(eps)
+        cur = torch.cuda.current_stream(dev)
+        if self._stream is None or self._stream.cuda_stream != cur.cuda_stream:
+            cur.synchronize()
+        self._keep, self._keep_prev = (x, tgt, eps), getattr(self, "_keep", None)
+        return x, tgt, eps, B
+
     # ------------------------------------------------------------------------------------------------ run wrappers
     def train(self, input_batch, batch_target, eps=None, seed=None):
         """ONE training update (sequential_vae.py:1341-1375): schedules, forward + backward + clipped Adam, periodic
@@ -307,10 +350,8 @@ class SequentialVAE:
         seed = int(self.iteration if seed is None else seed)
         ls = _cabi.Losses()
         if _is_cuda_tensor(input_batch):
-            B = self._check_batch(input_batch)
-            e = None if eps is None else eps.contiguous()
-            self._chk(self._L.svae_train_step(self._h, C.c_void_p(input_batch.data_ptr()),
-                                              C.c_void_p(batch_target.data_ptr()), B,
+            x, tgt, e, B = self._device_args(input_batch, batch_target, eps)
+            self._chk(self._L.svae_train_step(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(tgt.data_ptr()), B,
                                               C.c_void_p(e.data_ptr()) if e is not None else None, seed,
                                               float(self.learning_rate), float(reg)))
             self._chk(self._L.svae_read_losses(self._h, C.byref(ls)))
@@ -382,7 +423,7 @@ class SequentialVAE:
         self.iteration += 1
         self.learning_rate *= self.learning_rate_decay
         reg = 1 - math.exp(-self.iteration / self.reg_coeff_rate)
-        B = int(x_dev.shape[0])
+        x_dev, tgt_dev, eps_dev, B = self._device_args(x_dev, tgt_dev, eps_dev)
         self._chk(self._L.svae_train_step(self._h, C.c_void_p(x_dev.data_ptr()), C.c_void_p(tgt_dev.data_ptr()), B,
                                           C.c_void_p(eps_dev.data_ptr()) if eps_dev is not None else None,
                                           int(self.iteration if seed is None else seed), float(self.learning_rate),
@@ -414,6 +455,21 @@ class SequentialVAE:
         """Reverse-mode through the whole chain for the last ``forward``; read results with ``gradients()``."""
         self._chk(self._L.svae_backward(self._h))
         self.sync()
+
+    _NETS = dict(inf=0, enc=1, encfc=2, lat=3, decfc=4, ta=5, tb=6, out=7, gate=8)
+    _WHICH = dict(input=0, y=1, out=2, da=3, dy=4, res=5)
+
+    def block_tensor(self, step, net, index, which):
+        """Parity probe (TF lets callers ``sess.run`` any tensor of the graph): one tensor of one block of the last
+        ``forward`` / ``backward`` as the kernels consumed or produced it, as a dense [B,H,W,C] float32 array.
+        net: inf | enc | encfc | lat | decfc | ta | tb | out | gate; which: input | y | out | da | dy | res
+        (include/svae.h, svae_debug_block_tensor)."""
+        dims = (C.c_int32 * 4)()
+        args = (self._h, int(step), self._NETS[net], int(index), self._WHICH[which])
+        self._chk(self._L.svae_debug_block_tensor(*args, None, 0, dims))
+        out = np.empty([int(d) for d in dims], np.float32)
+        self._chk(self._L.svae_debug_block_tensor(*args, out.ctypes.data_as(C.c_void_p), out.size, dims))
+        return out
 
     def adam_step(self, learning_rate=None):
         self._chk(self._L.svae_adam_step(self._h, float(self.learning_rate if learning_rate is None else learning_rate)))

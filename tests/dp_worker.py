@@ -94,7 +94,7 @@ def main():
     else:
         dev = int(os.environ["LOCAL_RANK"])
         ds = S.SyntheticDataset("x", hi - lo, data_dims=DIMS, data_range=list(RNG))
-        model = S.SequentialVAE(ds, hi - lo, net, device=dev, restore=False, **OVER)
+        model = S.SequentialVAE(ds, hi - lo, net, device=dev, operand_dtype="fp32", restore=False, **OVER)
         model.set_params({k: v.numpy() for k, v in P.items()})
         attach_communicator(model, dist, rank, world)
         model.iteration = 4999          # reg_coeff = 1 - exp(-1) on the step below
@@ -112,7 +112,7 @@ def main():
             for r in range(world):
                 a, b = shard_batch(GB, r, world)
                 dsr = S.SyntheticDataset("x", b - a, data_dims=DIMS, data_range=list(RNG))
-                m2 = S.SequentialVAE(dsr, b - a, net, device=dev, restore=False, **OVER)
+                m2 = S.SequentialVAE(dsr, b - a, net, device=dev, operand_dtype="fp32", restore=False, **OVER)
                 m2.set_params({k: v.numpy() for k, v in P.items()})
                 m2.forward(x[a:b].numpy(), None, eps[:, a:b].numpy(), reg)
                 m2.backward()

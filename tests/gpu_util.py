@@ -29,7 +29,7 @@ def op_handle():
     """A tiny model whose handle is used for the layer-level svae_op_* entry points."""
     if "m" not in _handle_model:
         ds = S.SyntheticDataset("celebA", 2, data_dims=[16, 16, 3], data_range=[-1.0, 1.0])
-        _handle_model["m"] = S.SequentialVAE(ds, 2, "c_inhomog", restore=False, **TINY)
+        _handle_model["m"] = S.SequentialVAE(ds, 2, "c_inhomog", operand_dtype="fp32", restore=False, **TINY)
     m = _handle_model["m"]
     return m, m._L, m._h
 

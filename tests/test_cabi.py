@@ -129,6 +129,11 @@ def test_netname_rows():
     assert set(S.NETNAMES) == set(O._NETNAMES)
     hp = S.hyperparams("c_homog", [64, 64, 3], (-1, 1))
     assert hp["mc_steps"] == 25 and hp["share_theta_weights"] and hp["share_phi_weights"]
+    # regularized_steps = range(mc_steps) is evaluated at sequential_vae.py:224, before the netname row lengthens the chain (:733)
+    assert hp["regularized_steps"] == list(range(8))
+    assert to_cabi_config(hp, 4).regularized_mask == 0xFF
+    assert S.hyperparams("m_inhomog", [32, 32, 1], (0, 1))["regularized_steps"] == list(range(5))
+    assert S.hyperparams("c_inhomog", [64, 64, 3], (-1, 1), mc_steps=3, regularized_steps=[0, 2, 7])["regularized_steps"] == [0, 2]
     assert not S.hyperparams("sequential_vae_celebA_homog_fixed_length", [64, 64, 3], (-1, 1))["share_phi_weights"]
 
 
@@ -166,7 +171,7 @@ def test_synthetic_dataset_shapes():
 def test_checkpoint_layout_is_the_tf_saver_variable_set():
     """abstract_network.py:124-152: tf.train.Saver() writes every global variable - trainables, BN moving statistics,
     Adam slots of the variables that receive a gradient (not the dead branch), beta powers."""
-    from seqvae_b200.checkpoint import adam_t_from_beta1_power, beta_powers, tf_checkpoint_layout
+    from seqvae_b200.checkpoint import adam_t_from_beta_powers, beta_powers, tf_checkpoint_layout
 
     L = _cabi.lib()
     for name, shared in (("c_inhomog", False), ("sequential_vae_celebA_homog", True)):
@@ -193,7 +198,13 @@ def test_checkpoint_layout_is_the_tf_saver_variable_set():
             assert "theta/generative_network/BatchNorm/moving_mean" in names and not any("_step_1/" in x for x in names)
         assert len(tf_checkpoint_layout(table, train=False)) == n + 2 * n_bn
     for t in (0, 1, 7, 250):
-        assert adam_t_from_beta1_power(beta_powers(t)[0]) == t
+        assert adam_t_from_beta_powers(*beta_powers(t)) == t
+        assert adam_t_from_beta_powers(beta_powers(t)[0], None) == t
+    # a real TF checkpoint: the fp32 beta1_power has underflowed to 0, beta2_power still resolves the step count
+    for t in (1500, 20000, 80000):
+        b1p, b2p = (np.float32(v) for v in beta_powers(t))
+        assert b1p == 0.0 and abs(adam_t_from_beta_powers(b1p, b2p) - t) <= max(2, t * 2e-4)
+    assert adam_t_from_beta_powers(np.float32(0.0), np.float32(0.0)) == 1000000
 
 
 def test_noisy_trainer_host_logic_with_a_fake_network():

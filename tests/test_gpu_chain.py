@@ -210,10 +210,27 @@ def test_loss_flags():
     over = dict(TINY, mc_steps=3, first_step_loss_coeff=0.5, intermediate_reconstruction=False, regularized_steps=[0, 2],
                 latent_mean_clip=0.05, latent_prior_stddev=2.0, min_highway_ratio=0.1, max_highway_ratio=0.8)
     model, hp, P = make_pair("c_inhomog", [16, 16, 3], (-1.0, 1.0), 16, "fp32", **over)
-    hp["regularized_steps"] = [0, 2]
+    assert hp["regularized_steps"] == [0, 2]
     x, eps = make_inputs(hp, 16)
     fw, grads, fw32, g32 = _oracle_pair(hp, P, x, x, eps, 0.8)
     out = model.forward(x.numpy(), None, eps.numpy(), 0.8)
+    _check_forward(out, fw, "fp32", fw32)
+    model.backward()
+    _check_grads(model, grads, hp, "fp32", g32)
+    model.close()
+
+
+def test_long_chain_regularizes_the_first_eight_steps_only():
+    """A chain longer than the default 8 steps keeps the KL term on steps 0..7 only (sequential_vae.py:224 runs before the
+    netname rows / overrides change mc_steps): steps 8, 9 contribute reconstruction terms only."""
+    over = dict(TINY, mc_steps=10)
+    model, hp, P = make_pair("c_inhomog", [16, 16, 3], (-1.0, 1.0), 6, "fp32", **over)
+    assert hp["regularized_steps"] == list(range(8)) and model.hp["regularized_steps"] == list(range(8))
+    x, eps = make_inputs(hp, 6)
+    fw, grads, fw32, g32 = _oracle_pair(hp, P, x, x, eps, 0.8)
+    out = model.forward(x.numpy(), None, eps.numpy(), 0.8)
+    total = sum(16 * r for r in out["recon"]) + 0.8 * sum(out["kl"][:8])
+    assert math.isclose(out["loss"], total, rel_tol=1e-5)
     _check_forward(out, fw, "fp32", fw32)
     model.backward()
     _check_grads(model, grads, hp, "fp32", g32)
@@ -322,7 +339,7 @@ def test_full_size_properties_celeba_b100():
     finite per-step ELBO terms in the expected range at init, loss decreases over a few Adam steps on a fixed batch,
     dead / inert variables untouched, per-step losses consistent with the returned total."""
     ds = S.SyntheticDataset("celebA", 100)
-    model = S.SequentialVAE(ds, 100, "c_inhomog", restore=False)
+    model = S.SequentialVAE(ds, 100, "c_inhomog", operand_dtype="fp32", restore=False)
     x = ds.next_batch(100)
     before = model.get_params()
     first = None

@@ -72,8 +72,8 @@ def test_train_denoise_equals_train_on_the_corrupted_batch():
     """svae_train_step_host_denoise == apply_noise followed by train(noisy, clean) (trainer.py:100-104)."""
     B = 6
     ds = S.SyntheticDataset("x", B, data_dims=[16, 16, 3], data_range=[-1.0, 1.0])
-    a = S.SequentialVAE(ds, B, "c_inhomog", restore=False, **TINY)
-    b = S.SequentialVAE(ds, B, "c_inhomog", restore=False, **TINY)
+    a = S.SequentialVAE(ds, B, "c_inhomog", operand_dtype="fp32", restore=False, **TINY)
+    b = S.SequentialVAE(ds, B, "c_inhomog", operand_dtype="fp32", restore=False, **TINY)
     b.set_params(a.get_params())
     rng = np.random.default_rng(0)
     for it in range(3):                                          # eager step, then the captured graph
@@ -104,7 +104,7 @@ def test_noisy_trainer_loop(denoise):
     """NoisyTrainer(network, dataset, args, logger, base_dir).train() as main.py drives it (main.py:87-89)."""
     B = 8
     ds = S.SyntheticDataset("x", B, data_dims=[16, 16, 3], data_range=[-1.0, 1.0])
-    net = S.SequentialVAE(ds, B, "c_inhomog", restore=False, **TINY)
+    net = S.SequentialVAE(ds, B, "c_inhomog", operand_dtype="fp32", restore=False, **TINY)
     args = argparse.Namespace(batch_size=B, denoise_train=denoise, vis_frequency=4, plot_reconstruction=False, use_gui=False)
     tr = S.NoisyTrainer(net, ds, args, logging.getLogger("test"), "unused")
     if not denoise:
