@@ -206,6 +206,22 @@ struct BnBwdFuse {
   int C, act;
   long long rows;
 };
+// Batch-norm FORWARD fused into the contraction that produces the block's pre-BN tensor (conv2d_bn_lrelu / conv2d_t_bn[_relu]
+// as ONE kernel, abstract_network.py:17-24,36-61): every accumulator tile of the CTA stays in tensor memory, pass 1 writes the
+// pre-BN tensor (kept for the backward) and reduces the channel statistics, a grid-wide barrier makes them final, pass 2 reads
+// the accumulators again, normalises, adds the ladder shortcut, applies the activation and writes the activated output in
+// the layouts its consumers read (fp32 channel window and / or the bf16 planar copy of the next TMA-fed contraction).
+struct BnFwdFuse {
+  const float* beta;                 // [C]
+  const float* res;                  // tensor added before the activation (4-D view) or nullptr
+  int res_ld, res_coff;
+  float* out;                        // fp32 activated output (channel window of a concat buffer) or nullptr
+  int out_ld, out_coff;
+  BfDst bf;                          // bf16 planar copy of the activated output (bf.a.p == nullptr: none)
+  unsigned* counter;                 // grid-barrier counter, zeroed by the caller before the launch
+  int act;
+  long long rows;                    // B*Hout*Wout (batch-norm population)
+};
 BfAct bf_act_describe(int kind, int B, int H, int W, int C);
 size_t bf_act_bytes(const BfAct& d);
 int bf_act_fill(const LaunchCtx& lc, const BfAct& d, View src, int C);   // fp32 NHWC window -> padded bf16 copy (incl. zeros)
@@ -213,7 +229,10 @@ bool tc2_supported(const Geom& g);
 int tc2_input_kind(const Geom& g);
 // w_tile_width: tile width the weights were packed with (tc_pack_entry / tc_pack_weights): 128 or tc2_pick_ntw(g)
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
-                    double* stats, const BnBwdFuse* fuse = nullptr, int w_tile_width = 128);
+                    double* stats, const BnBwdFuse* fuse = nullptr, int w_tile_width = 128, const BnFwdFuse* fwd_fuse = nullptr);
+// can the contraction g (B set, weights packed with w_tile_width) keep all of its accumulator tiles in tensor memory, i.e. run
+// with a BnFwdFuse?  C = output channels
+bool tc2_bnf_supported(const Geom& g, int w_tile_width, int sm_count, View out, int C);
 int tc2_pick_ntw(const Geom& g, int sm_count);
 bool tc2_fuse_supported(const Geom& g, View out, int C);   // can this launch carry a BnBwdFuse over its first C output channels?
 bool tc2_wgrad_supported(const Geom& g);   // g: conv-gather geometry (see tc_wgrad)

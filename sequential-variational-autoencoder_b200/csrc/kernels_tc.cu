@@ -728,6 +728,7 @@ namespace {
 
 constexpr int A_STAGES_MAX = 4;
 constexpr unsigned W_RESIDENT_MAX = 144 * 1024;
+constexpr int ACC_BUFS_MAX = 16;   // accumulator sets of a CTA (MODE 2 keeps one per tile: 16 x 32 columns = all of TMEM)
 
 struct Tc2Params {
   TcParams t;               // geometry (mode, padded space, taps, chunking) as for the SIMT-staged kernel
@@ -749,6 +750,8 @@ struct Tc2Params {
   long long plane_rows;     // rows between parity planes
   long long group_rows;     // rows between 8-channel groups
   BnBwdFuse fz;             // fz.y != nullptr: batch-norm backward pass 1 of the consuming block fused into the epilogue
+  BnFwdFuse ff;             // MODE 2: batch-norm forward of THIS block fused (all tiles resident in TMEM, grid barrier, pass 2)
+  unsigned grid_ctas;       // MODE 2: CTAs of the launch (grid-barrier target)
   // per-tap issue table (host-built): A start offset inside a halo stage in 16-byte units (parity plane + lo + shift), and
   // accumulator index | 0x80 when the tap is the first one that writes its accumulator
   unsigned tap_a[16];
@@ -757,7 +760,7 @@ struct Tc2Params {
 
 struct SmemHeader2 {
   unsigned long long a_full[A_STAGES_MAX], a_empty[A_STAGES_MAX], w_full[W2_STAGES_MAX], w_empty[W2_STAGES_MAX];
-  unsigned long long acc_full[2], acc_empty[2];
+  unsigned long long acc_full[ACC_BUFS_MAX], acc_empty[2];
   unsigned tmem_base, pad;
   float s_sum[4][128], s_sq[4][128];
   // fused batch-norm backward: per channel of this CTA  f_mean = shift (-mean*rstd), f_rstd = scale, f_beta (read as float4)
@@ -769,10 +772,28 @@ struct SmemHeader2 {
 };
 #define DBG2(slot) do { if (P.dbg != nullptr) { const unsigned long long t_ = gtimer(); if ((threadIdx.x & 31) == 0) hdr->ts[slot] = t_; } } while (0)
 
-// FUSED: the epilogue carries batch-norm backward pass 1 of the consuming block (BnBwdFuse); a separate instantiation so
-// that the plain kernel keeps its register budget.
-template <bool FUSED>
-__global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
+// grid-wide barrier of the MODE 2 kernel: every CTA of the launch is resident (the host sizes the grid to the SMs' capacity and
+// the only other barrier user, if any, is an earlier launch on the same stream whose CTAs are all resident already), so the
+// wait is bounded by the slowest CTA's pass 1.  A protocol bug becomes a trap (reported CUDA error), never a hung GPU.
+__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsigned target) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+  unsigned seen = 0;
+  for (unsigned it = 0;; ++it) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    if (seen >= target) break;
+    __nanosleep(64);
+    if (it > (1u << 24)) __trap();
+  }
+}
+
+// MODE 0: plain contraction (+ forward statistics).  MODE 1: the epilogue carries batch-norm backward pass 1 of the consuming
+// block (BnBwdFuse).  MODE 2: batch-norm forward of this block fused (BnFwdFuse).  Separate instantiations so that the plain
+// kernel keeps its register budget.
+template <int MODE>
+__global__ void __launch_bounds__(224, MODE != 0 ? 2 : 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
+  constexpr bool FUSED = MODE == 1;
+  constexpr bool BNF = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const TcParams& P = PP.t;
   SmemHeader2* hdr = reinterpret_cast<SmemHeader2*>(smem_raw);
@@ -796,7 +817,8 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
   if (tid == 0) {
     for (int s = 0; s < A_STAGES_MAX; ++s) { mbar_init(smem_u32(&hdr->a_full[s]), 1); mbar_init(smem_u32(&hdr->a_empty[s]), 1); }
     for (int s = 0; s < W2_STAGES_MAX; ++s) { mbar_init(smem_u32(&hdr->w_full[s]), 1); mbar_init(smem_u32(&hdr->w_empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&hdr->acc_full[b]), 1); mbar_init(smem_u32(&hdr->acc_empty[b]), 128); }
+    for (int b = 0; b < ACC_BUFS_MAX; ++b) mbar_init(smem_u32(&hdr->acc_full[b]), 1);
+    for (int b = 0; b < 2; ++b) mbar_init(smem_u32(&hdr->acc_empty[b]), 128);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(&hdr->tmem_base), PP.tmem_cols);
@@ -897,8 +919,8 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
     if (PP.w_resident && my_tiles > 0) mbar_wait(smem_u32(&hdr->w_full[0]), 0);
     DBG2(3);
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int b = ti % PP.acc_bufs;
-      if (ti >= PP.acc_bufs) mbar_wait(smem_u32(&hdr->acc_empty[b]), (unsigned)((ti / PP.acc_bufs) - 1) & 1u);
+      const int b = BNF ? ti : ti % PP.acc_bufs;     // MODE 2: every tile keeps its own accumulator set until pass 2
+      if (!BNF && ti >= PP.acc_bufs) mbar_wait(smem_u32(&hdr->acc_empty[b]), (unsigned)((ti / PP.acc_bufs) - 1) & 1u);
       tc_fence_after();
       const unsigned acc_base = tmem_base + (unsigned)b * PP.acc_cols;
       for (int c = 0; c < P.NC; ++c, ++it) {
@@ -977,8 +999,8 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int b = ti % PP.acc_bufs;
-      mbar_wait(smem_u32(&hdr->acc_full[b]), (unsigned)(ti / PP.acc_bufs) & 1u);
+      const int b = BNF ? ti : ti % PP.acc_bufs;
+      mbar_wait(smem_u32(&hdr->acc_full[b]), BNF ? 0u : ((unsigned)(ti / PP.acc_bufs) & 1u));
       tc_fence_after();
       if (ti == 0 && warp == 3) DBG2(6);
       const int q0 = ((int)blockIdx.x + ti * (int)gridDim.x) * TILE_M;
@@ -1103,7 +1125,7 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&hdr->acc_empty[b]));
+      if (!BNF) mbar_arrive(smem_u32(&hdr->acc_empty[b]));
       if (ti == 0 && warp == 3) DBG2(7);
       if (ti == my_tiles - 1 && warp == 3) DBG2(9);
     }
@@ -1129,6 +1151,85 @@ __global__ void __launch_bounds__(224, FUSED ? 2 : 1) tc2_conv_kernel(const __gr
           atomicAdd(&P.stats[P.n_valid + n0 + col], (double)s2);
         }
       }
+    }
+    if constexpr (BNF) {
+      // ---- grid-wide barrier: the channel statistics are final once every CTA of the launch has added its share ----
+      const BnFwdFuse& ff = PP.ff;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) grid_barrier_arrive_wait(ff.counter, PP.grid_ctas);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int col = et; col < 128; col += 128) {
+        const int c = n0 + col;
+        float scale = 0.f, shift = 0.f;
+        if (col < Nt && c < P.n_valid) {
+          const double m = __ldcg(&P.stats[c]) / (double)ff.rows;
+          double var = __ldcg(&P.stats[P.n_valid + c]) / (double)ff.rows - m * m;
+          if (var < 0.0) var = 0.0;
+          const float mean = (float)m;
+          scale = (float)(1.0 / sqrt(var + (double)SVAE_BN_EPS));
+          shift = ff.beta[c] - mean * scale;
+        }
+        hdr->f_rstd[col] = scale; hdr->f_mean[col] = shift;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- pass 2: accumulators -> normalise (+ shortcut) -> activation -> fp32 channel window and / or bf16 planar copy ----
+      const float neg = ff.act == ACT_LRELU ? SVAE_LRELU_SLOPE : ff.act == ACT_RELU ? 0.f : 1.f;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int q0 = ((int)blockIdx.x + ti * (int)gridDim.x) * TILE_M;
+        const int q = q0 + quarter * 32 + lane;
+        bool valid = q < (int)P.Q;
+        int n = 0, r = 0, cc = 0;
+        if (valid) {
+          const int t = q / P.Wp;
+          cc = q - t * P.Wp;
+          n = t / P.Hp;
+          r = t - n * P.Hp;
+          valid = r < P.Hv && cc < P.Wv;
+        }
+        const unsigned acc_base = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)ti * PP.acc_cols;
+        for (int a = 0; a < P.nacc; ++a) {
+          int oh = r, ow = cc;
+          if (P.mode == 2) { oh = 2 * r + (a >> 1); ow = 2 * cc + (a & 1); }
+          const size_t pix = ((size_t)n * P.Hout + oh) * P.Wout + ow;
+          for (int nn = 0; nn < Nt; nn += 32) {
+            float v[32];
+            tmem_ld_upto32(acc_base + (unsigned)(a * Nt + nn), v, Nt - nn);      // warp-collective: outside the `valid` branch
+            const int ncols = max(0, min(min(32, Nt - nn), P.n_valid - (n0 + nn)));
+            if (!valid) continue;
+            const int cbase = n0 + nn;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              if (k < ncols) {
+                float o[8];
+                const float4 sc0 = *reinterpret_cast<const float4*>(&hdr->f_rstd[nn + k]);
+                const float4 sc1 = *reinterpret_cast<const float4*>(&hdr->f_rstd[nn + k + 4]);
+                const float4 sh0 = *reinterpret_cast<const float4*>(&hdr->f_mean[nn + k]);
+                const float4 sh1 = *reinterpret_cast<const float4*>(&hdr->f_mean[nn + k + 4]);
+                const float ss[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                const float hh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(v[k + e], ss[e], hh[e]);
+                if (ff.res != nullptr) {
+                  const float4* rp = reinterpret_cast<const float4*>(ff.res + pix * ff.res_ld + ff.res_coff + cbase + k);
+                  const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                  o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * neg;
+                if (ff.out != nullptr) {
+                  float4* op = reinterpret_cast<float4*>(ff.out + pix * ff.out_ld + ff.out_coff + cbase + k);
+                  op[0] = make_float4(o[0], o[1], o[2], o[3]);
+                  op[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+                if (ff.bf.a.p != nullptr)
+                  *reinterpret_cast<uint4*>(ff.bf.a.p + bf_index(ff.bf.a, n, oh, ow, ff.bf.coff + cbase + k)) = pack8_bf16(o);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
     }
   }
   __syncthreads();
@@ -1266,7 +1367,7 @@ BfAct bf_act_describe(int kind, int B, int H, int W, int C) {
   const int reach = 2 * d.Wp + 2;         // largest |tap shift| of any geometry that reads this layout
   d.front = (reach + 7) & ~7;
   d.plane_rows = kind == 2 ? ((Q + reach + 7) & ~7LL) : Q;
-  const long long tail = 128 + reach + 8;
+  const long long tail = 128 + 2 * reach + 24;   // the tap-stacked weight gradient reads copies shifted by up to one padded row + 3 pixels
   d.group_rows = (d.front + (kind == 2 ? 4 : 1) * d.plane_rows + tail + 7) & ~7LL;
   d.p = nullptr;
   return d;
@@ -1321,8 +1422,67 @@ bool tc2_fuse_supported(const Geom& g, View out, int C) {
          (((uintptr_t)out.p & 15) == 0) && tc2_supported(g);
 }
 
+// Launch shape of geometry g: CTAs along x, CTAs per SM, and - for the all-resident (MODE 2) variant - accumulator sets per
+// CTA and the tensor-memory allocation that holds them.  Returns false when the all-resident variant does not fit.
+namespace {
+struct Tc2Launch { int ctas, per_sm, ntiles, nsub, tpc; unsigned tmem_cols; };
+bool tc2_launch_shape(const Tc2Params& PP, int sm_count, bool all_resident, Tc2Launch& L) {
+  const TcParams& P = PP.t;
+  const size_t smem = smem_bytes2(PP);
+  L.nsub = ((P.N_p < 128 ? P.N_p : 128) + PP.ntw - 1) / PP.ntw;
+  L.ntiles = (P.N_p + 127) / 128;
+  int per_sm = (int)((227 * 1024) / smem);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  if (!all_resident) {
+    if (PP.tmem_cols * (unsigned)per_sm > 512) per_sm = 1;
+    int ctas = sm_count * per_sm / (L.ntiles * L.nsub);
+    if (ctas < 1) ctas = 1;
+    if (ctas > PP.tiles) ctas = PP.tiles;
+    L.ctas = ctas; L.per_sm = per_sm; L.tpc = 0; L.tmem_cols = PP.tmem_cols;
+    return true;
+  }
+  for (; per_sm >= 1; --per_sm) {
+    int ctas = sm_count * per_sm / (L.ntiles * L.nsub);
+    if (ctas < 1) return false;            // more channel tiles than the machine holds at once: no grid barrier possible
+    if (ctas > PP.tiles) ctas = PP.tiles;
+    const int tpc = (PP.tiles + ctas - 1) / ctas;
+    unsigned cols = 32;
+    while (cols < (unsigned)tpc * PP.acc_cols) cols <<= 1;
+    if (tpc <= ACC_BUFS_MAX && cols * (unsigned)per_sm <= 512) {
+      L.ctas = ctas; L.per_sm = per_sm; L.tpc = tpc; L.tmem_cols = cols;
+      return true;
+    }
+  }
+  return false;
+}
+}  // namespace
+
+bool tc2_bnf_supported(const Geom& g, int w_tile_width, int sm_count, View out, int C) {
+  // SVAE_BNF=1 enables the single-kernel conv + batch-norm forward.  Measured on B200 (CelebA-64, B = 100, T = 8): 97 fewer
+  // launches per step but 12.39 instead of 11.94 ms/step - the all-resident accumulators take most of an SM's tensor memory, so
+  // the next kernel's programmatic-dependent-launch prologue can no longer overlap, and 4 epilogue warps per CTA do the work a
+  // standalone elementwise kernel spreads over the whole SM.  It also shares the hazard of every grid barrier outside a
+  // cooperative launch: a co-resident CTA of another stream that blocks in tcgen05.alloc on columns held by a spinning CTA while
+  // occupying the shared memory its sibling needs closes a cycle (seen at B = 256).  Off by default; kept for the record.
+  static const bool enabled = getenv("SVAE_BNF") && getenv("SVAE_BNF")[0] == '1';
+  if (!enabled || C <= 0 || C % 8 != 0 || C != g.Cout) return false;
+  if (out.ld % 4 || out.coff % 4 || (((uintptr_t)out.p) & 15)) return false;
+  Tc2Params PP;
+  if (!build_params2(g, PP)) return false;
+  const int best = w_tile_width < 128 ? w_tile_width : tc2_pick_ntw(g, sm_count);
+  if (best < 128) {
+    Tc2Params Q2;
+    if (build_params2(g, Q2, best) && smem_bytes2(Q2) <= 227 * 1024) PP = Q2;
+    else if (w_tile_width < 128) return false;
+  }
+  if (smem_bytes2(PP) > 227 * 1024) return false;
+  Tc2Launch L;
+  return tc2_launch_shape(PP, sm_count, true, L);
+}
+
 int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int chan0, const void* w_packed, View out,
-                    double* stats, const BnBwdFuse* fuse, int w_tile_width) {
+                    double* stats, const BnBwdFuse* fuse, int w_tile_width, const BnFwdFuse* fwd_fuse) {
   Tc2Params PP;
   if (!build_params2(g, PP)) { svae_global_error() = "tc2: unsupported geometry"; return -1; }
   {
@@ -1356,26 +1516,50 @@ int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int cha
   PP.group_rows = in.group_rows;
   const size_t smem = smem_bytes2(PP);
   static bool configured = false;
+  static int occ[3] = {1, 1, 1};
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int nsub = ((P.N_p < 128 ? P.N_p : 128) + PP.ntw - 1) / PP.ntw;
-  const int ntiles = (P.N_p + 127) / 128;
-  int per_sm = (int)((227 * 1024) / smem);
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  if (PP.tmem_cols * (unsigned)per_sm > 512) per_sm = 1;
-  int ctas = lc.sm_count * per_sm / (ntiles * nsub);
-  if (ctas < 1) ctas = 1;
-  if (ctas > PP.tiles) ctas = PP.tiles;
+  Tc2Launch L;
+  const bool bnf = fwd_fuse != nullptr;
+  if (bnf && (fuse != nullptr || stats == nullptr || g.accumulate)) { svae_global_error() = "tc2: fused batch-norm forward needs forward statistics and a plain store"; return -1; }
+  if (!tc2_launch_shape(PP, lc.sm_count, bnf, L)) { svae_global_error() = "tc2: accumulator tiles do not fit tensor memory for the fused batch-norm forward"; return -1; }
+  if (bnf) {
+    // the grid barrier needs every CTA resident at once: check what the device really grants this kernel at this footprint
+    int fit = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, tc2_conv_kernel<2>, 224, smem));
+    (void)occ;
+    if (fit < L.per_sm) {
+      if (fit < 1) { svae_global_error() = "tc2: fused batch-norm forward kernel does not fit an SM"; return -1; }
+      Tc2Params Q1 = PP;       // retry with one CTA per SM
+      const int ctas = lc.sm_count / (L.ntiles * L.nsub);
+      if (ctas < 1) { svae_global_error() = "tc2: fused batch-norm forward grid exceeds the machine"; return -1; }
+      L.ctas = ctas > PP.tiles ? PP.tiles : ctas; L.per_sm = 1;
+      L.tpc = (PP.tiles + L.ctas - 1) / L.ctas;
+      unsigned cols = 32;
+      while (cols < (unsigned)L.tpc * PP.acc_cols) cols <<= 1;
+      if (L.tpc > ACC_BUFS_MAX || cols > 512) { svae_global_error() = "tc2: accumulator tiles do not fit tensor memory (one CTA per SM)"; return -1; }
+      L.tmem_cols = cols;
+      (void)Q1;
+    }
+    PP.acc_bufs = L.tpc;
+    PP.tmem_cols = L.tmem_cols;
+    PP.ff = *fwd_fuse;
+    PP.grid_ctas = (unsigned)(L.ctas * L.ntiles * L.nsub);
+  }
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
+  const double out_elems = (double)g.B * g.Hout * g.Wout * g.Cout;
   ProfScope ps(lc, KC_GEMM_TC, 2.0 * pix * g.KH * g.KW * g.Cin * g.Cout,
-               2.0 * (double)g.B * g.Hin * g.Win * g.Cin + 4.0 * (double)g.B * g.Hout * g.Wout * g.Cout +
-                   2.0 * g.KH * g.KW * g.Cin * g.Cout, &g);
-  if (fuse != nullptr) CUDA_TRY(launch_k(lc, tc2_conv_kernel<true>, dim3((unsigned)ctas, (unsigned)ntiles, (unsigned)nsub), dim3(224), smem, PP));
-  else CUDA_TRY(launch_k(lc, tc2_conv_kernel<false>, dim3((unsigned)ctas, (unsigned)ntiles, (unsigned)nsub), dim3(224), smem, PP));
+               2.0 * (double)g.B * g.Hin * g.Win * g.Cin + 4.0 * out_elems + 2.0 * g.KH * g.KW * g.Cin * g.Cout +
+                   (bnf ? (fwd_fuse->res ? 4.0 : 0.0) * out_elems + (fwd_fuse->out ? 4.0 : 0.0) * out_elems +
+                              (fwd_fuse->bf.a.p ? 2.0 : 0.0) * out_elems : 0.0), &g);
+  const dim3 grid((unsigned)L.ctas, (unsigned)L.ntiles, (unsigned)L.nsub);
+  if (bnf) CUDA_TRY(launch_k(lc, tc2_conv_kernel<2>, grid, dim3(224), smem, PP));
+  else if (fuse != nullptr) CUDA_TRY(launch_k(lc, tc2_conv_kernel<1>, grid, dim3(224), smem, PP));
+  else CUDA_TRY(launch_k(lc, tc2_conv_kernel<0>, grid, dim3(224), smem, PP));
   return 0;
 }
 
@@ -1390,6 +1574,15 @@ namespace {
 
 constexpr int W_STAGES_MAX = 4;
 
+// Tap stacking.  The MMA is always M = 128 rows (X channels) x N (dY channels) x K = 16 pixels, and costs the same ~59 cycles
+// whatever M holds: with CaB = 32 X channels three quarters of every instruction were padding.  Instead S = 128 / CaB taps are
+// STACKED along M: the shared-memory X buffer holds `ncopy` plane blocks (JA 8-channel planes each) whose sources are
+// pre-shifted so that ONE start-address offset serves every block of a tap set -
+//   stride 1: S copies of the halo shifted by 0..3 pixels (and by one padded row for S = 8); a set = the kw (and kh pair) taps
+//             of its rows, reached by moving the start address by (kh-1)*Wp - 1 pixels;
+//   stride 2: the four parity planes, plane (ph,pw) shifted by its first tap's (dh,dw): tap (i,j) of EVERY plane is then
+//             i*Wp + j pixels further, so one MMA covers the four taps that share (i,j) - without a single extra load.
+// 16 / S instructions per 16 pixels instead of 16, 16 / S accumulators of N columns instead of 16.
 struct Tw2Params {
   TwParams t;
   const __nv_bfloat16* x_src;   // X copy at (group 0, pixel 0 of plane 0)
@@ -1399,6 +1592,11 @@ struct Tw2Params {
   unsigned x_bytes, y_bytes;    // per stage
   unsigned stage_bytes;
   int stages;
+  int S, nsets, sets_per_cta, ngroups, ncopy;
+  int copy_plane[8], copy_off[8];            // source parity plane and pixel offset of every plane block
+  int set_block[16], set_off[16];            // per tap set: first plane block, start offset in pixels (added to lo)
+  signed char set_tap[16][8];                // per tap set: tap of row block i (i < S)
+  unsigned tmem_cols;
 };
 
 struct SmemHeaderW2 {
@@ -1425,7 +1623,7 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
     mbar_init(smem_u32(&hdr->acc_done), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&hdr->tmem_base), P.tmem_cols);
+  if (warp == 1) tmem_alloc(smem_u32(&hdr->tmem_base), PP.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1444,9 +1642,10 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
         mbar_expect_tx(bar, PP.x_bytes + PP.y_bytes);
         const unsigned xb = smem_u32(bufs + (size_t)s * PP.stage_bytes);
         const unsigned yb = xb + PP.x_bytes;
-        for (int pl = 0; pl < P.nplanes; ++pl)
+        for (int c = 0; c < PP.ncopy; ++c)
           for (int j = 0; j < P.JA; ++j)
-            bulk_g2s(xb + (unsigned)(pl * P.JA + j) * PP.x_pitch, xs + ((long long)j * PP.x_group_rows + pl * PP.x_plane_rows + (q0 - P.lo)) * 8,
+            bulk_g2s(xb + (unsigned)(c * P.JA + j) * PP.x_pitch,
+                     xs + ((long long)j * PP.x_group_rows + PP.copy_plane[c] * PP.x_plane_rows + (q0 - P.lo + PP.copy_off[c])) * 8,
                      PP.x_pitch, bar);
         for (int j = 0; j < P.JN; ++j)
           bulk_g2s(yb + (unsigned)j * PP.y_pitch, ys + ((long long)j * PP.y_group_rows + q0) * 8, PP.y_pitch, bar);
@@ -1469,10 +1668,10 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
       if (leader) {
         const unsigned xb4 = smem_u32(bufs + (size_t)s * PP.stage_bytes) >> 4;
         const unsigned yb4 = xb4 + (PP.x_bytes >> 4);
-        for (int tl = 0; tl < P.taps_per_cta; ++tl) {
-          const int tap = grp * P.taps_per_cta + tl;
+        for (int tl = 0; tl < PP.sets_per_cta; ++tl) {
+          const int set = grp * PP.sets_per_cta + tl;
           const unsigned d_tmem = tmem_base + (unsigned)(tl * P.N);
-          unsigned a_lo = xb4 + (unsigned)(P.plane[tap] * P.JA) * (PP.x_pitch >> 4) + (unsigned)(P.lo + P.shift[tap]);
+          unsigned a_lo = xb4 + (unsigned)(PP.set_block[set] * P.JA) * (PP.x_pitch >> 4) + (unsigned)(P.lo + PP.set_off[set]);
           unsigned b_lo = yb4;
           unsigned acc_flag = first ^ 1u;
 #pragma unroll
@@ -1495,13 +1694,16 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
     mbar_wait(smem_u32(&hdr->acc_done), 0);
     tc_fence_after();
     const int quarter = warp & 3;
-    const int a = quarter * 32 + lane;
-    for (int tl = 0; tl < P.taps_per_cta; ++tl) {
-      const int tap = grp * P.taps_per_cta + tl;
+    const int m = quarter * 32 + lane;           // accumulator row = (row block i, X channel a)
+    const int iblk = m / P.CaB;
+    const int a = m - iblk * P.CaB;
+    for (int tl = 0; tl < PP.sets_per_cta; ++tl) {
+      const int set = grp * PP.sets_per_cta + tl;
+      const int tap = iblk < PP.S ? PP.set_tap[set][iblk] : 0;
       for (int n0 = 0; n0 < P.N; n0 += 32) {
         float v[32];
         tmem_ld_upto32(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(tl * P.N + n0), v, P.N - n0);
-        if (a < P.CaB && a0 + a < P.Ca && my_tiles > 0) {
+        if (iblk < PP.S && a0 + a < P.Ca && my_tiles > 0) {
           float* dst = P.dw + ((size_t)tap * P.Ca + a0 + a) * P.Cb + b0 + n0;
           const int ncols = max(0, min(min(32, P.N - n0), P.Cb - (b0 + n0)));
           if (P.dw_vec) {
@@ -1521,7 +1723,7 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, P.tmem_cols);
+    tmem_dealloc(tmem_base, PP.tmem_cols);
   }
 }
 
@@ -1534,11 +1736,68 @@ bool build_wparams2(const Geom& g, Tw2Params& PP, bool two_per_sm = false) {
   memset(&PP, 0, sizeof PP);
   TwParams& P = PP.t;
   if (!build_wparams(g, P, 148, two_per_sm ? 256 : 512)) return false;
-  if (two_per_sm && (P.N > 64 || P.tmem_cols > 256)) return false;
+  // ---- tap stacking tables (see Tw2Params)
+  {
+    static const bool stack = !(getenv("SVAE_WGRAD_STACK") && getenv("SVAE_WGRAD_STACK")[0] == '0');
+    int S = stack ? 128 / P.CaB : 1;
+    if (P.mode == 1 && S > 4) S = 4;
+    if (S > 8) S = 8;
+    PP.S = S; PP.nsets = 16 / S;
+    const int Wp = P.Wp;
+    if (P.mode == 0) {
+      PP.ncopy = S;
+      for (int c = 0; c < S; ++c) { PP.copy_plane[c] = 0; PP.copy_off[c] = (c >> 2) * Wp + (c & 3); }
+      if (S == 1) PP.copy_off[0] = 0;
+      if (S == 2) { PP.copy_off[0] = 0; PP.copy_off[1] = 1; }
+      for (int st = 0; st < PP.nsets; ++st) {
+        PP.set_block[st] = 0;
+        if (S == 1) { PP.set_off[st] = P.shift[st]; PP.set_tap[st][0] = (signed char)st; }
+        else if (S == 2) { const int kh = st >> 1, kp = st & 1; PP.set_off[st] = (kh - 1) * Wp + 2 * kp - 1;
+                           for (int i = 0; i < 2; ++i) PP.set_tap[st][i] = (signed char)(kh * 4 + 2 * kp + i); }
+        else if (S == 4) { PP.set_off[st] = (st - 1) * Wp - 1; for (int i = 0; i < 4; ++i) PP.set_tap[st][i] = (signed char)(st * 4 + i); }
+        else { PP.set_off[st] = (2 * st - 1) * Wp - 1; for (int i = 0; i < 8; ++i) PP.set_tap[st][i] = (signed char)((2 * st + (i >> 2)) * 4 + (i & 3)); }
+      }
+    } else {
+      // parity plane p = (ph << 1) | pw holds taps kh in {1,3} (ph = 0: dh = 0,+1) or {0,2} (ph = 1: dh = -1,0), same for kw
+      PP.ncopy = 4;
+      for (int pl = 0; pl < 4; ++pl) {
+        const int ph = pl >> 1, pw = pl & 1;
+        PP.copy_plane[pl] = pl;
+        PP.copy_off[pl] = S > 1 ? (ph ? -Wp : 0) + (pw ? -1 : 0) : 0;
+      }
+      auto tap_of = [](int pl, int i, int j) {
+        const int ph = pl >> 1, pw = pl & 1;
+        const int kh = ph == 0 ? (i == 0 ? 1 : 3) : (i == 0 ? 0 : 2);
+        const int kw = pw == 0 ? (j == 0 ? 1 : 3) : (j == 0 ? 0 : 2);
+        return kh * 4 + kw;
+      };
+      if (S == 1) {
+        for (int st = 0; st < 16; ++st) { PP.set_block[st] = P.plane[st]; PP.set_off[st] = P.shift[st]; PP.set_tap[st][0] = (signed char)st; }
+      } else {
+        // sets ordered (first plane block, i, j); S planes per set
+        int st = 0;
+        for (int pb = 0; pb < 4; pb += S)
+          for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j, ++st) {
+              PP.set_block[st] = pb; PP.set_off[st] = i * Wp + j;
+              for (int k = 0; k < S; ++k) PP.set_tap[st][k] = (signed char)tap_of(pb + k, i, j);
+            }
+      }
+    }
+    int cap = two_per_sm ? 256 : 512;
+    PP.sets_per_cta = cap / P.N; if (PP.sets_per_cta > PP.nsets) PP.sets_per_cta = PP.nsets;
+    if (PP.sets_per_cta < 1) return false;
+    while (PP.nsets % PP.sets_per_cta) --PP.sets_per_cta;
+    PP.ngroups = PP.nsets / PP.sets_per_cta;
+    unsigned cols = (unsigned)(PP.sets_per_cta * P.N), t = 32;
+    while (t < cols) t <<= 1;
+    PP.tmem_cols = t;
+  }
+  if (two_per_sm && (P.N > 64 || PP.tmem_cols > 256)) return false;
   const unsigned hl = (unsigned)((P.HL + 7) & ~7);
   PP.x_pitch = hl * 16u;
   PP.y_pitch = 128u * 16u;
-  PP.x_bytes = (unsigned)(P.nplanes * P.JA) * PP.x_pitch;
+  PP.x_bytes = (unsigned)(PP.ncopy * P.JA) * PP.x_pitch;
   PP.y_bytes = (unsigned)P.JN * PP.y_pitch;
   PP.stage_bytes = PP.x_bytes + PP.y_bytes;
   // The A descriptor always spans 16 planes (M = 128 rows): planes beyond the JA real ones are never copied, they only have
@@ -1562,7 +1821,9 @@ size_t smem_bytes_w2(const Tw2Params& PP) {
   const TwParams& P = PP.t;
   // last stage's X buffer must see 16 readable planes from its highest parity-plane base
   const size_t last_x = 128 + (size_t)(PP.stages - 1) * PP.stage_bytes;
-  const size_t need_read = last_x + (size_t)((P.nplanes - 1) * P.JA + 16) * PP.x_pitch;
+  int max_block = 0;
+  for (int st = 0; st < PP.nsets; ++st) if (PP.set_block[st] > max_block) max_block = PP.set_block[st];
+  const size_t need_read = last_x + (size_t)(max_block * P.JA + 16) * PP.x_pitch;
   size_t sz = 128 + (size_t)PP.stages * PP.stage_bytes;
   if (need_read > sz) sz = need_read;
   return sz + 128;
@@ -1590,7 +1851,7 @@ int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& d
   TwParams& P = PP.t;
   const int ykind = g.stride == 1 ? 0 : 1;
   if (x.kind != tc2_input_kind(g) || x.Hp != P.Hp || x.Wp != P.Wp || dy.kind != ykind || dy.Hp != P.Hp || dy.Wp != P.Wp ||
-      P.lo > x.front || P.mblocks * P.CaB > x.Cpad || P.nblocks * P.N > dy.Cpad) {
+      P.lo + (P.mode == 1 && PP.S > 1 ? P.Wp + 1 : 0) > x.front || P.mblocks * P.CaB > x.Cpad || P.nblocks * P.N > dy.Cpad) {
     svae_global_error() = "tc2 wgrad: operand copies are not in the layouts this geometry reads";
     return -1;
   }
@@ -1605,7 +1866,7 @@ int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& d
     CUDA_TRY(cudaFuncSetAttribute(tc2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int gy = P.ngroups * P.mblocks * P.nblocks;
+  const int gy = PP.ngroups * P.mblocks * P.nblocks;
   long long splits = ((long long)lc.sm_count * per_sm + gy - 1) / gy;
   if (splits > P.tiles) splits = P.tiles;
   if (splits < 1) splits = 1;

@@ -60,6 +60,7 @@ struct Block {
   float* y = nullptr;        // pre-BN output [rows, feats]
   double* stats = nullptr;   // [2*feats] sum, sumsq (forward-zeroed)
   double* S = nullptr;       // [2*feats] backward sums (backward-zeroed)
+  unsigned* fwd_bar = nullptr;   // grid-barrier counter of the fused conv + batch-norm forward kernel (forward-zeroed)
   FeatView out{};            // activated output location
   FeatView res{};            // residual added before the activation (ladder shortcut)
   void* w_packed = nullptr;      // tcgen05 packed weights (forward form)
@@ -246,6 +247,7 @@ struct svae_handle {
   // suite passes with it) but measured SLOWER on B200 (13.5 vs 12.7 ms/step): the epilogue has 4 warps per SM for work a
   // standalone kernel spreads over 64, and it sits on the chain's critical path.  Off by default.
   bool use_fuse = false;
+  bool no_bnf = false;   // set around the recognition nets: they run beside the chain (side streams) and keep the two-kernel blocks
   int ablate = 0;       // SVAE_ABLATE, TIMING EXPERIMENTS ONLY (results are wrong): 1 skip weight gradients, 2 skip the recognition / latent backward
   int eager_steps = 0;
   std::vector<GraphEntry> graphs;
@@ -515,6 +517,7 @@ void place_block(Block& b, Arena& act, Arena& zf, Arena& zb, int64_t maxB, bool 
   size_t n = (size_t)maxB * b.rpi * b.feats;
   b.y = act.get<float>(n);
   b.stats = zf.get<double>(2 * (size_t)b.feats);
+  b.fwd_bar = zf.get<unsigned>(4);
   b.S = zb.get<double>(2 * (size_t)b.feats + 1);   // + the grid-barrier counter of the fused backward kernel
   if (n > max_y) max_y = n;
 }
@@ -533,7 +536,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
     if (share) {
       const Step& r = h->steps[1];
       auto alias = [](Block& b, const Block& q) {
-        b.rpi = q.rpi; b.feats = q.feats; b.act = q.act; b.y = q.y; b.stats = q.stats; b.S = q.S; b.out = q.out; b.res = q.res;
+        b.rpi = q.rpi; b.feats = q.feats; b.act = q.act; b.y = q.y; b.stats = q.stats; b.S = q.S; b.out = q.out; b.res = q.res; b.fwd_bar = q.fwd_bar;
         b.in_bf = q.in_bf; b.tc2_fwd = q.tc2_fwd; b.out_bf = q.out_bf;
       };
       for (size_t i = 0; i < s.inf.size(); ++i) alias(s.inf[i], r.inf[i]);
@@ -908,9 +911,32 @@ bool make_fuse(svae_handle* h, Block* up, int B, float* dres, int dres_acc, Geom
 // fully-connected block with a 2-D batch norm (enc.fc, dec.fc): statistics + normalisation in one kernel (bn2d_fwd / bn2d_bwd)
 bool is_fc2d(const Block& b, int B) { return b.g.KH == 1 && b.rpi == 1 && b.res.p == nullptr && B <= 2048; }
 
+// conv / deconv + batch norm (+ shortcut) + activation as ONE kernel (BnFwdFuse): on the chain stream only - the kernel holds
+// its CTAs at a grid barrier, and two such kernels from different streams could each keep the other's remaining CTAs out.
+bool bnf_fusable(svae_handle* h, const Block& b, int B) {
+  if (!b.tc2_fwd || b.rpi <= 1 || b.g.KH != 4 || b.fwd_bar == nullptr || h->no_bnf) return false;
+  if (cur_stream(h) != h->stream) return false;
+  auto aligned4 = [](const float* p, int ld, int coff) { return ld % 4 == 0 && coff % 4 == 0 && (((uintptr_t)p) & 15) == 0; };
+  if (b.res.p != nullptr && !(b.res.ppr == 1 && b.res.inner == b.feats && aligned4(b.res.p, b.res.ld, b.res.coff))) return false;
+  const bool want_f32 = b.out.p != nullptr && !b.skip_f32;
+  if (want_f32 && !(b.out.ppr == 1 && b.out.inner == b.feats && aligned4(b.out.p, b.out.ld, b.out.coff))) return false;
+  if (b.out_bf.a.p != nullptr && (b.out_bf.inner != 0 || (b.out_bf.coff & 7))) return false;
+  if (!want_f32 && b.out_bf.a.p == nullptr) return false;
+  Geom g = b.g; g.B = B;
+  return tc2_bnf_supported(g, b.tw_f, h->sm_count, mkview(b.y, b.feats, 0), b.feats);
+}
+
 int block_fwd(svae_handle* h, Block& b, int B, View in) {
   const bool fc2d = is_fc2d(b, B);
   b.dbg_in = in;
+  if (bnf_fusable(h, b, B)) {
+    const bool want_f32 = b.out.p != nullptr && !b.skip_f32;
+    BnFwdFuse ff{h->pw(b.beta), b.res.p, b.res.ld, b.res.coff, want_f32 ? b.out.p : nullptr, b.out.ld, b.out.coff, b.out_bf,
+                 b.fwd_bar, b.act, (long long)B * b.rpi};
+    Geom g = b.g; g.B = B;
+    LaunchCtx lc = h->lc();
+    return tc2_gather_gemm(lc, g, b.in_bf, 0, b.w_packed, mkview(b.y, b.feats, 0), b.stats, nullptr, b.tw_f, &ff);
+  }
   H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
                     fc2d ? nullptr : b.stats, nullptr, b.tw_f));
   LaunchCtx lc = h->lc();
@@ -1106,7 +1132,14 @@ HeadSet make_headset(svae_handle* h, Step& s, int l) {
   return hs;
 }
 
+int recognition_fwd_impl(svae_handle* h, Step& s, int B, const float* x, const float* eps, double* kl_sum);
 int recognition_fwd(svae_handle* h, Step& s, int B, const float* x, const float* eps, double* kl_sum) {
+  h->no_bnf = true;
+  const int r = recognition_fwd_impl(h, s, B, x, eps, kl_sum);
+  h->no_bnf = false;
+  return r;
+}
+int recognition_fwd_impl(svae_handle* h, Step& s, int B, const float* x, const float* eps, double* kl_sum) {
   const int L = h->L;
   LaunchCtx lc = h->lc();
   // the heads accumulate into mu_pre / sd_pre (adjacent in the arena) with atomics
