@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <new>
 
 #include <string>
 #include <vector>
@@ -73,11 +76,16 @@ struct Profiler {
   }
 };
 
+struct MultiRec;
 struct LaunchCtx {
   cudaStream_t stream;
   int64_t* launches;
   int sm_count;
   Profiler* prof;
+  // Batched ("multi") launches: while set, the kernel wrappers that support it RECORD their launch (kernel, grid, argument
+  // block) instead of launching; multi_flush (model.cu) then issues ONE launch per recorded slot over all recorded items, the item
+  // index being blockIdx.z.  See MultiRec below.
+  MultiRec* multi = nullptr;
   // Programmatic dependent launch (chain stream only, see launch_k): *pdl_state == 1 when the node enqueued last on this
   // stream is a kernel; nullptr: never use it.  ProfScope sets it after every launch, non-kernel operations clear it.
   int* pdl_state = nullptr;
@@ -89,6 +97,7 @@ struct ProfScope {
   cudaEvent_t b = nullptr;
   int kc;
   ProfScope(const LaunchCtx& lc_, int kc_, double flops, double bytes, const Geom* g = nullptr) : lc(lc_), kc(kc_) {
+    if (lc.multi != nullptr) { multi_note(lc.multi, kc_, flops, bytes); return; }   // recorded, not launched: counted at the flush
     ++*lc.launches;
     Profiler* p = lc.prof;
     if (p && p->enabled) {
@@ -103,9 +112,11 @@ struct ProfScope {
     }
   }
   ~ProfScope() {
+    if (lc.multi != nullptr) return;
     if (b) cudaEventRecord(b, lc.stream);
     if (lc.pdl_state) *lc.pdl_state = 1;
   }
+  static void multi_note(MultiRec* m, int kc, double flops, double bytes);
 };
 
 // ---- programmatic dependent launch -----------------------------------------------------------------------------------
@@ -123,6 +134,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(const LaunchCtx& lc, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                    Args&&... args) {
+  if (lc.multi != nullptr) return cudaErrorNotSupported;   // a sequence is being recorded and this wrapper cannot record
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = lc.stream;
   cudaLaunchAttribute at[1];
@@ -158,6 +170,110 @@ static inline cudaError_t launch_coop(const LaunchCtx& lc, void (*kernel)(KArgs.
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// ---- batched ("multi") launches ---------------------------------------------------------------------------------------
+// The T recognition nets of a step (sequential_vae.py:1022: q(z_t | x) depends on x only) and their latent projections are T
+// independent copies of the same layer sequence on different buffers and weights.  Instead of T x ~47 small launches, the
+// sequence is RECORDED once per net - every wrapper appends its kernel's argument block to the slot it occupies in the
+// sequence - and issued as ONE launch per slot whose grid is the single-net grid times T along z: the kernel picks the
+// argument block of item blockIdx.z from its parameter space and runs the unchanged single-net body.  Buffers, layouts,
+// weights and numerics are exactly those of the per-net launches (every parity test applies unchanged); only the launch
+// count and the machine fill (T x more CTAs per launch) change.
+struct MultiSlot {
+  void (*launch)(const void* host_args, int items, dim3 grid, dim3 block, size_t smem, cudaStream_t st) = nullptr;
+  dim3 grid, block;
+  size_t smem = 0, psize = 0;
+  int kc = KC_MISC;
+  double flops = 0, bytes = 0;
+  std::vector<unsigned char> host;   // items * psize argument bytes
+  int count = 0;
+  int lane = 0;                      // 1: weight gradient (may be issued on a second stream, see multi_flush)
+};
+struct MultiRec {
+  std::vector<MultiSlot> slots;
+  int cursor = 0, items = 0, lane = 0;
+  int pend_kc = KC_MISC; double pend_flops = 0, pend_bytes = 0;
+  bool pending = false;   // a wrapper announced a launch (ProfScope) that has not been recorded yet
+  std::string err;
+  void begin_item() { cursor = 0; ++items; }
+  // returns 0, or -1 when the sequence of this item differs from the first item's (not batchable)
+  int add(void (*launch)(const void*, int, dim3, dim3, size_t, cudaStream_t), const void* args, size_t psize, dim3 grid, dim3 block,
+          size_t smem) {
+    if (items == 1) {
+      MultiSlot sl;
+      sl.launch = launch; sl.grid = grid; sl.block = block; sl.smem = smem; sl.psize = psize; sl.kc = pend_kc; sl.lane = lane;
+      slots.push_back(sl);
+    }
+    if (cursor >= (int)slots.size()) { err = "batched launch: items record different kernel sequences"; return -1; }
+    MultiSlot& sl = slots[cursor++];
+    if (sl.launch != launch || sl.psize != psize || sl.grid.x != grid.x || sl.grid.y != grid.y || sl.grid.z != grid.z ||
+        sl.block.x != block.x || sl.block.y != block.y || sl.block.z != block.z || sl.smem != smem) {
+      err = "batched launch: items record different kernels / grids for the same slot";
+      return -1;
+    }
+    sl.host.insert(sl.host.end(), static_cast<const unsigned char*>(args), static_cast<const unsigned char*>(args) + psize);
+    sl.count += 1;
+    sl.flops += pend_flops; sl.bytes += pend_bytes;
+    pend_flops = pend_bytes = 0;
+    pending = false;
+    return 0;
+  }
+};
+inline void ProfScope::multi_note(MultiRec* m, int kc, double flops, double bytes) {
+  // a wrapper without batched-launch support would have LAUNCHED its kernel while the sequence is being recorded: caught here
+  // (by the next wrapper) or at the flush
+  if (m->pending) m->err = "batched launch: a kernel wrapper without batched-launch support ran inside a recorded sequence";
+  m->pend_kc = kc; m->pend_flops = flops; m->pend_bytes = bytes; m->pending = true;
+}
+
+// Generic trampoline for kernels whose body is a __device__ function of plain arguments: the argument tuples of up to
+// MULTI_MAX items travel BY VALUE in the kernel parameter space (constant bank, like ordinary kernel arguments: no device-side
+// argument buffer, nothing to upload, capturable as is); item blockIdx.z runs the unchanged single-item body (it may use
+// blockIdx.x / blockIdx.y, static and dynamic shared memory, __syncthreads ...).  More than MULTI_MAX items: several launches.
+#include <cuda/std/tuple>
+constexpr int MULTI_MAX = 8;
+template <typename T>
+struct MultiArgs { T v[MULTI_MAX]; };
+template <auto Body, int MAXT, typename... A>
+__global__ void __launch_bounds__(MAXT) svae_multi_kernel(const __grid_constant__ MultiArgs<cuda::std::tuple<A...>> args) {
+  const cuda::std::tuple<A...>& t = args.v[blockIdx.z];
+  cuda::std::apply([](const A&... a) { Body(a...); }, t);
+}
+// launcher shared by every batched kernel: K = the __global__ function taking MultiArgs<T> (+ extra trailing arguments)
+template <typename T, typename K, typename... Extra>
+static inline void multi_launch_chunks(K kernel, const void* host_args, int items, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       unsigned z_per_item, Extra... extra) {
+  static_assert(sizeof(MultiArgs<T>) <= 16 * 1024, "argument blocks of one batched launch must fit the kernel parameter space");
+  for (int i0 = 0; i0 < items; i0 += MULTI_MAX) {
+    const int n = items - i0 < MULTI_MAX ? items - i0 : MULTI_MAX;
+    MultiArgs<T> a;
+    memset(static_cast<void*>(&a), 0, sizeof a);
+    memcpy(static_cast<void*>(a.v), static_cast<const unsigned char*>(host_args) + (size_t)i0 * sizeof(T), (size_t)n * sizeof(T));
+    grid.z = z_per_item * (unsigned)n;
+    kernel<<<grid, block, smem, st>>>(a, extra...);
+  }
+}
+template <auto Body, int MAXT, typename... A>
+struct MultiLaunch {
+  static void launch(const void* host_args, int items, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    multi_launch_chunks<cuda::std::tuple<A...>>(svae_multi_kernel<Body, MAXT, A...>, host_args, items, grid, block, smem, st, 1u);
+  }
+};
+template <auto Body, int MAXT, typename... KA, typename... Args>
+static inline int multi_record(void (*)(KA...), const LaunchCtx& lc, dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  static_assert(sizeof...(KA) == sizeof...(Args), "argument count of the batched launch differs from the kernel body's");
+  alignas(16) unsigned char buf[sizeof(cuda::std::tuple<KA...>)];
+  memset(buf, 0, sizeof buf);
+  new (buf) cuda::std::tuple<KA...>(static_cast<KA>(args)...);
+  if (grid.z != 1) { svae_global_error() = "batched launch: the kernel already uses grid.z"; return -1; }
+  if (lc.multi->add(&MultiLaunch<Body, MAXT, KA...>::launch, buf, sizeof buf, grid, block, smem) != 0) {
+    svae_global_error() = lc.multi->err;
+    return -1;
+  }
+  return 0;
+}
+// MULTI_RECORD(body, max threads, lc, grid, block, smem, args...): record one launch of `body` (see LaunchCtx::multi)
+#define MULTI_RECORD(body, maxt, lc, grid, block, smem, ...) multi_record<body, maxt>(body, lc, grid, block, smem, __VA_ARGS__)
 
 // ---- bf16 activation copies for the TMA-fed kernels ------------------------------------------------------------------
 // A [B,H,W,C] tensor stored as bf16, PLANAR by 8-channel group, over the zero-padded linear pixel space of its consumer:

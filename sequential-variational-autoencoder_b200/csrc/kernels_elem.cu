@@ -90,7 +90,7 @@ __device__ __forceinline__ size_t bf_elem(const BfDst& bf, int64_t r, int f, int
   return bf_index(bf.a, n, hh, hw - hh * bf.a.W, bf.coff + c);
 }
 
-__global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+__device__ __forceinline__ void bn_act_fwd_kernel_body(const float* __restrict__ y, const double* __restrict__ stats,
                                   const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
                                   FeatView out, BfDst bf) {
   pdl_wait();
@@ -113,12 +113,14 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __r
     if (bf.a.p != nullptr) bf.a.p[bf_elem(bf, r, f, bf.inner ? bf.inner : out.inner, bf.inner ? bf.ppr : out.ppr)] = __float2bfloat16_rn(v);
   }
 }
+__global__ void bn_act_fwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                  const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
+                                  FeatView out, BfDst bf) { bn_act_fwd_kernel_body(y, stats, beta, rows, feats, act, res, out, bf); }
 
 // Vectorised 4-D batch-norm apply (rows = pixels, C % 8 == 0): one thread per (pixel, 8-channel group) - two float4
 // loads of y (+ residual), optional fp32 NHWC store (channel window of a concat buffer), optional bf16 planar store
 // (one 16-byte write = exactly one pixel of one 8-channel plane of the consumer's TMA layout).
-__global__ void __launch_bounds__(256)
-bn_act_fwd_v8_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ beta,
+__device__ __forceinline__ void bn_act_fwd_v8_kernel_body(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ beta,
                      int64_t rows, int C, int act, const float* __restrict__ res, int res_ld, int res_coff,
                      float* __restrict__ out, int out_ld, int out_coff, BfDst bf) {
   pdl_wait();
@@ -162,8 +164,12 @@ bn_act_fwd_v8_kernel(const float* __restrict__ y, const double* __restrict__ sta
     }
   }
 }
+__global__ void __launch_bounds__(256)
+bn_act_fwd_v8_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ beta,
+                     int64_t rows, int C, int act, const float* __restrict__ res, int res_ld, int res_coff,
+                     float* __restrict__ out, int out_ld, int out_coff, BfDst bf) { bn_act_fwd_v8_kernel_body(y, stats, beta, rows, C, act, res, res_ld, res_coff, out, out_ld, out_coff, bf); }
 
-__global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
+__device__ __forceinline__ void bn_bwd_reduce_kernel_body(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
                                      const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
                                      float* __restrict__ dyhat, double* __restrict__ S, float* __restrict__ dres,
                                      int dres_acc) {
@@ -203,13 +209,16 @@ __global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, c
     atomicAdd(&S[feats + f], db_);
   }
 }
+__global__ void bn_bwd_reduce_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
+                                     const float* __restrict__ beta, int64_t rows, int feats, int act, FeatView res,
+                                     float* __restrict__ dyhat, double* __restrict__ S, float* __restrict__ dres,
+                                     int dres_acc) { bn_bwd_reduce_kernel_body(da, y, stats, beta, rows, feats, act, res, dyhat, S, dres, dres_acc); }
 
 // Vectorised 4-D batch-norm backward, pass 1 (rows = pixels, C % 8 == 0, C/8 divides the block): one thread per
 // (pixel, 8-channel group) with the group fixed per thread, so the two per-channel sums (sum g, sum g*xhat) stay in
 // registers across the grid-stride loop; one shared-memory reduction and one fp64 atomic per channel per block.
 // g = da * act'(xhat + beta + residual) is written for pass 2 and, when requested, (accumulated) into the shortcut gradient.
-__global__ void __launch_bounds__(256)
-bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, const float* __restrict__ y,
+__device__ __forceinline__ void bn_bwd_reduce_v8_kernel_body(const float* __restrict__ da, int da_ld, int da_coff, const float* __restrict__ y,
                         const double* __restrict__ stats, const float* __restrict__ beta, int64_t rows, int C, int act,
                         const float* __restrict__ res, int res_ld, int res_coff, float* __restrict__ dyhat,
                         double* __restrict__ S, float* __restrict__ dres, int dres_acc) {
@@ -277,6 +286,11 @@ bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, co
     atomicAdd(&S[which * C + c], (double)tot);
   }
 }
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, const float* __restrict__ y,
+                        const double* __restrict__ stats, const float* __restrict__ beta, int64_t rows, int C, int act,
+                        const float* __restrict__ res, int res_ld, int res_coff, float* __restrict__ dyhat,
+                        double* __restrict__ S, float* __restrict__ dres, int dres_acc) { bn_bwd_reduce_v8_kernel_body(da, da_ld, da_coff, y, stats, beta, rows, C, act, res, res_ld, res_coff, dyhat, S, dres, dres_acc); }
 
 // Both passes of the 4-D batch-norm backward in one cooperative kernel (see bn_bwd_fused in common.cuh).  Thread mapping as in
 // bn_bwd_reduce_v8_kernel: one (pixel, 8-channel group) per thread and iteration, the group fixed per thread.
@@ -410,7 +424,7 @@ bn_bwd_fused_v8_kernel(const float* __restrict__ da, int da_ld, int da_coff, con
   }
 }
 
-__global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
+__device__ __forceinline__ void bn_bwd_apply_kernel_body(float* __restrict__ dyhat, const float* __restrict__ y,
                                     const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
                                     int feats, float* __restrict__ dbeta, BfDst bf) {
   pdl_wait();
@@ -430,11 +444,13 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __re
     if (bf.a.p != nullptr) bf.a.p[bf_elem(bf, r, f, feats, 1)] = __float2bfloat16_rn(d);
   }
 }
+__global__ void bn_bwd_apply_kernel(float* __restrict__ dyhat, const float* __restrict__ y,
+                                    const double* __restrict__ stats, const double* __restrict__ S, int64_t rows,
+                                    int feats, float* __restrict__ dbeta, BfDst bf) { bn_bwd_apply_kernel_body(dyhat, y, stats, S, rows, feats, dbeta, bf); }
 
 // Vectorised 4-D batch-norm backward, pass 2 (rows = pixels, C % 8 == 0): dy = rstd * (dyhat - S1/rows - xhat*S2/rows),
 // written in place (fp32, for the weight-gradient kernel) and as the bf16 planar copy the input-gradient kernel reads.
-__global__ void __launch_bounds__(256)
-bn_bwd_apply_v8_kernel(const float* g_in, int g_ld, int g_coff, float* dy_out, const float* __restrict__ y,
+__device__ __forceinline__ void bn_bwd_apply_v8_kernel_body(const float* g_in, int g_ld, int g_coff, float* dy_out, const float* __restrict__ y,
                        const double* __restrict__ stats, const double* __restrict__ S, int64_t rows, int C,
                        float* __restrict__ dbeta, BfDst bf) {
   pdl_wait();
@@ -481,6 +497,10 @@ bn_bwd_apply_v8_kernel(const float* g_in, int g_ld, int g_coff, float* dy_out, c
     }
   }
 }
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v8_kernel(const float* g_in, int g_ld, int g_coff, float* dy_out, const float* __restrict__ y,
+                       const double* __restrict__ stats, const double* __restrict__ S, int64_t rows, int C,
+                       float* __restrict__ dbeta, BfDst bf) { bn_bwd_apply_v8_kernel_body(g_in, g_ld, g_coff, dy_out, y, stats, S, rows, C, dbeta, bf); }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
@@ -691,8 +711,7 @@ __global__ void fill_normal_kernel(float* __restrict__ dst, int64_t n, uint64_t 
     dst[i] = philox_normal(seed, base + (uint64_t)i);
 }
 
-__global__ void __launch_bounds__(256)
-reparam_fwd_kernel(ReparamParams p, const float* __restrict__ mu_pre, const float* __restrict__ sd_pre,
+__device__ __forceinline__ void reparam_fwd_kernel_body(ReparamParams p, const float* __restrict__ mu_pre, const float* __restrict__ sd_pre,
                    const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, int T, int t, uint64_t stride,
                    float* __restrict__ eps_store, float* __restrict__ mu, float* __restrict__ sd, float* __restrict__ z,
                    double* __restrict__ kl_sum) {
@@ -715,8 +734,13 @@ reparam_fwd_kernel(ReparamParams p, const float* __restrict__ mu_pre, const floa
   float tot = block_sum<float>(kl, red);
   if (threadIdx.x == 0) atomicAdd(kl_sum, (double)tot);
 }
+__global__ void __launch_bounds__(256)
+reparam_fwd_kernel(ReparamParams p, const float* __restrict__ mu_pre, const float* __restrict__ sd_pre,
+                   const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, int T, int t, uint64_t stride,
+                   float* __restrict__ eps_store, float* __restrict__ mu, float* __restrict__ sd, float* __restrict__ z,
+                   double* __restrict__ kl_sum) { reparam_fwd_kernel_body(p, mu_pre, sd_pre, eps, dyn, T, t, stride, eps_store, mu, sd, z, kl_sum); }
 
-__global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz, const float* __restrict__ mu_pre,
+__device__ __forceinline__ void reparam_bwd_kernel_body(ReparamParams p, const float* __restrict__ dz, const float* __restrict__ mu_pre,
                                    const float* __restrict__ mu, const float* __restrict__ sd,
                                    const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, float kl_scale,
                                    float* __restrict__ dmu_pre, float* __restrict__ dsd_pre) {
@@ -733,6 +757,10 @@ __global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz
     dsd_pre[i] = ds * s * (1.f - s);
   }
 }
+__global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz, const float* __restrict__ mu_pre,
+                                   const float* __restrict__ mu, const float* __restrict__ sd,
+                                   const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, float kl_scale,
+                                   float* __restrict__ dmu_pre, float* __restrict__ dsd_pre) { reparam_bwd_kernel_body(p, dz, mu_pre, mu, sd, eps, dyn, kl_scale, dmu_pre, dsd_pre); }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
@@ -804,10 +832,13 @@ int bn_act_fwd(const LaunchCtx& lc, const float* y, const double* stats, const f
                   (bf.a.p == nullptr || (bf.coff % 8 == 0 && bf.inner == 0 && (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows));
   if (v8) {
     const int64_t items = rows * (feats / 8);
+    if (lc.multi != nullptr) return MULTI_RECORD(bn_act_fwd_v8_kernel_body, 256, lc, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 2 * feats * sizeof(float), y, stats,
+                      beta, rows, feats, act, residual.p, residual.ld, residual.coff, out.p, out.ld, out.coff, bf);
     CUDA_TRY(launch_k(lc, bn_act_fwd_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 2 * feats * sizeof(float), y, stats,
                       beta, rows, feats, act, residual.p, residual.ld, residual.coff, out.p, out.ld, out.coff, bf));
   } else {
     ColGrid cg = col_grid(rows, feats, lc.sm_count);
+    if (lc.multi != nullptr) return MULTI_RECORD(bn_act_fwd_kernel_body, 256, lc, cg.grid, cg.block, 0, y, stats, beta, rows, feats, act, residual, out, bf);
     CUDA_TRY(launch_k(lc, bn_act_fwd_kernel, cg.grid, cg.block, 0, y, stats, beta, rows, feats, act, residual, out, bf));
   }
   CUDA_TRY(cudaGetLastError());
@@ -836,12 +867,16 @@ int bn_bwd_reduce(const LaunchCtx& lc, FeatView da, const float* y, const double
     const int64_t cap = (int64_t)lc.sm_count * red_per_sm;
     if (blocks > cap) blocks = cap;
     const size_t smem = (3 * (size_t)feats + (size_t)threads * 17) * sizeof(float);
+    if (lc.multi != nullptr) return MULTI_RECORD(bn_bwd_reduce_v8_kernel_body, 256, lc, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
+                      rows, feats, act, residual.p, residual.ld, residual.coff, dyhat, S, dres, dres_accumulate);
     CUDA_TRY(launch_k(lc, bn_bwd_reduce_v8_kernel, dim3((unsigned)blocks), dim3(threads), smem, da.p, da.ld, da.coff, y, stats, beta,
                       rows, feats, act, residual.p, residual.ld, residual.coff, dyhat, S, dres, dres_accumulate));
     return 0;
   }
   ColGrid cg = col_grid(rows, feats, lc.sm_count);
-  CUDA_TRY(launch_k(lc, bn_bwd_reduce_kernel, cg.grid, cg.block, 0, da, y, stats, beta, rows, feats, act, residual, dyhat, S, dres,
+  if (lc.multi != nullptr) return MULTI_RECORD(bn_bwd_reduce_kernel_body, 256, lc, cg.grid, cg.block, 0, da, y, stats, beta, rows, feats, act, residual, dyhat, S, dres,
+                    dres_accumulate);
+    CUDA_TRY(launch_k(lc, bn_bwd_reduce_kernel, cg.grid, cg.block, 0, da, y, stats, beta, rows, feats, act, residual, dyhat, S, dres,
                     dres_accumulate));
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -855,10 +890,13 @@ int bn_bwd_apply(const LaunchCtx& lc, float* dyhat, const float* y, const double
                   (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows;
   if (v8) {
     const int64_t items = rows * (feats / 8);
+    if (lc.multi != nullptr) return MULTI_RECORD(bn_bwd_apply_v8_kernel_body, 256, lc, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), dyhat,
+                      feats, 0, dyhat, y, stats, S, rows, feats, dbeta, bf);
     CUDA_TRY(launch_k(lc, bn_bwd_apply_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), dyhat,
                       feats, 0, dyhat, y, stats, S, rows, feats, dbeta, bf));
   } else {
     ColGrid cg = col_grid(rows, feats, lc.sm_count);
+    if (lc.multi != nullptr) return MULTI_RECORD(bn_bwd_apply_kernel_body, 256, lc, cg.grid, cg.block, 0, dyhat, y, stats, S, rows, feats, dbeta, bf);
     CUDA_TRY(launch_k(lc, bn_bwd_apply_kernel, cg.grid, cg.block, 0, dyhat, y, stats, S, rows, feats, dbeta, bf));
   }
   CUDA_TRY(cudaGetLastError());
@@ -915,7 +953,9 @@ int bn_bwd_apply_from(const LaunchCtx& lc, View g, float* dy, const float* y, co
                   (bf.a.p == nullptr || (bf.coff % 8 == 0 && (int64_t)bf.a.B * bf.a.H * bf.a.W >= rows));
   if (!ok) { svae_global_error() = "bn_bwd_apply_from: unsupported layout"; return -1; }
   const int64_t items = rows * (feats / 8);
-  CUDA_TRY(launch_k(lc, bn_bwd_apply_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), g.p, g.ld,
+  if (lc.multi != nullptr) return MULTI_RECORD(bn_bwd_apply_v8_kernel_body, 256, lc, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), g.p, g.ld,
+                    g.coff, dy, y, stats, S, rows, feats, dbeta, bf);
+    CUDA_TRY(launch_k(lc, bn_bwd_apply_v8_kernel, dim3(flat_blocks(items, lc.sm_count)), dim3(256), 4 * feats * sizeof(float), g.p, g.ld,
                     g.coff, dy, y, stats, S, rows, feats, dbeta, bf));
   return 0;
 }
@@ -947,6 +987,9 @@ int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre
                 const SvaeDyn* dyn, int T, int t, uint64_t stride, float* eps_store, float* mu, float* sd, float* z,
                 double* kl_sum) {
   ProfScope ps(lc, KC_REPARAM, 20.0 * p.B * p.Z, 28.0 * p.B * p.Z);
+  if (lc.multi != nullptr)
+    return MULTI_RECORD(reparam_fwd_kernel_body, 256, lc, dim3(flat_blocks((int64_t)p.B * p.Z, lc.sm_count)), dim3(256), 0, p, mu_pre,
+                        sd_pre, eps, dyn, T, t, stride, eps_store, mu, sd, z, kl_sum);
   reparam_fwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(
       p, mu_pre, sd_pre, eps, dyn, T, t, stride, eps_store, mu, sd, z, kl_sum);
   CUDA_TRY(cudaGetLastError());
@@ -956,6 +999,9 @@ int reparam_fwd(const LaunchCtx& lc, const ReparamParams& p, const float* mu_pre
 int reparam_bwd(const LaunchCtx& lc, const ReparamParams& p, const float* dz, const float* mu_pre, const float* mu,
                 const float* sd, const float* eps, const SvaeDyn* dyn, float kl_scale, float* dmu_pre, float* dsd_pre) {
   ProfScope ps(lc, KC_REPARAM, 12.0 * p.B * p.Z, 28.0 * p.B * p.Z);
+  if (lc.multi != nullptr)
+    return MULTI_RECORD(reparam_bwd_kernel_body, 256, lc, dim3(flat_blocks((int64_t)p.B * p.Z, lc.sm_count)), dim3(256), 0, p, dz, mu_pre,
+                        mu, sd, eps, dyn, kl_scale, dmu_pre, dsd_pre);
   reparam_bwd_kernel<<<flat_blocks((int64_t)p.B * p.Z, lc.sm_count), 256, 0, lc.stream>>>(p, dz, mu_pre, mu, sd, eps, dyn,
                                                                                         kl_scale, dmu_pre, dsd_pre);
   CUDA_TRY(cudaGetLastError());

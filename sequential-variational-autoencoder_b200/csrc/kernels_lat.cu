@@ -31,8 +31,7 @@ __device__ __forceinline__ float lat_act_grad(float pre, int act) {
 // Block = 32 features (x, one warp per row phase: coalesced 128-byte rows) x LAT_RY row phases (y): a thread owns feature
 // f for the rows b = y, y + LAT_RY, ...; per-feature sums are combined across the row phases through shared memory.
 template <int NM>
-__global__ void __launch_bounds__(LAT_THREADS)
-lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
+__device__ __forceinline__ void lat_fwd_fused_kernel_body(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
                      const float* __restrict__ beta, int B, int KZ, int N, int act, float* __restrict__ y,
                      double* __restrict__ stats, FeatView out, BfDst bf) {
   extern __shared__ float s_z[];   // [B][NM]
@@ -98,14 +97,18 @@ lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const fl
     }
   }
 }
+template <int NM>
+__global__ void __launch_bounds__(LAT_THREADS)
+lat_fwd_fused_kernel(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
+                     const float* __restrict__ beta, int B, int KZ, int N, int act, float* __restrict__ y,
+                     double* __restrict__ stats, FeatView out, BfDst bf) { lat_fwd_fused_kernel_body<NM>(z, z_ld, z_coff, w, beta, B, KZ, N, act, y, stats, out, bf); }
 
 // Forward for narrow latent groups (K <= 8): y = z.W is a rank-K map of the batch, so its batch statistics follow from the
 // K x K second moments of z -  mean_y[f] = m.W[:,f],  var_y[f] = W[:,f]^T Cov(z) W[:,f]  - and no pass over the batch is needed
 // to normalise: every block first reduces the moments of z (B x K values, L2-resident), then the kernel is a pure map over
 // (row chunk, feature tile) with K FMAs per element.  Rows split freely over blockIdx.y (generation runs B = 4096).
 template <int NM>
-__global__ void __launch_bounds__(LAT_THREADS)
-lat_fwd_moment_kernel(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
+__device__ __forceinline__ void lat_fwd_moment_kernel_body(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
                       const float* __restrict__ beta, int B, int KZ, int N, int act, int rows_per_block,
                       float* __restrict__ y, double* __restrict__ stats, FeatView out, BfDst bf,
                       const double* __restrict__ mom_in, double* __restrict__ mom_out) {
@@ -215,13 +218,18 @@ lat_fwd_moment_kernel(const float* __restrict__ z, int z_ld, int z_coff, const f
     }
   }
 }
+template <int NM>
+__global__ void __launch_bounds__(LAT_THREADS)
+lat_fwd_moment_kernel(const float* __restrict__ z, int z_ld, int z_coff, const float* __restrict__ w,
+                      const float* __restrict__ beta, int B, int KZ, int N, int act, int rows_per_block,
+                      float* __restrict__ y, double* __restrict__ stats, FeatView out, BfDst bf,
+                      const double* __restrict__ mom_in, double* __restrict__ mom_out) { lat_fwd_moment_kernel_body<NM>(z, z_ld, z_coff, w, beta, B, KZ, N, act, rows_per_block, y, stats, out, bf, mom_in, mom_out); }
 
 // RB rows of NM products are reduced across the warp (= 32 features of one row phase) at a time: 32 values per
 // transpose-reduction.  A block walks feature tiles blockIdx.x, +gridDim.x, ... and keeps its dz partial sums in shared
 // memory across them, so the global atomics on dz number gridDim.x per element, not N/32.
 template <int NM>
-__global__ void __launch_bounds__(LAT_THREADS)
-lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
+__device__ __forceinline__ void lat_bwd_fused_kernel_body(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
                      const float* __restrict__ beta, const float* __restrict__ z, int z_ld, int z_coff,
                      const float* __restrict__ w, int B, int KZ, int N, int act, float* __restrict__ dw,
                      float* __restrict__ dbeta, float* __restrict__ dz, int dz_ld, int dz_coff) {
@@ -324,6 +332,12 @@ lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __r
     if (k < KZ) atomicAdd(dz + (size_t)b * dz_ld + dz_coff + k, s_dz[i]);
   }
 }
+template <int NM>
+__global__ void __launch_bounds__(LAT_THREADS)
+lat_bwd_fused_kernel(FeatView da, const float* __restrict__ y, const double* __restrict__ stats,
+                     const float* __restrict__ beta, const float* __restrict__ z, int z_ld, int z_coff,
+                     const float* __restrict__ w, int B, int KZ, int N, int act, float* __restrict__ dw,
+                     float* __restrict__ dbeta, float* __restrict__ dz, int dz_ld, int dz_coff) { lat_bwd_fused_kernel_body<NM>(da, y, stats, beta, z, z_ld, z_coff, w, B, KZ, N, act, dw, dbeta, dz, dz_ld, dz_coff); }
 
 // ---- 2-D batch norm of a fully-connected block (fc_bn_lrelu, abstract_network.py:64-71: enc.fc, dec.fc) ------------------
 // rows = batch (<= a few hundred), feats = 384 .. 6144.  The same ownership as above - 32 features x LAT_RY row phases per
@@ -457,7 +471,14 @@ int lat_fwd_fused(const LaunchCtx& lc, View z, const float* w, const float* beta
     const int rpb = B <= 128 ? B : 128;
     const dim3 grid(blocks, (unsigned)((B + rpb - 1) / rpb));
     // large batches: the moments of z are reduced once by a one-block launch instead of by every block
-    const double* mom = (B > 512 && mom_scratch != nullptr) ? mom_scratch : nullptr;
+    const double* mom = (B > 512 && mom_scratch != nullptr && lc.multi == nullptr) ? mom_scratch : nullptr;
+    if (lc.multi != nullptr) {   // batched launch: recorded, every block reduces the moments of z itself
+      if (KZ <= 4)
+        return MULTI_RECORD(lat_fwd_moment_kernel_body<4>, LAT_THREADS, lc, grid, dim3(32, LAT_RY), (size_t)rpb * 4 * sizeof(float), z.p, z.ld,
+                            z.coff, w, beta, B, KZ, N, act, rpb, y, stats, out, bf, (const double*)nullptr, (double*)nullptr);
+      return MULTI_RECORD(lat_fwd_moment_kernel_body<8>, LAT_THREADS, lc, grid, dim3(32, LAT_RY), (size_t)rpb * 8 * sizeof(float), z.p, z.ld,
+                          z.coff, w, beta, B, KZ, N, act, rpb, y, stats, out, bf, (const double*)nullptr, (double*)nullptr);
+    }
     if (KZ <= 4) {
       if (mom) lat_fwd_moment_kernel<4><<<dim3(1, 1), dim3(32, LAT_RY), 0, lc.stream>>>(
                    z.p, z.ld, z.coff, w, beta, B, KZ, N, act, 0, nullptr, nullptr, FeatView{}, BfDst{}, nullptr, mom_scratch);
@@ -474,6 +495,11 @@ int lat_fwd_fused(const LaunchCtx& lc, View z, const float* w, const float* beta
   }
   LAT_DISPATCH(KZ, {
     const size_t smem = (size_t)B * NM * sizeof(float);
+    if (lc.multi != nullptr) {
+      if (smem > 40 * 1024) { svae_global_error() = "lat_fwd_fused: batch too large for a batched launch"; return -1; }
+      return MULTI_RECORD(lat_fwd_fused_kernel_body<NM>, LAT_THREADS, lc, dim3(blocks), dim3(32, LAT_RY), smem, z.p, z.ld, z.coff, w, beta, B, KZ,
+                          N, act, y, stats, out, bf);
+    }
     if (allow_smem(lat_fwd_fused_kernel<NM>, smem) != 0) return -3;
     lat_fwd_fused_kernel<NM><<<blocks, dim3(32, LAT_RY), smem, lc.stream>>>(z.p, z.ld, z.coff, w, beta, B, KZ, N, act, y, stats, out, bf);
   });
@@ -490,6 +516,11 @@ int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double
   if (blocks > 4u * (unsigned)lc.sm_count) blocks = 4u * (unsigned)lc.sm_count;
   LAT_DISPATCH(KZ, {
     const size_t smem = 2 * (size_t)B * NM * sizeof(float);
+    if (lc.multi != nullptr) {
+      if (smem > 40 * 1024) { svae_global_error() = "lat_bwd_fused: batch too large for a batched launch"; return -1; }
+      return MULTI_RECORD(lat_bwd_fused_kernel_body<NM>, LAT_THREADS, lc, dim3(blocks), dim3(32, LAT_RY), smem, da, y, stats, beta, z.p, z.ld,
+                          z.coff, w, B, KZ, N, act, dw, dbeta, dz.p, dz.ld, dz.coff);
+    }
     if (allow_smem(lat_bwd_fused_kernel<NM>, smem) != 0) return -3;
     lat_bwd_fused_kernel<NM><<<blocks, dim3(32, LAT_RY), smem, lc.stream>>>(da, y, stats, beta, z.p, z.ld, z.coff, w, B, KZ, N, act, dw,
                                                                         dbeta, dz.p, dz.ld, dz.coff);

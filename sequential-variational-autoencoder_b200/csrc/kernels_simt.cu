@@ -250,8 +250,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // NM: compile-time bound on the widths in this launch (the latent groups are 2-3 wide in the MNIST / CelebA nets, 20-30
 // in the LSUN one): the per-element inner loops are NM long, not SK_NMAX.
 template <int NM>
-__global__ void __launch_bounds__(256)
-heads_fwd_kernel(const float* __restrict__ flat, int K, HeadSet hs, float* __restrict__ mu_pre, float* __restrict__ sd_pre,
+__device__ __forceinline__ void heads_fwd_kernel_body(const float* __restrict__ flat, int K, HeadSet hs, float* __restrict__ mu_pre, float* __restrict__ sd_pre,
                  int Z) {
   __shared__ float red[8][SK_NMAX];
   const int b = blockIdx.x;
@@ -290,10 +289,13 @@ heads_fwd_kernel(const float* __restrict__ flat, int K, HeadSet hs, float* __res
     __syncthreads();
   }
 }
+template <int NM>
+__global__ void __launch_bounds__(256)
+heads_fwd_kernel(const float* __restrict__ flat, int K, HeadSet hs, float* __restrict__ mu_pre, float* __restrict__ sd_pre,
+                 int Z) { heads_fwd_kernel_body<NM>(flat, K, hs, mu_pre, sd_pre, Z); }
 
 // d_flat[b, k] = sum_h sum_n d_h[b, col_h + n] * W_h[k, n]   (overwrite)
-__global__ void __launch_bounds__(256)
-heads_dgrad_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int Z, int K,
+__device__ __forceinline__ void heads_dgrad_kernel_body(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int Z, int K,
                    float* __restrict__ d_flat) {
   __shared__ float s_d[4 * SK_NMAX];
   const int b = blockIdx.y;
@@ -312,11 +314,13 @@ heads_dgrad_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __res
   }
   d_flat[(size_t)b * K + k] = v;
 }
+__global__ void __launch_bounds__(256)
+heads_dgrad_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int Z, int K,
+                   float* __restrict__ d_flat) { heads_dgrad_kernel_body(hs, dmu, dsd, Z, K, d_flat); }
 
 // gw_h[k, n] += sum_{b in slice} flat[b, k] * d_h[b, col_h + n] ; gb_h[n] += sum_b d_h[b, col_h + n]   (grads pre-zeroed)
 template <int NM>
-__global__ void __launch_bounds__(256)
-heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd,
+__device__ __forceinline__ void heads_wgrad_kernel_body(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd,
                    int B, int Z, int K) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int bper = (B + gridDim.y - 1) / gridDim.y;
@@ -346,6 +350,10 @@ heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __re
     }
   }
 }
+template <int NM>
+__global__ void __launch_bounds__(256)
+heads_wgrad_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd,
+                   int B, int Z, int K) { heads_wgrad_kernel_body<NM>(flat, hs, dmu, dsd, B, Z, K); }
 
 // ---- tiled head kernels (v2) ------------------------------------------------------------------------------------------
 // The kernels above walk ONE batch row per block (GEMV): every block re-reads the whole weight slice, with one load per
@@ -369,8 +377,7 @@ __device__ __forceinline__ int heads_ntot(const HeadSet& hs) {
 
 // forward: grid (row tiles, K slices); thread (tx, ty) owns rows ty*4..+4 and columns tx*TN..+TN of the tile
 template <int NT>
-__global__ void __launch_bounds__(256)
-heads_fwd_tiled_kernel(const float* __restrict__ flat, int B, int K, int kslice, HeadSet hs, float* __restrict__ mu_pre,
+__device__ __forceinline__ void heads_fwd_tiled_kernel_body(const float* __restrict__ flat, int B, int K, int kslice, HeadSet hs, float* __restrict__ mu_pre,
                        float* __restrict__ sd_pre, int Z) {
   constexpr int TN = NT / 16;
   __shared__ __align__(16) float s_a[HV_KC][HV_BM + 4];
@@ -476,12 +483,15 @@ heads_fwd_tiled_kernel(const float* __restrict__ flat, int B, int K, int kslice,
     }
   }
 }
+template <int NT>
+__global__ void __launch_bounds__(256)
+heads_fwd_tiled_kernel(const float* __restrict__ flat, int B, int K, int kslice, HeadSet hs, float* __restrict__ mu_pre,
+                       float* __restrict__ sd_pre, int Z) { heads_fwd_tiled_kernel_body<NT>(flat, B, K, kslice, hs, mu_pre, sd_pre, Z); }
 
 // input gradient: d_flat[b, k] = sum_c d[b, c] * W[k, c]  (overwrite).  Thread = one k with its NT weights in registers;
 // the d rows of the tile sit in shared memory and are read as broadcast float4 (4 FMAs per shared load).
 template <int NT>
-__global__ void __launch_bounds__(256)
-heads_dgrad_tiled_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int B, int Z, int K,
+__device__ __forceinline__ void heads_dgrad_tiled_kernel_body(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int B, int Z, int K,
                          float* __restrict__ d_flat) {
   __shared__ __align__(16) float s_d[HV_BM][NT];
   const int tid = threadIdx.x;
@@ -524,6 +534,10 @@ heads_dgrad_tiled_kernel(HeadSet hs, const float* __restrict__ dmu, const float*
     d_flat[(size_t)(row0 + r) * K + k] = v;
   }
 }
+template <int NT>
+__global__ void __launch_bounds__(256)
+heads_dgrad_tiled_kernel(HeadSet hs, const float* __restrict__ dmu, const float* __restrict__ dsd, int B, int Z, int K,
+                         float* __restrict__ d_flat) { heads_dgrad_tiled_kernel_body<NT>(hs, dmu, dsd, B, Z, K, d_flat); }
 
 // weight gradient: gw[k, c] = sum_b flat[b, k] * d[b, c].  Thread = one k with CT accumulators in registers for the CT dense
 // columns of its column group (blockIdx.y); the d rows sit in shared memory (broadcast float4).  Every (k, c) has exactly one
@@ -531,8 +545,7 @@ heads_dgrad_tiled_kernel(HeadSet hs, const float* __restrict__ dmu, const float*
 // for the LSUN heads); machine filling comes from 128-thread blocks and the column groups instead.
 // gb[c] = sum_b d[b, c] from the blocks of row blockIdx.x == 0.
 template <int CT>
-__global__ void __launch_bounds__(128)
-heads_wgrad_tiled_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu,
+__device__ __forceinline__ void heads_wgrad_tiled_kernel_body(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu,
                          const float* __restrict__ dsd, int B, int Z, int K) {
   __shared__ __align__(16) float s_d[HV_BM][CT];
   __shared__ int s_src[CT];      // source offset inside a [Z] row, bit 30: dsd, -1: pad column
@@ -606,6 +619,10 @@ heads_wgrad_tiled_kernel(const float* __restrict__ flat, HeadSet hs, const float
     }
   }
 }
+template <int CT>
+__global__ void __launch_bounds__(128)
+heads_wgrad_tiled_kernel(const float* __restrict__ flat, HeadSet hs, const float* __restrict__ dmu,
+                         const float* __restrict__ dsd, int B, int Z, int K) { heads_wgrad_tiled_kernel_body<CT>(flat, hs, dmu, dsd, B, Z, K); }
 
 // Latent projections (split_latent, sequential_vae.py:1801-1806): [B, kz<=32] x [kz, N] with N up to 32768.
 // dW[k, f] += sum_{b in slice} z[b, k] * dy[b, f]      (grid: f tiles x batch slices, grads pre-zeroed)
@@ -766,10 +783,21 @@ int heads_fwd(const LaunchCtx& lc, const float* flat, int B, int K, const HeadSe
     if (kslices < 1) kslices = 1;
     const int kslice = ((K + kslices - 1) / kslices + HV_KC - 1) / HV_KC * HV_KC;
     kslices = (K + kslice - 1) / kslice;
+    if (lc.multi != nullptr) {
+      int r = 0;
+      HV_DISPATCH(ntot, (r = MULTI_RECORD(heads_fwd_tiled_kernel_body<NT>, 256, lc, dim3(rt, kslices), dim3(256), 0, flat, B, K, kslice, hs,
+                                          mu_pre, sd_pre, Z)));
+      return r;
+    }
     HV_DISPATCH(ntot, (heads_fwd_tiled_kernel<NT><<<dim3(rt, kslices), 256, 0, lc.stream>>>(flat, B, K, kslice, hs, mu_pre,
                                                                                             sd_pre, Z)));
     CUDA_TRY(cudaGetLastError());
     return 0;
+  }
+  if (lc.multi != nullptr) {
+    int r = 0;
+    SK_DISPATCH(heads_nmax(hs), (r = MULTI_RECORD(heads_fwd_kernel_body<NM>, 256, lc, dim3(B, ks), dim3(256), 0, flat, K, hs, mu_pre, sd_pre, Z)));
+    return r;
   }
   SK_DISPATCH(heads_nmax(hs), (heads_fwd_kernel<NM><<<dim3(B, ks), 256, 0, lc.stream>>>(flat, K, hs, mu_pre, sd_pre, Z)));
   CUDA_TRY(cudaGetLastError());
@@ -782,11 +810,18 @@ int heads_dgrad(const LaunchCtx& lc, const HeadSet& hs, const float* dmu, const 
   for (int h = 0; h < hs.nheads; ++h) ntot += hs.n[h];
   ProfScope ps(lc, KC_SKINNY, 2.0 * B * K * ntot, 4.0 * ((double)B * K + (double)K * ntot));
   if (heads_use_tiled(ntot)) {
+    if (lc.multi != nullptr) {
+      int r = 0;
+      HV_DISPATCH(ntot, (r = MULTI_RECORD(heads_dgrad_tiled_kernel_body<NT>, 256, lc, dim3((K + 255) / 256, (B + HV_BM - 1) / HV_BM),
+                                          dim3(256), 0, hs, dmu, dsd, B, Z, K, d_flat)));
+      return r;
+    }
     HV_DISPATCH(ntot, (heads_dgrad_tiled_kernel<NT><<<dim3((K + 255) / 256, (B + HV_BM - 1) / HV_BM), 256, 0, lc.stream>>>(
                           hs, dmu, dsd, B, Z, K, d_flat)));
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
+  if (lc.multi != nullptr) return MULTI_RECORD(heads_dgrad_kernel_body, 256, lc, dim3((K + 255) / 256, B), dim3(256), 0, hs, dmu, dsd, Z, K, d_flat);
   heads_dgrad_kernel<<<dim3((K + 255) / 256, B), 256, 0, lc.stream>>>(hs, dmu, dsd, Z, K, d_flat);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -803,12 +838,19 @@ int heads_wgrad(const LaunchCtx& lc, const float* flat, const HeadSet& hs, const
     // 128 k per block x column groups of 16 or 32: narrower groups when the k blocks alone do not fill the machine
     const int kb128 = (K + 127) / 128;
     if (kb128 * ((ntot + 31) / 32) >= 2 * lc.sm_count) {
+      if (lc.multi != nullptr) return MULTI_RECORD(heads_wgrad_tiled_kernel_body<32>, 128, lc, dim3(kb128, (ntot + 31) / 32), dim3(128), 0, flat, hs, dmu, dsd, B, Z, K);
       heads_wgrad_tiled_kernel<32><<<dim3(kb128, (ntot + 31) / 32), 128, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K);
     } else {
+      if (lc.multi != nullptr) return MULTI_RECORD(heads_wgrad_tiled_kernel_body<16>, 128, lc, dim3(kb128, (ntot + 15) / 16), dim3(128), 0, flat, hs, dmu, dsd, B, Z, K);
       heads_wgrad_tiled_kernel<16><<<dim3(kb128, (ntot + 15) / 16), 128, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
+  }
+  if (lc.multi != nullptr) {
+    int r = 0;
+    SK_DISPATCH(heads_nmax(hs), (r = MULTI_RECORD(heads_wgrad_kernel_body<NM>, 256, lc, dim3(kb, bs), dim3(256), 0, flat, hs, dmu, dsd, B, Z, K)));
+    return r;
   }
   SK_DISPATCH(heads_nmax(hs), (heads_wgrad_kernel<NM><<<dim3(kb, bs), 256, 0, lc.stream>>>(flat, hs, dmu, dsd, B, Z, K)));
   CUDA_TRY(cudaGetLastError());

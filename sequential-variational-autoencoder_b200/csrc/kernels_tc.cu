@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -791,7 +792,7 @@ __device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsi
 // block (BnBwdFuse).  MODE 2: batch-norm forward of this block fused (BnFwdFuse).  Separate instantiations so that the plain
 // kernel keeps its register budget.
 template <int MODE>
-__global__ void __launch_bounds__(224, MODE != 0 ? 2 : 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
+__device__ __forceinline__ void tc2_conv_body(const Tc2Params& PP, const int zsub) {
   constexpr bool FUSED = MODE == 1;
   constexpr bool BNF = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -801,8 +802,8 @@ __global__ void __launch_bounds__(224, MODE != 0 ? 2 : 1) tc2_conv_kernel(const 
   // Output-channel tiling: blockIdx.y = 128-column tile of the packed weights, blockIdx.z = sub-tile of PP.ntw columns
   // inside it.  Layers with few pixel tiles (4x4 / 8x8 maps, B = 100) are bound by streaming their weights into one CTA
   // per tile; splitting the channels spreads that stream (and the MMAs) over up to 4x as many SMs.
-  const int n0 = blockIdx.y * 128 + blockIdx.z * PP.ntw;
-  const int Nt = min(PP.ntw, min(128, P.N_p - (int)blockIdx.y * 128) - (int)blockIdx.z * PP.ntw);
+  const int n0 = blockIdx.y * 128 + zsub * PP.ntw;
+  const int Nt = min(PP.ntw, min(128, P.N_p - (int)blockIdx.y * 128) - zsub * PP.ntw);
   const int wtile = n0 / PP.wtw;                                  // packed tile holding this CTA's columns
   const int tile_w = min(PP.wtw, P.N_p - wtile * PP.wtw);         // its width
   const bool w_sub = Nt != tile_w;     // sub-tile: one bulk copy per (chunk, tap, 8-channel group) row of Nt*16 bytes
@@ -1244,6 +1245,20 @@ __global__ void __launch_bounds__(224, MODE != 0 ? 2 : 1) tc2_conv_kernel(const 
   }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(224, MODE != 0 ? 2 : 1) tc2_conv_kernel(const __grid_constant__ Tc2Params PP) {
+  tc2_conv_body<MODE>(PP, (int)blockIdx.z);
+}
+// batched variant (LaunchCtx::multi): blockIdx.z = item * nsub + channel sub-tile; the items' parameter blocks travel by value
+__global__ void __launch_bounds__(224, 1) tc2_conv_multi_kernel(const __grid_constant__ MultiArgs<Tc2Params> A, int nsub) {
+  tc2_conv_body<0>(A.v[blockIdx.z / nsub], (int)(blockIdx.z % nsub));
+}
+static void tc2_conv_multi_launch(const void* host_args, int items, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  const int nsub = (int)grid.z;
+  multi_launch_chunks<Tc2Params>(tc2_conv_multi_kernel, host_args, items, grid, block, smem, st, (unsigned)nsub, nsub);
+}
+
+constexpr size_t TC2_SMEM_CAP = 227 * 1024;   // shared-memory budget of the TMA-fed conv kernel
 bool build_params2(const Geom& g, Tc2Params& PP, int ntw = 128) {
   memset(&PP, 0, sizeof PP);
   TcParams& P = PP.t;
@@ -1275,13 +1290,13 @@ bool build_params2(const Geom& g, Tc2Params& PP, int ntw = 128) {
   } else {
     static const int ws_max = getenv("SVAE_W_STAGES") ? atoi(getenv("SVAE_W_STAGES")) : W2_STAGES_MAX;
     PP.w_stages = ws_max < 2 ? 2 : (ws_max > W2_STAGES_MAX ? W2_STAGES_MAX : ws_max);
-    while (PP.w_stages > 2 && hdr + (size_t)PP.w_stages * P.b_stage_max + 2 * (size_t)PP.a_bytes + 256 > 227 * 1024) --PP.w_stages;
+    while (PP.w_stages > 2 && hdr + (size_t)PP.w_stages * P.b_stage_max + 2 * (size_t)PP.a_bytes + 256 > TC2_SMEM_CAP) --PP.w_stages;
     w_region = (size_t)PP.w_stages * P.b_stage_max;
   }
   w_region = (w_region + 127) & ~(size_t)127;
   PP.w_region = (unsigned)w_region;
-  size_t left = 227 * 1024 - hdr - w_region - 256;
-  if (hdr + w_region + 256 > 227 * 1024 || left < PP.a_bytes) return false;
+  size_t left = TC2_SMEM_CAP - hdr - w_region - 256;
+  if (hdr + w_region + 256 > TC2_SMEM_CAP || left < PP.a_bytes) return false;
   PP.a_stages = (int)(left / PP.a_bytes);
   if (PP.a_stages > A_STAGES_MAX) PP.a_stages = A_STAGES_MAX;
   const int want = P.NC > 1 ? 3 : 2;   // keep the footprint modest: two CTAs per SM help the short layers
@@ -1521,6 +1536,7 @@ int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int cha
     CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(tc2_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_conv_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_CAP));
     configured = true;
   }
   Tc2Launch L;
@@ -1557,6 +1573,11 @@ int tc2_gather_gemm(const LaunchCtx& lc, const Geom& g, const BfAct& in, int cha
                    (bnf ? (fwd_fuse->res ? 4.0 : 0.0) * out_elems + (fwd_fuse->out ? 4.0 : 0.0) * out_elems +
                               (fwd_fuse->bf.a.p ? 2.0 : 0.0) * out_elems : 0.0), &g);
   const dim3 grid((unsigned)L.ctas, (unsigned)L.ntiles, (unsigned)L.nsub);
+  if (lc.multi != nullptr) {
+    if (bnf || fuse != nullptr) { svae_global_error() = "tc2: fused epilogues are not available in batched launches"; return -1; }
+    if (lc.multi->add(&tc2_conv_multi_launch, &PP, sizeof PP, grid, dim3(224), smem) != 0) { svae_global_error() = lc.multi->err; return -1; }
+    return 0;
+  }
   if (bnf) CUDA_TRY(launch_k(lc, tc2_conv_kernel<2>, grid, dim3(224), smem, PP));
   else if (fuse != nullptr) CUDA_TRY(launch_k(lc, tc2_conv_kernel<1>, grid, dim3(224), smem, PP));
   else CUDA_TRY(launch_k(lc, tc2_conv_kernel<0>, grid, dim3(224), smem, PP));
@@ -1604,7 +1625,7 @@ struct SmemHeaderW2 {
   unsigned tmem_base, pad;
 };
 
-__global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant__ Tw2Params PP) {
+__device__ __forceinline__ void tc2_wgrad_body(const Tw2Params& PP) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const TwParams& P = PP.t;
   SmemHeaderW2* hdr = reinterpret_cast<SmemHeaderW2*>(smem_raw);
@@ -1727,6 +1748,13 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
   }
 }
 
+__global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant__ Tw2Params PP) { tc2_wgrad_body(PP); }
+// batched variant (LaunchCtx::multi): blockIdx.z = item
+__global__ void __launch_bounds__(192, 1) tc2_wgrad_multi_kernel(const __grid_constant__ MultiArgs<Tw2Params> A) { tc2_wgrad_body(A.v[blockIdx.z]); }
+static void tc2_wgrad_multi_launch(const void* host_args, int items, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  multi_launch_chunks<Tw2Params>(tc2_wgrad_multi_kernel, host_args, items, grid, block, smem, st, 1u);
+}
+
 size_t smem_bytes_w2(const Tw2Params& PP);
 
 // two_per_sm: half the tensor memory (half the taps per CTA) and at most ~110 KB of shared memory, so that two CTAs share an
@@ -1786,6 +1814,8 @@ bool build_wparams2(const Geom& g, Tw2Params& PP, bool two_per_sm = false) {
     }
     int cap = two_per_sm ? 256 : 512;
     PP.sets_per_cta = cap / P.N; if (PP.sets_per_cta > PP.nsets) PP.sets_per_cta = PP.nsets;
+    { static const int spc = getenv("SVAE_WGRAD_SPC") ? atoi(getenv("SVAE_WGRAD_SPC")) : 0;   // experiment: cap on tap sets per CTA
+      if (spc > 0 && PP.sets_per_cta > spc) PP.sets_per_cta = spc; }
     if (PP.sets_per_cta < 1) return false;
     while (PP.nsets % PP.sets_per_cta) --PP.sets_per_cta;
     PP.ngroups = PP.nsets / PP.sets_per_cta;
@@ -1864,15 +1894,61 @@ int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& d
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(tc2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc2_wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_CAP));
     configured = true;
   }
+  // How the work is cut: `sets_per_cta` tap sets per CTA (the rest of the sets go to other CTAs of blockIdx.y, which re-read
+  // the operands) x `splits` CTAs along the pixels (each flushes its partial dW with vector red.global.add).  Measured on
+  // B200 (scripts/wgrad_ab.sh, profiles/r2_wgrad_split.md): the flush sustains ~800 B/cycle over the whole chip whatever the
+  // number of CTAs, one CTA pulls ~34 B/cycle of operands from L2, an MMA issues every 59 (N <= 64) or 64 cycles.  With every
+  // SM holding all sets of a 16..128-channel layer the flush was 2-6x the MMA time; the model picks the cheapest cut.
+  int best_sets = PP.sets_per_cta;
+  long long best_splits = 1;
+  {
+    static const bool model = !(getenv("SVAE_WGRAD_MODEL") && getenv("SVAE_WGRAD_MODEL")[0] == '0');
+    double best = 1e30;
+    const int sm = lc.sm_count * per_sm;
+    for (int sets = PP.sets_per_cta; sets >= 1; --sets) {
+      if (PP.nsets % sets) continue;
+      const int gy_ = (PP.nsets / sets) * P.mblocks * P.nblocks;
+      long long smax = ((long long)sm + gy_ - 1) / gy_;
+      if (smax > P.tiles) smax = P.tiles;
+      if (smax < 1) smax = 1;
+      for (long long sp = smax; sp >= 1; sp = (sp > 8 ? sp * 7 / 8 : sp - 1)) {
+        const double tpc = (double)((P.tiles + sp - 1) / sp);
+        const double load = tpc * PP.stage_bytes / 34.0;
+        const double mma = tpc * sets * 8.0 * (P.N > 64 ? 64.0 : 59.0);
+        const double acc_bytes = (double)sets * 128.0 * P.N * 4.0;
+        const double flush = std::max(acc_bytes / 32.0, (double)gy_ * sp * acc_bytes / 800.0);
+        const double cost = std::max(load, mma) + flush + 1500.0;
+        if (cost < best) { best = cost; best_sets = sets; best_splits = sp; }
+        if (!model) break;   // SVAE_WGRAD_MODEL=0: all sets on every CTA, as many pixel splits as SMs (round-1 behaviour)
+      }
+      if (!model) break;
+    }
+  }
+  if (best_sets != PP.sets_per_cta) {
+    PP.sets_per_cta = best_sets;
+    PP.ngroups = PP.nsets / best_sets;
+    unsigned cols = (unsigned)(best_sets * P.N), t = 32;
+    while (t < cols) t <<= 1;
+    PP.tmem_cols = t;
+  }
   const int gy = PP.ngroups * P.mblocks * P.nblocks;
-  long long splits = ((long long)lc.sm_count * per_sm + gy - 1) / gy;
-  if (splits > P.tiles) splits = P.tiles;
+  long long splits = best_splits;
+  { static const int ms = getenv("SVAE_WGRAD_MAXSPLIT") ? atoi(getenv("SVAE_WGRAD_MAXSPLIT")) : 0;   // experiment: cap on the pixel splits
+    if (ms > 0 && splits > ms) splits = ms; }
   if (splits < 1) splits = 1;
   const double pix = (double)g.B * (g.Hin * g.Win < g.Hout * g.Wout ? g.Hin * g.Win : g.Hout * g.Wout);
   ProfScope ps(lc, KC_WGRAD_TC, 2.0 * pix * 16 * g.Cin * g.Cout,
                2.0 * ((double)g.B * g.Hin * g.Win * g.Cin + (double)g.B * g.Hout * g.Wout * g.Cout) + 4.0 * 16.0 * g.Cin * g.Cout, &g);
+  if (lc.multi != nullptr) {
+    if (lc.multi->add(&tc2_wgrad_multi_launch, &PP, sizeof PP, dim3((unsigned)splits, (unsigned)gy), dim3(192), smem) != 0) {
+      svae_global_error() = lc.multi->err;
+      return -1;
+    }
+    return 0;
+  }
   tc2_wgrad_kernel<<<dim3((unsigned)splits, (unsigned)gy), 192, smem, lc.stream>>>(PP);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -128,6 +128,7 @@ struct Step {
   double* lat_mom = nullptr;              // [L][64] scratch: second moments of z_t per latent group (lat_fwd_fused)
   BfAct xt_bf{};                          // bf16 copy of x_t for the next step's chain encoder
   int64_t p_begin, p_end;                 // parameter range (all-reduce bucket)
+  int64_t p_rec_end;                      // [p_begin, p_rec_end): recognition net, [p_rec_end, p_end): chain encoder + decoder
 };
 
 struct Arena {
@@ -224,7 +225,7 @@ struct svae_handle {
   std::vector<Mark> marks;
   int bf_last_B = -1;                             // batch the copies were last written with (stale rows are zeroed on change)
   // execution: main stream (`stream`) + side streams; `cur` is where the next launch goes
-  cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // 0: chain weight gradients, 1: recognition / latent branch, 2: its weight gradients
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // 0: chain weight gradients, 1: recognition / latent branch, 2: its weight gradients, 3: latent branch when the recognition backward is batched
   cudaStream_t cur = nullptr;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   bool use_streams = true, use_graph = true, capturing = false;
@@ -237,6 +238,8 @@ struct svae_handle {
   bool use_bucket_update = true;     // SVAE_BUCKET_UPDATE=0: one Adam launch + one repack launch after the backward
   std::vector<int> pack_step_begin;  // pack-table entry range of every chain step (T + 1 offsets)
   std::vector<double> pack_step_elems;
+  std::vector<int> pack_rec_end;     // end of the recognition net's entries inside every step's range
+  std::vector<double> pack_entry_elems;
   int pdl_prev = 0;     // 1: the last node enqueued on the chain stream is a kernel (see launch_k)
   bool use_pdl = true;  // SVAE_PDL=0 disables programmatic dependent launch
   // SVAE_COOP_BN=1: batch-norm backward as ONE cooperative kernel (reduce, grid barrier, apply) instead of two.  Correct and
@@ -270,9 +273,28 @@ struct svae_handle {
   NcclApi* nccl = nullptr; void* comm = nullptr; int rank = 0, nranks = 1;
   std::vector<cudaEvent_t> bucket_ev; cudaEvent_t comm_done = nullptr;
 
+  // Batched launches of the T recognition nets (MultiRec, common.cuh): q(z_t | x) depends on x only (sequential_vae.py:1022),
+  // so the T nets + latent projections are recorded net by net and issued as ONE launch per layer kernel over a group of
+  // chain steps (blockIdx.z = step), forward before / beside the chain and backward in groups behind it.
+  bool use_multi = true;             // SVAE_MULTI=0: per-step launches on the side streams (round-1 behaviour)
+  MultiRec* multi = nullptr;         // recording in progress (see lc())
+  // SMs every recorded item sizes its grid for: a batched launch carries `items` grids side by side, so each is sized for
+  // ~1/items of the machine (fewer, longer-lived CTAs per item: resident weights are fetched once per CTA, the weight
+  // gradient flushes fewer partial sums) instead of `items` full-machine grids queueing behind each other
+  int multi_sm = 148;
+  float multi_sm_factor = 1.f;       // SVAE_MULTI_SM_FACTOR
+  void begin_multi(MultiRec* m, int items) {
+    multi = m;
+    int v = (int)(multi_sm_factor * (float)sm_count / (float)(items > 0 ? items : 1) + 0.999f);
+    multi_sm = v < 8 ? 8 : (v > sm_count ? sm_count : v);
+  }
+  std::vector<int> rec_fwd_groups;   // chain steps per forward group (SVAE_REC_FWD_GROUPS, default 2,6,6,...)
+  std::vector<int> rec_bwd_groups;   // chain steps per backward group, in backward order (SVAE_REC_BWD_GROUPS, default 5,2,1)
+
   Profiler prof;
   LaunchCtx lc() {
     LaunchCtx c{cur ? cur : stream, &launches, sm_count, &prof};
+    if (multi != nullptr) { c.multi = multi; c.sm_count = multi_sm; return c; }
     if (use_pdl && !prof.enabled && (cur == nullptr || cur == stream)) c.pdl_state = &pdl_prev;
     return c;
   }
@@ -398,6 +420,7 @@ void build_params(svae_handle* h) {
         s.heads[L - 2].push_back(hd);
       }
     }
+    s.p_rec_end = h->arena_numel;
     // --- chain encoder: theta/generative_encoder_step_t (:1757-1777), t >= 1
     if (t > 0) {
       Namer nm{"theta/generative_encoder_step_" + std::to_string(t)};
@@ -1001,6 +1024,7 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
   }
   if (!(h->ablate & 1)) {
     OnStream os(h, wst);
+    struct Lane { MultiRec* m; Lane(MultiRec* m_) : m(m_) { if (m) m->lane = 1; } ~Lane() { if (m) m->lane = 0; } } lane(h->multi);
     LaunchCtx lw = h->lc();
     if (b.g.mode == 0) {
       Geom g = b.g; g.B = B;
@@ -1060,6 +1084,40 @@ int dyn_push(svae_handle* h) {
   h->dyn_ring[slot] = h->dyn_host;
   H_CUDA(cudaMemcpyAsync(h->dyn_dev, &h->dyn_ring[slot], sizeof(SvaeDyn), cudaMemcpyHostToDevice, h->stream));
   H_CUDA(cudaEventRecord(h->dyn_ev[slot], h->stream));
+  return 0;
+}
+
+// ---- batched launches (MultiRec, common.cuh) --------------------------------------------------------------------------
+// Issue a recorded sequence on the current stream: one launch per slot with grid.z = items (the argument blocks travel in the
+// kernel parameter space, see multi_launch_chunks).
+int multi_flush(svae_handle* h, MultiRec& m, cudaStream_t wst = nullptr) {
+  if (m.pending && m.err.empty()) m.err = "batched launch: a kernel wrapper without batched-launch support ran inside a recorded sequence";
+  if (!m.err.empty()) return fail(h, SVAE_ESTATE, m.err);
+  if (m.items == 0 || m.slots.empty()) return 0;
+  for (const MultiSlot& sl : m.slots)
+    if (sl.count != m.items) return fail(h, SVAE_ESTATE, "batched launch: an item recorded fewer kernels than the first one");
+  cudaStream_t st = cur_stream(h);
+  // Lane-1 slots (weight gradients) only consume what earlier lane-0 slots produced and nothing in the sequence consumes
+  // them: they go to `wst`, ordered behind the lane-0 slots recorded before them.
+  bool need_link = true;
+  for (size_t i = 0; i < m.slots.size(); ++i) {
+    MultiSlot& sl = m.slots[i];
+    cudaStream_t ls = st;
+    if (sl.lane == 1 && wst != nullptr && wst != st) {
+      if (need_link) { H_TRY(link(h, st, wst)); need_link = false; }
+      ls = wst;
+    } else {
+      need_link = true;
+    }
+    OnStream os(h, ls);
+    LaunchCtx lc = h->lc();
+    lc.pdl_state = nullptr;
+    ProfScope ps(lc, sl.kc, sl.flops, sl.bytes);
+    h->launches += (m.items - 1) / MULTI_MAX;   // more than MULTI_MAX items: one launch per chunk
+    sl.launch(sl.host.data(), m.items, sl.grid, sl.block, sl.smem, ls);
+    H_CUDA(cudaGetLastError());
+  }
+  if (st == h->stream) h->pdl_prev = 0;
   return 0;
 }
 
@@ -1176,6 +1234,23 @@ float step_coef(const svae_handle* h, int t) { return t == 0 ? h->cfg.first_step
 bool step_has_recon(const svae_handle* h, int t) { return h->cfg.intermediate_reconstruction || t == h->T - 1; }
 bool step_has_kl(const svae_handle* h, int t) { return (h->cfg.regularized_mask >> t) & 1ull; }
 
+// The recognition nets + latent projections of all chain steps can run as batched launches when every kernel on that path
+// records (TMA-fed convs / input gradients / weight gradients, fused latent kernels, separate batch-norm passes) and every
+// chain step owns its buffers and gradient scratch set.
+bool rec_multi_ok(const svae_handle* h, int B) {
+  if (!h->use_multi || !h->cfg.train_capacity || h->act_sets != h->T || h->T < 2) return false;
+  if (h->use_fuse || h->use_coop_bn || (h->ablate & 3) || h->timeline) return false;
+  for (const Step& s : h->steps) {
+    for (size_t k = 0; k < s.inf.size(); ++k) {
+      const Block& b = s.inf[k];
+      if (!b.tc2_fwd || b.in_bf.p == nullptr || !b.tc2_wgrad || (k > 0 && !b.tc2_dgrad)) return false;
+    }
+    for (const Block& b : s.lat)
+      if (!lat_fused_supported(B, b.g.Cin) || (size_t)B * 32 * 8 > 40 * 1024) return false;
+  }
+  return true;
+}
+
 int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const float* eps, uint64_t seed, float reg,
                  float* mu_out, float* sd_out, float* xs_out) {
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
@@ -1197,7 +1272,39 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
   }
   const bool fork = forked(h) && h->act_sets == h->T && (h->fork_mask & 8);
   std::vector<cudaEvent_t> rec_ev(h->T, nullptr);
-  if (fork) {
+  const bool multi = rec_multi_ok(h, B);
+  if (multi) {
+    // Batched: the nets of a GROUP of chain steps are recorded one after the other and issued as one launch per layer kernel
+    // (blockIdx.z = step).  The first group is small so that the chain can start early; the groups run side by side on the
+    // side streams (on the main stream, before the chain, when the step is not forked).
+    int t0 = 0;
+    for (int gi = 0; t0 < h->T; ++gi) {
+      const int n = h->rec_fwd_groups[std::min((size_t)gi, h->rec_fwd_groups.size() - 1)];
+      const int t1 = std::min(h->T, t0 + n);
+      cudaStream_t sd = fork ? h->side[gi % 3] : h->stream;
+      if (fork && gi < 3) H_TRY(link(h, h->stream, sd));
+      OnStream os(h, sd);
+      MultiRec rec;
+      h->begin_multi(&rec, t1 - t0);
+      int r = 0;
+      for (int t = t0; t < t1 && r == 0; ++t) {
+        Step& s = h->steps[t];
+        rec.begin_item();
+        r = recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, h->loss_sums + h->T + t);
+        if (r == 0) r = latent_fwd(h, s, B, s.z);
+      }
+      h->multi = nullptr;
+      H_TRY(r);
+      H_TRY(multi_flush(h, rec));
+      if (fork) {
+        cudaEvent_t e = next_event(h);
+        H_CUDA(cudaEventRecord(e, sd));
+        for (int t = t0; t < t1; ++t) rec_ev[t] = e;
+        tl_mark(h, sd, "side: recognition fwd group done", t0);
+      }
+      t0 = t1;
+    }
+  } else if (fork) {
     // The recognition nets read only x (sequential_vae.py:1011-1025) and the latent projections only z_t: all T of them
     // run on the side streams, off the chain's critical path.
     for (int t = 0; t < h->T; ++t) {
@@ -1217,9 +1324,10 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
     Step& s = h->steps[t];
     // forward-only handles alias steps >= 2 onto step 1's buffers: restart their batch-norm statistics
     if (t >= 2 && h->act_sets < h->T) H_TRY(zero_region(h, h->zf_base, h->zf_bytes));
-    if (!fork) H_TRY(recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, h->loss_sums + h->T + t));
+    if (!fork && !multi) H_TRY(recognition_fwd(h, s, B, x, eps ? eps + t * bz : nullptr, h->loss_sums + h->T + t));
     if (t > 0) H_TRY(encoder_fwd(h, s, B, prev));
-    if (fork) H_CUDA(cudaStreamWaitEvent(h->stream, rec_ev[t], 0)); else H_TRY(latent_fwd(h, s, B, s.z));
+    if (fork) { if (t == 0 || rec_ev[t] != rec_ev[t - 1]) H_CUDA(cudaStreamWaitEvent(h->stream, rec_ev[t], 0)); }
+    else if (!multi) H_TRY(latent_fwd(h, s, B, s.z));
     H_TRY(decoder_fwd(h, s, B, prev, tgt, s.xt, h->loss_sums + t));
     tl_mark(h, h->stream, "main: fwd chain step done", t);
     if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out + t * img, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -1241,7 +1349,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
 // Streams of one step's backward: the chain (decoder, chain encoder: bn backward + input gradients) stays on the main
 // stream; weight gradients of the chain go to side[0]; the latent projections' backward and the whole recognition net go
 // to side[1] with its weight gradients on side[2].
-struct BwdStreams { cudaStream_t chain, w, rec, recw; };
+struct BwdStreams { cudaStream_t chain, w, rec, recw, lat; };   // lat: the latent projections' backward (the recognition stream unless its work is batched)
 
 int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int B, const float* gx_in, float* gx_prev,
                 const float* xprev) {
@@ -1303,8 +1411,8 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
                     has_gate ? gs.d_e[2 * l + 1] : nullptr, 0));
     // P_l = lrelu(bn(fc(z_l))): second channel window of d_dcat, on the recognition stream
     {
-      H_TRY(link(h, st.chain, st.rec));
-      OnStream os(h, st.rec);
+      H_TRY(link(h, st.chain, st.lat));
+      OnStream os(h, st.lat);
       const Block& lb = s.lat[l];
       FeatView da{gs.d_dcat[l], 2 * Fl, Fl, Fl, lb.out.ppr};
       H_TRY(skinny_block_bwd(h, gs, s.lat[l], B, da, mkview(s.z, h->Z, h->zoff[l]), h->cfg.latent_dims[l],
@@ -1324,8 +1432,8 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   }
   // P_{L-1}
   {
-    H_TRY(link(h, st.chain, st.rec));
-    OnStream os(h, st.rec);
+    H_TRY(link(h, st.chain, st.lat));
+    OnStream os(h, st.lat);
     const int coffP = s.t > 0 ? F[L] : 0;
     FeatView da{gs.d_cc, s.ncc, coffP, F[L + 1], 1};
     H_TRY(skinny_block_bwd(h, gs, s.lat[L - 1], B, da, mkview(s.z, h->Z, h->zoff[L - 1]), h->cfg.latent_dims[L - 1],
@@ -1368,7 +1476,10 @@ int recognition_bwd(svae_handle* h, GradSet& gs, Step& s, int B, cudaStream_t ws
     const int K = fb.rpi * fb.feats;
     HeadSet hs = make_headset(h, s, l);
     H_TRY(heads_dgrad(lc, hs, gs.d_mu_pre, gs.d_sd_pre, B, h->Z, K, gs.d_inf[2 * l + 1]));
-    H_TRY(heads_wgrad(lc, fb.out.p, hs, gs.d_mu_pre, gs.d_sd_pre, B, h->Z, K));
+    if (h->multi) h->multi->lane = 1;
+    const int rw = heads_wgrad(lc, fb.out.p, hs, gs.d_mu_pre, gs.d_sd_pre, B, h->Z, K);
+    if (h->multi) h->multi->lane = 0;
+    H_TRY(rw);
   }
   for (int k = 2 * (L - 1) - 1; k >= 0; --k) {
     Block& b = s.inf[k];
@@ -1383,17 +1494,25 @@ int recognition_bwd(svae_handle* h, GradSet& gs, Step& s, int B, cudaStream_t ws
   return 0;
 }
 
-int allreduce_bucket(svae_handle* h, int t, const BwdStreams& st) {
+// part: 0 = the whole slice of chain step t, 1 = its chain encoder + decoder, 2 = its recognition net (the two halves are
+// used when the recognition backward is deferred to a batched group: the chain half is final long before the other)
+void bucket_range(const svae_handle* h, int t, int part, int64_t& b, int64_t& e) {
+  const Step& s = h->steps[t];
+  b = part == 1 ? s.p_rec_end : s.p_begin;
+  e = part == 2 ? s.p_rec_end : s.p_end;
+}
+
+int allreduce_bucket(svae_handle* h, int t, const BwdStreams& st, int part = 0) {
   if (h->comm == nullptr) return 0;
-  Step& s = h->steps[t];
+  int64_t pb, pe;
+  bucket_range(h, t, part, pb, pe);
   // the bucket is complete when every stream that produced gradients of step t has finished its part
   H_TRY(link(h, st.chain, h->comm_stream));
   H_TRY(link(h, st.w, h->comm_stream));
   H_TRY(link(h, st.rec, h->comm_stream));
   H_TRY(link(h, st.recw, h->comm_stream));
   h->pdl_prev = 0;
-  int r = h->nccl->AllReduce(h->G + s.p_begin, h->G + s.p_begin, (size_t)(s.p_end - s.p_begin), /*ncclFloat*/ 7,
-                             /*ncclSum*/ 0, h->comm, h->comm_stream);
+  int r = h->nccl->AllReduce(h->G + pb, h->G + pb, (size_t)(pe - pb), /*ncclFloat*/ 7, /*ncclSum*/ 0, h->comm, h->comm_stream);
   if (r != 0) return fail(h, SVAE_ENCCL, std::string("ncclAllReduce failed: ") + h->nccl->GetErrorString(r));
   return 0;
 }
@@ -1401,9 +1520,10 @@ int allreduce_bucket(svae_handle* h, int t, const BwdStreams& st) {
 int ensure_pack_table(svae_handle* h);
 
 // clipped Adam + operand repack of chain step t's parameter slice (see svae_handle::upd_stream)
-int update_bucket(svae_handle* h, int t, const BwdStreams& st) {
+int update_bucket(svae_handle* h, int t, const BwdStreams& st, int part = 0) {
   if (!h->bucket_update) return 0;
-  Step& s = h->steps[t];
+  int64_t pb, pe;
+  bucket_range(h, t, part, pb, pe);
   cudaStream_t us = h->comm != nullptr ? h->comm_stream : h->upd_stream;
   if (h->comm == nullptr) {   // with a communicator the all-reduce of this bucket was just enqueued on the same stream
     H_TRY(link(h, st.chain, us));
@@ -1413,13 +1533,15 @@ int update_bucket(svae_handle* h, int t, const BwdStreams& st) {
   }
   OnStream os(h, us);
   LaunchCtx lc = h->lc();
-  const int64_t n = s.p_end - s.p_begin;
-  H_TRY(adam_update(lc, h->P + s.p_begin, h->G + s.p_begin, h->M + s.p_begin, h->V + s.p_begin, n, h->dyn_dev, h->dyn_host.lr_t,
+  const int64_t n = pe - pb;
+  H_TRY(adam_update(lc, h->P + pb, h->G + pb, h->M + pb, h->V + pb, n, h->dyn_dev, h->dyn_host.lr_t,
                     h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->cfg.clip_value, 1.f / (float)h->nranks));
   if (h->cfg.operand_dtype == SVAE_OPERAND_BF16 && h->pack_table != nullptr) {
-    const int b0 = h->pack_step_begin[t], b1 = h->pack_step_begin[t + 1];
-    if (b1 > b0)
-      H_TRY(tc_pack_batched(lc, reinterpret_cast<const TcPackEntry*>(h->pack_table) + b0, b1 - b0, h->pack_step_elems[t]));
+    const int b0 = part == 1 ? h->pack_rec_end[t] : h->pack_step_begin[t];
+    const int b1 = part == 2 ? h->pack_rec_end[t] : h->pack_step_begin[t + 1];
+    double elems = 0;
+    for (int i = b0; i < b1; ++i) elems += h->pack_entry_elems[i];
+    if (b1 > b0) H_TRY(tc_pack_batched(lc, reinterpret_cast<const TcPackEntry*>(h->pack_table) + b0, b1 - b0, elems));
   }
   return 0;
 }
@@ -1432,42 +1554,121 @@ int backward_impl(svae_handle* h) {
   H_TRY(zero_region(h, h->zb_base, h->zb_bytes));
   H_TRY(zero_region(h, h->G, (size_t)h->arena_numel * 4));
   const bool fork = forked(h);
-  BwdStreams st{h->stream, h->stream, h->stream, h->stream};
+  BwdStreams st{h->stream, h->stream, h->stream, h->stream, h->stream};
   if (fork) {
     if (h->fork_mask & 1) st.w = h->side[0];
     if (h->fork_mask & 2) st.rec = h->side[1];
     st.recw = (h->fork_mask & 4) ? h->side[2] : st.rec;
   }
+  st.lat = st.rec;
   // side_done[t][i]: side stream i has finished step t's work (its scratch set may be reused two steps later)
   std::vector<cudaEvent_t> side_done((size_t)T * 3, nullptr);
   int cur = 0;
   const float* gx_in = nullptr;  // dL/dx_t from later steps
+  // Deferred recognition backward (rec_multi_ok): the latent projections' and the recognition nets' backward of a GROUP of chain
+  // steps is recorded step by step once the chain has passed the group's last decoder and issued as one launch per layer
+  // kernel (blockIdx.z = step) on the recognition stream, beside the chain's backward of the earlier steps.  Every step of
+  // a group keeps its own gradient scratch set (group size <= n_gs).  The step's parameter slice is then all-reduced /
+  // updated in two halves: chain encoder + decoder right after the chain step, recognition net after its group.
+  const bool multi = rec_multi_ok(h, B);
+  // batched: side[1] / side[2] carry the groups (input-gradient sequence / weight gradients), side[3] the per-step latent
+  // projections (their parameters belong to the decoder's half of the slice)
+  if (multi && fork && h->side[3] != nullptr && (h->fork_mask & 2)) st.lat = h->side[3];
+  size_t gi = 0;
+  auto group_size = [&]() { return std::max(1, std::min(h->rec_bwd_groups[std::min(gi, h->rec_bwd_groups.size() - 1)], h->n_gs)); };
+  int group = group_size();
+  std::vector<int> pending;
+  struct Unmulti { svae_handle* h; ~Unmulti() { h->multi = nullptr; } } unmulti{h};
   for (int t = T - 1; t >= 0; --t) {
     Step& s = h->steps[t];
     const int NS = h->n_gs;
     GradSet& gs = h->gs[t % NS];
-    if (fork && t + NS < T)
-      for (int i = 0; i < 3; ++i) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + NS) * 3 + i], 0));
+    if ((fork || multi) && t + NS < T)
+      for (int i = 0; i < 3; ++i)
+        if (side_done[(size_t)(t + NS) * 3 + i] != nullptr) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + NS) * 3 + i], 0));
     const float* xprev = t > 0 ? h->steps[t - 1].xt : nullptr;
     float* gx_prev = h->gx[cur ^ 1];
     H_TRY(decoder_bwd(h, gs, st, s, B, gx_in, gx_prev, xprev));
-    {
+    if (!multi) {
       // recognition net of this step: needs d_z (complete once the last latent projection's backward has run on st.rec)
       OnStream os(h, st.rec);
       if (!(h->ablate & 2)) H_TRY(recognition_bwd(h, gs, s, B, st.recw));
+    } else {
+      pending.push_back(t);
+      if ((int)pending.size() == group || t == 0) {
+        H_TRY(link(h, st.lat, st.rec));   // d_z of every step of the group is final
+        OnStream os(h, st.rec);
+        MultiRec rec;
+        h->begin_multi(&rec, (int)pending.size());
+        int r = 0;
+        for (size_t i = 0; i < pending.size() && r == 0; ++i) {
+          Step& ps = h->steps[pending[i]];
+          GradSet& pgs = h->gs[pending[i] % NS];
+          rec.begin_item();
+          r = recognition_bwd(h, pgs, ps, B, st.rec);
+        }
+        h->multi = nullptr;
+        H_TRY(r);
+        H_TRY(multi_flush(h, rec, st.recw));
+        tl_mark(h, st.rec, "R: recognition bwd group done", t);
+      }
     }
     if (t > 0) H_TRY(encoder_bwd(h, gs, st, s, B, gx_prev, xprev));
     tl_mark(h, st.chain, "main: bwd chain step done", t);
     if (fork) { tl_mark(h, st.w, "W: chain wgrads done", t); tl_mark(h, st.rec, "R: recognition bwd done", t); tl_mark(h, st.recw, "W2: recognition wgrads done", t); }
-    if (fork) {
+    if (!multi) {
+      if (fork) {
+        cudaStream_t sd[3] = {st.w, st.rec, st.recw};
+        for (int i = 0; i < 3; ++i) {
+          side_done[(size_t)t * 3 + i] = next_event(h);
+          H_CUDA(cudaEventRecord(side_done[(size_t)t * 3 + i], sd[i]));
+        }
+      }
+      H_TRY(allreduce_bucket(h, t, st));
+      H_TRY(update_bucket(h, t, st));
+    } else if (pending.size() == 1 && pending[0] == t && (group == 1 || t == 0)) {
+      // a group of one, issued in this iteration: the whole slice is final together, as without batching
+      if (st.lat != st.rec) H_TRY(link(h, st.lat, st.rec));
       cudaStream_t sd[3] = {st.w, st.rec, st.recw};
-      for (int i = 0; i < 3; ++i) {
-        side_done[(size_t)t * 3 + i] = next_event(h);
-        H_CUDA(cudaEventRecord(side_done[(size_t)t * 3 + i], sd[i]));
+      for (int i = 0; i < 3; ++i)
+        if (sd[i] != st.chain) {
+          side_done[(size_t)t * 3 + i] = next_event(h);
+          H_CUDA(cudaEventRecord(side_done[(size_t)t * 3 + i], sd[i]));
+        }
+      H_TRY(allreduce_bucket(h, t, st));
+      H_TRY(update_bucket(h, t, st));
+      pending.clear();
+      ++gi;
+      group = group_size();
+    } else {
+      // chain half of the slice: final once the chain, its weight-gradient stream and the latent projections are done with step t
+      BwdStreams ch{st.chain, st.w, st.lat, st.w, st.lat};
+      if (st.w != st.chain) {
+        side_done[(size_t)t * 3] = next_event(h);
+        H_CUDA(cudaEventRecord(side_done[(size_t)t * 3], st.w));
+      }
+      if (st.lat != st.chain) {
+        side_done[(size_t)t * 3 + 2] = next_event(h);
+        H_CUDA(cudaEventRecord(side_done[(size_t)t * 3 + 2], st.lat));
+      }
+      H_TRY(allreduce_bucket(h, t, ch, 1));
+      H_TRY(update_bucket(h, t, ch, 1));
+      if ((int)pending.size() == group || t == 0) {
+        // recognition halves of the group that was just issued on st.rec
+        BwdStreams rs{st.rec, st.recw, st.rec, st.recw, st.rec};
+        if (st.recw != st.rec) H_TRY(link(h, st.recw, st.rec));   // the scratch sets of the group are free when both lanes are done
+        cudaEvent_t e = nullptr;
+        if (st.rec != st.chain) { e = next_event(h); H_CUDA(cudaEventRecord(e, st.rec)); }
+        for (int pt : pending) {
+          side_done[(size_t)pt * 3 + 1] = e;
+          H_TRY(allreduce_bucket(h, pt, rs, 2));
+          H_TRY(update_bucket(h, pt, rs, 2));
+        }
+        pending.clear();
+        ++gi;
+        group = group_size();
       }
     }
-    H_TRY(allreduce_bucket(h, t, st));
-    H_TRY(update_bucket(h, t, st));
     gx_in = gx_prev;
     cur ^= 1;
   }
@@ -1476,6 +1677,7 @@ int backward_impl(svae_handle* h) {
     H_TRY(link(h, st.w, h->stream));
     H_TRY(link(h, st.rec, h->stream));
     H_TRY(link(h, st.recw, h->stream));
+    H_TRY(link(h, st.lat, h->stream));
   }
   if (h->comm != nullptr) {
     H_CUDA(cudaEventRecord(h->comm_done, h->comm_stream));
@@ -1581,10 +1783,12 @@ int ensure_pack_table(svae_handle* h) {
   std::vector<TcPackEntry> v;
   h->pack_step_begin.assign(h->T + 1, 0);
   h->pack_step_elems.assign(h->T, 0.0);
+  h->pack_rec_end.assign(h->T, 0);
   for (int t = 0; t < h->T; ++t) {     // for_each_block order, one step at a time: every step's entries are contiguous
     Step& s = h->steps[t];
     h->pack_step_begin[t] = (int)v.size();
     for (Block& b : s.inf) collect_pack(h, b, &v);
+    h->pack_rec_end[t] = (int)v.size();
     for (Block& b : s.enc) collect_pack(h, b, &v);
     if (s.t > 0) collect_pack(h, s.encfc, &v);
     for (Block& b : s.lat) collect_pack(h, b, &v);
@@ -1597,6 +1801,8 @@ int ensure_pack_table(svae_handle* h) {
   }
   h->pack_step_begin[h->T] = (int)v.size();
   h->pack_entries = (int)v.size();
+  h->pack_entry_elems.resize(v.size());
+  for (size_t i = 0; i < v.size(); ++i) h->pack_entry_elems[i] = (double)v[i].total;
   if (v.empty()) return 0;
   H_CUDA(cudaMalloc(&h->pack_table, sizeof(TcPackEntry) * v.size()));
   H_CUDA(cudaMemcpy(h->pack_table, v.data(), sizeof(TcPackEntry) * v.size(), cudaMemcpyHostToDevice));
@@ -1615,21 +1821,26 @@ int repack_if_dirty(svae_handle* h) {
   return 0;
 }
 
+void drop_graph(svae_handle* h, GraphEntry& e) { (void)h; cudaGraphExecDestroy(e.exec); }
+void drop_graphs(svae_handle* h) {
+  for (GraphEntry& e : h->graphs) drop_graph(h, e);
+  h->graphs.clear();
+}
+
 void destroy_impl(svae_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamSynchronize(h->side[i]);
+  for (int i = 0; i < 4; ++i) if (h->side[i]) cudaStreamSynchronize(h->side[i]);
   if (h->upd_stream) cudaStreamSynchronize(h->upd_stream);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
   // captured graphs hold the communicator's collectives: they must go before the communicator does
-  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);
-  h->graphs.clear();
+  drop_graphs(h);
   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
   for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->dyn_ev) if (e) cudaEventDestroy(e);
-  for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
+  for (int i = 0; i < 4; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
   if (h->upd_stream) cudaStreamDestroy(h->upd_stream);
   cudaFree(h->dyn_dev);
   if (h->dyn_ring) cudaFreeHost(h->dyn_ring);
@@ -1780,10 +1991,27 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     if (e5) h->ablate = atoi(e5);
   }
   if (cfg->train_capacity) {
-    for (int i = 0; i < 3; ++i) C_CUDA(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio_lo));
+    for (int i = 0; i < 4; ++i) C_CUDA(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio_lo));
     C_CUDA(cudaStreamCreateWithPriority(&h->upd_stream, cudaStreamNonBlocking, prio_lo));
     const char* e8 = getenv("SVAE_BUCKET_UPDATE");
     h->use_bucket_update = !(e8 && e8[0] == '0');
+    // chain steps per group, the last entry repeats.  Forward: the chain needs net t at step t, so the first groups are
+    // small; backward (steps T-1 .. 0): whatever is issued behind the chain's last step is exposed, so the LAST groups are small.
+    auto parse = [](const char* e, const char* dflt, std::vector<int>& out) {
+      for (const char* q = e ? e : dflt; *q;) {
+        const int v = atoi(q);
+        if (v > 0) out.push_back(v);
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+      if (out.empty()) out.push_back(1);
+    };
+    parse(getenv("SVAE_REC_FWD_GROUPS"), "1,1,6", h->rec_fwd_groups);
+    parse(getenv("SVAE_REC_BWD_GROUPS"), "5,2,1", h->rec_bwd_groups);
+    const char* e13 = getenv("SVAE_MULTI_SM_FACTOR");
+    if (e13 && atof(e13) > 0) h->multi_sm_factor = (float)atof(e13);
+    const char* e10 = getenv("SVAE_MULTI");
+    h->use_multi = !(e10 && e10[0] == '0') && cfg->operand_dtype == SVAE_OPERAND_BF16;
   }
   C_CUDA(cudaMalloc((void**)&h->dyn_dev, sizeof(SvaeDyn)));
   C_CUDA(cudaMemset(h->dyn_dev, 0, sizeof(SvaeDyn)));
@@ -1844,15 +2072,14 @@ int svae_set_stream(svae_handle* h, void* s) {
   if (!h) return SVAE_EINVAL;
   h->stream = s ? (cudaStream_t)s : h->own_stream;
   h->cur = nullptr;
-  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);   // captured on the previous stream's dependencies
-  h->graphs.clear();
+  drop_graphs(h);   // captured on the previous stream's dependencies
   return SVAE_OK;
 }
 int svae_sync(svae_handle* h) {
   if (!h) return SVAE_EINVAL;
   H_CUDA(cudaSetDevice(h->device));
   H_CUDA(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < 3; ++i) if (h->side[i]) H_CUDA(cudaStreamSynchronize(h->side[i]));
+  for (int i = 0; i < 4; ++i) if (h->side[i]) H_CUDA(cudaStreamSynchronize(h->side[i]));
   if (h->comm_stream) H_CUDA(cudaStreamSynchronize(h->comm_stream));
   if (h->timeline && !h->marks.empty()) {
     // print the most recent step only (marks since the last "step start")
@@ -1966,7 +2193,7 @@ static int train_step_graph(svae_handle* h, const float* x, const float* tgt, in
   H_TRY(dyn_push(h));
   if (ge == nullptr) {
     if (h->graphs.size() >= 8) {   // callers that rotate many buffers: drop the oldest
-      cudaGraphExecDestroy(h->graphs.front().exec);
+      drop_graph(h, h->graphs.front());
       h->graphs.erase(h->graphs.begin());
     }
     const int64_t adam_t0 = h->adam_t, launches0 = h->launches;
@@ -2210,8 +2437,7 @@ int svae_comm_init(svae_handle* h, int rank, int nranks, const char id[128], con
   H_CUDA(cudaSetDevice(h->device));
   h->nccl = nccl_load(path);
   if (!h->nccl) return fail(h, SVAE_ENCCL, "libnccl not found: " + nccl_load_error());
-  for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);   // captured without the all-reduces
-  h->graphs.clear();
+  drop_graphs(h);   // captured without the all-reduces
   int r = h->nccl->CommInitRank(&h->comm, nranks, id, rank);
   if (r != 0) { h->comm = nullptr; return fail(h, SVAE_ENCCL, std::string("ncclCommInitRank: ") + h->nccl->GetErrorString(r)); }
   h->rank = rank; h->nranks = nranks;
@@ -2225,8 +2451,7 @@ int svae_comm_destroy(svae_handle* h) {
   if (!h) return SVAE_EINVAL;
   if (h->comm && h->nccl) {
     svae_sync(h);
-    for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);   // they contain this communicator's collectives
-    h->graphs.clear();
+    drop_graphs(h);   // they contain this communicator's collectives
     h->nccl->CommDestroy(h->comm);
   }
   h->comm = nullptr; h->nranks = 1; h->rank = 0;
