@@ -212,7 +212,7 @@ int tc_fc(const LaunchCtx& lc, int mode, const float* x, int ldx, const float* w
   P.out = out; P.out_ld = ldo;
   const int ct = (cols + 127) / 128, rt = (rows + 127) / 128;
   const int nchunks = (P.R + FC_RC - 1) / FC_RC;
-  int split = (lc.sm_count + ct * rt - 1) / (ct * rt);     // about one CTA per SM
+  int split = ct * rt <= lc.sm_count ? lc.sm_count / (ct * rt) : 1;     // at most one CTA per SM: a second, nearly empty wave doubles the launch
   if (split > nchunks) split = nchunks;
   if (split < 1) split = 1;
   P.chunks_per_split = (nchunks + split - 1) / split;

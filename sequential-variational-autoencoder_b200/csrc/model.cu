@@ -282,10 +282,13 @@ struct svae_handle {
   // ~1/items of the machine (fewer, longer-lived CTAs per item: resident weights are fetched once per CTA, the weight
   // gradient flushes fewer partial sums) instead of `items` full-machine grids queueing behind each other
   int multi_sm = 148;
-  float multi_sm_factor = 1.f;       // SVAE_MULTI_SM_FACTOR
-  void begin_multi(MultiRec* m, int items) {
+  float multi_sm_factor = 0.5f;      // SVAE_MULTI_SM_FACTOR (measured: 0.5 -> 10.70, 1 -> 10.83, 2 -> 11.03, full grids -> 11.30 ms/step)
+  int wgrad_sm = 0;                  // SVAE_WGRAD_SM: SM budget of the chain's weight-gradient launches (side stream), 0 = all
+  // exposed: nothing runs beside this group (first forward group: the chain waits for it; last backward group: the chain is
+  // done) - its items share the whole machine
+  void begin_multi(MultiRec* m, int items, bool exposed) {
     multi = m;
-    int v = (int)(multi_sm_factor * (float)sm_count / (float)(items > 0 ? items : 1) + 0.999f);
+    int v = (int)((exposed ? 1.f : multi_sm_factor) * (float)sm_count / (float)(items > 0 ? items : 1) + 0.999f);
     multi_sm = v < 8 ? 8 : (v > sm_count ? sm_count : v);
   }
   std::vector<int> rec_fwd_groups;   // chain steps per forward group (SVAE_REC_FWD_GROUPS, default 2,6,6,...)
@@ -1026,6 +1029,7 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     OnStream os(h, wst);
     struct Lane { MultiRec* m; Lane(MultiRec* m_) : m(m_) { if (m) m->lane = 1; } ~Lane() { if (m) m->lane = 0; } } lane(h->multi);
     LaunchCtx lw = h->lc();
+    if (h->wgrad_sm > 0 && h->multi == nullptr && wst != h->stream) lw.sm_count = std::min(lw.sm_count, h->wgrad_sm);
     if (b.g.mode == 0) {
       Geom g = b.g; g.B = B;
       if (tc2w) H_TRY(tc2_wgrad(lw, g, b.in_bf, gs.dy_bf[b.dy_slot], h->pg(b.w)));
@@ -1285,7 +1289,7 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
       if (fork && gi < 3) H_TRY(link(h, h->stream, sd));
       OnStream os(h, sd);
       MultiRec rec;
-      h->begin_multi(&rec, t1 - t0);
+      h->begin_multi(&rec, t1 - t0, t0 == 0);
       int r = 0;
       for (int t = t0; t < t1 && r == 0; ++t) {
         Step& s = h->steps[t];
@@ -1391,6 +1395,7 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
     H_TRY(link(h, st.chain, st.w));
     OnStream os(h, st.w);
     LaunchCtx lw = h->lc();
+    if (h->wgrad_sm > 0 && st.w != h->stream) lw.sm_count = std::min(lw.sm_count, h->wgrad_sm);
     Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
     if (s.outb.tc2_wgrad && gs.du_out_bf.p) H_TRY(tc2_wgrad(lw, gw, gs.du_out_bf, s.outb.in_bf, h->pg(s.w_out)));
     else if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
@@ -1599,7 +1604,7 @@ int backward_impl(svae_handle* h) {
         H_TRY(link(h, st.lat, st.rec));   // d_z of every step of the group is final
         OnStream os(h, st.rec);
         MultiRec rec;
-        h->begin_multi(&rec, (int)pending.size());
+        h->begin_multi(&rec, (int)pending.size(), t == 0);
         int r = 0;
         for (size_t i = 0; i < pending.size() && r == 0; ++i) {
           Step& ps = h->steps[pending[i]];
@@ -2008,6 +2013,8 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     };
     parse(getenv("SVAE_REC_FWD_GROUPS"), "1,1,6", h->rec_fwd_groups);
     parse(getenv("SVAE_REC_BWD_GROUPS"), "5,2,1", h->rec_bwd_groups);
+    const char* e14 = getenv("SVAE_WGRAD_SM");
+    if (e14) h->wgrad_sm = atoi(e14);
     const char* e13 = getenv("SVAE_MULTI_SM_FACTOR");
     if (e13 && atof(e13) > 0) h->multi_sm_factor = (float)atof(e13);
     const char* e10 = getenv("SVAE_MULTI");

@@ -120,22 +120,37 @@ def replay(model, hp, P, operand, steps=None):
                     note("bn_act_out", _rel(out_gpu, out_ref.detach()), where)
                     # ---- batch-norm backward on the device's own da
                     da = tens(t, net, idx, "da").reshape(out_ref.shape)
-                    # The activation branch is taken from the DEVICE's own output: a pre-activation within fp32 rounding of
-                    # zero may legitimately land on the other side (one such element moves dy by ~1/sqrt(numel), more than
-                    # the bound), so the branches must agree except where the oracle's pre-activation is ~0, and the
-                    # derivative is then evaluated on the device's branch - everything else (statistics, both sums, the
-                    # scaling, the shortcut) is compared at the fixed bound.
+                    # Activation branch of BORDERLINE elements.  The device evaluates the pre-activation in fp32, once in the
+                    # forward kernel and once more in the backward kernel; an element within fp32 rounding of zero may land on
+                    # either side in either of them (and in the oracle).  One such element moves dy and dbeta by ~1/sqrt(numel)
+                    # - more than the bounds below - without any kernel being wrong.  So: elements with |pre| below a few fp32
+                    # ulps of the terms that form it are borderline; for each of them the branch the device took is read off
+                    # its own dy (a flipped branch shows up as a spike of rstd * da * (1 - slope) at exactly that element);
+                    # every other element, the statistics, both sums, the scaling and the shortcut are compared at the bound.
                     if act is None:
                         g_pre = da
                     else:
-                        pos_gpu, pos_ref = out_gpu > 0, pre.detach() > 0
-                        differ = pos_gpu != pos_ref
-                        if bool(differ.any()):
-                            lim = 1e-5 * (1.0 + float(pre.detach().abs().max()))
-                            assert float(pre.detach()[differ].abs().max()) < lim, ("activation branch", where)
-                            assert int(differ.sum()) <= 4 + differ.numel() // 100000, ("activation branch count", where)
                         slope = 0.1 if act == "lrelu" else 0.0
-                        g_pre = da * torch.where(pos_gpu, torch.ones_like(da), torch.full_like(da, slope))
+                        pre_d = pre.detach()
+                        pos = pre_d > 0
+
+                        def g_of(mask):
+                            return da * torch.where(mask, torch.ones_like(da), torch.full_like(da, slope))
+
+                        g_pre = g_of(pos)
+                        border = pre_d.abs() < 4e-6 * (1.0 + float(pre_d.abs().mean()))
+                        nb = int(border.sum())
+                        if nb:
+                            assert nb <= 64 + border.numel() // 20000, ("borderline pre-activations", where, nb)
+                            dy0, = torch.autograd.grad(pre, yv, g_pre, retain_graph=True)
+                            y2 = yv.detach().reshape(-1, yv.shape[-1])
+                            rstd = (1.0 / torch.sqrt(y2.var(0, unbiased=False) + 1e-3)).expand_as(pre_d)
+                            resp = ((g_of(~pos) - g_pre) * rstd)[border]
+                            resid = (dy_gpu.reshape(dy0.shape) - dy0)[border]
+                            flip = (resid - resp).abs() < resid.abs()
+                            pos = pos.clone()
+                            pos[border] = pos[border] ^ flip
+                            g_pre = g_of(pos)
                     dy_ref, = torch.autograd.grad(pre, yv, g_pre)
                     note("bn_bwd_dy", _rel(dy_gpu.reshape(dy_ref.shape), dy_ref), where)
                     dbeta_ref = g_pre.reshape(-1, g_pre.shape[-1]).sum(0) if not flat else g_pre.sum(0)
