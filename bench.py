@@ -351,6 +351,11 @@ def main():
                 roof["traffic_source"] = ent.get("source")
         except (OSError, ValueError):
             pass
+    step_traffic = None
+    try:      # whole-step DRAM bytes from the committed ncu launch list of the same command (profiles/rN_launches.md)
+        step_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("step")
+    except (OSError, ValueError):
+        pass
     parity = None
     try:      # measured by tests/test_gpu_fullsize.py::test_full_size_oracle_parity on a B200 (committed copy under profiles/)
         parity = json.load(open(os.path.join(ROOT, "profiles", "parity_fullsize.json")))
@@ -419,12 +424,14 @@ def main():
                        "operands": "bf16 tcgen05 + fp32 accumulate" if operand_used == "bf16" else "fp32 SIMT",
                        "l2": "per-step working set (activations+weights+Adam state, >3 GB) exceeds the 126 MB L2",
                        "eps": "in-kernel Philox",
-                       "execution": "CUDA graph of the whole step (5 streams: chain with programmatic dependent launch, its "
-                                    "weight gradients, recognition nets, their weight gradients, per-chain-step Adam + "
-                                    "repack); `kernels`/`roofline` come from %d extra serialised, event-bracketed steps "
-                                    "right after the timed region" % prof_steps},
+                       "execution": "CUDA graph of the whole step (chain stream with programmatic dependent launch; side "
+                                    "streams: the chain's weight gradients, the latent projections, the recognition nets of "
+                                    "all chain steps as batched launches (blockIdx.z = chain step) in groups, their weight "
+                                    "gradients, per-chain-step Adam + operand repack); `kernels`/`roofline` come from %d "
+                                    "extra serialised, event-bracketed steps right after the timed region" % prof_steps},
             "roofline": roof, "path_roofline": path_roof, "kernels": table, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "generation": generation,
+            "step_traffic": step_traffic if args.workload == "celeba64_b100" else None,
             "parity": parity if args.workload == "celeba64_b100" else None, "dp_consistency": dp_check,
         }
         print(json.dumps(line), flush=True)

@@ -26,6 +26,11 @@ from seqvae_b200.dist import attach_communicator, shard_batch  # noqa: E402
 
 OVER = dict(filter_sizes=[3, 8, 16, 16, 24, 24], vlae_latent_dims=[2, 3, 2, 2], mc_steps=2)
 DIMS, RNG, GB = [16, 16, 3], (-1.0, 1.0), 12
+OPERAND = sys.argv[4] if len(sys.argv) > 4 else "fp32"
+if OPERAND == "bf16":   # every conv on the TMA-fed tcgen05 kernels: the recognition nets run as batched launches and the
+    # gradient slice of a chain step is all-reduced in two halves (chain encoder + decoder, recognition net)
+    OVER = dict(filter_sizes=[3, 32, 32, 64, 64, 64], vlae_latent_dims=[2, 3, 2, 2], mc_steps=3)
+    DIMS = [32, 32, 3]
 
 
 def inputs(hp):
@@ -94,7 +99,7 @@ def main():
     else:
         dev = int(os.environ["LOCAL_RANK"])
         ds = S.SyntheticDataset("x", hi - lo, data_dims=DIMS, data_range=list(RNG))
-        model = S.SequentialVAE(ds, hi - lo, net, device=dev, operand_dtype="fp32", restore=False, **OVER)
+        model = S.SequentialVAE(ds, hi - lo, net, device=dev, operand_dtype=OPERAND, restore=False, **OVER)
         model.set_params({k: v.numpy() for k, v in P.items()})
         attach_communicator(model, dist, rank, world)
         model.iteration = 4999          # reg_coeff = 1 - exp(-1) on the step below
@@ -112,7 +117,7 @@ def main():
             for r in range(world):
                 a, b = shard_batch(GB, r, world)
                 dsr = S.SyntheticDataset("x", b - a, data_dims=DIMS, data_range=list(RNG))
-                m2 = S.SequentialVAE(dsr, b - a, net, device=dev, operand_dtype="fp32", restore=False, **OVER)
+                m2 = S.SequentialVAE(dsr, b - a, net, device=dev, operand_dtype=OPERAND, restore=False, **OVER)
                 m2.set_params({k: v.numpy() for k, v in P.items()})
                 m2.forward(x[a:b].numpy(), None, eps[:, a:b].numpy(), reg)
                 m2.backward()
