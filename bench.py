@@ -30,6 +30,7 @@ WORKLOADS = {
     "mnist32_b100": ("m_inhomog", "mnist", 100, {}),
     "cifar32_b100": ("c_inhomog", "cifar", 100, {}),
     "lsun64_b256_t16": ("sequential_vae_lsun", "lsun", 256, {"mc_steps": 16}),
+    "lsun64_b256_t25": ("sequential_vae_lsun", "lsun", 256, {"mc_steps": 25}),      # BASELINE configs[3]: "long chain"
     # homogeneous (weight-shared) chains, SURVEY 8 f1: the same per-image work as celeba64_b100 at T=8
     "celeba64_b100_homog": ("sequential_vae_celebA_homog", "celebA", 100, {}),
     "celeba64_b100_homog_t25": ("c_homog", "celebA", 100, {}),
@@ -40,6 +41,8 @@ ALGO = {
     "mnist32_b100": dict(train_flops=4.9002e9, train_bytes=16.46e6),
     "cifar32_b100": dict(train_flops=3.2517e9, train_bytes=22.56e6),
     "lsun64_b256_t16": dict(train_flops=26.8676e9, train_bytes=101.42e6),
+    # the T = 16 figures scaled by 25/16 (step 0 has no chain encoder: overestimates the work by < 0.5 %)
+    "lsun64_b256_t25": dict(train_flops=26.8676e9 * 25 / 16, train_bytes=101.42e6 * 25 / 16),
     # 5 x 3.294 M activation elements x 2 B + 40 B x 14.87 M live (shared) parameters / 100
     "celeba64_b100_homog": dict(train_flops=13.0065e9, train_bytes=38.89e6),
 }

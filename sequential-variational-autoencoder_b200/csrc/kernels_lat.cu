@@ -9,6 +9,7 @@
 //   backward: g = da*lrelu', S1 = sum g, S2 = sum g*xhat, dy = rstd*(g - S1/B - xhat*S2/B),
 //             dW[:,f] = z^T dy, dbeta[f] = S1, dz[b,:] += dy[b,f] W[:,f] (warp transpose-reduction -> shared -> global)
 // HBM-bound: forward writes 4+4+2 bytes per element, backward reads 8.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -513,7 +514,8 @@ int lat_bwd_fused(const LaunchCtx& lc, FeatView da, const float* y, const double
   Geom tg{}; tg.B = B; tg.Cin = KZ; tg.Cout = N;
   ProfScope ps(lc, KC_SKINNY, 8.0 * B * KZ * (double)N, 8.0 * B * (double)N, &tg);
   unsigned blocks = (unsigned)((N + 31) / 32);
-  if (blocks > 4u * (unsigned)lc.sm_count) blocks = 4u * (unsigned)lc.sm_count;
+  static const unsigned per_sm = getenv("SVAE_LAT_BLOCKS_PER_SM") ? (unsigned)atoi(getenv("SVAE_LAT_BLOCKS_PER_SM")) : 4u;
+  if (blocks > per_sm * (unsigned)lc.sm_count) blocks = per_sm * (unsigned)lc.sm_count;
   LAT_DISPATCH(KZ, {
     const size_t smem = 2 * (size_t)B * NM * sizeof(float);
     if (lc.multi != nullptr) {
