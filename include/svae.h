@@ -66,7 +66,10 @@ typedef struct svae_config {
   int32_t share_theta_weights;              /* :213  homogeneous chain: one chain encoder and one decoder for all
                                                steps t >= 1 (step 0 keeps its own decoder, :1683-1687,1757-1761)  */
   int32_t share_phi_weights;                /* :214  one recognition net for all steps (:1573-1577)              */
-  int32_t reserved[6];
+  int32_t add_noise_to_chain;               /* :233  x_t fed to step t+1 = mle_t + reg_coeff * noise_stddevs[t] * N(0,I)
+                                               (:1088-1091; netnames c_sample_images, c_homog_sample_images :761-767)  */
+  int32_t reserved[5];
+  float noise_stddevs[SVAE_MAX_STEPS];      /* :239  fixed per-step stddev of the chain noise (mc_steps entries used)   */
 } svae_config;
 
 /* Per-step ELBO terms of the last forward.  Replaces the scalars TF lets callers fetch: self.loss, self.final_loss
@@ -199,6 +202,16 @@ int svae_read_losses(svae_handle* h, svae_losses* out);
  *   out_dev : [T,B,H,W,C]  (x_1..x_T; the reference's leading uniform-noise x_0 is produced by the Python wrapper) */
 int svae_generate(svae_handle* h, int batch, const float* z_dev, uint64_t seed, float* out_dev);
 int svae_generate_host(svae_handle* h, int batch, const float* z_host, uint64_t seed, float* out_host);
+
+/* ---- chain noise (svae_config.add_noise_to_chain) ------------------------------------------------------------------
+ * Replaces the tf.random_normal(image_batch_shape) of create_generator_network (sequential_vae.py:1088-1091).  By default the
+ * draws are counter-based Philox inside the kernel (keyed by the step's seed; a different stream than the latent eps).
+ * svae_set_chain_noise_host injects them instead - [T,B,H,W,C] standard-normal values used by every following forward /
+ * train step / generation with that batch size - so that a parity test can feed the oracle the same draws; NULL restores
+ * Philox.  svae_read_chain_samples_host returns the samples x_t + noise of the last forward or generation, [T,B,H,W,C]
+ * (training_samples / generative_samples; the mles are what svae_forward / svae_generate return). */
+int svae_set_chain_noise_host(svae_handle* h, const float* noise_host_or_null, int batch);
+int svae_read_chain_samples_host(svae_handle* h, float* out_host, int batch);
 
 /* ---- data parallel ----------------------------------------------------------------------------------------------
  * The reference has no multi-device path for this model.  Batch-sharded DP: per-replica BN, gradients

@@ -51,6 +51,9 @@ _NETNAMES = {
                          "share_phi_weights": True, "mc_steps": 1},
     "vlae_celebA": {"mc_steps": 1, "vlae_latent_dims": [16, 16, 16, 16]},                             # :704-707
     "sequential_vae_lsun_final": {"vlae_latent_dims": [20, 30, 30, 30], "intermediate_reconstruction": False},  # :721-725
+    # chain noise with fixed per-step stddevs (first slice)
+    "c_sample_images": {"add_noise_to_chain": True},                                                  # :761-762
+    "c_homog_sample_images": {"share_theta_weights": True, "share_phi_weights": True, "add_noise_to_chain": True},  # :764-767
 }
 
 
@@ -70,6 +73,8 @@ def hyperparams(netname: str, data_dims: Sequence[int], data_range=(0.0, 1.0), *
         learning_rate=0.0002, learning_rate_decay=1.0, reg_coeff_rate=5000.0,          # :250-252
         clip_grads=True, clip_grad_value=10.0,                                         # :257-258
         share_theta_weights=False, share_phi_weights=False,                            # :213-214
+        add_noise_to_chain=False,                                                      # :233
+        noise_stddevs=[0.5 ** 1, 0.5 ** 2, 0.5 ** 3, 0.5 ** 4, 0.5 ** 5, 0.5 ** 6, 0.5 ** 7, 0],   # :239
     )
     hp["regularized_steps"] = list(range(hp["mc_steps"]))     # :224 - runs BEFORE the netname rows, i.e. with mc_steps == 8:
     row = dict(_NETNAMES[netname])                             # a row that lengthens the chain (c_homog, :733) keeps KL on steps 0..7
@@ -81,6 +86,7 @@ def hyperparams(netname: str, data_dims: Sequence[int], data_range=(0.0, 1.0), *
     hp["regularized_steps"] = [int(t) for t in hp["regularized_steps"] if 0 <= int(t) < hp["mc_steps"]]   # `step in ...`, :1154
     L = hp["vlae_levels"]
     assert len(hp["image_sizes"]) == L + 1 and len(hp["filter_sizes"]) == L + 2 and len(hp["vlae_latent_dims"]) == L
+    assert not hp["add_noise_to_chain"] or len(hp["noise_stddevs"]) == hp["mc_steps"]   # :151, indexed per step at :1736
     return hp
 
 
@@ -453,14 +459,17 @@ def init_params(hp, seed=0, dtype=torch.float64) -> "OrderedDict[str, torch.Tens
 # Chain, loss, optimiser (sequential_vae.py:877-1093, 1101-1212, 1246-1320)
 # --------------------------------------------------------------------------------------------------------------
 
-def forward_chain(hp, P, x_in, x_target, eps, reg_coeff=1.0):
+def forward_chain(hp, P, x_in, x_target, eps, reg_coeff=1.0, chain_eps=None):
     """Training-mode chain (construct_network, sequential_vae.py:934-975): for every step a recognition net on x_in
     (:1022), z = mu + sigma*eps (:1023, eps injected), the generator on (x_{t-1}, z) with gradient flowing through
     x_{t-1} (Q4: the stop_gradient at :1211-1212 is a no-op), and the per-step ELBO terms (:1146-1176).
-    eps: [T,B,Z].  Returns a dict of per-step tensors and the total loss."""
+    eps: [T,B,Z].  add_noise_to_chain (:1088-1091): the SAMPLE x_t + reg_coeff * noise_stddevs[t] * chain_eps[t]
+    (chain_eps: [T,B,H,W,C], the injected tf.random_normal) is what step t+1 reads (:936,958); the losses stay on the mle.
+    Returns a dict of per-step tensors and the total loss."""
     T = hp["mc_steps"]
     prior = hp["latent_prior_stddev"]
-    out = dict(mu=[], sigma=[], z=[], x=[], ratio=[], recon=[], kl=[])
+    noisy = bool(hp.get("add_noise_to_chain", False))
+    out = dict(mu=[], sigma=[], z=[], x=[], ratio=[], recon=[], kl=[], sample=[])
     loss = 0.0
     prev = None
     for t in range(T):
@@ -476,32 +485,41 @@ def forward_chain(hp, P, x_in, x_target, eps, reg_coeff=1.0):
             loss = loss + reg_coeff * kl                                             # :1171-1172
         if t == 0:
             loss = loss * hp["first_step_loss_coeff"]                                # :1175-1176
-        for k, v in (("mu", mu), ("sigma", sd), ("z", z), ("x", xt), ("ratio", ratio), ("recon", recon), ("kl", kl)):
+        sample = xt                                                                  # training_sample == mle (:1090, stddev 0)
+        if noisy:
+            sample = xt + reg_coeff * hp["noise_stddevs"][t] * chain_eps[t]          # :1090 (stddevs = noise_stddevs[step], :1736)
+        for k, v in (("mu", mu), ("sigma", sd), ("z", z), ("x", xt), ("ratio", ratio), ("recon", recon), ("kl", kl),
+                     ("sample", sample)):
             out[k].append(v)
-        prev = xt                                                                    # training_sample == mle (:1090, stddev 0)
+        prev = sample                                                                # prev_training_sample (:936)
     out["loss"] = loss
     out["final_loss"] = out["recon"][-1]                                             # :1204
     return out
 
 
-def generate_chain(hp, P, z, batch_size):
+def generate_chain(hp, P, z, batch_size, chain_eps=None, samples_out=None):
     """Generation-mode chain (generative twins, sequential_vae.py:1068-1073,1397-1428): z[t] fed from the host;
-    recognition nets not evaluated; BN uses the generated batch's statistics (Q1).  Returns [x_1..x_T] (the
-    reference additionally prepends a uniform-noise x_0 that nothing depends on, :947-952)."""
+    recognition nets not evaluated; BN uses the generated batch's statistics (Q1).  Returns the mles [x_1..x_T] (the
+    reference additionally prepends a uniform-noise x_0 that nothing depends on, :947-952).  add_noise_to_chain: step t+1 reads
+    generative_sample = mle + reg_coeff * noise_stddevs[t] * chain_eps[t] with the placeholder's default reg_coeff = 1 (:917,1091);
+    the samples are appended to `samples_out`."""
     xs, prev = [], None
+    noisy = bool(hp.get("add_noise_to_chain", False))
     for t in range(hp["mc_steps"]):
         enc = compute_encodings(hp, Scope(encoder_scope(hp, t), P, None), prev) if t > 0 else None
         xt, _ = generator_ladder(hp, Scope(generator_scope(hp, t), P, None), enc, z[t], t == 0)
         xs.append(xt)
-        prev = xt
+        prev = xt + hp["noise_stddevs"][t] * chain_eps[t] if noisy else xt
+        if samples_out is not None:
+            samples_out.append(prev)
     return xs
 
 
-def loss_and_grads(hp, P, x_in, x_target, eps, reg_coeff=1.0):
+def loss_and_grads(hp, P, x_in, x_target, eps, reg_coeff=1.0, chain_eps=None):
     """Forward + reverse-mode through the whole chain (optimizer.compute_gradients, sequential_vae.py:1273).
     Returns (forward dict, {name: grad or None}); dead-branch variables get None like in TF."""
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in P.items())
-    fw = forward_chain(hp, leaves, x_in, x_target, eps, reg_coeff)
+    fw = forward_chain(hp, leaves, x_in, x_target, eps, reg_coeff, chain_eps)
     names = list(leaves.keys())
     gs = torch.autograd.grad(fw["loss"], [leaves[n] for n in names], allow_unused=True)
     grads = OrderedDict(zip(names, gs))

@@ -28,7 +28,8 @@ class Config(C.Structure):
         ("min_highway", C.c_float), ("max_highway", C.c_float), ("range_lo", C.c_float), ("range_hi", C.c_float),
         ("clip_value", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
         ("max_batch", C.c_int32), ("train_capacity", C.c_int32), ("operand_dtype", C.c_int32),
-        ("share_theta_weights", C.c_int32), ("share_phi_weights", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("share_theta_weights", C.c_int32), ("share_phi_weights", C.c_int32), ("add_noise_to_chain", C.c_int32),
+        ("reserved", C.c_int32 * 5), ("noise_stddevs", C.c_float * MAX_STEPS),
     ]
 
 
@@ -88,6 +89,8 @@ PROTOTYPES = {
     "svae_read_losses": (C.c_int, [_P, C.POINTER(Losses)]),
     "svae_generate": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),
     "svae_generate_host": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),
+    "svae_set_chain_noise_host": (C.c_int, [_P, _P, C.c_int]),
+    "svae_read_chain_samples_host": (C.c_int, [_P, _P, C.c_int]),
     "svae_nccl_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "svae_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "svae_comm_destroy": (C.c_int, [_P]),

@@ -24,6 +24,9 @@ NETNAMES = {
     "s_homog_one_step": {"vlae_latent_dims": [12, 12, 12, 12], "share_theta_weights": True,                # :301
                          "share_phi_weights": True, "mc_steps": 1},
     "vlae_celebA": {"mc_steps": 1, "vlae_latent_dims": [16, 16, 16, 16]},                                  # :704
+    # chain noise with the fixed per-step stddevs of :239 (first slice): x_t + reg * stddev_t * N(0,I) feeds step t+1
+    "c_sample_images": {"add_noise_to_chain": True},                                                        # :761
+    "c_homog_sample_images": {"share_theta_weights": True, "share_phi_weights": True, "add_noise_to_chain": True},   # :764
     "sequential_vae_lsun_final": {"vlae_latent_dims": [20, 30, 30, 30], "intermediate_reconstruction": False},   # :721
 }
 
@@ -44,6 +47,7 @@ def hyperparams(name, data_dims, data_range, **overrides):
         learning_rate=0.0002, learning_rate_decay=1.0, reg_coeff_rate=5000.0, save_freq=2000,
         clip_grads=True, clip_grad_value=10.0,
         share_theta_weights=False, share_phi_weights=False,
+        add_noise_to_chain=False, noise_stddevs=[0.5 ** 1, 0.5 ** 2, 0.5 ** 3, 0.5 ** 4, 0.5 ** 5, 0.5 ** 6, 0.5 ** 7, 0],   # :233,239
     )
     # sequential_vae.py:224 evaluates range(self.mc_steps) while mc_steps still holds its default 8, BEFORE the netname rows
     # run: a row that lengthens the chain (c_homog: 25 steps, :733) keeps the KL term on steps 0..7 only
@@ -63,6 +67,9 @@ def hyperparams(name, data_dims, data_range, **overrides):
         raise ValueError("self.image_sizes and image_sizes in inference/generative networks don't match")
     if len(hp["filter_sizes"]) != L + 2 or len(hp["vlae_latent_dims"]) != L:
         raise ValueError("filter_sizes needs vlae_levels+2 entries and vlae_latent_dims vlae_levels entries")
+    if hp["add_noise_to_chain"] and len(hp["noise_stddevs"]) != hp["mc_steps"]:
+        # "an array which must be exactly of length self.mc_steps" (sequential_vae.py:151): the graph indexes it per step (:1736)
+        raise ValueError("noise_stddevs needs exactly mc_steps entries")
     return hp
 
 
@@ -92,4 +99,8 @@ def to_cabi_config(hp, max_batch, train=True, operand_dtype="fp32"):
     cfg.operand_dtype = {"fp32": _cabi.OPERAND_FP32, "bf16": _cabi.OPERAND_BF16}[operand_dtype]
     cfg.share_theta_weights = int(bool(hp.get("share_theta_weights", False)))
     cfg.share_phi_weights = int(bool(hp.get("share_phi_weights", False)))
+    cfg.add_noise_to_chain = int(bool(hp.get("add_noise_to_chain", False)))
+    if cfg.add_noise_to_chain:
+        for t, v in enumerate(hp["noise_stddevs"]):
+            cfg.noise_stddevs[t] = float(v)
     return cfg

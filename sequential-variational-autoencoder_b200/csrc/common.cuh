@@ -455,6 +455,10 @@ int tie_reduce(const LaunchCtx& lc, float* grad_arena, const TieRun& run);
 int apply_noise(const LaunchCtx& lc, const float* x, float* out, int64_t n, float pepper_prob, float salt_prob, float scale,
                 float lo, float hi, uint64_t seed, float* draws /* [3,n] keep, salt, gaussian; may be nullptr */);
 int fill_normal(const LaunchCtx& lc, float* dst, int64_t n, uint64_t seed, uint64_t counter_base);
+// xs = xt + (dyn ? dyn->reg : reg_fixed) * sigma * noise  (+ bf16 planar copy); noise == NULL: Philox keyed (dyn->seed ^ key_xor)
+// at counter (dyn ? dyn->iteration * t_stride : 0) + base_fixed + element
+int chain_noise(const LaunchCtx& lc, const float* xt, const float* noise, const SvaeDyn* dyn, float reg_fixed, float sigma,
+                uint64_t key_xor, uint64_t base_fixed, uint64_t t_stride, float* xs, int64_t pixels, int C, BfDst xt_bf);
 int axpy_inplace(const LaunchCtx& lc, float* dst, const float* src, int64_t n);  // dst += src
 // debug probes (parity tests only): dense fp32 copies of a bf16 planar copy / of a feature view
 int probe_bf_unpack(const LaunchCtx& lc, const BfAct& a, int coff, int C, int B, float* dst);   // -> [B,H,W,C]

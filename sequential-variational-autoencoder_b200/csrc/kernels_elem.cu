@@ -762,6 +762,35 @@ __global__ void reparam_bwd_kernel(ReparamParams p, const float* __restrict__ dz
                                    const float* __restrict__ eps, const SvaeDyn* __restrict__ dyn, float kl_scale,
                                    float* __restrict__ dmu_pre, float* __restrict__ dsd_pre) { reparam_bwd_kernel_body(p, dz, mu_pre, mu, sd, eps, dyn, kl_scale, dmu_pre, dsd_pre); }
 
+// Chain noise (add_noise_to_chain, sequential_vae.py:1088-1091): training_sample = training_mle + reg_coeff * stddev_t * N(0, I).
+// The sample - not the mle - is what the next chain step reads (:936,958), so the kernel also writes the bf16 copy of the next
+// step's chain encoder.  noise == nullptr: counter-based Philox draws keyed by `key` at counter base + element index.
+__global__ void __launch_bounds__(256)
+chain_noise_kernel(const float* __restrict__ xt, const float* __restrict__ noise, const SvaeDyn* __restrict__ dyn, float reg_fixed,
+                   float sigma, uint64_t key_xor, uint64_t base_fixed, uint64_t t_stride, float* __restrict__ xs, int64_t pixels, int C,
+                   BfDst xbf) {
+  pdl_wait();
+  pdl_trigger();
+  const float scale = (dyn != nullptr ? dyn->reg : reg_fixed) * sigma;
+  const uint64_t key = (dyn != nullptr ? dyn->seed : 0ull) ^ key_xor;
+  const uint64_t base = dyn != nullptr ? dyn->iteration * t_stride + base_fixed : base_fixed;
+  const int HWb = xbf.a.p != nullptr ? xbf.a.H * xbf.a.W : 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int c = 0; c < C; ++c) {
+      const int64_t e = i * C + c;
+      const float n = noise != nullptr ? noise[e] : (scale != 0.f ? philox_normal(key, base + (uint64_t)e) : 0.f);
+      const float v = xt[e] + scale * n;
+      xs[e] = v;
+      if (xbf.a.p != nullptr) {
+        const int im = (int)(i / HWb);
+        const int hw = (int)(i - (int64_t)im * HWb);
+        const int hh = hw / xbf.a.W;
+        xbf.a.p[bf_index(xbf.a, im, hh, hw - hh * xbf.a.W, c)] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
             int64_t n, const SvaeDyn* __restrict__ dyn, float lr_t, float b1, float b2, float eps, float clip, float gscale) {
@@ -968,6 +997,14 @@ int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
   CUDA_TRY(launch_k(lc, out_mix_fwd_kernel, dim3(flat_blocks(p.pixels, lc.sm_count)), dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt,
                     recon_sum, xt_bf));
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int chain_noise(const LaunchCtx& lc, const float* xt, const float* noise, const SvaeDyn* dyn, float reg_fixed, float sigma,
+                uint64_t key_xor, uint64_t base_fixed, uint64_t t_stride, float* xs, int64_t pixels, int C, BfDst xt_bf) {
+  ProfScope ps(lc, KC_OUT_MIX, 2.0 * pixels * C, 4.0 * pixels * C * (noise ? 3 : 2) + (xt_bf.a.p ? 2.0 * pixels * C : 0.0));
+  CUDA_TRY(launch_k(lc, chain_noise_kernel, dim3(flat_blocks(pixels, lc.sm_count)), dim3(256), 0, xt, noise, dyn, reg_fixed, sigma, key_xor,
+                    base_fixed, t_stride, xs, pixels, C, xt_bf));
   return 0;
 }
 

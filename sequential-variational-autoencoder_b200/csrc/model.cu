@@ -125,6 +125,7 @@ struct Step {
   Geom g_out, g_gate;
   Block outb, gateb;                      // the same two deconvs as contraction blocks (no batch-norm) for TC routing
   float *u, *xt;
+  float* xs = nullptr;                    // add_noise_to_chain: the sample x_t + noise that the next step reads (own buffer per step)
   double* lat_mom = nullptr;              // [L][64] scratch: second moments of z_t per latent group (lat_fwd_fused)
   BfAct xt_bf{};                          // bf16 copy of x_t for the next step's chain encoder
   int64_t p_begin, p_end;                 // parameter range (all-reduce bucket)
@@ -293,6 +294,11 @@ struct svae_handle {
   }
   std::vector<int> rec_fwd_groups;   // chain steps per forward group (SVAE_REC_FWD_GROUPS, default 2,6,6,...)
   std::vector<int> rec_bwd_groups;   // chain steps per backward group, in backward order (SVAE_REC_BWD_GROUPS, default 5,2,1)
+
+  // chain noise (cfg.add_noise_to_chain): injected draws [T, chain_noise_B, H, W, C] or Philox
+  float* chain_noise_dev = nullptr; int chain_noise_B = 0;
+  bool noisy() const { return cfg.add_noise_to_chain != 0; }
+  const float* chain_in(int t) const { return noisy() ? steps[t].xs : steps[t].xt; }   // what chain step t + 1 reads
 
   Profiler prof;
   LaunchCtx lc() {
@@ -850,6 +856,8 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
   h->in_tgt = act.get<float>((size_t)B * h->D * h->D * C);
   h->in_eps = act.get<float>((size_t)T * B * Z);
   h->gen_prev = act.get<float>((size_t)B * h->D * h->D * C);
+  if (c.add_noise_to_chain)   // one sample buffer per chain step, also on forward-only handles (svae_read_chain_samples_host)
+    for (int t = 0; t < T; ++t) h->steps[t].xs = act.get<float>((size_t)B * h->D * h->D * C);
 }
 
 // ---- contraction dispatch ------------------------------------------------------------------------------------------
@@ -1178,8 +1186,24 @@ int decoder_fwd(svae_handle* h, Step& s, int B, const float* xprev, const float*
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
   H_TRY(out_mix_fwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, tgt, xt_out, recon_sum,
-                    s.xt_bf.p ? BfDst{s.xt_bf, 0, 0, 0} : BfDst{}));
+                    (s.xt_bf.p && !h->noisy()) ? BfDst{s.xt_bf, 0, 0, 0} : BfDst{}));
   return 0;
+}
+
+// add_noise_to_chain (sequential_vae.py:1088-1091): s.xs = xt + reg * noise_stddevs[t] * N(0, I), and the bf16 copy the next
+// step's chain encoder reads.  dyn != nullptr: reg and the Philox key / counter base come from the per-iteration scalars (training
+// forward); else reg_fixed (generation: the placeholder's default 1.0) and `seed`.
+int chain_noise_step(svae_handle* h, Step& s, int B, const float* xt, const SvaeDyn* dyn, float reg_fixed, uint64_t seed) {
+  const int64_t pixels = (int64_t)B * h->D * h->D;
+  const uint64_t img = (uint64_t)h->cfg.max_batch * h->D * h->D * h->C;
+  const float* inj = nullptr;
+  if (h->chain_noise_dev != nullptr) {
+    if (h->chain_noise_B != B) return fail(h, SVAE_EINVAL, "injected chain noise was set for a different batch size");
+    inj = h->chain_noise_dev + (size_t)s.t * B * h->D * h->D * h->C;
+  }
+  LaunchCtx lc = h->lc();
+  return chain_noise(lc, xt, inj, dyn, reg_fixed, h->cfg.noise_stddevs[s.t], 0xC4A17015E5EEDull ^ seed, (uint64_t)s.t * img, (uint64_t)h->T * img,
+                     s.xs, pixels, h->C, s.xt_bf.p ? BfDst{s.xt_bf, 0, 0, 0} : BfDst{});
 }
 
 HeadSet make_headset(svae_handle* h, Step& s, int l) {
@@ -1337,9 +1361,10 @@ int forward_impl(svae_handle* h, const float* x, const float* tgt, int B, const 
     if (xs_out) H_CUDA(cudaMemcpyAsync(xs_out + t * img, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (mu_out) H_CUDA(cudaMemcpyAsync(mu_out + t * bz, s.mu, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
     if (sd_out) H_CUDA(cudaMemcpyAsync(sd_out + t * bz, s.sd, bz * 4, cudaMemcpyDeviceToDevice, h->stream));
-    prev = s.xt;
-    if (h->act_sets < h->T && t >= 1 && t + 1 < h->T) {
-      // the next step overwrites s.xt (aliased): keep x_t in the staging target buffer
+    if (h->noisy()) H_TRY(chain_noise_step(h, s, B, s.xt, h->dyn_dev, 0.f, 0));
+    prev = h->chain_in(t);
+    if (!h->noisy() && h->act_sets < h->T && t >= 1 && t + 1 < h->T) {
+      // the next step overwrites s.xt (aliased): keep x_t in the staging target buffer (samples have one buffer per step)
       H_CUDA(cudaMemcpyAsync(h->gen_prev, s.xt, img * 4, cudaMemcpyDeviceToDevice, h->stream));
       prev = h->gen_prev;
     }
@@ -1591,7 +1616,7 @@ int backward_impl(svae_handle* h) {
     if ((fork || multi) && t + NS < T)
       for (int i = 0; i < 3; ++i)
         if (side_done[(size_t)(t + NS) * 3 + i] != nullptr) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + NS) * 3 + i], 0));
-    const float* xprev = t > 0 ? h->steps[t - 1].xt : nullptr;
+    const float* xprev = t > 0 ? h->chain_in(t - 1) : nullptr;   // d sample / d mle = 1: the chain gradient is unchanged
     float* gx_prev = h->gx[cur ^ 1];
     H_TRY(decoder_bwd(h, gs, st, s, B, gx_in, gx_prev, xprev));
     if (!multi) {
@@ -1842,6 +1867,7 @@ void destroy_impl(svae_handle* h) {
   // captured graphs hold the communicator's collectives: they must go before the communicator does
   drop_graphs(h);
   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
+  if (h->chain_noise_dev) cudaFree(h->chain_noise_dev);
   for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->dyn_ev) if (e) cudaEventDestroy(e);
@@ -1907,6 +1933,9 @@ static int validate_cfg(const svae_config* cfg) {
   for (int i = 1; i < L + 2; ++i)
     if (cfg->filter_sizes[i] < 1) return fail(nullptr, SVAE_EINVAL, "filter_sizes entries must be positive");
   if (cfg->filter_sizes[0] != cfg->channels) return fail(nullptr, SVAE_EINVAL, "filter_sizes[0] must equal channels");
+  if (cfg->add_noise_to_chain)
+    for (int t = 0; t < cfg->mc_steps; ++t)
+      if (!(cfg->noise_stddevs[t] >= 0.f)) return fail(nullptr, SVAE_EINVAL, "noise_stddevs entries must be >= 0");
   return 0;
 }
 
@@ -2410,8 +2439,38 @@ int svae_generate(svae_handle* h, int B, const float* z, uint64_t seed, float* o
     H_TRY(latent_fwd(h, s, B, z + t * bz));
     H_TRY(decoder_fwd(h, s, B, prev, nullptr, out + t * img, nullptr));
     prev = out + t * img;
+    if (h->noisy()) {   // generative_sample = generative_mle + reg_coeff (placeholder default 1.0) * stddev * N(0, I), :1090
+      H_TRY(chain_noise_step(h, s, B, out + t * img, nullptr, 1.f, seed));
+      prev = s.xs;
+    }
   }
   h->have_fwd = false;
+  h->last_B = B;
+  return SVAE_OK;
+}
+int svae_set_chain_noise_host(svae_handle* h, const float* noise, int B) {
+  if (!h) return SVAE_EINVAL;
+  if (!h->noisy()) return fail(h, SVAE_ESTATE, "handle created without add_noise_to_chain");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->chain_noise_dev) { cudaFree(h->chain_noise_dev); h->chain_noise_dev = nullptr; h->chain_noise_B = 0; }
+  drop_graphs(h);   // captured steps hold the old pointer (or the Philox branch)
+  if (noise == nullptr) return SVAE_OK;
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  const size_t n = (size_t)h->T * B * h->D * h->D * h->C;
+  H_CUDA(cudaMalloc((void**)&h->chain_noise_dev, n * sizeof(float)));
+  H_CUDA(cudaMemcpy(h->chain_noise_dev, noise, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->chain_noise_B = B;
+  return SVAE_OK;
+}
+int svae_read_chain_samples_host(svae_handle* h, float* out, int B) {
+  if (!h || !out) return fail(h, SVAE_EINVAL, "null argument");
+  if (!h->noisy()) return fail(h, SVAE_ESTATE, "handle created without add_noise_to_chain");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, SVAE_EINVAL, "batch exceeds max_batch");
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t img = (size_t)B * h->D * h->D * h->C;
+  for (int t = 0; t < h->T; ++t) H_CUDA(cudaMemcpyAsync(out + t * img, h->steps[t].xs, img * 4, cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
   return SVAE_OK;
 }
 int svae_generate_host(svae_handle* h, int B, const float* z, uint64_t seed, float* out) {

@@ -62,6 +62,8 @@ class SequentialVAE:
         self.reg_coeff_rate = hp["reg_coeff_rate"]
         self.share_theta_weights = bool(hp["share_theta_weights"])        # sequential_vae.py:213-214
         self.share_phi_weights = bool(hp["share_phi_weights"])
+        self.add_noise_to_chain = bool(hp["add_noise_to_chain"])          # :233
+        self.noise_stddevs = list(hp["noise_stddevs"])                    # :239
         self.save_freq = hp["save_freq"]
         # A main.py-style caller (SequentialVAE(dataset, batch_size=..., name=...)) gets the production kernel family: bf16
         # operands on the tcgen05 tensor cores with fp32 accumulation.  operand_dtype="fp32" (or SVAE_OPERAND=fp32) selects the
@@ -487,9 +489,32 @@ class SequentialVAE:
         return last
 
     def training_mc_samples(self, input_batch, eps=None, seed=0):
-        """sequential_vae.py:1434-1455: list of the T training-mode samples."""
+        """sequential_vae.py:1434-1455: list of the T training-mode samples; with add_noise_to_chain the T mles followed by
+        the T samples (:1450-1451)."""
         out = self.forward(input_batch, None, eps, 1.0, seed)
-        return [out["x"][t] for t in range(self.mc_steps)]
+        mles = [out["x"][t] for t in range(self.mc_steps)]
+        if not self.add_noise_to_chain:
+            return mles
+        smp = self.chain_samples(out["x"].shape[1])
+        return mles + [smp[t] for t in range(self.mc_steps)]
+
+    # ---- chain noise (add_noise_to_chain, sequential_vae.py:1088-1091) ------------------------------------------------
+    def set_chain_noise(self, noise):
+        """Inject the tf.random_normal(image_batch_shape) draws of every chain step ([T,B,H,W,C]) for the following calls with
+        that batch size (parity tests feed the oracle the same values); None: counter-based Philox draws in the kernel."""
+        if noise is None:
+            self._chk(self._L.svae_set_chain_noise_host(self._h, None, 0))
+            return
+        n = _f32(noise)
+        if n.ndim != 5 or list(n.shape[2:]) != list(self.data_dims) or n.shape[0] != self.mc_steps:
+            raise ValueError("chain noise must be [T,B,H,W,C]")
+        self._chk(self._L.svae_set_chain_noise_host(self._h, n.ctypes.data_as(C.c_void_p), int(n.shape[1])))
+
+    def chain_samples(self, batch):
+        """The samples x_t + noise of the last forward / generation, [T,B,H,W,C] (training_samples / generative_samples)."""
+        out = np.empty([self.mc_steps, int(batch)] + self.data_dims, np.float32)
+        self._chk(self._L.svae_read_chain_samples_host(self._h, out.ctypes.data_as(C.c_void_p), int(batch)))
+        return out
 
     def generate_mc_samples(self, input_batch, batch_size=None, z=None, seed=0):
         """sequential_vae.py:1397-1428: generation-mode chain.  Returns T+1 arrays; the first is the uniform-noise x_0
@@ -508,6 +533,9 @@ class SequentialVAE:
         self._chk(self._L.svae_generate_host(self._h, B, zz.ctypes.data_as(C.c_void_p) if zz is not None else None,
                                              int(seed), out.ctypes.data_as(C.c_void_p)))
         x0 = np.random.default_rng(seed).uniform(0.0, 1.0, size=[B] + self.data_dims).astype(np.float32)
+        if self.add_noise_to_chain:      # generative_mles + generative_samples (:1424-1425): T mles, x_0, T samples
+            smp = self.chain_samples(B)
+            return [out[t] for t in range(self.mc_steps)] + [x0] + [smp[t] for t in range(self.mc_steps)]
         return [x0] + [out[t] for t in range(self.mc_steps)]
 
     def generate_async(self, batch, out_dev, z_dev=None, seed=0):

@@ -265,3 +265,45 @@ def test_apply_noise_restatement():
     i = (keep == 0) & (salt == 0)
     np.testing.assert_allclose(out[i], gauss[i])
     assert O.NOISE_DEFAULTS == dict(pepper_prob=0.1, salt_prob=0.1, gaussian_noise_scale=0.1)
+
+
+def test_chain_noise_semantics_and_gradients():
+    """add_noise_to_chain (sequential_vae.py:1088-1091, netname c_sample_images :761): the sample mle_t + reg * stddev_t * eps_t is
+    what step t + 1 reads; the losses stay on the mles; the gradient flows through the additive noise unchanged."""
+    hp, P, x, eps = _tiny()
+    hp = dict(hp, add_noise_to_chain=True, noise_stddevs=[0.5, 0.0])
+    g = torch.Generator().manual_seed(3)
+    ce = torch.randn(2, *x.shape, generator=g, dtype=torch.float64)
+    base = O.forward_chain(dict(hp, add_noise_to_chain=False), P, x, x, eps, 0.7)
+    with torch.no_grad():
+        zero = O.forward_chain(hp, P, x, x, eps, 0.7, torch.zeros_like(ce))
+        fw = O.forward_chain(hp, P, x, x, eps, 0.7, ce)
+    assert all(torch.equal(a, b) for a, b in zip(zero["x"], base["x"])) and float(zero["loss"]) == float(base["loss"])
+    assert torch.allclose(fw["sample"][0], fw["x"][0] + 0.7 * 0.5 * ce[0], rtol=0, atol=1e-15)
+    assert torch.equal(fw["sample"][1], fw["x"][1])                     # stddev 0 on the last step (:152-153)
+    assert torch.equal(fw["x"][0], base["x"][0]) and not torch.allclose(fw["x"][1], base["x"][1])   # step 1 reads the sample
+    _, grads = O.loss_and_grads(hp, P, x, x, eps, 0.7, ce)
+    name, h = "theta/generative_step_0/Conv2d_transpose_6/weights", 1e-5    # reaches the loss of step 1 through the sample
+    idx = (1, 2, 0, 3)
+    vals = []
+    for sgn in (+1, -1):
+        Q = {k: v.clone() for k, v in P.items()}
+        Q[name][idx] += sgn * h
+        with torch.no_grad():
+            vals.append(float(O.forward_chain(hp, Q, x, x, eps, 0.7, ce)["loss"]))
+    fd = (vals[0] - vals[1]) / (2 * h)
+    assert abs(fd - float(grads[name][idx])) <= 1e-5 * max(1.0, abs(fd))
+    # generation: reg_coeff is the placeholder's default 1 (:917), the samples feed the next step
+    z = torch.randn(2, 3, hp["latent_dim"], generator=g, dtype=torch.float64)
+    smp = []
+    with torch.no_grad():
+        mles = O.generate_chain(hp, P, z, 3, ce, smp)
+        clean = O.generate_chain(dict(hp, add_noise_to_chain=False), P, z, 3)
+    assert torch.allclose(smp[0], mles[0] + 0.5 * ce[0], rtol=0, atol=1e-15) and torch.equal(mles[0], clean[0])
+    assert not torch.allclose(mles[1], clean[1])
+    # the netname rows: same variables as the noise-free nets, the reference's default stddevs (:239)
+    hs = O.hyperparams("c_sample_images", [64, 64, 3], (-1, 1))
+    assert hs["add_noise_to_chain"] and hs["noise_stddevs"] == [0.5 ** k for k in range(1, 8)] + [0]
+    assert [s["name"] for s in O.param_specs(hs)] == [s["name"] for s in O.param_specs(O.hyperparams("c_inhomog", [64, 64, 3], (-1, 1)))]
+    hh = O.hyperparams("c_homog_sample_images", [64, 64, 3], (-1, 1))
+    assert hh["share_theta_weights"] and hh["share_phi_weights"] and hh["add_noise_to_chain"]
