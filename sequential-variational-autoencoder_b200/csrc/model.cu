@@ -80,6 +80,7 @@ struct Block {
   bool g_fused = false;
   // what the last forward / backward of this block read (svae_debug_block_tensor: local-replay parity tests)
   View dbg_in{}; FeatView dbg_da{}; int dbg_gs = -1;
+  bool y_zeroed = false;       // plan: y lives in the forward-zeroed arena (split-K fc output: no memset node on the chain)
   bool in_f32_valid = true;    // plan: the fp32 tensor this block reads is materialised (its producer does not skip_f32)
   bool dbg_dy_f32 = false;     // last backward: the fp32 dL/dy was written (some consumer is not TMA-fed)
 };
@@ -213,6 +214,7 @@ struct svae_handle {
   static constexpr int MAX_GS = 8;
   GradSet gs[MAX_GS];
   int n_gs = 2;
+  bool bwd_prezero = false;   // d_z / d_cc / d_e[last] of every scratch set are zeroed with the backward arena (n_gs >= T)
   int n_dy_slots = 0;
   std::vector<size_t> dy_slot_elems;
   float* gx[2] = {nullptr, nullptr};
@@ -544,10 +546,13 @@ void build_pub(svae_handle* h) {
 }
 
 // ---- activation arena ----------------------------------------------------------------------------------------------
-void place_block(Block& b, Arena& act, Arena& zf, Arena& zb, int64_t maxB, bool plane2d, size_t& max_y) {
+void place_block(Block& b, Arena& act, Arena& zf, Arena& zb, int64_t maxB, bool plane2d, size_t& max_y, bool y_in_zf = false) {
   if (plane2d) { b.rpi = 1; b.feats = b.g.Cout; } else { b.rpi = b.g.Hout * b.g.Wout; b.feats = b.g.Cout; }
   size_t n = (size_t)maxB * b.rpi * b.feats;
-  b.y = act.get<float>(n);
+  // y_in_zf: the split-K fully-connected kernels accumulate their partial sums with atomics; an output that lives in the
+  // forward-zeroed arena (one memset at the start of the step) needs no memset node in front of every launch on the chain
+  b.y = y_in_zf ? zf.get<float>(n) : act.get<float>(n);
+  b.y_zeroed = y_in_zf;
   b.stats = zf.get<double>(2 * (size_t)b.feats);
   b.fwd_bar = zf.get<unsigned>(4);
   b.S = zb.get<double>(2 * (size_t)b.feats + 1);   // + the grid-barrier counter of the fused backward kernel
@@ -606,7 +611,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
         float* a = act.get<float>((size_t)B * b.rpi * b.feats);
         b.out = fv4(a, b.feats, 0, b.feats);
       }
-      place_block(s.encfc, act, zf, zb, B, true, max_y);
+      place_block(s.encfc, act, zf, zb, B, true, max_y, c.train_capacity != 0);
       s.encfc.act = ACT_LRELU;
       s.encfc.out = fv4(s.cc, s.ncc, 0, F[L]);           // e[L] is the first window of the concat (:1696-1697,1834)
     }
@@ -619,7 +624,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       else b.out = fv4(s.cc, s.ncc, t > 0 ? F[L] : 0, F[L + 1]);
     }
     // dec.fc (:1704-1705)
-    place_block(s.decfc, act, zf, zb, B, true, max_y);
+    place_block(s.decfc, act, zf, zb, B, true, max_y, c.train_capacity != 0);
     s.decfc.act = ACT_LRELU;
     {
       float* a = act.get<float>((size_t)B * s.decfc.feats);
@@ -731,6 +736,11 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       if (want > svae_handle::MAX_GS) want = svae_handle::MAX_GS;
       h->n_gs = T < want ? (T < 2 ? 2 : T) : want;
     }
+    // Every chain step has its own scratch set: the buffers that are accumulated into with atomics (d_z by the latent
+    // projections, d_cc / d_e[last] by the split-K fully-connected input gradients) live in the backward-zeroed arena - one
+    // memset at the start of the backward instead of five memset nodes per chain step in front of kernels of the chain.
+    h->bwd_prezero = h->n_gs >= T;
+    Arena& za = h->bwd_prezero ? zb : gr;
     for (int p = 0; p < h->n_gs; ++p) {
       GradSet& g = h->gs[p];
       g.d_c.resize(L - 1); g.d_dcat.resize(L - 1);
@@ -739,8 +749,8 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
         g.d_dcat[l] = gr.get<float>((size_t)B * S[l + 1] * S[l + 1] * 2 * F[l + 1]);
       }
       g.d_fca = gr.get<float>((size_t)B * S[L] * S[L] * F[L]);
-      g.d_cc = gr.get<float>((size_t)B * (F[L] + F[L + 1]));
-      g.d_z = gr.get<float>((size_t)B * Z);
+      g.d_cc = za.get<float>((size_t)B * (F[L] + F[L + 1]));
+      g.d_z = za.get<float>((size_t)B * Z);
       g.d_mu_pre = gr.get<float>((size_t)B * Z);
       g.d_sd_pre = gr.get<float>((size_t)B * Z);
       g.d_u = gr.get<float>((size_t)B * h->D * h->D * (C + 1));
@@ -753,7 +763,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       if (T > 1)
         for (int k = 0; k <= 2 * (L - 1); ++k) {
           const Block& b = s1.enc[k];
-          g.d_e[k] = gr.get<float>((size_t)B * b.rpi * b.feats);
+          g.d_e[k] = (k == 2 * (L - 1) ? za : gr).get<float>((size_t)B * b.rpi * b.feats);
         }
       g.dy.assign(h->n_dy_slots, nullptr);
       for (int k = 0; k < h->n_dy_slots; ++k)
@@ -971,7 +981,9 @@ int block_fwd(svae_handle* h, Block& b, int B, View in) {
     LaunchCtx lc = h->lc();
     return tc2_gather_gemm(lc, g, b.in_bf, 0, b.w_packed, mkview(b.y, b.feats, 0), b.stats, nullptr, b.tw_f, &ff);
   }
-  H_TRY(contract_bf(h, b.g, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
+  Geom gf = b.g;
+  if (b.y_zeroed && b.g.KH == 1) gf.accumulate = 1;   // y was zeroed with the forward arena: += is =, without a memset node
+  H_TRY(contract_bf(h, gf, B, b.tc2_fwd, b.in_bf, in, h->pw(b.w), b.w_packed, b.tc_fwd, mkview(b.y, b.feats, 0),
                     fc2d ? nullptr : b.stats, nullptr, b.tw_f));
   LaunchCtx lc = h->lc();
   FeatView out = b.out;
@@ -1392,7 +1404,7 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
                          ? 16.f * step_coef(h, s.t) * 2.f / ((float)B * h->D * h->D * C) : 0.f;   // :1146,1163,1168
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
-  H_CUDA(cudaMemsetAsync(gs.d_z, 0, sizeof(float) * (size_t)B * h->Z, st.chain));   // lat_dz accumulates with atomics
+  if (!h->bwd_prezero) H_CUDA(cudaMemsetAsync(gs.d_z, 0, sizeof(float) * (size_t)B * h->Z, st.chain));   // lat_dz accumulates with atomics
   H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
                     coef, gs.d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr,
                     gs.du_out_bf.p ? BfDst{gs.du_out_bf, 0, 0, 0} : BfDst{},
@@ -1458,7 +1470,7 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   {
     View d_cc = mkview(gs.d_cc, s.ncc, 0);
     H_TRY(block_bwd(h, gs, s.decfc, B, fv4(gs.d_fca, s.decfc.feats, 0, s.decfc.feats), mkview(s.cc, s.ncc, 0), nullptr, 0,
-                    &d_cc, 0, st.w));
+                    &d_cc, h->bwd_prezero ? 1 : 0, st.w));   // pre-zeroed: += is = (no memset node for the split-K kernel)
   }
   // P_{L-1}
   {
@@ -1480,7 +1492,7 @@ int encoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   {
     View flat = mkview(s.enc[last].out.p, s.encfc.g.Cin, 0);
     View d_flat = mkview(gs.d_e[last], s.encfc.g.Cin, 0);
-    H_TRY(block_bwd(h, gs, s.encfc, B, fv4(gs.d_cc, s.ncc, 0, F[L]), flat, nullptr, 0, &d_flat, 0, st.w));
+    H_TRY(block_bwd(h, gs, s.encfc, B, fv4(gs.d_cc, s.ncc, 0, F[L]), flat, nullptr, 0, &d_flat, h->bwd_prezero ? 1 : 0, st.w));
   }
   for (int k = last; k >= 0; --k) {
     Block& b = s.enc[k];
@@ -1582,7 +1594,6 @@ int backward_impl(svae_handle* h) {
   const int B = h->last_B, T = h->T;
   h->cur = h->stream;
   H_TRY(zero_region(h, h->zb_base, h->zb_bytes));
-  H_TRY(zero_region(h, h->G, (size_t)h->arena_numel * 4));
   const bool fork = forked(h);
   BwdStreams st{h->stream, h->stream, h->stream, h->stream, h->stream};
   if (fork) {
@@ -1591,6 +1602,19 @@ int backward_impl(svae_handle* h) {
     st.recw = (h->fork_mask & 4) ? h->side[2] : st.rec;
   }
   st.lat = st.rec;
+  // Gradient arena: 4 B x all parameters (335 MB for CelebA T = 8: ~55 us of memset).  Only the slice of the LAST chain step is
+  // needed at once; the slices of the earlier steps are zeroed on the weight-gradient stream beside the first chain step.
+  cudaEvent_t g_zeroed = nullptr;
+  if (fork && T > 1 && st.w != st.chain) {
+    const int64_t last = h->steps[T - 1].p_begin;
+    H_TRY(zero_region(h, h->G + last, (size_t)(h->arena_numel - last) * 4));
+    H_TRY(link(h, st.chain, st.w));
+    H_CUDA(cudaMemsetAsync(h->G, 0, (size_t)last * 4, st.w));
+    g_zeroed = next_event(h);
+    H_CUDA(cudaEventRecord(g_zeroed, st.w));
+  } else {
+    H_TRY(zero_region(h, h->G, (size_t)h->arena_numel * 4));
+  }
   // side_done[t][i]: side stream i has finished step t's work (its scratch set may be reused two steps later)
   std::vector<cudaEvent_t> side_done((size_t)T * 3, nullptr);
   int cur = 0;
@@ -1616,6 +1640,7 @@ int backward_impl(svae_handle* h) {
     if ((fork || multi) && t + NS < T)
       for (int i = 0; i < 3; ++i)
         if (side_done[(size_t)(t + NS) * 3 + i] != nullptr) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + NS) * 3 + i], 0));
+    if (t == T - 2 && g_zeroed != nullptr) H_CUDA(cudaStreamWaitEvent(h->stream, g_zeroed, 0));
     const float* xprev = t > 0 ? h->chain_in(t - 1) : nullptr;   // d sample / d mle = 1: the chain gradient is unchanged
     float* gx_prev = h->gx[cur ^ 1];
     H_TRY(decoder_bwd(h, gs, st, s, B, gx_in, gx_prev, xprev));
