@@ -1998,7 +1998,7 @@ int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double 
   // (one launch after a full Adam step) or one chain step's layers (bucketed update)
   // (entries differ 1000x in size: blocks beyond an entry's element count exit at once, the large entries need the threads)
   int bx = (64 * lc.sm_count + n - 1) / n;
-  if (bx < 32) bx = 32;
+  if (bx < (lc.sm_count >= 100 ? 32 : 4)) bx = lc.sm_count >= 100 ? 32 : 4;   // a reduced SM budget (bucketed update beside the chain): few blocks
   if (bx > 256) bx = 256;
   tc_pack_batched_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, lc.stream>>>(reinterpret_cast<const TcPackEntry*>(dev_entries));
   CUDA_TRY(cudaGetLastError());

@@ -287,6 +287,7 @@ struct svae_handle {
   int multi_sm = 148;
   float multi_sm_factor = 0.5f;      // SVAE_MULTI_SM_FACTOR (measured: 0.5 -> 10.70, 1 -> 10.83, 2 -> 11.03, full grids -> 11.30 ms/step)
   int wgrad_sm = 0;                  // SVAE_WGRAD_SM: SM budget of the chain's weight-gradient launches (side stream), 0 = all
+  int upd_sm = 37;                   // SVAE_UPD_SM: SM budget of the per-bucket Adam + repack launches (update stream), 0 = all
   // exposed: nothing runs beside this group (first forward group: the chain waits for it; last backward group: the chain is
   // done) - its items share the whole machine
   void begin_multi(MultiRec* m, int items, bool exposed) {
@@ -1575,6 +1576,11 @@ int update_bucket(svae_handle* h, int t, const BwdStreams& st, int part = 0) {
   }
   OnStream os(h, us);
   LaunchCtx lc = h->lc();
+  // The update runs beside the chain's backward of the earlier steps.  Sized for the whole machine, the Adam kernel (1 184
+  // persistent 256-thread blocks = every thread slot of every SM for ~60 us) and the repack kept the chain's next kernels waiting
+  // for a free slot: 70-80 us per chain step in the kernel timeline (profiles/r2_step_analysis.md).  Sized for upd_sm SMs'
+  // worth of blocks they stream at a fraction of the HBM rate - there is ~1 ms until the next bucket - and leave the slots free.
+  if (h->upd_sm > 0 && us != h->stream) lc.sm_count = std::min(lc.sm_count, h->upd_sm);
   const int64_t n = pe - pb;
   H_TRY(adam_update(lc, h->P + pb, h->G + pb, h->M + pb, h->V + pb, n, h->dyn_dev, h->dyn_host.lr_t,
                     h->cfg.adam_beta1, h->cfg.adam_beta2, h->cfg.adam_eps, h->cfg.clip_value, 1.f / (float)h->nranks));
@@ -2067,6 +2073,8 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     };
     parse(getenv("SVAE_REC_FWD_GROUPS"), "1,1,6", h->rec_fwd_groups);
     parse(getenv("SVAE_REC_BWD_GROUPS"), "5,2,1", h->rec_bwd_groups);
+    const char* e15 = getenv("SVAE_UPD_SM");
+    if (e15) h->upd_sm = atoi(e15);
     const char* e14 = getenv("SVAE_WGRAD_SM");
     if (e14) h->wgrad_sm = atoi(e14);
     const char* e13 = getenv("SVAE_MULTI_SM_FACTOR");
