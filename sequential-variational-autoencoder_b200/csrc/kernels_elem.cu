@@ -8,6 +8,7 @@
 // reductions (:1146-1164), reparameterisation (:1023), clip_by_value + AdamOptimizer (:18-25,1267-1276).
 #include <stdlib.h>
 
+#include <initializer_list>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -627,6 +628,167 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
   }
 }
 
+// ---- vectorised output head for 3-channel images (every reference dataset but MNIST): one thread = 4 consecutive pixels -------
+// The scalar kernels above issue ~50 four-byte accesses per pixel group (12-byte pixel stride) and three two-byte stores into the
+// bf16 copy; here a thread moves whole 16-byte vectors: 12 floats of x_prev / target / x_t / dL/dx_t as three float4 each, u and
+// du as one float4 per pixel (ldu = 4) or three per group (ldu = 3), and one 16-byte row (3 values + the zero padding channels)
+// per pixel of the bf16 copies.  Same arithmetic, same order per element as the scalar kernels.
+__device__ __forceinline__ void ld12(const float* p, float (&v)[12]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1), c = __ldg(reinterpret_cast<const float4*>(p) + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+}
+__device__ __forceinline__ void st12(float* p, const float (&v)[12]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  reinterpret_cast<float4*>(p)[2] = make_float4(v[8], v[9], v[10], v[11]);
+}
+__device__ __forceinline__ void bf_row_store(const BfAct& a, int64_t pix, int HW, int W, const float (&f)[8]) {
+  const int n = (int)(pix / HW);
+  const int hw = (int)(pix - (int64_t)n * HW);
+  const int hh = hw / W;
+  *reinterpret_cast<uint4*>(a.p + bf_index(a, n, hh, hw - hh * W, 0)) = tcptx::pack8_bf16(f);
+}
+
+template <int GATE>
+__global__ void __launch_bounds__(256)
+out_mix_fwd_v4_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out, const float* __restrict__ b_gate,
+                      const float* __restrict__ xprev, const float* __restrict__ tgt, float* __restrict__ xt,
+                      double* __restrict__ recon_sum, BfDst xbf) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  constexpr int LDU = 3 + GATE;
+  const float bo[3] = {b_out[0], b_out[1], b_out[2]};
+  const float bg = GATE ? b_gate[0] : 0.f;
+  const int HWb = xbf.a.p != nullptr ? xbf.a.H * xbf.a.W : 1, Wb = xbf.a.p != nullptr ? xbf.a.W : 1;
+  float se = 0.f;
+  const int64_t groups = p.pixels >> 2;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < groups; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = j << 2;
+    float uu[4 * LDU];
+    {
+      const float4* up = reinterpret_cast<const float4*>(u + i0 * LDU);
+#pragma unroll
+      for (int k = 0; k < LDU; ++k) { const float4 t = __ldg(up + k); uu[4 * k] = t.x; uu[4 * k + 1] = t.y; uu[4 * k + 2] = t.z; uu[4 * k + 3] = t.w; }
+    }
+    float xp[12], tg[12], xo[12];
+    if (GATE) ld12(xprev + i0 * 3, xp);
+    if (tgt != nullptr) ld12(tgt + i0 * 3, tg);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float r = 1.f;
+      if (GATE) r = p.minr + (p.maxr - p.minr) * sigmoidf_(uu[q * LDU + 3] + bg);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float o = sigmoidf_(uu[q * LDU + c] + bo[c]);
+        float v = p.lo + (p.hi - p.lo) * o;
+        if (GATE) v = r * v + (1.f - r) * xp[q * 3 + c];
+        xo[q * 3 + c] = v;
+        if (tgt != nullptr) { const float d = v - tg[q * 3 + c]; se += d * d; }
+      }
+      if (xbf.a.p != nullptr) {
+        const float f[8] = {xo[q * 3], xo[q * 3 + 1], xo[q * 3 + 2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        bf_row_store(xbf.a, i0 + q, HWb, Wb, f);
+      }
+    }
+    st12(xt + i0 * 3, xo);
+  }
+  if (recon_sum != nullptr) {
+    float tot = block_sum<float>(se, red);
+    if (threadIdx.x == 0) atomicAdd(recon_sum, (double)tot);
+  }
+}
+
+template <int GATE>
+__global__ void __launch_bounds__(256)
+out_mix_bwd_v4_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out, const float* __restrict__ b_gate,
+                      const float* __restrict__ xprev, const float* __restrict__ tgt, const float* __restrict__ xt,
+                      const float* __restrict__ gx_in, float coef, float* __restrict__ du, float* __restrict__ gx_prev,
+                      float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  constexpr int LDU = 3 + GATE;
+  const float bo[3] = {b_out[0], b_out[1], b_out[2]};
+  const float bg = GATE ? b_gate[0] : 0.f;
+  const BfAct& la = obf.a.p != nullptr ? obf.a : gbf.a;
+  const int HWb = la.p != nullptr ? la.H * la.W : 1, Wb = la.p != nullptr ? la.W : 1;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t groups = p.pixels >> 2;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < groups; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = j << 2;
+    float uu[4 * LDU], dd[4 * LDU];
+    {
+      const float4* up = reinterpret_cast<const float4*>(u + i0 * LDU);
+#pragma unroll
+      for (int k = 0; k < LDU; ++k) { const float4 t = __ldg(up + k); uu[4 * k] = t.x; uu[4 * k + 1] = t.y; uu[4 * k + 2] = t.z; uu[4 * k + 3] = t.w; }
+    }
+    float xp[12], tg[12], xo[12], gi[12], gp[12];
+    ld12(xt + i0 * 3, xo);
+    ld12(tgt + i0 * 3, tg);
+    if (GATE) ld12(xprev + i0 * 3, xp);
+    if (gx_in != nullptr) ld12(gx_in + i0 * 3, gi);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float s = 0.f, r = 1.f;
+      if (GATE) {
+        s = sigmoidf_(uu[q * LDU + 3] + bg);
+        r = p.minr + (p.maxr - p.minr) * s;
+      }
+      float dgate = 0.f;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float g = coef * (xo[q * 3 + c] - tg[q * 3 + c]);
+        if (gx_in != nullptr) g += gi[q * 3 + c];
+        const float o = sigmoidf_(uu[q * LDU + c] + bo[c]);
+        const float outv = p.lo + (p.hi - p.lo) * o;
+        const float d_u = g * r * (p.hi - p.lo) * o * (1.f - o);
+        dd[q * LDU + c] = d_u;
+        f[c] = d_u;
+        bsum[c] += d_u;
+        if (GATE) {
+          dgate += g * (outv - xp[q * 3 + c]);
+          gp[q * 3 + c] = g * (1.f - r);
+        }
+      }
+      if (obf.a.p != nullptr) bf_row_store(obf.a, i0 + q, HWb, Wb, f);
+      if (GATE) {
+        const float d_g = dgate * (p.maxr - p.minr) * s * (1.f - s);
+        dd[q * LDU + 3] = d_g;
+        bsum[3] += d_g;
+        if (gbf.a.p != nullptr) {
+          const float fg[8] = {d_g, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          bf_row_store(gbf.a, i0 + q, HWb, Wb, fg);
+        }
+      }
+    }
+    {
+      float4* dp = reinterpret_cast<float4*>(du + i0 * LDU);
+#pragma unroll
+      for (int k = 0; k < LDU; ++k) dp[k] = make_float4(dd[4 * k], dd[4 * k + 1], dd[4 * k + 2], dd[4 * k + 3]);
+    }
+    if (GATE) st12(gx_prev + i0 * 3, gp);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float t = block_sum<float>(bsum[c], red);
+    if (threadIdx.x == 0) atomicAdd(&db_out[c], t);
+  }
+  if (GATE) {
+    const float t = block_sum<float>(bsum[3], red);
+    if (threadIdx.x == 0) atomicAdd(&db_gate[0], t);
+  }
+}
+
+static inline bool out_mix_v4_ok(const OutMixParams& p, std::initializer_list<const void*> ptrs, const BfDst& a, const BfDst& b) {
+  static const bool enabled = !(getenv("SVAE_OUTMIX_V4") && getenv("SVAE_OUTMIX_V4")[0] == '0');
+  if (!enabled || p.C != 3 || (p.pixels & 3)) return false;
+  for (const void* q : ptrs) if (q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15)) return false;
+  for (const BfDst* d : {&a, &b}) if (d->a.p != nullptr && (d->coff != 0 || d->inner != 0)) return false;
+  return true;
+}
+
 // ---- counter-based Philox4x32-10 (same generator family as tf.random_normal) ---------------------
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
@@ -994,6 +1156,12 @@ int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 20.0 * p.pixels * p.C,
                4.0 * p.pixels * (p.C + p.has_gate + p.C * (1 + (p.has_gate ? 1 : 0) + (tgt ? 1 : 0))));
+  if (out_mix_v4_ok(p, {u, xprev, tgt, xt}, xt_bf, BfDst{})) {
+    const dim3 grid(flat_blocks(p.pixels >> 2, lc.sm_count));
+    if (p.has_gate) CUDA_TRY(launch_k(lc, out_mix_fwd_v4_kernel<1>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, recon_sum, xt_bf));
+    else CUDA_TRY(launch_k(lc, out_mix_fwd_v4_kernel<0>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, recon_sum, xt_bf));
+    return 0;
+  }
   CUDA_TRY(launch_k(lc, out_mix_fwd_kernel, dim3(flat_blocks(p.pixels, lc.sm_count)), dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt,
                     recon_sum, xt_bf));
   CUDA_TRY(cudaGetLastError());
@@ -1014,6 +1182,14 @@ int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 30.0 * p.pixels * p.C,
                4.0 * p.pixels * (2 * (p.C + p.has_gate) + p.C * (2 + (gx_in ? 1 : 0) + (p.has_gate ? 2 : 0))));
+  if (tgt != nullptr && out_mix_v4_ok(p, {u, xprev, tgt, xt, gx_in, du, gx_prev}, du_out_bf, du_gate_bf)) {
+    const dim3 grid(flat_blocks(p.pixels >> 2, lc.sm_count));
+    if (p.has_gate) CUDA_TRY(launch_k(lc, out_mix_bwd_v4_kernel<1>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, gx_in, coef, du, gx_prev,
+                                      db_out, db_gate, du_out_bf, du_gate_bf));
+    else CUDA_TRY(launch_k(lc, out_mix_bwd_v4_kernel<0>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, gx_in, coef, du, gx_prev,
+                           db_out, db_gate, du_out_bf, du_gate_bf));
+    return 0;
+  }
   CUDA_TRY(launch_k(lc, out_mix_bwd_kernel, dim3(flat_blocks(p.pixels, lc.sm_count)), dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt,
                     gx_in, coef, du, gx_prev, db_out, db_gate, du_out_bf, du_gate_bf));
   CUDA_TRY(cudaGetLastError());

@@ -1018,7 +1018,7 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     H_TRY(bn2d_bwd(lc, da, b.y, b.stats, h->pw(b.beta), B, b.feats, b.act, dy, h->pg(b.beta)));
   } else {
     int fr = 1;   // 1: not fused
-    if (h->use_coop_bn) {
+    if (h->use_coop_bn && h->multi == nullptr && cur_stream(h) == h->stream) {   // chain stream only: one grid barrier at a time
       const bool need_f32 = !tc2w || (din != nullptr && !tc2d);
       fr = bn_bwd_fused(lc, da, b.y, b.stats, h->pw(b.beta), rows, b.feats, b.act, b.res, need_f32 ? dy : nullptr, b.S, dres,
                         dres_acc, h->pg(b.beta), dy_bf);
@@ -1041,7 +1041,7 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     Geom g = dgrad_geom(b.g);
     g.accumulate = din_acc;
     BnBwdFuse fz;
-    const bool fuse = tc2d && make_fuse(h, up, B, up_dres, up_dres_acc, g, *din, fz);
+    const bool fuse = tc2d && h->multi == nullptr && make_fuse(h, up, B, up_dres, up_dres_acc, g, *din, fz);
     H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr,
                       fuse ? &fz : nullptr, b.tw_d));
     if (fuse) up->g_fused = true;
@@ -1280,7 +1280,7 @@ bool step_has_kl(const svae_handle* h, int t) { return (h->cfg.regularized_mask 
 // chain step owns its buffers and gradient scratch set.
 bool rec_multi_ok(const svae_handle* h, int B) {
   if (!h->use_multi || !h->cfg.train_capacity || h->act_sets != h->T || h->T < 2) return false;
-  if (h->use_fuse || h->use_coop_bn || (h->ablate & 3) || h->timeline) return false;
+  if ((h->ablate & 3) || h->timeline) return false;
   for (const Step& s : h->steps) {
     for (size_t k = 0; k < s.inf.size(); ++k) {
       const Block& b = s.inf[k];
