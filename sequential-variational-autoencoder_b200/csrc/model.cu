@@ -12,6 +12,7 @@
 
 #include <map>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "../../include/svae.h"
@@ -287,6 +288,12 @@ struct svae_handle {
   int multi_sm = 148;
   float multi_sm_factor = 0.5f;      // SVAE_MULTI_SM_FACTOR (measured: 0.5 -> 10.70, 1 -> 10.83, 2 -> 11.03, full grids -> 11.30 ms/step)
   int wgrad_sm = 0;                  // SVAE_WGRAD_SM: SM budget of the chain's weight-gradient launches (side stream), 0 = all
+  // Deferred chain weight gradients: while set, the TMA-fed weight gradients of the chain's blocks are RECORDED (one item per
+  // chain step) instead of being launched on the weight-gradient stream; backward_impl issues them per group of chain steps as
+  // one launch per layer (blockIdx.z = chain step), every item cut for wrec_sm SMs (fewer pixel splits = fewer partial-sum flushes).
+  MultiRec* wrec = nullptr;
+  int wrec_sm = 148;
+  std::vector<int> wgrad_groups;     // chain steps per deferred weight-gradient group, backward order (SVAE_WGRAD_GROUPS; 0 = off)
   int upd_sm = 37;                   // SVAE_UPD_SM: SM budget of the per-bucket Adam + repack launches (update stream), 0 = all
   // exposed: nothing runs beside this group (first forward group: the chain waits for it; last backward group: the chain is
   // done) - its items share the whole machine
@@ -1035,8 +1042,9 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
     }
   }
   View dyv = mkview(dy, b.feats, 0);
+  const bool wdefer = h->wrec != nullptr && h->multi == nullptr && tc2w;
   // dy is final here: the weight gradient (side stream) depends on this point only, not on the input gradient below
-  H_TRY(link(h, cur_stream(h), wst));
+  if (!wdefer) H_TRY(link(h, cur_stream(h), wst));
   if (din != nullptr) {
     Geom g = dgrad_geom(b.g);
     g.accumulate = din_acc;
@@ -1046,7 +1054,12 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
                       fuse ? &fz : nullptr, b.tw_d));
     if (fuse) up->g_fused = true;
   }
-  if (!(h->ablate & 1)) {
+  if (wdefer) {
+    LaunchCtx lw = h->lc();
+    lw.multi = h->wrec; lw.sm_count = h->wrec_sm; lw.pdl_state = nullptr;
+    if (b.g.mode == 0) { Geom g = b.g; g.B = B; H_TRY(tc2_wgrad(lw, g, b.in_bf, gs.dy_bf[b.dy_slot], h->pg(b.w))); }
+    else { Geom g = dgrad_geom(b.g); g.B = B; g.mode = 0; H_TRY(tc2_wgrad(lw, g, gs.dy_bf[b.dy_slot], b.in_bf, h->pg(b.w))); }
+  } else if (!(h->ablate & 1)) {
     OnStream os(h, wst);
     struct Lane { MultiRec* m; Lane(MultiRec* m_) : m(m_) { if (m) m->lane = 1; } ~Lane() { if (m) m->lane = 0; } } lane(h->multi);
     LaunchCtx lw = h->lc();
@@ -1430,17 +1443,23 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
                         h->pw(s.w_gate), s.gateb.w_packed_d, s.gateb.tc_dgrad, dc0, nullptr, fuse_g ? &fz : nullptr));
       if (fuse_g) s.tb[0].g_fused = true;
     }
-    H_TRY(link(h, st.chain, st.w));
+    const bool wdef_o = h->wrec != nullptr && s.outb.tc2_wgrad && gs.du_out_bf.p;
+    const bool wdef_g = h->wrec != nullptr && has_gate && s.gateb.tc2_wgrad && gs.du_gate_bf.p;
+    LaunchCtx lr = h->lc();
+    lr.multi = h->wrec; lr.sm_count = h->wrec_sm; lr.pdl_state = nullptr;
+    if (!(wdef_o && (wdef_g || !has_gate))) H_TRY(link(h, st.chain, st.w));
     OnStream os(h, st.w);
     LaunchCtx lw = h->lc();
     if (h->wgrad_sm > 0 && st.w != h->stream) lw.sm_count = std::min(lw.sm_count, h->wgrad_sm);
     Geom gw = dgrad_geom(s.g_out); gw.B = B; gw.mode = 0;
-    if (s.outb.tc2_wgrad && gs.du_out_bf.p) H_TRY(tc2_wgrad(lw, gw, gs.du_out_bf, s.outb.in_bf, h->pg(s.w_out)));
+    if (wdef_o) H_TRY(tc2_wgrad(lr, gw, gs.du_out_bf, s.outb.in_bf, h->pg(s.w_out)));
+    else if (s.outb.tc2_wgrad && gs.du_out_bf.p) H_TRY(tc2_wgrad(lw, gw, gs.du_out_bf, s.outb.in_bf, h->pg(s.w_out)));
     else if (s.outb.tc_wgrad) H_TRY(tc_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
     else H_TRY(simt_wgrad(lw, gw, mkview(gs.d_u, ldu, 0), c0, h->pg(s.w_out)));
     if (has_gate) {
       Geom gw2 = dgrad_geom(s.g_gate); gw2.B = B; gw2.mode = 0;
-      if (s.gateb.tc2_wgrad && gs.du_gate_bf.p) H_TRY(tc2_wgrad(lw, gw2, gs.du_gate_bf, s.gateb.in_bf, h->pg(s.w_gate)));
+      if (wdef_g) H_TRY(tc2_wgrad(lr, gw2, gs.du_gate_bf, s.gateb.in_bf, h->pg(s.w_gate)));
+      else if (s.gateb.tc2_wgrad && gs.du_gate_bf.p) H_TRY(tc2_wgrad(lw, gw2, gs.du_gate_bf, s.gateb.in_bf, h->pg(s.w_gate)));
       else if (s.gateb.tc_wgrad) H_TRY(tc_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
       else H_TRY(simt_wgrad(lw, gw2, mkview(gs.d_u, ldu, C), c0, h->pg(s.w_gate)));
     }
@@ -1638,7 +1657,14 @@ int backward_impl(svae_handle* h) {
   auto group_size = [&]() { return std::max(1, std::min(h->rec_bwd_groups[std::min(gi, h->rec_bwd_groups.size() - 1)], h->n_gs)); };
   int group = group_size();
   std::vector<int> pending;
-  struct Unmulti { svae_handle* h; ~Unmulti() { h->multi = nullptr; } } unmulti{h};
+  struct Unmulti { svae_handle* h; ~Unmulti() { h->multi = nullptr; h->wrec = nullptr; } } unmulti{h};
+  // Deferred chain weight gradients (svae_handle::wrec): recorded per chain step, issued per group on the weight-gradient
+  // stream; step 0 (no chain encoder, no gate: a different kernel sequence) is always a group of its own.
+  const bool wdefer = multi && fork && st.w != st.chain && !h->wgrad_groups.empty() && h->wgrad_groups[0] > 0 && !(h->ablate & 1);
+  size_t wgi = 0;
+  int wgroup = 0;
+  std::vector<int> wpending;
+  std::unique_ptr<MultiRec> wrec;
   for (int t = T - 1; t >= 0; --t) {
     Step& s = h->steps[t];
     const int NS = h->n_gs;
@@ -1647,6 +1673,19 @@ int backward_impl(svae_handle* h) {
       for (int i = 0; i < 3; ++i)
         if (side_done[(size_t)(t + NS) * 3 + i] != nullptr) H_CUDA(cudaStreamWaitEvent(h->stream, side_done[(size_t)(t + NS) * 3 + i], 0));
     if (t == T - 2 && g_zeroed != nullptr) H_CUDA(cudaStreamWaitEvent(h->stream, g_zeroed, 0));
+    if (wdefer) {
+      if (wpending.empty()) {
+        const int want = h->wgrad_groups[std::min(wgi, h->wgrad_groups.size() - 1)];
+        wgroup = t == 0 ? 1 : std::max(1, std::min(std::min(want, t), h->n_gs));   // steps t .. t - wgroup + 1, never step 0 with others
+        wrec.reset(new MultiRec);
+        h->wrec = wrec.get();
+        const int v = (int)((t == 0 ? 1.f : h->multi_sm_factor) * (float)h->sm_count / (float)wgroup + 0.999f);
+        h->wrec_sm = v < 8 ? 8 : (v > h->sm_count ? h->sm_count : v);
+        ++wgi;
+      }
+      wrec->begin_item();
+      wpending.push_back(t);
+    }
     const float* xprev = t > 0 ? h->chain_in(t - 1) : nullptr;   // d sample / d mle = 1: the chain gradient is unchanged
     float* gx_prev = h->gx[cur ^ 1];
     H_TRY(decoder_bwd(h, gs, st, s, B, gx_in, gx_prev, xprev));
@@ -1675,6 +1714,23 @@ int backward_impl(svae_handle* h) {
       }
     }
     if (t > 0) H_TRY(encoder_bwd(h, gs, st, s, B, gx_prev, xprev));
+    std::vector<int> chain_ready;          // chain steps whose encoder + decoder gradients are final as of this iteration
+    if (!wdefer) {
+      chain_ready.push_back(t);
+    } else if ((int)wpending.size() == wgroup) {
+      h->wrec = nullptr;
+      H_TRY(link(h, st.chain, st.w));       // every dy / activation copy of the group is final
+      {
+        OnStream os(h, st.w);
+        H_TRY(multi_flush(h, *wrec));
+      }
+      cudaEvent_t e = next_event(h);
+      H_CUDA(cudaEventRecord(e, st.w));
+      for (int pt : wpending) side_done[(size_t)pt * 3] = e;
+      chain_ready.swap(wpending);
+      wpending.clear();
+      wrec.reset();
+    }
     tl_mark(h, st.chain, "main: bwd chain step done", t);
     if (fork) { tl_mark(h, st.w, "W: chain wgrads done", t); tl_mark(h, st.rec, "R: recognition bwd done", t); tl_mark(h, st.recw, "W2: recognition wgrads done", t); }
     if (!multi) {
@@ -1687,7 +1743,7 @@ int backward_impl(svae_handle* h) {
       }
       H_TRY(allreduce_bucket(h, t, st));
       H_TRY(update_bucket(h, t, st));
-    } else if (pending.size() == 1 && pending[0] == t && (group == 1 || t == 0)) {
+    } else if (!wdefer && pending.size() == 1 && pending[0] == t && (group == 1 || t == 0)) {
       // a group of one, issued in this iteration: the whole slice is final together, as without batching
       if (st.lat != st.rec) H_TRY(link(h, st.lat, st.rec));
       cudaStream_t sd[3] = {st.w, st.rec, st.recw};
@@ -1704,7 +1760,7 @@ int backward_impl(svae_handle* h) {
     } else {
       // chain half of the slice: final once the chain, its weight-gradient stream and the latent projections are done with step t
       BwdStreams ch{st.chain, st.w, st.lat, st.w, st.lat};
-      if (st.w != st.chain) {
+      if (!wdefer && st.w != st.chain) {
         side_done[(size_t)t * 3] = next_event(h);
         H_CUDA(cudaEventRecord(side_done[(size_t)t * 3], st.w));
       }
@@ -1712,8 +1768,10 @@ int backward_impl(svae_handle* h) {
         side_done[(size_t)t * 3 + 2] = next_event(h);
         H_CUDA(cudaEventRecord(side_done[(size_t)t * 3 + 2], st.lat));
       }
-      H_TRY(allreduce_bucket(h, t, ch, 1));
-      H_TRY(update_bucket(h, t, ch, 1));
+      for (int pt : chain_ready) {
+        H_TRY(allreduce_bucket(h, pt, ch, 1));
+        H_TRY(update_bucket(h, pt, ch, 1));
+      }
       if ((int)pending.size() == group || t == 0) {
         // recognition halves of the group that was just issued on st.rec
         BwdStreams rs{st.rec, st.recw, st.rec, st.recw, st.rec};
@@ -2073,6 +2131,8 @@ int svae_create(const svae_config* cfg, int device, svae_handle** out) {
     };
     parse(getenv("SVAE_REC_FWD_GROUPS"), "1,1,6", h->rec_fwd_groups);
     parse(getenv("SVAE_REC_BWD_GROUPS"), "5,2,1", h->rec_bwd_groups);
+    { const char* eg = getenv("SVAE_WGRAD_GROUPS");   // deferred, batched chain weight gradients (default 4,3: steps 7..4, 3..1, 0); 0: per-step launches
+      if (eg && atoi(eg) <= 0) h->wgrad_groups.assign(1, 0); else parse(eg, "4,3", h->wgrad_groups); }
     const char* e15 = getenv("SVAE_UPD_SM");
     if (e15) h->upd_sm = atoi(e15);
     const char* e14 = getenv("SVAE_WGRAD_SM");
