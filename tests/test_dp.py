@@ -56,7 +56,7 @@ def test_dp_nccl_world2(tmp_path):
     res = _launch("nccl", 2, tmp_path, 29542)
     assert res["all_same"]
     assert res["all_same_after_graph_steps"], res
-    assert res["err"] < 2e-2, res       # Adam's first step normalises gradient noise to ~lr: compare updates loosely
+    assert res["err"] < 2e-2 and res["err_max"] < 0.5, res   # Adam's first step normalises gradient noise to ~lr: 90th percentile / maximum over the tensors
 
 
 def test_dp_semantics_gloo_world2_homogeneous(tmp_path):
@@ -77,7 +77,7 @@ def test_dp_nccl_world2_homogeneous(tmp_path):
     assert res["all_same"]
     assert res["all_same_after_graph_steps"], res
     assert res["slices_tied"] and res["shared_variables"] > 40, res
-    assert res["err"] < 2e-2, res
+    assert res["err"] < 2e-2 and res["err_max"] < 0.5, res
 
 
 @pytest.mark.gpu
