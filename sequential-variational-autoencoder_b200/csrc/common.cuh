@@ -352,7 +352,8 @@ bool tc2_bnf_supported(const Geom& g, int w_tile_width, int sm_count, View out, 
 int tc2_pick_ntw(const Geom& g, int sm_count);
 bool tc2_fuse_supported(const Geom& g, View out, int C);   // can this launch carry a BnBwdFuse over its first C output channels?
 bool tc2_wgrad_supported(const Geom& g);   // g: conv-gather geometry (see tc_wgrad)
-int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw);
+// dw2 != nullptr: rows (X channels) [a_split, Ca) of the gradient belong to a second parameter tensor [16][Ca - a_split][Cb]
+int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw, float* dw2 = nullptr, int a_split = 0);
 // ---- SIMT fp32 contractions (kernels_simt.cu) ------------------------------------------------------------------
 int simt_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const float* w, View out, double* stats);
 // dW(tap,a,b) = sum_rows X(gathered at tap, channel a) * dY(row, channel b); layout w[(tap*Ca + a)*Cb + b].
@@ -421,7 +422,8 @@ int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
 // g = gx_in (or 0) + coef*(x_t - tgt) ; du, gx_prev, bias grads
 int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
                 const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
-                float* gx_prev, float* db_out, float* db_gate, BfDst du_out_bf = BfDst{}, BfDst du_gate_bf = BfDst{});
+                float* gx_prev, float* db_out, float* db_gate, BfDst du_out_bf = BfDst{}, BfDst du_gate_bf = BfDst{},
+                int gate_in_out_bf = 0);   // 1: the gate's gradient goes to channel C of du_out_bf (merged output + gate contraction)
 struct ReparamParams {
   int B, Z;
   float clip, prior;
@@ -473,8 +475,11 @@ int tc_wgrad(const LaunchCtx& lc, const Geom& g, View x, View dy, float* dw);
 int tc_gather_gemm(const LaunchCtx& lc, const Geom& g, View in, const void* w_packed, View out, double* stats);
 size_t tc_packed_bytes(const Geom& g);
 int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_packed, int tile_width = 128);
-struct TcPackEntry { Geom g; const float* w; void* out; int KC, Cin_p, N_p, TW; long long total; };
-TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed, int tile_width = 128);
+// w2 != nullptr: the layer's weights are TWO parameter tensors side by side along the deconv's output-channel dimension (the
+// output (C channels) and gate (1 channel) deconvs of a chain step run as one contraction): channels [0, n1) come from w, the
+// rest from w2; that dimension is `co` for the forward form (w_out_major 1) and `ci` for the input-gradient form (w_out_major 0).
+struct TcPackEntry { Geom g; const float* w; void* out; int KC, Cin_p, N_p, TW; long long total; const float* w2; int n1; };
+TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed, int tile_width = 128, const float* w2 = nullptr, int n1 = 0);
 int tc_pack_batched(const LaunchCtx& lc, const void* dev_entries, int n, double total_elems);
 // ---- tcgen05 fully-connected kernel (kernels_fc.cu): fp32 operands read directly, bf16 in shared memory -----------
 bool tc_fc_supported(int K, int N);

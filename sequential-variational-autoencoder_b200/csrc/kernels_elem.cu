@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(256)
 out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out,
                    const float* __restrict__ b_gate, const float* __restrict__ xprev, const float* __restrict__ tgt,
                    const float* __restrict__ xt, const float* __restrict__ gx_in, float coef, float* __restrict__ du,
-                   float* __restrict__ gx_prev, float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf) {
+                   float* __restrict__ gx_prev, float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf,
+                   int gate_in_obf) {
   pdl_wait();
   pdl_trigger();
   __shared__ float red[32];
@@ -613,6 +614,7 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
       float d_g = dgate * (p.maxr - p.minr) * s * (1.f - s);
       dr[p.C] = d_g;
       if (gbf.a.p != nullptr) gbf.a.p[bf_index(gbf.a, bn_, bh_, bw_, 0)] = __float2bfloat16_rn(d_g);
+      if (gate_in_obf && obf.a.p != nullptr) obf.a.p[bf_index(obf.a, bn_, bh_, bw_, p.C)] = __float2bfloat16_rn(d_g);
       bsum[MAXC] += d_g;
     }
   }
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(256)
 out_mix_bwd_v4_kernel(OutMixParams p, const float* __restrict__ u, const float* __restrict__ b_out, const float* __restrict__ b_gate,
                       const float* __restrict__ xprev, const float* __restrict__ tgt, const float* __restrict__ xt,
                       const float* __restrict__ gx_in, float coef, float* __restrict__ du, float* __restrict__ gx_prev,
-                      float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf) {
+                      float* __restrict__ db_out, float* __restrict__ db_gate, BfDst obf, BfDst gbf, int gate_in_obf) {
   pdl_wait();
   pdl_trigger();
   __shared__ float red[32];
@@ -752,9 +754,13 @@ out_mix_bwd_v4_kernel(OutMixParams p, const float* __restrict__ u, const float* 
           gp[q * 3 + c] = g * (1.f - r);
         }
       }
+      float d_g = 0.f;
+      if (GATE) {
+        d_g = dgate * (p.maxr - p.minr) * s * (1.f - s);
+        if (gate_in_obf) f[3] = d_g;          // merged output + gate contraction: one 4-channel operand copy
+      }
       if (obf.a.p != nullptr) bf_row_store(obf.a, i0 + q, HWb, Wb, f);
       if (GATE) {
-        const float d_g = dgate * (p.maxr - p.minr) * s * (1.f - s);
         dd[q * LDU + 3] = d_g;
         bsum[3] += d_g;
         if (gbf.a.p != nullptr) {
@@ -1178,20 +1184,20 @@ int chain_noise(const LaunchCtx& lc, const float* xt, const float* noise, const 
 
 int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,
                 const float* xprev, const float* tgt, const float* xt, const float* gx_in, float coef, float* du,
-                float* gx_prev, float* db_out, float* db_gate, BfDst du_out_bf, BfDst du_gate_bf) {
+                float* gx_prev, float* db_out, float* db_gate, BfDst du_out_bf, BfDst du_gate_bf, int gate_in_out_bf) {
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 30.0 * p.pixels * p.C,
                4.0 * p.pixels * (2 * (p.C + p.has_gate) + p.C * (2 + (gx_in ? 1 : 0) + (p.has_gate ? 2 : 0))));
   if (tgt != nullptr && out_mix_v4_ok(p, {u, xprev, tgt, xt, gx_in, du, gx_prev}, du_out_bf, du_gate_bf)) {
     const dim3 grid(flat_blocks(p.pixels >> 2, lc.sm_count));
     if (p.has_gate) CUDA_TRY(launch_k(lc, out_mix_bwd_v4_kernel<1>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, gx_in, coef, du, gx_prev,
-                                      db_out, db_gate, du_out_bf, du_gate_bf));
+                                      db_out, db_gate, du_out_bf, du_gate_bf, gate_in_out_bf));
     else CUDA_TRY(launch_k(lc, out_mix_bwd_v4_kernel<0>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, gx_in, coef, du, gx_prev,
-                           db_out, db_gate, du_out_bf, du_gate_bf));
+                           db_out, db_gate, du_out_bf, du_gate_bf, gate_in_out_bf));
     return 0;
   }
   CUDA_TRY(launch_k(lc, out_mix_bwd_kernel, dim3(flat_blocks(p.pixels, lc.sm_count)), dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt,
-                    gx_in, coef, du, gx_prev, db_out, db_gate, du_out_bf, du_gate_bf));
+                    gx_in, coef, du, gx_prev, db_out, db_gate, du_out_bf, du_gate_bf, gate_in_out_bf));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

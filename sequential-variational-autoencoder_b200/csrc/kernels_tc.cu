@@ -407,7 +407,8 @@ __global__ void tc_pack_kernel(Geom g, const float* __restrict__ w, __nv_bfloat1
 }
 
 __device__ __forceinline__ void pack_one(const Geom& g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                         int KC, int Cin_p, int N_p, int TW, long long e) {
+                                         int KC, int Cin_p, int N_p, int TW, long long e, const float* __restrict__ w2 = nullptr,
+                                         int n1 = 0) {
   const int JC = KC / 8;
   const int ntaps = g.KH * g.KW;
   const long long per_tile = (long long)TW * Cin_p * ntaps;
@@ -421,8 +422,15 @@ __device__ __forceinline__ void pack_one(const Geom& g, const float* __restrict_
   const int c = (int)t;
   const int ci = c * KC + j * 8 + k8, co = tile * TW + n;
   float v = 0.f;
-  if (ci < g.Cin && co < g.Cout)
-    v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + co] : w[((size_t)s * g.Cout + co) * g.Cin + ci];
+  if (ci < g.Cin && co < g.Cout) {
+    if (w2 == nullptr) {
+      v = g.w_out_major == 0 ? w[((size_t)s * g.Cin + ci) * g.Cout + co] : w[((size_t)s * g.Cout + co) * g.Cin + ci];
+    } else if (g.w_out_major == 1) {   // forward form: [tap][co][ci], the two tensors split the co range
+      v = co < n1 ? w[((size_t)s * n1 + co) * g.Cin + ci] : w2[((size_t)s * (g.Cout - n1) + (co - n1)) * g.Cin + ci];
+    } else {                           // input-gradient form: [tap][ci][co], the two tensors split the ci range
+      v = ci < n1 ? w[((size_t)s * n1 + ci) * g.Cout + co] : w2[((size_t)s * (g.Cin - n1) + (ci - n1)) * g.Cout + co];
+    }
+  }
   out[e] = __float2bfloat16_rn(v);
 }
 
@@ -430,7 +438,7 @@ __device__ __forceinline__ void pack_one(const Geom& g, const float* __restrict_
 __global__ void tc_pack_batched_kernel(const TcPackEntry* __restrict__ tab) {
   const TcPackEntry E = tab[blockIdx.y];
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E.total; e += (long long)gridDim.x * blockDim.x)
-    pack_one(E.g, E.w, reinterpret_cast<__nv_bfloat16*>(E.out), E.KC, E.Cin_p, E.N_p, E.TW, e);
+    pack_one(E.g, E.w, reinterpret_cast<__nv_bfloat16*>(E.out), E.KC, E.Cin_p, E.N_p, E.TW, e, E.w2, E.n1);
 }
 
 bool build_params(const Geom& g, TcParams& P) {
@@ -526,6 +534,7 @@ struct TwParams {
   const float* x; int x_ld, x_coff, x_vec;
   const float* dy; int dy_ld, dy_coff, dy_vec;
   float* dw; int dw_vec;
+  float* dw2; int a_split;  // rows (X channels) >= a_split go to dw2 [16][Ca - a_split][Cb] (two parameter tensors, one contraction)
   int B, Hx, Wx, Ca, Hy, Wy, Cb;   // Ca, Cb: real channel counts (dw is [16][Ca][Cb]); padded counts are mblocks*CaB, nblocks*N
   int mode;                 // 0 stride 1 (one plane), 1 stride 2 (four parity planes of X)
   int Hp, Wp, Hv, Wv, lo, HL, HLpad, YLpad;
@@ -1725,7 +1734,10 @@ __device__ __forceinline__ void tc2_wgrad_body(const Tw2Params& PP) {
         float v[32];
         tmem_ld_upto32(tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(tl * P.N + n0), v, P.N - n0);
         if (iblk < PP.S && a0 + a < P.Ca && my_tiles > 0) {
-          float* dst = P.dw + ((size_t)tap * P.Ca + a0 + a) * P.Cb + b0 + n0;
+          const int aa = a0 + a;
+          float* dst = P.dw2 == nullptr ? P.dw + ((size_t)tap * P.Ca + aa) * P.Cb + b0 + n0
+                       : aa < P.a_split ? P.dw + ((size_t)tap * P.a_split + aa) * P.Cb + b0 + n0
+                                        : P.dw2 + ((size_t)tap * (P.Ca - P.a_split) + (aa - P.a_split)) * P.Cb + b0 + n0;
           const int ncols = max(0, min(min(32, P.N - n0), P.Cb - (b0 + n0)));
           if (P.dw_vec) {
 #pragma unroll
@@ -1869,7 +1881,7 @@ bool tc2_wgrad_supported(const Geom& g) {
 
 // g: conv-gather geometry (X = conv input side in its tc2 input layout, dY = conv output side in the layout of the SAME
 // padded pixel space: kind 0 for stride 1, kind 1 for stride 2)
-int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw) {
+int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& dy, float* dw, float* dw2, int a_split) {
   Tw2Params PP;
   if (!build_wparams2(g, PP)) { svae_global_error() = "tc2 wgrad: unsupported geometry"; return -1; }
   int per_sm = 1;
@@ -1888,8 +1900,8 @@ int tc2_wgrad(const LaunchCtx& lc, const Geom& g, const BfAct& x, const BfAct& d
   PP.x_src = x.p + (long long)x.front * 8;
   PP.y_src = dy.p + (long long)dy.front * 8;
   PP.x_plane_rows = x.plane_rows; PP.x_group_rows = x.group_rows; PP.y_group_rows = dy.group_rows;
-  P.dw = dw;
-  P.dw_vec = (g.Cout % 4 == 0) && (((uintptr_t)dw & 15) == 0);
+  P.dw = dw; P.dw2 = dw2; P.a_split = a_split;
+  P.dw_vec = (g.Cout % 4 == 0) && (((uintptr_t)dw & 15) == 0) && (((uintptr_t)dw2 & 15) == 0);
   const size_t smem = smem_bytes_w2(PP);
   static bool configured = false;
   if (!configured) {
@@ -1983,9 +1995,9 @@ int tc_pack_weights(const LaunchCtx& lc, const Geom& g, const float* w, void* w_
   return 0;
 }
 
-TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed, int tile_width) {
+TcPackEntry tc_pack_entry(const Geom& g, const float* w, void* w_packed, int tile_width, const float* w2, int n1) {
   TcPackEntry e;
-  e.g = g; e.w = w; e.out = w_packed; e.TW = tile_width;
+  e.g = g; e.w = w; e.out = w_packed; e.TW = tile_width; e.w2 = w2; e.n1 = n1;
   e.Cin_p = round16(g.Cin); e.N_p = round16(g.Cout); e.KC = pick_kc(e.Cin_p);
   e.total = (long long)g.KH * g.KW * e.Cin_p * e.N_p;
   return e;

@@ -126,6 +126,11 @@ struct Step {
   int w_out, b_out, w_gate, b_gate;       // output deconvs (live bias)
   Geom g_out, g_gate;
   Block outb, gateb;                      // the same two deconvs as contraction blocks (no batch-norm) for TC routing
+  // t >= 1, TMA-fed kernels: the output (C columns) and gate (1 column) deconvs read the same input and are each padded to 16
+  // columns - ONE contraction with the two weight tensors packed side by side writes all C + 1 columns of u, one input
+  // gradient reads the C + 1 channel copy of d_u, one weight gradient scatters its rows to the two parameter tensors: two
+  // dependent kernels less per chain step on the chain, one less beside it (sequential_vae.py:1720,1727 share cur_sample).
+  Block ogb; Geom g_og; bool merge_og = false;
   float *u, *xt;
   float* xs = nullptr;                    // add_noise_to_chain: the sample x_t + noise that the next step reads (own buffer per step)
   double* lat_mom = nullptr;              // [L][64] scratch: second moments of z_t per latent group (lat_fwd_fused)
@@ -495,6 +500,8 @@ void build_params(svae_handle* h) {
         s.b_gate = add_param(h, r + "/biases", {1}, t, SVAE_PF_THETA);
         s.g_gate = deconv_geom(S[1], S[1], F[1], 1, 2);
         s.gateb.g = s.g_gate; s.gateb.w = s.w_gate;
+        s.g_og = deconv_geom(S[1], S[1], F[1], C + 1, 2);
+        s.ogb.g = s.g_og; s.ogb.w = s.w_out;
       }
     }
     s.p_end = h->arena_numel;
@@ -696,6 +703,8 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
       if (want(s.outb.g) && (t == 0 || want(s.gateb.g))) {
         feed(s.outb, &s.tb[0]);
         if (t > 0) { s.gateb.in_bf = s.outb.in_bf; s.gateb.tc2_fwd = true; }
+        static const bool merge = !(getenv("SVAE_MERGE_OG") && getenv("SVAE_MERGE_OG")[0] == '0');
+        if (t > 0 && merge && want(s.ogb.g)) { s.ogb.in_bf = s.outb.in_bf; s.ogb.tc2_fwd = true; s.merge_og = !c.train_capacity; }
       }
     }
     for (int t = 1; t < T; ++t) {   // enc[0] of step t reads the copy of x_{t-1}
@@ -709,7 +718,7 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
         alias_bf(s.encfc, r.encfc); alias_bf(s.decfc, r.decfc);
         for (size_t i = 0; i < s.lat.size(); ++i) alias_bf(s.lat[i], r.lat[i]);
         for (size_t i = 0; i < s.ta.size(); ++i) { alias_bf(s.ta[i], r.ta[i]); alias_bf(s.tb[i], r.tb[i]); }
-        alias_bf(s.outb, r.outb); alias_bf(s.gateb, r.gateb);
+        alias_bf(s.outb, r.outb); alias_bf(s.gateb, r.gateb); alias_bf(s.ogb, r.ogb); s.merge_og = r.merge_og;
         s.xt_bf = r.xt_bf;
       }
       if (want(s.enc[0].g)) { s.enc[0].in_bf = pr.xt_bf; s.enc[0].tc2_fwd = true; }
@@ -813,6 +822,11 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
           if (t > 0) {
             Geom wgt = dgrad_geom(s.g_gate); wgt.mode = 0; wgt.B = (int)B;
             s.gateb.tc2_wgrad = g.du_gate_bf.Cpad && s.gateb.tc2_fwd && tc_wgrad_supported(s.gateb.g) && tc2_wgrad_supported(wgt);
+            // merged form: the gate's gradient is channel C of the d_u copy (Cpad = 16 holds it)
+            Geom d4 = dgrad_geom(s.g_og), w4 = dgrad_geom(s.g_og); w4.mode = 0; w4.B = (int)B;
+            s.ogb.tc2_dgrad = s.ogb.tc2_fwd && g.du_out_bf.Cpad >= 16 && want(d4);
+            s.ogb.tc2_wgrad = s.ogb.tc2_dgrad && s.outb.tc2_wgrad && s.gateb.tc2_wgrad && tc_wgrad_supported(s.ogb.g) && tc2_wgrad_supported(w4);
+            s.merge_og = s.ogb.tc2_fwd && s.ogb.tc2_dgrad && s.ogb.tc2_wgrad;
           }
         }
       }
@@ -1204,11 +1218,16 @@ int decoder_fwd(svae_handle* h, Step& s, int B, const float* xprev, const float*
   }
   const int has_gate = s.t > 0 ? 1 : 0;
   const int ldu = C + has_gate;
+  if (has_gate && s.merge_og) {
+    H_TRY(contract_bf(h, s.g_og, B, true, s.ogb.in_bf, cur, h->pw(s.w_out), s.ogb.w_packed, true, mkview(s.u, ldu, 0), nullptr, nullptr,
+                      s.ogb.tw_f));
+  } else {
   H_TRY(contract_bf(h, s.g_out, B, s.outb.tc2_fwd, s.outb.in_bf, cur, h->pw(s.w_out), s.outb.w_packed, s.outb.tc_fwd,
                     mkview(s.u, ldu, 0), nullptr));
   if (has_gate)
     H_TRY(contract_bf(h, s.g_gate, B, s.gateb.tc2_fwd, s.gateb.in_bf, cur, h->pw(s.w_gate), s.gateb.w_packed, s.gateb.tc_fwd,
                       mkview(s.u, ldu, C), nullptr));
+  }
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
                  h->cfg.max_highway};
   H_TRY(out_mix_fwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, tgt, xt_out, recon_sum,
@@ -1422,10 +1441,29 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
                     coef, gs.d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr,
                     gs.du_out_bf.p ? BfDst{gs.du_out_bf, 0, 0, 0} : BfDst{},
-                    (has_gate && gs.du_gate_bf.p) ? BfDst{gs.du_gate_bf, 0, 0, 0} : BfDst{}));
+                    (has_gate && gs.du_gate_bf.p && !s.merge_og) ? BfDst{gs.du_gate_bf, 0, 0, 0} : BfDst{}, (has_gate && s.merge_og) ? 1 : 0));
   // output deconvs: dgrad into d_c[0], wgrads
   View c0 = mkview(s.tb[0].out.p, F[1], 0);
   View dc0 = mkview(gs.d_c[0], F[1], 0);
+  if (has_gate && s.merge_og) {
+    // merged output + gate deconv: one input gradient from the C + 1 channel copy of d_u, one weight gradient whose rows go to
+    // the two parameter tensors
+    Geom g4 = dgrad_geom(s.g_og);
+    H_TRY(contract_bf(h, g4, B, true, gs.du_out_bf, mkview(gs.d_u, ldu, 0), h->pw(s.w_out), s.ogb.w_packed_d, true, dc0, nullptr, nullptr,
+                      s.ogb.tw_d));
+    Geom gw4 = dgrad_geom(s.g_og); gw4.B = B; gw4.mode = 0;
+    if (h->wrec != nullptr) {
+      LaunchCtx lr = h->lc();
+      lr.multi = h->wrec; lr.sm_count = h->wrec_sm; lr.pdl_state = nullptr;
+      H_TRY(tc2_wgrad(lr, gw4, gs.du_out_bf, s.ogb.in_bf, h->pg(s.w_out), h->pg(s.w_gate), C));
+    } else if (!(h->ablate & 1)) {
+      H_TRY(link(h, st.chain, st.w));
+      OnStream os(h, st.w);
+      LaunchCtx lw = h->lc();
+      if (h->wgrad_sm > 0 && st.w != h->stream) lw.sm_count = std::min(lw.sm_count, h->wgrad_sm);
+      H_TRY(tc2_wgrad(lw, gw4, gs.du_out_bf, s.ogb.in_bf, h->pg(s.w_out), h->pg(s.w_gate), C));
+    }
+  } else
   {
     // d_c[0] is complete after the LAST of the two input gradients: that one carries pass 1 of tb[0]'s batch-norm backward
     Geom g = dgrad_geom(s.g_out);
@@ -1867,6 +1905,7 @@ void for_each_block(svae_handle* h, void (*fn)(svae_handle*, Block&, void*), voi
     for (Block& b : s.tb) fn(h, b, ctx);
     fn(h, s.outb, ctx);
     if (s.t > 0) fn(h, s.gateb, ctx);
+    if (s.t > 0 && s.merge_og) fn(h, s.ogb, ctx);
   }
 }
 
@@ -1917,8 +1956,14 @@ int ensure_pack_table(svae_handle* h) {
     collect_pack(h, s.decfc, &v);
     for (Block& b : s.ta) collect_pack(h, b, &v);
     for (Block& b : s.tb) collect_pack(h, b, &v);
-    collect_pack(h, s.outb, &v);
-    if (s.t > 0) collect_pack(h, s.gateb, &v);
+    if (s.t > 0 && s.merge_og) {   // one packed operand from the two parameter tensors (the separate forms are not used)
+      Block& b = s.ogb;
+      if (b.tc_fwd && b.w_packed) { Geom f = b.g; f.B = 1; v.push_back(tc_pack_entry(f, h->pw(s.w_out), b.w_packed, b.tw_f, h->pw(s.w_gate), h->C)); }
+      if (b.tc_dgrad && b.w_packed_d) { Geom d = dgrad_geom(b.g); d.B = 1; v.push_back(tc_pack_entry(d, h->pw(s.w_out), b.w_packed_d, b.tw_d, h->pw(s.w_gate), h->C)); }
+    } else {
+      collect_pack(h, s.outb, &v);
+      if (s.t > 0) collect_pack(h, s.gateb, &v);
+    }
     for (int i = h->pack_step_begin[t]; i < (int)v.size(); ++i) h->pack_step_elems[t] += (double)v[i].total;
   }
   h->pack_step_begin[h->T] = (int)v.size();
