@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-generation"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { tail -20 gpurun_out/${TAG}_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
-    -s 2600 -c 858 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
+    -s 2550 -c 842 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "list rc=$?"
 cap() {   # name, kernel regex, skip, count
   ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/prof_$1 $CMD > gpurun_out/${TAG}_ncu_full_$1.log 2>&1

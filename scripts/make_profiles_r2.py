@@ -41,8 +41,8 @@ T = sum(a[1] for a in agg.values()); R = sum(a[2] for a in agg.values()); W = su
 md = """# Round 2: ncu launch list of ONE graph-replayed training step with per-launch DRAM traffic (CelebA-64, B=100, T=8, bf16 tcgen05)
 
 Command (scripts/gpu_evidence_r2.sh): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none
---cache-control none -s 2600 -c 858 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-generation`, right after the same
-command exited 0 without ncu.  858 launches = one step (round 1: 1 167).  Per-launch times under ncu are serialised: compare SHARES
+--cache-control none -s 2550 -c 842 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-generation`, right after the same
+command exited 0 without ncu.  842 launches = one step (round 1: 1 167).  Per-launch times under ncu are serialised: compare SHARES
 with the `kernels` table of `profiles/%s_bench_final.json` (same build, no profiler: %.2f ms/step, %.0f img/s).
 
 Whole step: %d launches, %.2f ms of kernel time, **DRAM read %.2f GB + write %.2f GB = %.2f GB** against 6.29 GB algorithmic
