@@ -415,6 +415,7 @@ struct OutMixParams {
   int C;
   int has_gate;
   float lo, hi, minr, maxr;
+  int gxld;        // channel stride of the dL/dx_t buffers gx_in / gx_prev (0: = C)
 };
 // x_t = mix(sigmoid(u+bias)) ; accumulates sum (x_t - tgt)^2 into *recon_sum
 int out_mix_fwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, const float* b_out, const float* b_gate,

@@ -597,8 +597,9 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
     for (int c = 0; c < MAXC; ++c) {
       if (c >= p.C) break;
       const size_t ix = (size_t)i * p.C + c;
+      const size_t gix = (size_t)i * (p.gxld ? p.gxld : p.C) + c;
       float g = coef * (xt[ix] - tgt[ix]);
-      if (gx_in != nullptr) g += gx_in[ix];
+      if (gx_in != nullptr) g += gx_in[gix];
       float o = sigmoidf_(ur[c] + b_out[c]);
       float outv = p.lo + (p.hi - p.lo) * o;
       float d_u = g * r * (p.hi - p.lo) * o * (1.f - o);
@@ -607,7 +608,7 @@ out_mix_bwd_kernel(OutMixParams p, const float* __restrict__ u, const float* __r
       bsum[c] += d_u;
       if (p.has_gate) {
         dgate += g * (outv - xprev[ix]);
-        gx_prev[ix] = g * (1.f - r);
+        gx_prev[gix] = g * (1.f - r);
       }
     }
     if (p.has_gate) {
@@ -729,7 +730,14 @@ out_mix_bwd_v4_kernel(OutMixParams p, const float* __restrict__ u, const float* 
     ld12(xt + i0 * 3, xo);
     ld12(tgt + i0 * 3, tg);
     if (GATE) ld12(xprev + i0 * 3, xp);
-    if (gx_in != nullptr) ld12(gx_in + i0 * 3, gi);
+    if (gx_in != nullptr) {
+      if (p.gxld == 4) {   // 4-channel gradient buffer (the fourth is zero): one float4 per pixel
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 t = __ldg(reinterpret_cast<const float4*>(gx_in + (i0 + q) * 4)); gi[q * 3] = t.x; gi[q * 3 + 1] = t.y; gi[q * 3 + 2] = t.z; }
+      } else {
+        ld12(gx_in + i0 * 3, gi);
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float s = 0.f, r = 1.f;
@@ -774,7 +782,14 @@ out_mix_bwd_v4_kernel(OutMixParams p, const float* __restrict__ u, const float* 
 #pragma unroll
       for (int k = 0; k < LDU; ++k) dp[k] = make_float4(dd[4 * k], dd[4 * k + 1], dd[4 * k + 2], dd[4 * k + 3]);
     }
-    if (GATE) st12(gx_prev + i0 * 3, gp);
+    if (GATE) {
+      if (p.gxld == 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(gx_prev + (i0 + q) * 4)[0] = make_float4(gp[q * 3], gp[q * 3 + 1], gp[q * 3 + 2], 0.f);
+      } else {
+        st12(gx_prev + i0 * 3, gp);
+      }
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -1188,7 +1203,7 @@ int out_mix_bwd(const LaunchCtx& lc, const OutMixParams& p, const float* u, cons
   if (p.C > MAXC) return -1;
   ProfScope ps(lc, KC_OUT_MIX, 30.0 * p.pixels * p.C,
                4.0 * p.pixels * (2 * (p.C + p.has_gate) + p.C * (2 + (gx_in ? 1 : 0) + (p.has_gate ? 2 : 0))));
-  if (tgt != nullptr && out_mix_v4_ok(p, {u, xprev, tgt, xt, gx_in, du, gx_prev}, du_out_bf, du_gate_bf)) {
+  if (tgt != nullptr && (p.gxld == 0 || p.gxld == 3 || p.gxld == 4) && out_mix_v4_ok(p, {u, xprev, tgt, xt, gx_in, du, gx_prev}, du_out_bf, du_gate_bf)) {
     const dim3 grid(flat_blocks(p.pixels >> 2, lc.sm_count));
     if (p.has_gate) CUDA_TRY(launch_k(lc, out_mix_bwd_v4_kernel<1>, grid, dim3(256), 0, p, u, b_out, b_gate, xprev, tgt, xt, gx_in, coef, du, gx_prev,
                                       db_out, db_gate, du_out_bf, du_gate_bf, gate_in_out_bf));

@@ -224,6 +224,10 @@ struct svae_handle {
   int n_dy_slots = 0;
   std::vector<size_t> dy_slot_elems;
   float* gx[2] = {nullptr, nullptr};
+  // channel stride of the dL/dx_t buffers: 4 for 3-channel images on the TMA-fed kernels, so that the first chain-encoder conv's
+  // input gradient accumulates with 16-byte accesses (as a 4-column output whose fourth column has zero weights) instead of
+  // scalar read-modify-writes at a 12-byte stride
+  int gxld = 0;
   char* grad_base = nullptr; size_t grad_bytes = 0;
   char* bf_base = nullptr; size_t bf_bytes = 0;   // bf16 planar activation copies (zero-initialised once: the padding stays zero)
   BfAct x_bf{};                                   // copy of the input batch for the recognition nets' first conv
@@ -831,8 +835,12 @@ void build_buffers(svae_handle* h, Arena& act, Arena& zf, Arena& zb, Arena& gr, 
         }
       }
     }
-    h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * C);
-    h->gx[1] = gr.get<float>((size_t)B * h->D * h->D * C);
+    {
+      static const bool wide = !(getenv("SVAE_GX4") && getenv("SVAE_GX4")[0] == '0');
+      h->gxld = (wide && tc2 && C == 3 && T > 1 && h->steps[1].enc[0].tc2_dgrad) ? 4 : C;
+    }
+    h->gx[0] = gr.get<float>((size_t)B * h->D * h->D * h->gxld);
+    h->gx[1] = gr.get<float>((size_t)B * h->D * h->D * h->gxld);
   }
   // ---- which blocks may skip the fp32 copy of their activated output (see Block::skip_f32) -----------------------------
   {
@@ -1062,6 +1070,9 @@ int block_bwd(svae_handle* h, GradSet& gs, Block& b, int B, FeatView da, View in
   if (din != nullptr) {
     Geom g = dgrad_geom(b.g);
     g.accumulate = din_acc;
+    // 3-channel image gradient in a 4-channel buffer (svae_handle::gxld): written as 4 columns - the packed weights of the
+    // fourth are zero - so that the epilogue takes its 16-byte path
+    if (tc2d && g.Cout == 3 && din->ld == 4 && din->coff == 0) g.Cout = 4;
     BnBwdFuse fz;
     const bool fuse = tc2d && h->multi == nullptr && make_fuse(h, up, B, up_dres, up_dres_acc, g, *din, fz);
     H_TRY(contract_bf(h, g, B, tc2d, gs.dy_bf[b.dy_slot], dyv, h->pw(b.w), b.w_packed_d, b.tc_dgrad, *din, nullptr,
@@ -1436,7 +1447,7 @@ int decoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   const float coef = step_has_recon(h, s.t)
                          ? 16.f * step_coef(h, s.t) * 2.f / ((float)B * h->D * h->D * C) : 0.f;   // :1146,1163,1168
   OutMixParams p{(int64_t)B * h->D * h->D, C, has_gate, h->cfg.range_lo, h->cfg.range_hi, h->cfg.min_highway,
-                 h->cfg.max_highway};
+                 h->cfg.max_highway, h->gxld};
   if (!h->bwd_prezero) H_CUDA(cudaMemsetAsync(gs.d_z, 0, sizeof(float) * (size_t)B * h->Z, st.chain));   // lat_dz accumulates with atomics
   H_TRY(out_mix_bwd(lc, p, s.u, h->pw(s.b_out), has_gate ? h->pw(s.b_gate) : nullptr, xprev, h->last_tgt, s.xt, gx_in,
                     coef, gs.d_u, gx_prev, h->pg(s.b_out), has_gate ? h->pg(s.b_gate) : nullptr,
@@ -1555,7 +1566,7 @@ int encoder_bwd(svae_handle* h, GradSet& gs, const BwdStreams& st, Step& s, int 
   for (int k = last; k >= 0; --k) {
     Block& b = s.enc[k];
     View in = k > 0 ? mkview(s.enc[k - 1].out.p, s.enc[k - 1].feats, 0) : mkview(const_cast<float*>(xprev), h->C, 0);
-    View din = k > 0 ? mkview(gs.d_e[k - 1], s.enc[k - 1].feats, 0) : mkview(gx_prev, h->C, 0);
+    View din = k > 0 ? mkview(gs.d_e[k - 1], s.enc[k - 1].feats, 0) : mkview(gx_prev, h->gxld, 0);
     // d_e[k-1] already holds the decoder shortcut gradient when k-1 is odd (e[l+1] = enc[2l+1]); gx_prev always holds
     // the highway gradient
     const int acc = k > 0 ? ((k - 1) & 1) : 1;
