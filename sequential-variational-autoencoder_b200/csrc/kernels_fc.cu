@@ -54,13 +54,16 @@ __device__ __forceinline__ void fc_stage(unsigned char* dst, const FcOperand& op
   const unsigned pitch = op.mn_major ? FC_PITCH_MN : FC_PITCH_K;
   const int o_base = op.mn_major ? r0 : mn0, i_base = op.mn_major ? mn0 : r0;
   const int o_lim = op.mn_major ? R : op.mn_extent, i_lim = op.mn_major ? op.mn_extent : R;
-  constexpr int U = 4;
+#ifndef SVAE_FC_U
+#define SVAE_FC_U 8
+#endif
+  constexpr int U = SVAE_FC_U;   // loads in flight per thread and pass (the stage is 1024 16-byte items: one pass at U = 8)
   for (int base = tid; base < outer * groups; base += 128 * U) {
     float4 v0[U], v1[U];
     unsigned off[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int it = base + u * 128;            // outer*groups is a multiple of 512: never out of range
+      const int it = base + u * 128;            // outer*groups = 1024: never out of range
       const int o = it / groups, g = it - o * groups;
       off[u] = (unsigned)g * pitch + (unsigned)o * 16u;
       const int row = o_base + o, col = i_base + g * 8;
